@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the PdsNetwork.forward hot path (stereo pairs / second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--precision fp32|bf16x3|bf16x2|bf16] [--workload C2|C3|C4|C1]
+
+One process per GPU (torchrun for N > 1: ranks are independent replicas, one
+NCCL broadcast of the weights at start-up, NO collective in the timed region).
+A step = one PdsNetwork.forward (eval) over one batch of synthetic stereo pairs.
+Rank 0 prints ONE JSON line (see DESIGN.md "Measurement").
+
+--impl reference times the reference's CPU implementation of the same path on
+the host cores: the torch port under oracle/ (the reference itself is Python on
+ATen operators and cannot travel to the GPU box; the port dispatches to the
+same CPU kernels).  That leg, and cpu_baseline, are the only places this file
+touches oracle/.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {   # name: (H, W, maximum_disparity, description)
+    'C1': (64, 128, 63, '128x64 md=63 (unit-test scale)'),
+    'C2': (540, 960, 191, '960x540 D=192 (FlyingThings3D shape)'),
+    'C3': (540, 960, 255, '960x540 D=256 (extended disparity range)'),
+    'C4': (375, 1242, 191, '1242x375 D=192 (KITTI shape)'),
+}
+METRIC = 'stereo pairs/sec at 960x540 D=192'
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self._stop_evt.is_set():
+                    break
+                self.samples.append([f.strip() for f in line.split(',')])
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for name, flag in zip(names, s[3:7]):
+                    if flag.lower().startswith('active'):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def synthetic_pairs(n, batch, H, W, device, seed=0, pinned=False):
+    """`n` distinct seeded stereo pairs: right = left shifted by a few px + noise, 0..255."""
+    g = torch.Generator().manual_seed(seed)
+    pairs = []
+    for i in range(n):
+        left = torch.rand(batch, 3, H, W, generator=g) * 255
+        right = torch.rand(batch, 3, H, W, generator=g) * 255
+        s = 4 + 3 * i
+        right[..., :-s] = 0.8 * left[..., s:] + 0.2 * right[..., :-s]
+        if pinned:
+            pairs.append((left.pin_memory(), right.pin_memory()))
+        else:
+            pairs.append((left.to(device), right.to(device)))
+    return pairs
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': p['hbm_gbs'], 'bf16_tflops': p['bf16_tflops'],
+                'bf16_tflops_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0,
+            'source': 'fallback'}
+
+
+def kernel_rooflines(report, steps, batch, Hp, Wp, md, precision, peaks):
+    """Per-kernel-class roofline from the live CUDA-event profile of `steps` steps.
+    Algorithmic bytes / flops per launch are the DESIGN.md figures."""
+    Hq, Wq, Dq, Dc = Hp // 4, Wp // 4, (md + 1) // 4, (md + 1) // 2
+    out = []
+    n_slices = batch * Dq
+    conv64_flops = 2.0 * 9 * 64 * 64 * Hq * Wq * n_slices        # one 64->64 3x3 layer
+    for name, (launches, ms) in sorted(report.items(), key=lambda kv: -kv[1][1]):
+        if launches == 0:
+            continue
+        avg_s = ms / launches / 1e3
+        entry = {'kernel': name, 'launches_per_step': launches / steps,
+                 'ms_per_step': ms / steps, 'avg_us': avg_s * 1e6}
+        if name == 'subpixel_map':
+            by = batch * (Dc * (Hp - (Hp - 0)) * 0 + Dc * Hp * Wp * 4 + Hp * Wp * 4)
+            entry.update(bound='hbm', unit='GB/s', achieved=by / avg_s / 1e9, peak=peaks['hbm_gbs'])
+        elif name == 'matching_concat':
+            by = batch * (2 * 64 * Hq * Wq * 4 + 128 * Dq * Hq * Wq * 4)
+            entry.update(bound='hbm', unit='GB/s', achieved=by / avg_s / 1e9, peak=peaks['hbm_gbs'])
+        elif name.startswith('conv_igemm_f32<8,8,8') or name.startswith('conv3x3_tc'):
+            # the matching 64->64 layers dominate this class (4 of its launches per step
+            # at C2 are exactly conv64_flops; conv0 is 2x that) -> use the class total
+            fl = conv64_flops * (4 + 2) / max(launches / steps, 1) if launches / steps >= 5 else conv64_flops
+            entry.update(bound='tensor', unit='TFLOP/s', achieved=fl / avg_s / 1e12,
+                         peak=peaks['bf16_tflops_sustained'])
+        if 'achieved' in entry:
+            entry['frac'] = entry['achieved'] / entry['peak']
+        out.append(entry)
+    return out
+
+
+def cpu_forward_seconds(H, W, md, reps, threads=None):
+    """Times the torch port of the reference forward on the host cores."""
+    from oracle import synth, torch_port
+    if threads:
+        torch.set_num_threads(threads)
+    params = {k: torch.from_numpy(v) for k, v in
+              synth.make_params(synth.network_specs(), 61).items()}
+    (left, right), = synthetic_pairs(1, 1, H, W, 'cpu')
+    times = []
+    with torch.no_grad():
+        for _ in range(reps + 1):
+            t0 = time.time()
+            torch_port.network_forward(left, right, params, md)
+            times.append(time.time() - t0)
+    return times[1:] if reps else times      # first run is the warm-up
+
+
+def run_reference(args, H, W, md, desc):
+    rank = env_int('RANK', 0)
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from oracle import synth, torch_port
+    params = {k: torch.from_numpy(v) for k, v in
+              synth.make_params(synth.network_specs(), 61).items()}
+    # bounded sample: full pair unless the run would not end within a few minutes,
+    # then a horizontal band of the pair (throughput scaled by the row ratio)
+    rows, budget_s = H, 240.0
+    (left, right), = synthetic_pairs(1, 1, H, W, 'cpu')
+    with torch.no_grad():
+        t0 = time.time()
+        torch_port.network_forward(left, right, params, md)
+        first = time.time() - t0
+        total_steps = args.steps + args.warmup
+        if first * total_steps > budget_s:
+            rows = max(64, int(H * budget_s / (first * total_steps)) // 64 * 64)
+            left, right = left[..., :rows, :].contiguous(), right[..., :rows, :].contiguous()
+        for _ in range(args.warmup):
+            torch_port.network_forward(left, right, params, md)
+        t0 = time.time()
+        for _ in range(args.steps):
+            torch_port.network_forward(left, right, params, md)
+        elapsed = time.time() - t0
+    frac = rows / H
+    value = args.steps * frac / elapsed
+    sample = (f'{args.steps} x one full {W}x{H} pair' if rows == H else
+              f'{args.steps} x a {W}x{rows} band of the pair (pairs/s scaled by {frac:.3f})')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'pairs/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': elapsed / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': desc, 'batch_per_gpu': 1, 'maximum_disparity': md,
+                   'implementation': 'torch port of the reference forward on host cores '
+                                     '(oracle/torch_port.py, ATen CPU kernels)'},
+        'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('PDS_B200_PRECISION', 'fp32'))
+    ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=1, help='stereo pairs per GPU per step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    H, W, md, desc = WORKLOADS[args.workload]
+
+    if args.impl == 'reference':
+        run_reference(args, H, W, md, desc)
+        return
+
+    rank, world, local = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
+    assert torch.cuda.is_available(), 'bench.py --impl ours needs a CUDA device'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    from practicaldeepstereo_nips2018_b200 import PdsNetwork, _capi
+    from practicaldeepstereo_nips2018_b200 import parallel
+
+    torch.backends.cudnn.allow_tf32 = False        # embedding (cuDNN) stays fp32 like the oracle
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True          # as the reference trainer does (trainer.py:32-34)
+    torch.manual_seed(0)
+    net = PdsNetwork.default(md, precision=args.precision).to(dev).eval()
+    if world > 1:
+        parallel.broadcast_parameters(net, src=0)   # the only collective: weights, once
+
+    Hp, Wp = H + (-H) % 64, W + (-W) % 64
+    pairs = synthetic_pairs(4, args.batch, H, W, dev, seed=1000 + rank)
+    host_pairs = synthetic_pairs(4, args.batch, H, W, dev, seed=2000 + rank, pinned=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            net(*pairs[i % len(pairs)])
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)
+
+        # ---- value: inputs resident in HBM ------------------------------------------
+        barrier()
+        launches0 = _capi.launch_count()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for i in range(args.steps):
+            out = net(*pairs[i % len(pairs)])
+        stop.record()
+        barrier()
+        ms = max_over_ranks(start.elapsed_time(stop))
+        launches = _capi.launch_count() - launches0
+
+        # ---- e2e: public API with HOST buffers, H2D + D2H inside the timed region ------
+        d2h = torch.empty((args.batch, H, W), dtype=torch.float32).pin_memory()
+        for i in range(2):
+            l, r = host_pairs[i % len(host_pairs)]
+            d2h.copy_(net(l.to(dev, non_blocking=True), r.to(dev, non_blocking=True)))
+        barrier()
+        start.record()
+        for i in range(args.steps):
+            l, r = host_pairs[i % len(host_pairs)]
+            d2h.copy_(net(l.to(dev, non_blocking=True), r.to(dev, non_blocking=True)),
+                      non_blocking=True)
+        stop.record()
+        barrier()
+        e2e_ms = max_over_ranks(start.elapsed_time(stop))
+        if sampler:
+            sampler.stop()
+
+        # ---- per-kernel CUDA-event profile (separate instrumented pass) ----------------
+        report = {}
+        if rank == 0:
+            _capi.profiler_reset()
+            _capi.profiler_enable(True)
+            for i in range(args.steps):
+                net(*pairs[i % len(pairs)])
+            torch.cuda.synchronize()
+            _capi.profiler_enable(False)
+            report = _capi.profiler_report()
+    barrier()
+
+    if rank == 0:
+        peaks = load_peaks()
+        total_pairs = args.steps * args.batch * world
+        kernels = kernel_rooflines(report, args.steps, args.batch, Hp, Wp, md, args.precision, peaks)
+        dominant = next((k for k in kernels if 'achieved' in k), None)
+        roofline = None
+        if dominant:
+            roofline = {'bound': dominant['bound'], 'achieved': dominant['achieved'],
+                        'peak': dominant['peak'], 'unit': dominant['unit'],
+                        'frac': dominant['frac'], 'traffic': None, 'kernel': dominant['kernel'],
+                        'peak_source': peaks['source'],
+                        'timing': 'CUDA events around every launch, separate instrumented pass of '
+                                  f'{args.steps} steps'}
+        line = {
+            'metric': METRIC, 'value': total_pairs / (ms / 1e3), 'unit': 'pairs/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': (total_pairs / (ms / 1e3)) / (1.0 / 0.62) if args.workload == 'C2' else None,
+            'dtype': {'fp32': 'f32', 'bf16': 'bf16'}.get(args.precision, args.precision),
+            'data': 'synthetic',
+            'config': {'workload': desc, 'batch_per_gpu': args.batch, 'maximum_disparity': md,
+                       'precision': args.precision, 'parallelism': f'replicas x{world}',
+                       'l2': 'per-step working set > 1 GB (>> 126 MB L2); 4 rotating input pairs',
+                       'embedding': 'ATen/cuDNN fp32 (TF32 off)'},
+            'e2e': {'value': total_pairs / (e2e_ms / 1e3), 'unit': 'pairs/s',
+                    'h2d_bytes_per_step': 2 * args.batch * 3 * H * W * 4,
+                    'd2h_bytes_per_step': args.batch * H * W * 4},
+            'gpu_launches': launches,
+            'clocks': sampler.summary() if sampler else None,
+            'roofline': roofline,
+            'kernels': kernels,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            times = cpu_forward_seconds(H, W, md, reps=2, threads=cores)
+            line['cpu_baseline'] = {'value': 1.0 / statistics.median(times), 'unit': 'pairs/s',
+                                    'cores': cores, 'kind': 'port',
+                                    'sample': f'{len(times)} x one full {W}x{H} pair, torch port of '
+                                              'the reference forward (after 1 warm-up)'}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,160 @@
+/*
+ * pds_b200.h -- C-ABI of the B200-native stereo cost-volume pipeline that sits
+ * behind practical_deep_stereo.network.PdsNetwork.forward.
+ *
+ * The reference has NO FFI: its only seam is Python nn.Module duck typing
+ * (network.py:17-24, matching.py:17-29).  This header is therefore the surface
+ * a maintainer would bind from the reference's Python modules (ctypes stub in
+ * INTEGRATION.md); each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     its name ends in _host; tensors are contiguous, PyTorch layout
+ *     (NCHW / NCDHW), float32 unless a dtype argument says otherwise;
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and
+ *     returns without synchronising; no call allocates device memory except
+ *     the *_create functions (weights in kernel layout) -- scratch memory is
+ *     provided by the caller through (workspace, workspace_bytes);
+ *   - return value: PDS_OK or an error code; pds_last_error() gives the
+ *     message for the calling thread (the Python layer raises ValueError /
+ *     RuntimeError from it, mirroring network.py:28-31, estimator.py:34-41).
+ */
+#ifndef PDS_B200_H_
+#define PDS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDS_B200_VERSION 100
+
+enum pds_status {
+  PDS_OK = 0,
+  PDS_ERR_INVALID_ARGUMENT = 1, /* bad shape / parameter (-> ValueError)      */
+  PDS_ERR_CUDA = 2,             /* a CUDA runtime / driver call failed         */
+  PDS_ERR_WORKSPACE = 3,        /* workspace too small or misaligned           */
+  PDS_ERR_UNSUPPORTED = 4       /* valid request this build cannot serve       */
+};
+
+enum pds_dtype { PDS_F32 = 0, PDS_BF16 = 1 };
+
+/* Arithmetic of the convolution stacks.
+ *   PDS_PRECISION_FP32      CUDA-core FFMA, fp32 accumulate (bit-comparable to
+ *                           the reference up to summation order)
+ *   PDS_PRECISION_BF16X3    tcgen05 bf16 tensor cores, operands split in three
+ *                           bf16 terms, 6 partial products: fp32-equivalent
+ *   PDS_PRECISION_BF16X2    two terms, 3 partial products (~2^-16 relative)
+ *   PDS_PRECISION_BF16      plain bf16 operands, fp32 accumulate            */
+enum pds_precision {
+  PDS_PRECISION_FP32 = 0,
+  PDS_PRECISION_BF16X3 = 1,
+  PDS_PRECISION_BF16X2 = 2,
+  PDS_PRECISION_BF16 = 3
+};
+
+int pds_version(void);
+const char* pds_status_string(int status);
+const char* pds_last_error(void);
+
+/* ---- measurement hooks (bench.py) -----------------------------------------
+ * pds_launch_count: kernels launched by this library since load.
+ * Profiler: when enabled, every kernel launch is bracketed by CUDA events on
+ * its own stream; pds_profiler_read(i, ...) returns the i-th kernel class
+ * (name, launches, summed device milliseconds), 0 when i is out of range.   */
+unsigned long long pds_launch_count(void);
+void pds_profiler_enable(int on);
+void pds_profiler_reset(void);
+int pds_profiler_read(int index, char* name, int name_len,
+                      unsigned long long* launches, double* milliseconds);
+
+/* ---- a1: Matching.forward, data movement (matching.py:50-63) -------------
+ * Builds, for every disparity d in [0, D), the tensor the reference hands to
+ * `operation`: cat[left, shift_d(right)] with shift_d(right)[x] = right[x-d]
+ * and zeros for x < d (matching.py:12-13,56-60).
+ *   left, right : (B, C, H, W)
+ *   volume      : (B, D, 2C, H, W)  == (B*D, 2C, H, W) batched operation input
+ */
+int pds_matching_concat(const void* left, const void* right, void* volume,
+                        int B, int C, int H, int W, int D, int dtype,
+                        void* stream);
+
+/* th.stack(matching_signatures, dim=2) (matching.py:63) for a batched
+ * operation output: in (B*D, F, H, W) -> out (B, F, D, H, W). */
+int pds_matching_stack(const void* in, void* out, int B, int F, int D, int H,
+                       int W, int dtype, void* stream);
+
+/* ---- a2: MatchingOperation.forward over all disparities ------------------
+ * (matching.py:69-112 applied by the loop of matching.py:53-62.)
+ * Weights are given in the reference's own layout, in state_dict() order of
+ * MatchingOperation: conv0.w (F,2C,3,3), conv0.b, then per residual block
+ * 2 x [conv.w (F,F,3,3), conv.b, in.gamma, in.beta], then conv_last.w
+ * (S,F,3,3), conv_last.b; all float32 device pointers, copied and re-laid-out
+ * at create time.                                                            */
+typedef struct pds_matching_op pds_matching_op;
+
+int pds_matching_op_create(pds_matching_op** op, const float* const* params,
+                           int n_params, int descriptor_features /* C=64 */,
+                           int features /* F=64 */, int signature_features /* 8 */,
+                           int residual_blocks /* 2 */, int precision,
+                           void* stream);
+void pds_matching_op_destroy(pds_matching_op* op);
+size_t pds_matching_op_workspace_bytes(const pds_matching_op* op, int B, int H,
+                                       int W, int D);
+/* left, right (B, C, H, W) -> signatures (B, S, D, H, W), D = md + 1. */
+int pds_matching_op_forward(pds_matching_op* op, const float* left,
+                            const float* right, float* signatures, int B,
+                            int H, int W, int D, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ---- a3: Regularization.forward (regularization.py:94-126) ---------------
+ * params: state_dict() order of Regularization (74 tensors for F = 8).       */
+typedef struct pds_regularization pds_regularization;
+
+int pds_regularization_create(pds_regularization** reg,
+                              const float* const* params, int n_params,
+                              int features /* 8 */, int precision,
+                              void* stream);
+void pds_regularization_destroy(pds_regularization* reg);
+size_t pds_regularization_workspace_bytes(const pds_regularization* reg, int B,
+                                          int D, int H, int W);
+/* signatures (B, F, D, H, W), shortcut (B, F, H, W) -> cost (B, 2D, 4H, 4W) */
+int pds_regularization_forward(pds_regularization* reg,
+                               const float* signatures, const float* shortcut,
+                               float* cost, int B, int D, int H, int W,
+                               void* workspace, size_t workspace_bytes,
+                               void* stream);
+
+/* Individually tested reference blocks (test/test_regularization.py:13-28):
+ * ContractionBlock3d.forward (regularization.py:28-31) and
+ * ExpansionBlock3d.forward (regularization.py:54-57); params = the block's
+ * state_dict() order (8 tensors each), fp32 CUDA-core arithmetic.            */
+size_t pds_contraction_block_workspace_bytes(int B, int C, int D, int H, int W);
+int pds_contraction_block_forward(const float* const* params, const float* in,
+                                  float* down, float* smooth, int B, int C,
+                                  int D, int H, int W, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+size_t pds_expansion_block_workspace_bytes(int B, int C, int D, int H, int W);
+int pds_expansion_block_forward(const float* const* params, const float* in,
+                                const float* skip, float* out, int B, int C,
+                                int D, int H, int W, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* ---- a4: SubpixelMap.__call__ (estimator.py:45-91) -----------------------
+ * cost (B, D, H, W) of `dtype` -> disparity (B, H-crop_top, W-crop_left)
+ * float32; the crop is SizeAdapter.unpad (size_adapter.py:51-52) fused into
+ * the store.  argmax may be NULL, else (B, H-crop_top, W-crop_left) int64
+ * (th.max indices: lowest index on ties, first NaN wins).
+ * half_support_window >= 1, disparity_step >= 1 and hsw % step == 0, else
+ * PDS_ERR_INVALID_ARGUMENT (estimator.py:34-41).                             */
+int pds_subpixel_map(const void* cost, float* disparity, int64_t* argmax,
+                     int B, int D, int H, int W, int half_support_window,
+                     int disparity_step, int crop_top, int crop_left,
+                     int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDS_B200_H_ */

@@ -1,0 +1,258 @@
+// a4 -- SubpixelMap.__call__ (reference estimator.py:45-91) as ONE streaming
+// pass over the cost volume.
+//
+// cost is (B, D, H, W): the disparity axis is the OUTER (stride H*W) axis, so
+// the bandwidth-optimal mapping is threads along W with 128-bit loads and a
+// serial scan along D.  The reference needs ~70 kernels and 10 host syncs
+// (boolean-mask index_put_, estimator.py:74,77); here each thread keeps, in
+// registers, the running maximum with its index and the R values on either
+// side of it:
+//   - the R values BEFORE the maximum come from a rolling history,
+//   - the R values AFTER it are captured as the scan passes idx+1 .. idx+R,
+// so every cost element is read from HBM exactly once and nothing is re-read.
+// Algorithmic bytes: D*H'*W*sizeof(T) read + H'*W'*4 written (H', W' after the
+// fused SizeAdapter.unpad crop, size_adapter.py:51-52): cropped rows are never
+// loaded.
+#include "pds_common.cuh"
+
+namespace pds {
+namespace {
+
+template <typename T, int V>
+struct Vec;
+template <>
+struct Vec<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    float4 r = ldg_stream(reinterpret_cast<const float4*>(p));
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+  }
+};
+template <>
+struct Vec<float, 1> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
+};
+template <>
+struct Vec<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+    uint2 r = ldg_stream(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+  }
+};
+template <>
+struct Vec<__nv_bfloat16, 1> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) {
+    v[0] = __bfloat162float(*p);
+  }
+};
+
+// th.max semantics: strictly-greater keeps the LOWEST index on
+// ties; a NaN beats any number and the FIRST NaN is kept.
+__device__ __forceinline__ bool takes_over(float v, float best) {
+  return (v > best) || ((v != v) && (best == best));
+}
+
+// One thread = V consecutive pixels of one row.  R = half_support_window/step.
+template <typename T, int V, int R, int UNROLL>
+__global__ void __launch_bounds__(64)
+subpixel_map_kernel(const T* __restrict__ cost, float* __restrict__ disparity,
+                    int64_t* __restrict__ argmax, int D, int H, int W, int step,
+                    int crop_top, int crop_left, int quads_per_row) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Hc = H - crop_top;
+  const int b = blockIdx.y;
+  if (q >= quads_per_row * Hc) return;
+  const int y = crop_top + q / quads_per_row;
+  const int x0 = (q % quads_per_row) * V;
+  const size_t plane = (size_t)H * W;
+  const T* p = cost + (size_t)b * D * plane + (size_t)y * W + x0;
+
+  float best[V], before[V][R], after[V][R], hist[V][R];
+  int idx[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    idx[i] = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { before[i][r] = 0.f; after[i][r] = 0.f; hist[i][r] = 0.f; }
+  }
+  {
+    float v[V];
+    Vec<T, V>::load(p, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { best[i] = v[i]; hist[i][0] = v[i]; }
+  }
+  // hist[i][r] holds the value at (d - 1 - r) when element d is processed.
+  int d = 1;
+  for (; d + UNROLL <= D; d += UNROLL) {
+    float v[UNROLL][V];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) Vec<T, V>::load(p + (size_t)(d + u) * plane, v[u]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float x = v[u][i];
+        const int off = (d + u) - idx[i];        // >= 1
+        if (takes_over(x, best[i])) {
+          best[i] = x; idx[i] = d + u;
+#pragma unroll
+          for (int r = 0; r < R; ++r) before[i][r] = hist[i][r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) if (off == r + 1) after[i][r] = x;
+        }
+#pragma unroll
+        for (int r = R - 1; r > 0; --r) hist[i][r] = hist[i][r - 1];
+        hist[i][0] = x;
+      }
+    }
+  }
+  for (; d < D; ++d) {
+    float v[V];
+    Vec<T, V>::load(p + (size_t)d * plane, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float x = v[i];
+      const int off = d - idx[i];
+      if (takes_over(x, best[i])) {
+        best[i] = x; idx[i] = d;
+#pragma unroll
+        for (int r = 0; r < R; ++r) before[i][r] = hist[i][r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) if (off == r + 1) after[i][r] = x;
+      }
+#pragma unroll
+      for (int r = R - 1; r > 0; --r) hist[i][r] = hist[i][r - 1];
+      hist[i][0] = x;
+    }
+  }
+
+  const int Wc = W - crop_left;
+  const size_t orow = ((size_t)b * Hc + (y - crop_top)) * Wc;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int x = x0 + i;
+    if (x < crop_left || x >= W) continue;
+    // softmax over the window, max-subtracted (the centre IS the maximum):
+    // estimator.py:88-90.  Out-of-range taps: similarity -inf -> weight 0,
+    // disparity 0 (estimator.py:71-83).  Summation order = shift order.
+    float e[2 * R + 1], sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; ++k) {
+      const int j = idx[i] + k - R;
+      float s = k < R ? before[i][R - 1 - k] : (k == R ? best[i] : after[i][k - R - 1]);
+      const bool valid = (j >= 0) && (j < D);
+      e[k] = valid ? expf(s - best[i]) : 0.f;
+      sum += e[k];
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; ++k) {
+      const int j = idx[i] + k - R;
+      const bool valid = (j >= 0) && (j < D);
+      float pk = e[k] / sum;
+      if (sizeof(T) == 2) pk = __bfloat162float(__float2bfloat16_rn(pk));  // bf16 softmax
+      acc += pk * (valid ? (float)(step * j) : 0.f);
+    }
+    disparity[orow + (x - crop_left)] = acc;
+    if (argmax) argmax[orow + (x - crop_left)] = idx[i];
+  }
+}
+
+// Generic window radius (R > 4): arg-max pass, then gather the taps.
+template <typename T>
+__global__ void subpixel_map_generic_kernel(const T* __restrict__ cost,
+                                            float* __restrict__ disparity,
+                                            int64_t* __restrict__ argmax, int D, int H,
+                                            int W, int R, int step, int crop_top,
+                                            int crop_left) {
+  const int Hc = H - crop_top, Wc = W - crop_left;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= Hc * Wc) return;
+  const int y = crop_top + i / Wc, x = crop_left + i % Wc;
+  const size_t plane = (size_t)H * W;
+  const T* p = cost + (size_t)b * D * plane + (size_t)y * W + x;
+  float best = (float)p[0];
+  int idx = 0;
+  for (int d = 1; d < D; ++d) {
+    const float v = (float)p[(size_t)d * plane];
+    if (takes_over(v, best)) { best = v; idx = d; }
+  }
+  float sum = 0.f;
+  for (int k = -R; k <= R; ++k) {
+    const int j = idx + k;
+    if (j >= 0 && j < D) sum += expf((float)p[(size_t)j * plane] - best);
+  }
+  float acc = 0.f;
+  for (int k = -R; k <= R; ++k) {
+    const int j = idx + k;
+    if (j < 0 || j >= D) continue;
+    float pk = expf((float)p[(size_t)j * plane] - best) / sum;
+    if (sizeof(T) == 2) pk = __bfloat162float(__float2bfloat16_rn(pk));
+    acc += pk * (float)(step * j);
+  }
+  disparity[(size_t)b * Hc * Wc + i] = acc;
+  if (argmax) argmax[(size_t)b * Hc * Wc + i] = idx;
+}
+
+template <typename T, int V>
+int launch(const T* cost, float* disparity, int64_t* argmax, int B, int D, int H, int W,
+           int R, int step, int crop_top, int crop_left, cudaStream_t st) {
+  const int Hc = H - crop_top;
+  const int quads = (W + V - 1) / V;
+  dim3 grid((unsigned)(((size_t)quads * Hc + 63) / 64), (unsigned)B);
+  PDS_KERNEL("subpixel_map", st);
+#define PDS_EST(RR)                                                                  \
+  subpixel_map_kernel<T, V, RR, 8><<<grid, 64, 0, st>>>(cost, disparity, argmax, D, H, W, \
+                                                        step, crop_top, crop_left, quads)
+  switch (R) {
+    case 1: PDS_EST(1); break;
+    case 2: PDS_EST(2); break;
+    case 3: PDS_EST(3); break;
+    case 4: PDS_EST(4); break;
+    default: {
+      dim3 g((unsigned)(((size_t)Hc * (W - crop_left) + 127) / 128), (unsigned)B);
+      subpixel_map_generic_kernel<T><<<g, 128, 0, st>>>(cost, disparity, argmax, D, H, W, R,
+                                                       step, crop_top, crop_left);
+    }
+  }
+#undef PDS_EST
+  PDS_LAUNCH_CHECK("subpixel_map_kernel");
+  return PDS_OK;
+}
+
+}  // namespace
+}  // namespace pds
+
+extern "C" int pds_subpixel_map(const void* cost, float* disparity, int64_t* argmax, int B,
+                                int D, int H, int W, int half_support_window,
+                                int disparity_step, int crop_top, int crop_left, int dtype,
+                                void* stream) {
+  using namespace pds;
+  // estimator.py:34-41
+  PDS_CHECK_ARG(disparity_step >= 1, "\"disparity_step\" should be positive integer.");
+  PDS_CHECK_ARG(half_support_window >= 1, "\"half_support_window\" should be positive integer.");
+  PDS_CHECK_ARG(half_support_window % disparity_step == 0,
+                "\"half_support_window\" should be multiple of the\"disparity_step\"");
+  PDS_CHECK_ARG(cost && disparity, "pds_subpixel_map: null pointer");
+  PDS_CHECK_ARG(B >= 0 && D >= 1 && H >= 0 && W >= 0, "pds_subpixel_map: bad shape");
+  PDS_CHECK_ARG(crop_top >= 0 && crop_top <= H && crop_left >= 0 && crop_left <= W,
+                "pds_subpixel_map: crop outside the image");
+  PDS_CHECK_ARG(dtype == PDS_F32 || dtype == PDS_BF16, "pds_subpixel_map: bad dtype");
+  if (B == 0 || H - crop_top == 0 || W - crop_left == 0) return PDS_OK;
+  PDS_CHECK_ARG(B <= 65535, "pds_subpixel_map: batch > 65535");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = half_support_window / disparity_step;
+  const size_t esz = dtype == PDS_F32 ? 4 : 2;
+  const bool vec = (W % 4 == 0) && (((uintptr_t)cost) % (4 * esz) == 0);
+  if (dtype == PDS_F32) {
+    const float* c = (const float*)cost;
+    return vec ? launch<float, 4>(c, disparity, argmax, B, D, H, W, R, disparity_step, crop_top, crop_left, st)
+               : launch<float, 1>(c, disparity, argmax, B, D, H, W, R, disparity_step, crop_top, crop_left, st);
+  }
+  const __nv_bfloat16* c = (const __nv_bfloat16*)cost;
+  return vec ? launch<__nv_bfloat16, 4>(c, disparity, argmax, B, D, H, W, R, disparity_step, crop_top, crop_left, st)
+             : launch<__nv_bfloat16, 1>(c, disparity, argmax, B, D, H, W, R, disparity_step, crop_top, crop_left, st);
+}

@@ -1,0 +1,111 @@
+// Library-level C-ABI entry points and error plumbing (include/pds_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pds_common.cuh"
+
+namespace pds {
+namespace {
+thread_local char g_error[512] = "";
+}
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_profiling{0};
+std::mutex g_prof_mutex;
+struct Pending { const char* name; cudaEvent_t start, stop; };
+std::vector<Pending> g_pending;
+struct Total { unsigned long long launches = 0; double ms = 0.0; };
+std::map<std::string, Total> g_totals;
+
+void drain_pending() {  // caller holds g_prof_mutex
+  for (auto& p : g_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.stop) == cudaSuccess && cudaEventElapsedTime(&ms, p.start, p.stop) == cudaSuccess) {
+      Total& t = g_totals[p.name];
+      t.launches += 1;
+      t.ms += ms;
+    }
+    cudaEventDestroy(p.start);
+    cudaEventDestroy(p.stop);
+  }
+  g_pending.clear();
+}
+}  // namespace
+
+KernelScope::KernelScope(const char* name, cudaStream_t st) : name_(name), st_(st) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_profiling.load(std::memory_order_relaxed)) {
+    if (cudaEventCreate(&start_) == cudaSuccess) cudaEventRecord(start_, st_);
+    else start_ = nullptr;
+  }
+}
+
+KernelScope::~KernelScope() {
+  if (!start_) return;
+  cudaEvent_t stop;
+  if (cudaEventCreate(&stop) != cudaSuccess) { cudaEventDestroy(start_); return; }
+  cudaEventRecord(stop, st_);
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  g_pending.push_back({name_, start_, stop});
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return PDS_ERR_CUDA;
+}
+}  // namespace pds
+
+extern "C" int pds_version(void) { return PDS_B200_VERSION; }
+
+extern "C" const char* pds_last_error(void) { return pds::g_error; }
+
+extern "C" const char* pds_status_string(int status) {
+  switch (status) {
+    case PDS_OK: return "ok";
+    case PDS_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case PDS_ERR_CUDA: return "CUDA error";
+    case PDS_ERR_WORKSPACE: return "workspace too small or misaligned";
+    case PDS_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+  }
+}
+
+extern "C" unsigned long long pds_launch_count(void) { return pds::g_launches.load(); }
+
+extern "C" void pds_profiler_enable(int on) { pds::g_profiling.store(on ? 1 : 0); }
+
+extern "C" void pds_profiler_reset(void) {
+  std::lock_guard<std::mutex> lock(pds::g_prof_mutex);
+  pds::drain_pending();
+  pds::g_totals.clear();
+}
+
+extern "C" int pds_profiler_read(int index, char* name, int name_len, unsigned long long* launches,
+                                 double* milliseconds) {
+  std::lock_guard<std::mutex> lock(pds::g_prof_mutex);
+  pds::drain_pending();
+  if (index < 0 || index >= (int)pds::g_totals.size()) return 0;
+  auto it = pds::g_totals.begin();
+  std::advance(it, index);
+  if (name && name_len > 0) {
+    strncpy(name, it->first.c_str(), name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (launches) *launches = it->second.launches;
+  if (milliseconds) *milliseconds = it->second.ms;
+  return 1;
+}

@@ -1,0 +1,82 @@
+// Shared helpers of the sm_100a kernel library (device + host side).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pds_b200.h"
+
+namespace pds {
+
+// Thread-local error message returned by pds_last_error().
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define PDS_CHECK_ARG(cond, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::pds::set_error(__VA_ARGS__);             \
+      return PDS_ERR_INVALID_ARGUMENT;           \
+    }                                            \
+  } while (0)
+
+#define PDS_CUDA(call)                                          \
+  do {                                                          \
+    cudaError_t e__ = (call);                                   \
+    if (e__ != cudaSuccess) return ::pds::cuda_fail(e__, #call); \
+  } while (0)
+
+#define PDS_LAUNCH_CHECK(name)                                     \
+  do {                                                             \
+    cudaError_t e__ = cudaGetLastError();                          \
+    if (e__ != cudaSuccess) return ::pds::cuda_fail(e__, name);    \
+  } while (0)
+
+// Launch accounting (pds_launch_count) and the optional per-kernel CUDA-event
+// profiler (pds_profiler_*): every kernel launch in the library goes through a
+// KernelScope so bench.py can count launches and time each kernel class live.
+struct KernelScope {
+  KernelScope(const char* name, cudaStream_t st);
+  ~KernelScope();
+  const char* name_;
+  cudaStream_t st_;
+  cudaEvent_t start_ = nullptr;
+};
+#define PDS_KERNEL(name, st) ::pds::KernelScope pds_kernel_scope__(name, st)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Streaming 128-bit accesses that do not pollute L1 (data touched once).
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_stream(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+               : "=r"(r.x), "=r"(r.y)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+}  // namespace pds

@@ -1,0 +1,200 @@
+"""Matching + MatchingOperation (reference matching.py:16-112) on sm_100a kernels.
+
+Two kernel paths sit behind the reference API:
+
+* ``Matching`` with an arbitrary ``operation`` callable: one kernel builds the
+  disparity-stacked operation input ``(B*D, 2C, H, W)`` (csrc/matching_volume.cu),
+  ``operation`` runs ONCE on it, one kernel re-stacks the result to
+  ``(B, F, D, H, W)``.  Exact for any per-sample operation (the reference's own
+  MatchingOperation uses InstanceNorm, whose statistics are per sample).
+* ``Matching`` with a ``MatchingOperation``: the fused pipeline of
+  csrc/matching_op.cu -- the concatenated volume is never materialised.
+
+Gradient-enabled calls (training) are outside the inference hot path and run
+the plain ATen composition of the same modules.
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _capi, network_blocks
+
+
+def _needs_autograd(*tensors_and_modules):
+    if not torch.is_grad_enabled():
+        return False
+    for obj in tensors_and_modules:
+        if isinstance(obj, torch.Tensor):
+            if obj.requires_grad:
+                return True
+        elif isinstance(obj, nn.Module):
+            if any(p.requires_grad for p in obj.parameters()):
+                return True
+    return False
+
+
+class _KernelHandle(object):
+    """Owns a C-ABI handle built from a module's parameters; rebuilt whenever a
+    parameter is replaced or modified in place (optimizer step, load_state_dict)."""
+
+    def __init__(self, create, destroy):
+        self._create, self._destroy = create, destroy
+        self._handle, self._key = None, None
+        self._workspace = None
+
+    def get(self, params, precision, device):
+        key = (str(device), precision) + tuple((p.data_ptr(), p._version) for p in params)
+        if key != self._key:
+            self.release()
+            handle = ctypes.c_void_p()
+            with torch.cuda.device(device):
+                self._create(handle, [p.detach().contiguous().float() for p in params],
+                             precision, device)
+            self._handle, self._key = handle, key
+        return self._handle
+
+    def workspace(self, nbytes, device):
+        ws = self._workspace
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            self._workspace = ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8,
+                                               device=device)
+        return ws
+
+    def release(self):
+        if self._handle is not None:
+            self._destroy(self._handle)
+            self._handle, self._key = None, None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class MatchingOperation(nn.Module):
+    """Per-disparity 2-D network applied to cat[left, shifted right]:
+    conv3x3 2C->F, `number_of_residual_blocks` residual blocks, conv3x3 F->S."""
+
+    def __init__(self, number_of_concatenated_descriptor_features=128, number_of_features=64,
+                 number_of_compact_matching_signature_features=8,
+                 number_of_residual_blocks=2, precision='fp32'):
+        super().__init__()
+        if precision not in _capi.PRECISIONS:
+            raise ValueError(f'precision should be one of {sorted(_capi.PRECISIONS)}')
+        self._shape = (number_of_concatenated_descriptor_features, number_of_features,
+                       number_of_compact_matching_signature_features, number_of_residual_blocks)
+        self.precision = precision
+        layers = [network_blocks.convolution_3x3(number_of_concatenated_descriptor_features,
+                                                 number_of_features)]
+        layers += [network_blocks.ResidualBlock(number_of_features)
+                   for _ in range(number_of_residual_blocks)]
+        layers += [network_blocks.convolution_3x3(
+            number_of_features, number_of_compact_matching_signature_features)]
+        self._matching_operation_modules = nn.ModuleList(layers)
+        self.__dict__['_kernel'] = _KernelHandle(self._create_handle, self._destroy_handle)
+
+    # -- C-ABI plumbing -------------------------------------------------------
+    def _create_handle(self, handle, params, precision, device):
+        cin, f, s, n_res = self._shape
+        arr = _capi.pointer_array(params)
+        _capi.check(_capi.lib().pds_matching_op_create(
+            ctypes.byref(handle), arr, len(params), cin // 2, f, s, n_res,
+            _capi.PRECISIONS[precision], _capi.stream_ptr(device)))
+        torch.cuda.current_stream(device).synchronize()   # params may be temporaries
+
+    @staticmethod
+    def _destroy_handle(handle):
+        _capi.lib().pds_matching_op_destroy(handle)
+
+    def match_all_disparities(self, left, right, number_of_disparities):
+        """left, right [B, C, H, W] -> signatures [B, S, D, H, W] for d = 0..D-1,
+        i.e. th.stack([op(cat[left, shift_d(right)]) for d], dim=2)."""
+        _capi.require_cuda(left, right)
+        cin, _, s, _ = self._shape
+        if left.shape != right.shape or left.dim() != 4 or 2 * left.size(1) != cin:
+            raise ValueError(f'descriptors should be two [B, {cin // 2}, H, W] tensors')
+        left = left.detach().contiguous().float()
+        right = right.detach().contiguous().float()
+        B, _, H, W = left.shape
+        D = int(number_of_disparities)
+        params = list(self.parameters())
+        lib = _capi.lib()
+        handle = self._kernel.get(params, self.precision, left.device)
+        out = torch.empty((B, s, D, H, W), dtype=torch.float32, device=left.device)
+        with torch.cuda.device(left.device):
+            nbytes = lib.pds_matching_op_workspace_bytes(handle, B, H, W, D)
+            ws = self._kernel.workspace(nbytes, left.device)
+            _capi.check(lib.pds_matching_op_forward(
+                handle, _capi.ptr(left), _capi.ptr(right), _capi.ptr(out), B, H, W, D,
+                _capi.ptr(ws), ws.numel(), _capi.stream_ptr(left.device)))
+        return out
+
+    def forward(self, concatenated_descriptors):
+        """[N, 2C, H, W] -> compact matching signature [N, S, H, W]."""
+        if _needs_autograd(concatenated_descriptors, self):
+            out = concatenated_descriptors            # training: ATen composition
+            for module in self._matching_operation_modules:
+                out = module(out)
+            return out
+        half = self._shape[0] // 2
+        left, right = concatenated_descriptors[:, :half], concatenated_descriptors[:, half:]
+        return self.match_all_disparities(left, right, 1)[:, :, 0]
+
+
+class Matching(nn.Module):
+    def __init__(self, maximum_disparity, operation, batched_operation=True):
+        """maximum_disparity: disparity range is [0, maximum_disparity];
+        operation: module or function applied to the concatenated left / shifted
+        right descriptors of every disparity.  ``batched_operation=False`` calls a
+        generic operation once per disparity (as the reference does) instead of
+        once on the disparity-stacked batch."""
+        super().__init__()
+        self._maximum_disparity = maximum_disparity
+        self._operation = operation
+        self._batched_operation = batched_operation
+
+    def set_maximum_disparity(self, maximum_disparity):
+        self._maximum_disparity = maximum_disparity
+
+    def _autograd_forward(self, left, right):
+        md = self._maximum_disparity
+        padded = nn.functional.pad(right, (md, 0, 0, 0))
+        width = right.size(-1)
+        out = [self._operation(torch.cat(
+            [left, padded[..., md - d:md - d + width]], dim=1)) for d in range(md + 1)]
+        return torch.stack(out, dim=2)
+
+    def forward(self, left_embedding, right_embedding):
+        """[B, C, H, W] x 2 -> matching signatures [B, F, maximum_disparity + 1, H, W]."""
+        op = self._operation
+        if _needs_autograd(left_embedding, right_embedding, op):
+            return self._autograd_forward(left_embedding, right_embedding)
+        D = self._maximum_disparity + 1
+        if isinstance(op, MatchingOperation):
+            return op.match_all_disparities(left_embedding, right_embedding, D)
+        # generic operation: volume kernel -> operation -> stack kernel
+        _capi.require_cuda(left_embedding, right_embedding)
+        left = left_embedding.detach().contiguous()
+        right = right_embedding.detach().contiguous()
+        if left.shape != right.shape or left.dim() != 4:
+            raise ValueError('descriptors should be two [B, C, H, W] tensors')
+        B, C, H, W = left.shape
+        lib, dt = _capi.lib(), _capi.dtype_code(left)
+        volume = torch.empty((B, D, 2 * C, H, W), dtype=left.dtype, device=left.device)
+        with torch.cuda.device(left.device):
+            st = _capi.stream_ptr(left.device)
+            _capi.check(lib.pds_matching_concat(_capi.ptr(left), _capi.ptr(right),
+                                                _capi.ptr(volume), B, C, H, W, D, dt, st))
+            if self._batched_operation:
+                sig = op(volume.view(B * D, 2 * C, H, W))
+            else:
+                sig = torch.stack([op(volume[:, d]) for d in range(D)], dim=1)
+                sig = sig.reshape(B * D, *sig.shape[2:])
+            sig = sig.contiguous()
+            F = sig.size(1)
+            out = torch.empty((B, F, D, H, W), dtype=sig.dtype, device=sig.device)
+            _capi.check(lib.pds_matching_stack(_capi.ptr(sig), _capi.ptr(out), B, F, D, H, W,
+                                               _capi.dtype_code(sig), st))
+        return out

@@ -1,0 +1,65 @@
+"""PdsNetwork: drop-in for practical_deep_stereo.network.PdsNetwork
+(reference network.py:14-65) wired to the B200 kernel modules."""
+import torch
+from torch import nn
+
+from . import embedding, estimator, matching, regularization, size_adapter
+
+
+class PdsNetwork(nn.Module):
+    """Practical Deep Stereo network; same constructor (dependency injection of
+    the five stages), methods and tensor shapes as the reference."""
+
+    def __init__(self, size_adapter_module, embedding_module, matching_module,
+                 regularization_module, estimator_module):
+        super().__init__()
+        self._size_adapter = size_adapter_module
+        self._embedding = embedding_module
+        self._matching = matching_module
+        self._regularization = regularization_module
+        self._estimator = estimator_module
+
+    def set_maximum_disparity(self, maximum_disparity):
+        """Reconfigure the disparity range; (maximum_disparity + 1) % 64 == 0."""
+        if (maximum_disparity + 1) % 64 != 0:
+            raise ValueError(
+                '"maximum_disparity" + 1 should be multiple of 64, e.g.,'
+                '"maximum disparity" can be equal to 63, 191, 255, 319...')
+        self._maximum_disparity = maximum_disparity
+        # descriptors are 4x down-sampled -> matching range (md + 1) / 4 - 1
+        self._matching.set_maximum_disparity((maximum_disparity + 1) // 4 - 1)
+
+    def pass_through_network(self, left_image, right_image):
+        left_descriptor, shortcut_from_left = self._embedding(left_image)
+        right_descriptor = self._embedding(right_image)[0]
+        signatures = self._matching(left_descriptor, right_descriptor)
+        return self._regularization(signatures, shortcut_from_left), shortcut_from_left
+
+    def forward(self, left_image, right_image):
+        """Sub-pixel disparity [B, H, W] in eval mode, matching cost
+        [B, (md + 1) / 2, H, W] in training mode."""
+        cost = self.pass_through_network(self._size_adapter.pad(left_image),
+                                         self._size_adapter.pad(right_image))[0]
+        if self.training:
+            return self._size_adapter.unpad(cost)
+        if isinstance(self._estimator, estimator.SubpixelMap) and cost.is_cuda:
+            # SizeAdapter.unpad fused into the estimator's store
+            return self._estimator(cost,
+                                   crop_top=self._size_adapter._pixels_pad_to_height,
+                                   crop_left=self._size_adapter._pixels_pad_to_width)
+        return self._size_adapter.unpad(self._estimator(cost))
+
+    @staticmethod
+    def default(maximum_disparity=255, precision='fp32'):
+        """Network with the default modules; `precision` selects the arithmetic of
+        the convolution stacks (see include/pds_b200.h, enum pds_precision)."""
+        network = PdsNetwork(
+            size_adapter_module=size_adapter.SizeAdapter(),
+            embedding_module=embedding.Embedding(),
+            matching_module=matching.Matching(
+                operation=matching.MatchingOperation(precision=precision),
+                maximum_disparity=0),
+            regularization_module=regularization.Regularization(precision=precision),
+            estimator_module=estimator.SubpixelMap())
+        network.set_maximum_disparity(maximum_disparity)
+        return network

@@ -1,0 +1,93 @@
+"""a5 parity: PdsNetwork.forward end to end vs the golden vectors of the
+unmodified reference and vs the torch port (B200 only)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle, synth, torch_port
+from practicaldeepstereo_nips2018_b200 import PdsNetwork
+from gpu_util import cuda, load_module, max_abs, tdict
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs():
+    li = synth.tensor((1, 3, 62, 100), 62, scale=255.0, uniform=True)
+    ri = synth.tensor((1, 3, 62, 100), 63, scale=255.0, uniform=True)
+    ri[..., :-6] = 0.8 * li[..., 6:] + 0.2 * ri[..., :-6]
+    return li, ri
+
+
+def margin_aware(disp, idx, ref_disp, ref_cost, crop, cost_err):
+    """Disparity parity on pixels whose reference top-1/top-2 margin exceeds the
+    measured cost error; returns (flip fraction, max-abs there)."""
+    top2 = np.sort(ref_cost, axis=1)[:, -2:]
+    margin = (top2[:, 1] - top2[:, 0])[..., crop[0]:, crop[1]:]
+    ref_idx = ref_cost.argmax(axis=1)[..., crop[0]:, crop[1]:]
+    safe = margin > 4 * cost_err
+    assert np.array_equal(idx[safe], ref_idx[safe])          # bit-exact where well-defined
+    flips = float((idx != ref_idx).mean())
+    return flips, float(np.abs(disp - ref_disp)[safe].max()), float(safe.mean())
+
+
+def test_network_golden(golden):
+    torch.backends.cudnn.allow_tf32 = False
+    g = golden('network_md63')
+    net = load_module(PdsNetwork.default(63), synth.make_params(synth.network_specs(), 61))
+    li, ri = _inputs()
+    with torch.no_grad():
+        left, right = cuda(li), cuda(ri)
+        disp = net(left, right)
+        sig = net._matching(*[net._embedding(net._size_adapter.pad(t))[0] for t in (left, right)])
+        cost = net.pass_through_network(net._size_adapter.pad(left), net._size_adapter.pad(right))[0]
+        d2, idx = net._estimator(cost, crop_top=2, crop_left=28, return_argmax=True)
+    assert disp.shape == (1, 62, 100) and torch.equal(disp, d2)
+    assert max_abs(sig, g['signatures']) <= 2e-4
+    cost_err = max_abs(cost, g['cost_padded'])
+    assert cost_err <= 3e-3          # reference fp32 vs its own fp64: 1.3e-3 (1x1x2 bottleneck)
+    flips, err, safe = margin_aware(disp.cpu().numpy(), idx.cpu().numpy(), g['disparity'],
+                                    g['cost_padded'], (2, 28), cost_err)
+    assert safe > 0.95 and flips < 5e-3
+    assert err <= 1e-3 + 50 * cost_err
+    # estimator on the identical volume is exact
+    rd, ridx = oracle.subpixel_map(cost.cpu().numpy())
+    assert np.array_equal(ridx[..., 2:, 28:], idx.cpu().numpy())
+    assert max_abs(rd[..., 2:, 28:], disp) <= 1e-4
+
+
+def test_network_shapes_and_modes():
+    # reference test/test_network.py:11-27 with a legal size for torch >= 2
+    torch.manual_seed(0)
+    net = PdsNetwork.default(63).cuda()
+    left, right = torch.rand(1, 3, 120, 200).cuda(), torch.rand(1, 3, 120, 200).cuda()
+    net.train()
+    assert net(left, right).size() == (1, 32, 120, 200)
+    net.set_maximum_disparity(127)
+    assert net(left, right).size() == (1, 64, 120, 200)
+    net.eval()
+    with torch.no_grad():
+        assert net(left, right).size() == (1, 120, 200)
+    with pytest.raises(ValueError):
+        net.set_maximum_disparity(100)
+
+
+def test_network_vs_torch_port_kitti_like():
+    """C4-like aspect (ragged, needs both pads) at reduced size, batch 2."""
+    torch.backends.cudnn.allow_tf32 = False
+    params = synth.make_params(synth.network_specs(), 71)
+    net = load_module(PdsNetwork.default(63), params)
+    left = cuda(synth.tensor((2, 3, 100, 310), 72, scale=255.0, uniform=True))
+    right = cuda(synth.tensor((2, 3, 100, 310), 73, scale=255.0, uniform=True))
+    right[..., :-9] = 0.7 * left[..., 9:] + 0.3 * right[..., :-9]
+    with torch.no_grad():
+        disp = net(left, right)
+        cost = net.pass_through_network(net._size_adapter.pad(left), net._size_adapter.pad(right))[0]
+        _, idx = net._estimator(cost, crop_top=28, crop_left=10, return_argmax=True)
+        st = torch_port.network_stages(left, right, tdict(params), 63)
+    assert disp.shape == (2, 100, 310)
+    cost_err = max_abs(cost, st['cost'])
+    assert cost_err <= 1e-3
+    flips, err, safe = margin_aware(disp.cpu().numpy(), idx.cpu().numpy(),
+                                    st['disparity'].cpu().numpy(), st['cost'].cpu().numpy(),
+                                    (28, 10), cost_err)
+    assert safe > 0.9 and flips < 1e-2 and err <= 1e-3 + 50 * cost_err

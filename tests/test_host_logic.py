@@ -1,0 +1,122 @@
+"""CPU-only tests: host-side logic of the drop-in modules, state_dict
+compatibility with the reference, argument validation, and that the C-ABI
+library loads and exports every symbol declared in include/pds_b200.h."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import synth
+from practicaldeepstereo_nips2018_b200 import (PdsNetwork, _capi, embedding, estimator,
+                                               matching, network, regularization,
+                                               size_adapter)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'pds_b200.h')).read()
+    declared = set(re.findall(r'\b(pds_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    lib = _capi.lib()                      # raises if a symbol is missing
+    assert lib.pds_version() == 100
+    assert lib.pds_status_string(1) == b'invalid argument'
+
+
+def test_state_dict_matches_reference_layout():
+    net = PdsNetwork.default(191)
+    sd = net.state_dict()
+    specs = synth.network_specs()
+    assert list(sd.keys()) == [k for k, _ in specs]
+    assert len(sd) == 122
+    for k, shape in specs:
+        assert tuple(sd[k].shape) == shape, k
+    assert sum(v.numel() for v in sd.values()) == 2217717
+    assert list(matching.MatchingOperation().state_dict().keys()) == \
+        [k for k, _ in synth.matching_operation_specs()]
+    assert list(regularization.Regularization().state_dict().keys()) == \
+        [k for k, _ in synth.regularization_specs()]
+    assert list(embedding.Embedding().state_dict().keys()) == \
+        [k for k, _ in synth.embedding_specs()]
+
+
+def test_set_maximum_disparity_validation():
+    net = PdsNetwork.default(63)
+    assert net._matching._maximum_disparity == 15
+    net.set_maximum_disparity(255)
+    assert net._matching._maximum_disparity == 63
+    with pytest.raises(ValueError):
+        net.set_maximum_disparity(100)     # reference network.py:28-31
+
+
+def test_estimator_validation():
+    for hsw, step in ((4, 0), (0, 1), (3, 2)):
+        with pytest.raises(ValueError):    # reference estimator.py:34-41
+            estimator.SubpixelMap(hsw, step)
+    estimator.SubpixelMap(4, 2)
+    est = estimator.SubpixelMap()
+    assert not isinstance(est, torch.nn.Module)
+
+
+def test_size_adapter_roundtrip():
+    adapter = size_adapter.SizeAdapter()   # reference test_size_adapter.py
+    x = torch.rand(1, 10, 63, 100)
+    padded = adapter.pad(x)
+    assert padded.size() == (1, 10, 64, 128)
+    assert (padded[..., :1, :] == 0).all() and (padded[..., :28] == 0).all()
+    assert (adapter.unpad(padded) == x).all()
+    assert adapter.padding_for(540, 960) == (36, 0)
+    assert adapter.padding_for(375, 1242) == (9, 38)
+
+
+def test_inference_path_refuses_cpu_tensors():
+    # no CPU fallback: the kernel path must fail loudly
+    with torch.no_grad():
+        with pytest.raises(RuntimeError):
+            estimator.SubpixelMap()(torch.rand(1, 8, 4, 4))
+        with pytest.raises(RuntimeError):
+            matching.Matching(2, lambda x: x)(torch.rand(1, 2, 3, 4), torch.rand(1, 2, 3, 4))
+        with pytest.raises(RuntimeError):
+            matching.MatchingOperation()(torch.rand(1, 128, 8, 8))
+        with pytest.raises(RuntimeError):
+            regularization.Regularization()(torch.rand(1, 8, 16, 16, 16), torch.rand(1, 8, 16, 16))
+
+
+def test_training_mode_is_aten_composition():
+    # gradient-enabled calls are outside the inference hot path: ATen ops, autograd works
+    torch.manual_seed(0)
+    op = matching.MatchingOperation()
+    m = matching.Matching(maximum_disparity=3, operation=op)
+    left = torch.rand(1, 64, 6, 8, requires_grad=True)
+    out = m(left, torch.rand(1, 64, 6, 8))
+    assert out.shape == (1, 8, 4, 6, 8)
+    out.sum().backward()
+    assert left.grad is not None and op._matching_operation_modules[0].weight.grad is not None
+
+
+def test_training_regularization_shapes():
+    torch.manual_seed(0)                   # reference test_regularization.py:31-36 (smaller)
+    reg = regularization.Regularization()
+    cost = reg(torch.rand(1, 8, 16, 16, 32), torch.rand(1, 8, 16, 32))
+    assert cost.shape == (1, 32, 64, 128) and cost.requires_grad
+    down, smooth = regularization.ContractionBlock3d(6)(torch.rand(2, 6, 10, 14, 16))
+    assert down.shape == smooth.shape == (2, 12, 5, 7, 8)
+    out = regularization.ExpansionBlock3d(6)(torch.rand(2, 6, 10, 14, 16), torch.rand(2, 3, 20, 28, 32))
+    assert out.shape == (2, 3, 20, 28, 32)
+
+
+def test_network_train_mode_matches_golden(golden):
+    # train mode (cost volume output) runs the ATen composition on CPU: must equal the
+    # reference bit-for-bit-ish since it is the same operator sequence
+    g = golden('network_md63')
+    params = synth.make_params(synth.network_specs(), 61)
+    net = PdsNetwork.default(63)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    net.train()
+    li = synth.tensor((1, 3, 62, 100), 62, scale=255.0, uniform=True)
+    ri = synth.tensor((1, 3, 62, 100), 63, scale=255.0, uniform=True)
+    ri[..., :-6] = 0.8 * li[..., 6:] + 0.2 * ri[..., :-6]
+    cost = net(torch.from_numpy(li), torch.from_numpy(ri))
+    assert cost.shape == (1, 32, 62, 100)
+    assert torch.allclose(cost.detach(), torch.from_numpy(g['cost_unpadded']), atol=1e-4)
