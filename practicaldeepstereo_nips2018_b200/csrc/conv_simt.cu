@@ -186,12 +186,13 @@ __global__ void __launch_bounds__(128) conv_igemm_f32(const ConvParams p) {
   }
 
   // epilogue: bias, LeakyReLU, channels-last store, InstanceNorm partial sums
-  float bias[TN], s[TN], ss[TN];
+  float bias[TN];
+  double s[TN], ss[TN];  // InstanceNorm sums: double from the first addition on
   const int co0 = n0 + ng * TN;
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
     bias[j] = (co0 + j < p.Cout) ? __ldg(p.bias + co0 + j) : 0.f;
-    s[j] = 0.f; ss[j] = 0.f;
+    s[j] = 0.0; ss[j] = 0.0;
   }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(128) conv_igemm_f32(const ConvParams p) {
     for (int j = 0; j < TN; ++j) {
       float x = acc[i][j] + bias[j];
       if (p.lrelu) x = x > 0.f ? x : 0.1f * x;
-      v[j] = x; s[j] += x; ss[j] += x * x;
+      v[j] = x; s[j] += (double)x; ss[j] += (double)x * (double)x;
     }
     if (TN % 4 == 0 && (p.Cout % 4 == 0)) {
 #pragma unroll

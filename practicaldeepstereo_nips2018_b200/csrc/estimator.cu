@@ -236,8 +236,8 @@ extern "C" int pds_subpixel_map(const void* cost, float* disparity, int64_t* arg
   PDS_CHECK_ARG(half_support_window >= 1, "\"half_support_window\" should be positive integer.");
   PDS_CHECK_ARG(half_support_window % disparity_step == 0,
                 "\"half_support_window\" should be multiple of the\"disparity_step\"");
-  PDS_CHECK_ARG(cost && disparity, "pds_subpixel_map: null pointer");
   PDS_CHECK_ARG(B >= 0 && D >= 1 && H >= 0 && W >= 0, "pds_subpixel_map: bad shape");
+  PDS_CHECK_ARG((cost && disparity) || B == 0 || H == 0 || W == 0, "pds_subpixel_map: null pointer");
   PDS_CHECK_ARG(crop_top >= 0 && crop_top <= H && crop_left >= 0 && crop_left <= W,
                 "pds_subpixel_map: crop outside the image");
   PDS_CHECK_ARG(dtype == PDS_F32 || dtype == PDS_BF16, "pds_subpixel_map: bad dtype");

@@ -29,9 +29,21 @@ class PdsNetwork(nn.Module):
         # descriptors are 4x down-sampled -> matching range (md + 1) / 4 - 1
         self._matching.set_maximum_disparity((maximum_disparity + 1) // 4 - 1)
 
+    def _embed(self, left_image, right_image):
+        """Embedding of both images.  It still runs on ATen/cuDNN operators (row a6
+        of SURVEY.md 8, "next"); TF32 is switched off for it unless the convolution
+        stacks themselves run in reduced precision, so that the fp32 pipeline is
+        fp32 end to end."""
+        precision = getattr(getattr(self._matching, '_operation', None), 'precision', 'fp32')
+        exact = left_image.is_cuda and precision in ('fp32', 'bf16x3', 'bf16x2')
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=not exact):
+            left_descriptor, shortcut_from_left = self._embedding(left_image)
+            right_descriptor = self._embedding(right_image)[0]
+        return left_descriptor, right_descriptor, shortcut_from_left
+
     def pass_through_network(self, left_image, right_image):
-        left_descriptor, shortcut_from_left = self._embedding(left_image)
-        right_descriptor = self._embedding(right_image)[0]
+        left_descriptor, right_descriptor, shortcut_from_left = self._embed(left_image,
+                                                                            right_image)
         signatures = self._matching(left_descriptor, right_descriptor)
         return self._regularization(signatures, shortcut_from_left), shortcut_from_left
 

@@ -79,5 +79,5 @@ def test_hourglass_vs_torch_port():
         ref = torch_port.regularization(sig, sc, tdict(params))
     scale = float(ref.abs().max())
     assert max_abs(out, ref) <= 2e-5 * scale + 2e-4
-    with pytest.raises(ValueError):
+    with torch.no_grad(), pytest.raises(ValueError):
         reg(sig[:, :, :24], sc)               # D not a multiple of 16
