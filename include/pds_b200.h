@@ -44,15 +44,22 @@ enum pds_dtype { PDS_F32 = 0, PDS_BF16 = 1 };
 /* Arithmetic of the convolution stacks.
  *   PDS_PRECISION_FP32      CUDA-core FFMA, fp32 accumulate (bit-comparable to
  *                           the reference up to summation order)
- *   PDS_PRECISION_BF16X3    tcgen05 bf16 tensor cores, operands split in three
- *                           bf16 terms, 6 partial products: fp32-equivalent
- *   PDS_PRECISION_BF16X2    two terms, 3 partial products (~2^-16 relative)
- *   PDS_PRECISION_BF16      plain bf16 operands, fp32 accumulate            */
+ *   PDS_PRECISION_BF16X3    tcgen05 tensor cores, operands split in three bf16
+ *                           terms (24 significand bits), 6 partial products
+ *   PDS_PRECISION_BF16X2    two bf16 terms (16 bits), 3 partial products
+ *   PDS_PRECISION_BF16      plain bf16 operands, fp32 accumulate
+ *   PDS_PRECISION_FP16X2    two IEEE-half terms (22 significand bits), 3 partial
+ *                           products: fp32-grade results at half the bf16x3 cost
+ *   PDS_PRECISION_FP16      plain half operands, fp32 accumulate
+ * In every tensor-core mode accumulation is fp32, one accumulator per order of
+ * magnitude of the partial products, summed in fp32 in the epilogue.         */
 enum pds_precision {
   PDS_PRECISION_FP32 = 0,
   PDS_PRECISION_BF16X3 = 1,
   PDS_PRECISION_BF16X2 = 2,
-  PDS_PRECISION_BF16 = 3
+  PDS_PRECISION_BF16 = 3,
+  PDS_PRECISION_FP16X2 = 4,
+  PDS_PRECISION_FP16 = 5
 };
 
 int pds_version(void);

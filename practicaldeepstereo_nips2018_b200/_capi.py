@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'libpds_b200.so')
 
 PDS_OK, PDS_ERR_INVALID_ARGUMENT, PDS_ERR_CUDA, PDS_ERR_WORKSPACE, PDS_ERR_UNSUPPORTED = range(5)
 PDS_F32, PDS_BF16 = 0, 1
-PRECISIONS = {'fp32': 0, 'bf16x3': 1, 'bf16x2': 2, 'bf16': 3}
+PRECISIONS = {'fp32': 0, 'bf16x3': 1, 'bf16x2': 2, 'bf16': 3, 'fp16x2': 4, 'fp16': 5}
 
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
 

@@ -102,6 +102,14 @@ int instance_norm_apply(const float* y, const double* stats, const float* gamma,
                         const float* add, const float* add_bcast, float* out, float* out2, int N,
                         size_t S, size_t HW, int C, cudaStream_t st);
 
+// Hourglass tail (hourglass_tail.cu): InstanceNorm of the 4-channel half-size volume
+// fused into ConvTranspose3d(4 -> 1, (3,4,4), stride (1,2,2), padding 1).  in:
+// [B][D][H][W][4] post-LeakyReLU; stats [B][4][2] (null: already normalised);
+// gamma / beta / w (PyTorch layout) are HOST pointers; out: (B, D, 2H, 2W).
+int hourglass_tail_forward(const float* in, float* out, const double* stats, const float* gamma_host,
+                           const float* beta_host, const float* w_host, float bias, int B, int D,
+                           int H, int W, cudaStream_t st);
+
 // [N][C][S] <-> [N][S][C]
 int nchw_to_nhwc(const float* in, float* out, int N, int C, size_t S, cudaStream_t st);
 int nhwc_to_nchw(const float* in, float* out, int N, int C, size_t S, cudaStream_t st);

@@ -5,25 +5,35 @@
 // GEMM view per disparity slice: D[pixel, cout] = sum over (tap, cin) of
 // A[pixel + tap, cin] * W[tap, cin, cout].
 //   * One MMA tile = 128 pixels = 8 (x) by 16 (y); a CTA tile is NT such tiles
-//     side by side (8*NT x 16 pixels) sharing ONE haloed input tile in shared
-//     memory: (8*NT + 2) x 18 pixels per 16-channel K chunk, loaded once by TMA
-//     (OOB zero fill == the convolution's zero padding; for Matching's shifted
-//     right descriptor the box is simply placed at x - d, matching.py:56-60).
+//     side by side sharing ONE haloed input tile in shared memory:
+//     (8*NT + 2) x 18 pixels per 16-channel K chunk, loaded once by TMA (OOB zero
+//     fill == the convolution's zero padding; for Matching's shifted right
+//     descriptor the box is simply placed at x - d, matching.py:56-60).
 //   * Operands are K-major, no-swizzle UMMA tiles.  Activations live in HBM as
-//     [plane = 8-channel group][y][x][8] bf16 so that a TMA box lands in shared
+//     [plane = 8-channel group][y][x][8] 16-bit so that a TMA box lands in shared
 //     memory as [plane][y][x][16 B]: 8 consecutive pixels x 16 B is exactly one
 //     UMMA core matrix, the next image row is the next core-matrix group
 //     (SBO = halo pitch), the second 8-channel group is LBO away -- and a tap
 //     (dy, dx) is nothing but a start-address offset of (dy*pitch + dx)*16 B.
-//     No im2col, no per-tap reload: 9 taps x NT tiles of tcgen05.mma per chunk.
-//   * fp32 accuracy on bf16 tensor cores: operands are carried as S bf16 terms
-//     (x = hi + mid + lo); the kernel issues the leading partial products
-//     (S=3: 6 of them, S=2: 3, S=1: 1) into the same fp32 TMEM accumulator.
-//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
-//     warps 2-5 = epilogue (TMEM -> registers -> bias / LeakyReLU /
-//     InstanceNorm partial sums -> HBM).  Accumulators are double-buffered in
-//     TMEM so the epilogue of tile k overlaps the MMAs of tile k+1; CTAs are
-//     persistent (grid = #SMs) and walk the tile list with a static stride.
+//     No im2col, no per-tap reload.
+//   * fp32 accuracy on 16-bit tensor cores: x = t0 + t1 (+ t2).  The B operand of
+//     a (chunk, tap) holds the S weight terms CONCATENATED ALONG N, so one MMA
+//     with activation term s and N = 64*(S-s) produces the products
+//     a_s*w_0 .. a_s*w_{S-1-s} into S-s adjacent 64-column accumulators:
+//     accumulator k collects every product of order of magnitude k.  Measured
+//     (tools/mma_microbench.cu): an M128 N64 MMA is operand-fetch bound (48
+//     cycles), N >= 128 runs at the N/2-cycle math floor -- concatenation is what
+//     makes the split affordable, and the per-order accumulators keep the
+//     tensor core's truncating accumulation away from the small terms.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread, fully
+//     unrolled issue loop: descriptors advance by compile-time constants),
+//     warps 2-5 = epilogue (TMEM -> registers -> sum of the accumulators, bias,
+//     LeakyReLU, InstanceNorm partial sums -> HBM).  Accumulators are
+//     double-buffered in TMEM; CTAs are persistent (grid = #SMs).  When the whole
+//     weight tensor fits (64 -> 64 at S = 2: 147 KB) it is loaded ONCE per CTA and
+//     stays resident in shared memory.
+#include <stdlib.h>
+
 #include <string>
 
 #include "conv_tc.cuh"
@@ -34,23 +44,25 @@ namespace {
 constexpr int kPH = 18;          // halo rows of a CTA tile (16 + 2)
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 6;
-constexpr int kMaxProducts = 6;
 
-struct TcKernelParams {
-  const CUtensorMap* maps;       // [0] primary input, [1 + d] right descriptor at disparity d
-  const __nv_bfloat16* w;        // [s][chunk][tap][2][N][8]
+struct alignas(64) TcKernelParams {
+  CUtensorMap map0;              // primary input (AP planes)
+  const CUtensorMap* maps_d;     // [d]: right descriptors at disparity d (first convolution) or null
+  const uint16_t* w;             // [chunk][tap][2][S][N][8]
   const float* bias;             // [N]
   float* out_f32;
-  __nv_bfloat16* out_ap;
+  uint16_t* out_ap;
   float* out_sig;
   double* stats;
-  int n_slices, n_div, H, W, tiles_x, tiles_y;
-  int S, nprod, nchunks, nchunks1;   // chunks [0, nchunks1) come from maps[0]
-  int planes1, planes2;              // 8-channel planes per (slice, split) of the two inputs
-  int N, Cout, epilogue, sig_D;
+  int n_slices, n0, n_div, H, W, tiles_x, tiles_y;
+  int nchunks, nchunks1;             // chunks [0, nchunks1) come from map0
+  int planes1, planes2;              // 8-channel planes per (slice, term) of the two inputs
+  int in_global;                     // primary input indexed by sample (first convolution)
+  int Cout, epilogue, fp16;
   int stages;
-  uint32_t a_plane_bytes, w_plane_bytes, stage_bytes;
-  unsigned char prod_a[kMaxProducts], prod_b[kMaxProducts];
+  uint32_t stage_bytes, wres_bytes;
+  float inv_wscale;
+  int dbg;                           // PDS_B200_TC_DEBUG bit mask (experiments only; 0 in production)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------
@@ -101,13 +113,24 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// One lane of a fully converged warp (warp-uniform control flow stays on the uniform datapath).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                            uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]; `accumulate` == 0 overwrites D.
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                       uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -149,14 +172,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// x = t0 + t1 + t2 with bf16 terms (round-to-nearest residual splitting)
-__device__ __forceinline__ void split_bf16(float x, int S, __nv_bfloat16 (&t)[3]) {
-  t[0] = __float2bfloat16_rn(x);
-  float r = x - __bfloat162float(t[0]);
-  t[1] = __float2bfloat16_rn(r);
-  r -= __bfloat162float(t[1]);
-  t[2] = __float2bfloat16_rn(r);
-  (void)S;
+// x = t0 + t1 + t2 with 16-bit terms (round-to-nearest residual splitting).  fp16
+// terms saturate at the largest finite half instead of overflowing to infinity.
+template <bool FP16>
+__device__ __forceinline__ void split_terms(float x, uint16_t (&t)[3]) {
+  if (FP16) {
+    const float c = fminf(fmaxf(x, -65504.f), 65504.f);
+    const __half h0 = __float2half_rn(c);
+    float r = x - __half2float(h0);
+    const __half h1 = __float2half_rn(r);
+    r -= __half2float(h1);
+    const __half h2 = __float2half_rn(r);
+    t[0] = __half_as_ushort(h0); t[1] = __half_as_ushort(h1); t[2] = __half_as_ushort(h2);
+  } else {
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
+    float r = x - __bfloat162float(b0);
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(r);
+    r -= __bfloat162float(b1);
+    const __nv_bfloat16 b2 = __float2bfloat16_rn(r);
+    t[0] = __bfloat16_as_ushort(b0); t[1] = __bfloat16_as_ushort(b1); t[2] = __bfloat16_as_ushort(b2);
+  }
+}
+template <bool FP16>
+__device__ __forceinline__ float term_value(uint16_t t) {
+  return FP16 ? __half2float(__ushort_as_half(t)) : __uint_as_float((uint32_t)t << 16);
 }
 
 // Sum over the 32 lanes of each of 32 per-lane values; lane l ends with channel l.
@@ -174,29 +213,44 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcKernelParams p) {
-  constexpr int PW = 8 * NT + 2;                         // halo pitch in pixels
-  constexpr uint32_t TMEM_COLS = NT == 1 ? 128 : (NT == 2 ? 256 : 512);
+constexpr uint32_t pow2_cols(uint32_t c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+// S terms, NT MMA tiles per CTA tile, N rows per weight term, WRES: weights resident.
+template <int S, int NT, int N, bool WRES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
+  constexpr int PW = 8 * NT + 2;                          // halo pitch in pixels
+  constexpr uint32_t A_TERM_BYTES = 2 * kPH * PW * 16;    // one term of one 16-channel chunk
+  constexpr uint32_t W_CHUNK_BYTES = 9 * 2 * S * N * 16;  // all taps and terms of one chunk
+  constexpr uint32_t ACC_COLS = S * N;                    // accumulators of one MMA tile
+  constexpr uint32_t BUF_COLS = NT * ACC_COLS;
+  constexpr int NBUF = 2 * BUF_COLS <= 512 ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = pow2_cols(NBUF * BUF_COLS);
+  static_assert(BUF_COLS <= 512, "accumulators do not fit TMEM");
+
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-  const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_base = smem_base + (uint32_t)p.stages * p.stage_bytes;
-  // barriers: full[stages], empty[stages], tfull[2], tempty[2]; then tmem pointer; then bias
+  const uint32_t wres_base = smem_u32(smem);
+  const uint32_t stage_base = wres_base + p.wres_bytes;
+  const uint32_t bar_base = stage_base + (uint32_t)p.stages * p.stage_bytes;
+  // barriers: full[stages], empty[stages], tfull[2], tempty[2], wfull; then tmem pointer; then bias
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
-  uint32_t* tmem_slot = (uint32_t*)(smem + (size_t)p.stages * p.stage_bytes + 8 * (2 * kMaxStages + 4));
-  float* sbias = (float*)(tmem_slot + 4);
+  const uint32_t wfull_bar = bar_base + 8u * (2 * kMaxStages + 4);
+  unsigned char* tail = smem + p.wres_bytes + (size_t)p.stages * p.stage_bytes + 8 * (2 * kMaxStages + 5);
+  uint32_t* tmem_slot = (uint32_t*)(tail + 8);
+  float* sbias = (float*)(tail + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.N; i += kThreads) sbias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < N; i += kThreads) sbias[i] = p.bias[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -207,77 +261,93 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcKernelP
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // every CTA walks ONE contiguous range of tiles: consecutive tiles share halo rows in L2 and
+  // stay within one or two slices, so the InstanceNorm sums are flushed once per slice change
   const int tiles_per_slice = p.tiles_x * p.tiles_y;
   const int total_tiles = tiles_per_slice * p.n_slices;
+  const int tiles_per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_begin = min((int)blockIdx.x * tiles_per_cta, total_tiles);
+  const int tile_end = min(tile_begin + tiles_per_cta, total_tiles);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      if (WRES) {
+        mbar_expect_tx(wfull_bar, (uint32_t)p.nchunks * W_CHUNK_BYTES);
+        for (int c = 0; c < p.nchunks; ++c)
+          bulk_load(wres_base + c * W_CHUNK_BYTES, p.w + (size_t)c * (W_CHUNK_BYTES / 2), W_CHUNK_BYTES, wfull_bar);
+      }
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n = tile / tiles_per_slice, r = tile - n * tiles_per_slice;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int nl = tile / tiles_per_slice, r = tile - nl * tiles_per_slice;
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         const int x0 = tx * 8 * NT, y0 = ty * 16;
-        const int n_in = n / p.n_div, d = n - n_in * p.n_div;
+        const int ng = p.n0 + nl;
+        const int b = ng / p.n_div, d = ng - b * p.n_div;
+        const int slice1 = p.in_global ? b : nl;
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), p.S * (p.a_plane_bytes + p.w_plane_bytes));
-          const uint32_t sa = smem_base + stage * p.stage_bytes;
-          const uint32_t sw = sa + p.S * p.a_plane_bytes;
+          mbar_expect_tx(full_bar(stage), S * A_TERM_BYTES + (WRES ? 0u : W_CHUNK_BYTES));
+          const uint32_t sa = stage_base + stage * p.stage_bytes;
           const bool second = c >= p.nchunks1;
-          for (int s = 0; s < p.S; ++s) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
             if (!second)
-              tma_load_4d(sa + s * p.a_plane_bytes, p.maps, 0, x0 - 1, y0 - 1,
-                          (n_in * p.S + s) * p.planes1 + 2 * c, full_bar(stage));
+              tma_load_4d(sa + s * A_TERM_BYTES, &p.map0, 0, x0 - 1, y0 - 1,
+                          (slice1 * S + s) * p.planes1 + 2 * c, full_bar(stage));
             else  // d >= W: the shifted image is all zeros -> park the box fully out of bounds
-              tma_load_4d(sa + s * p.a_plane_bytes, p.maps + 1 + d, 0,
+              tma_load_4d(sa + s * A_TERM_BYTES, p.maps_d + d, 0,
                           d >= p.W ? -(PW + 16) : x0 - 1 - d, y0 - 1,
-                          (n_in * p.S + s) * p.planes2 + 2 * (c - p.nchunks1), full_bar(stage));
-            bulk_load(sw + s * p.w_plane_bytes,
-                      p.w + ((size_t)s * p.nchunks + c) * (p.w_plane_bytes / 2), p.w_plane_bytes,
-                      full_bar(stage));
+                          (b * S + s) * p.planes2 + 2 * (c - p.nchunks1), full_bar(stage));
           }
+          if (!WRES)
+            bulk_load(sa + S * A_TERM_BYTES, p.w + (size_t)c * (W_CHUNK_BYTES / 2), W_CHUNK_BYTES,
+                      full_bar(stage));
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
-      const uint32_t a_lbo = kPH * PW * 16, a_sbo = PW * 16;
-      const uint32_t b_lbo = p.N * 16, b_sbo = 128, tap_bytes = 2 * p.N * 16;
+    // ===== MMA issuer: the whole warp walks the (warp-uniform) loops, one elected lane issues =====
+    {
+      const uint32_t fmt = (1u << 4) | (p.fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t idesc[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) idesc[s] = fmt | ((uint32_t)((N * (S - s)) >> 3) << 17);
+      if (WRES) { mbar_wait(wfull_bar, 0); tc_fence_after(); }
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_base = tmem_base + acc * (NT * 64);
+        const uint32_t d_base = tmem_base + acc * BUF_COLS;
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * p.stage_bytes;
-          const uint32_t sw = sa + p.S * p.a_plane_bytes;
-          for (int q = 0; q < p.nprod; ++q) {
-            const uint32_t a0 = sa + p.prod_a[q] * p.a_plane_bytes;
-            const uint32_t w0 = sw + p.prod_b[q] * p.w_plane_bytes;
+          const uint32_t sa = stage_base + stage * p.stage_bytes;
+          const uint32_t sw = WRES ? wres_base + c * W_CHUNK_BYTES : sa + S * A_TERM_BYTES;
+          if (elect_one()) {
+            const uint64_t wdesc = umma_desc(sw, S * N * 16, 128);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3, dx = tap % 3;
-              const uint64_t bdesc = umma_desc(w0 + tap * tap_bytes, b_lbo, b_sbo);
+            for (int s = 0; s < S; ++s) {
+              const uint64_t adesc = umma_desc(sa + s * A_TERM_BYTES, kPH * PW * 16, PW * 16);
 #pragma unroll
-              for (int i = 0; i < NT; ++i) {
-                const uint64_t adesc = umma_desc(a0 + (dy * PW + 8 * i + dx) * 16, a_lbo, a_sbo);
-                tc_mma_bf16(d_base + i * 64, adesc, bdesc, idesc, (c | q | tap) != 0 ? 1u : 0u);
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint64_t bd = wdesc + (uint64_t)(tap * 2 * S * N);          // 16-byte units
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                  const uint64_t ad = adesc + (uint64_t)((tap / 3) * PW + 8 * i + tap % 3);
+                  tc_mma(d_base + i * ACC_COLS + s * N, ad, bd, idesc[s],
+                         (s == 0 && tap == 0) ? (c != 0 ? 1u : 0u) : 1u);
+                }
               }
             }
+            tc_commit(empty_bar(stage));       // frees the smem stage once these MMAs retire
+            if (c == p.nchunks - 1) tc_commit(tfull_bar(acc));   // accumulators ready for the epilogue
           }
-          tc_commit(empty_bar(stage));       // frees the smem stage once these MMAs retire
+          __syncwarp();
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar(acc));           // accumulator ready for the epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (NBUF == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
       }
     }
   } else {
@@ -287,63 +357,92 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcKernelP
     const int px = row & 7, py = row >> 3;
     const size_t HW = (size_t)p.H * p.W;
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n = tile / tiles_per_slice, r = tile - n * tiles_per_slice;
+    // InstanceNorm sums of the current slice: lane l holds channels l and 32 + l
+    double sa0 = 0.0, sa1 = 0.0, sb0 = 0.0, sb1 = 0.0;
+    int stat_slice = -1;
+    auto flush_stats = [&]() {
+      if (stat_slice >= 0 && !(p.dbg & 1)) {
+        double* dst = p.stats + ((size_t)stat_slice * N + lane) * 2;
+        atomicAdd(dst, sa0); atomicAdd(dst + 1, sa1);
+        atomicAdd(dst + 64, sb0); atomicAdd(dst + 65, sb1);
+      }
+      sa0 = sa1 = sb0 = sb1 = 0.0;
+    };
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int nl = tile / tiles_per_slice, r = tile - nl * tiles_per_slice;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const int y = ty * 16 + py;
+      const int ng = p.n0 + nl;
+      if (p.epilogue == TC_EPI_ACT && ng != stat_slice) { flush_stats(); stat_slice = ng; }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(32 * q) << 16) + acc * (NT * 64);
+      const uint32_t t_base = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BUF_COLS;
 #pragma unroll 1
-      for (int i = 0; i < NT; ++i) {
+      for (int i = 0; i < ((p.dbg & 4) ? 0 : NT); ++i) {
         const int x = tx * 8 * NT + 8 * i + px;
         const bool valid = (x < p.W) && (y < p.H);
         const size_t pix = (size_t)y * p.W + x;
-        if (p.epilogue == TC_EPI_SIG) {
+        if constexpr (N == 16) {   // last convolution: bias -> signatures (B, Cout, D, H, W)
           float v[16];
-          tmem_ld16(t_base + i * 64, v);
+          tmem_ld16(t_base + i * ACC_COLS + (S - 1) * N, v);
+#pragma unroll
+          for (int s = S - 2; s >= 0; --s) {
+            float u[16];
+            tmem_ld16(t_base + i * ACC_COLS + s * N, u);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += u[j];
+          }
           if (valid) {
-            const int b = n / p.sig_D, dd = n - b * p.sig_D;
+            const int b = ng / p.n_div, dd = ng - b * p.n_div;
 #pragma unroll
             for (int ch = 0; ch < 16; ++ch)
               if (ch < p.Cout)
-                p.out_sig[(((size_t)b * p.Cout + ch) * p.sig_D + dd) * HW + pix] = v[ch] + sbias[ch];
+                p.out_sig[(((size_t)b * p.Cout + ch) * p.n_div + dd) * HW + pix] =
+                    fmaf(v[ch], p.inv_wscale, sbias[ch]);
           }
-          continue;
-        }
+        } else {
 #pragma unroll 1
-        for (int col0 = 0; col0 < p.N; col0 += 32) {
+        for (int col0 = 0; col0 < N; col0 += 32) {
           float v[32];
-          tmem_ld32(t_base + i * 64 + col0, v);
+          tmem_ld32(t_base + i * ACC_COLS + (S - 1) * N + col0, v);   // smallest terms first
+#pragma unroll
+          for (int s = S - 2; s >= 0; --s) {
+            float u[32];
+            tmem_ld32(t_base + i * ACC_COLS + s * N + col0, u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += u[j];
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float t = v[j] + sbias[col0 + j];
+            float t = fmaf(v[j], p.inv_wscale, sbias[col0 + j]);
             if (p.epilogue == TC_EPI_ACT) t = t > 0.f ? t : 0.1f * t;
             v[j] = t;
-          }
-          if (valid) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32) +
-                        ((size_t)n * (p.N / 4) + col0 / 4) * HW + pix;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              o[(size_t)k * HW] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           }
           if (p.epilogue == TC_EPI_PLAIN) {
             if (valid) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                __nv_bfloat16 t[8][3];
+                uint16_t t[8][3];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) split_bf16(v[8 * g + e], p.S, t[e]);
-                for (int s = 0; s < p.S; ++s) {
-                  union { __nv_bfloat16 h[8]; uint4 u; } pk;
+                for (int e = 0; e < 8; ++e) {
+                  if (p.fp16) split_terms<true>(v[8 * g + e], t[e]); else split_terms<false>(v[8 * g + e], t[e]);
+                }
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                  union { uint16_t h[8]; uint4 u; } pk;
 #pragma unroll
                   for (int e = 0; e < 8; ++e) pk.h[e] = t[e][s];
-                  reinterpret_cast<uint4*>(p.out_ap)[((size_t)(n * p.S + s) * (p.N / 8) + col0 / 8 + g) * HW + pix] = pk.u;
+                  reinterpret_cast<uint4*>(p.out_ap)[((size_t)(nl * S + s) * (N / 8) + col0 / 8 + g) * HW + pix] = pk.u;
                 }
               }
             }
           } else {
+            if (valid && !(p.dbg & 2)) {
+              float4* o = reinterpret_cast<float4*>(p.out_f32) + ((size_t)nl * (N / 4) + col0 / 4) * HW + pix;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                o[(size_t)k * HW] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            }
             // InstanceNorm partial sums over this warp's 32 pixels, one channel per lane
             float sq[32];
 #pragma unroll
@@ -353,17 +452,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcKernelP
             }
             const float s1 = warp_transpose_reduce(v, lane);
             const float s2 = warp_transpose_reduce(sq, lane);
-            double* dst = p.stats + ((size_t)n * p.N + col0 + lane) * 2;
-            atomicAdd(dst, (double)s1);
-            atomicAdd(dst + 1, (double)s2);
+            if (col0 == 0) { sa0 += (double)s1; sa1 += (double)s2; }
+            else { sb0 += (double)s1; sb1 += (double)s2; }
           }
+        }
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (NBUF == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
     }
+    if (p.epilogue == TC_EPI_ACT) flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -375,23 +474,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcKernelP
 
 // ---- auxiliary kernels ------------------------------------------------------------------
 
-// (Cout, Cin, 3, 3) fp32 -> [s][chunk][tap][2][N][8] split bf16 (zero rows for cout >= Cout)
-__global__ void tc_prepare_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                          int Cout, int Cin, int N, int S) {
-  const int nchunks = Cin / 16;
-  const size_t per_split = (size_t)nchunks * 9 * 2 * N * 8;
+// (Cout, Cin, 3, 3) fp32 -> [chunk][tap][2][S][N][8] terms of w * wscale (zero rows for cout >= Cout)
+template <bool FP16>
+__global__ void tc_prepare_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out,
+                                          int Cout, int Cin, int N, int S, float wscale) {
+  const size_t total = (size_t)(Cin / 16) * 9 * 2 * N * 8;   // per term
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= per_split) return;
+  if (i >= total) return;
   const int e = i % 8;
   const int co = (i / 8) % N;
   const int j = (i / (8 * (size_t)N)) % 2;
   const int tap = (i / (16 * (size_t)N)) % 9;
   const int c = i / (144 * (size_t)N);
   const int ci = c * 16 + j * 8 + e;
-  const float x = co < Cout ? w[((size_t)co * Cin + ci) * 9 + tap] : 0.f;
-  __nv_bfloat16 t[3];
-  split_bf16(x, S, t);
-  for (int s = 0; s < S; ++s) out[s * per_split + i] = t[s];
+  const float x = co < Cout ? w[((size_t)co * Cin + ci) * 9 + tap] * wscale : 0.f;
+  uint16_t t[3];
+  split_terms<FP16>(x, t);
+  for (int s = 0; s < S; ++s)
+    out[((((size_t)c * 9 + tap) * 2 + j) * S + s) * N * 8 + (size_t)co * 8 + e] = t[s];
 }
 
 __global__ void tc_pad_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int Cout, int N) {
@@ -400,18 +500,19 @@ __global__ void tc_pad_bias_kernel(const float* __restrict__ b, float* __restric
 }
 
 // (B, C, H, W) fp32 -> AP [B][S][C/8][H][W][8]
-__global__ void tc_pack_nchw_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ ap,
+template <bool FP16>
+__global__ void tc_pack_nchw_kernel(const float* __restrict__ in, uint16_t* __restrict__ ap,
                                     int C, size_t HW, int S, size_t total) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const size_t pix = i % HW;
   const int c8 = (i / HW) % (C / 8);
   const size_t b = i / (HW * (C / 8));
-  __nv_bfloat16 t[8][3];
+  uint16_t t[8][3];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) split_bf16(in[(b * C + c8 * 8 + e) * HW + pix], S, t[e]);
+  for (int e = 0; e < 8; ++e) split_terms<FP16>(in[(b * C + c8 * 8 + e) * HW + pix], t[e]);
   for (int s = 0; s < S; ++s) {
-    union { __nv_bfloat16 h[8]; uint4 u; } pk;
+    union { uint16_t h[8]; uint4 u; } pk;
 #pragma unroll
     for (int e = 0; e < 8; ++e) pk.h[e] = t[e][s];
     reinterpret_cast<uint4*>(ap)[((b * S + s) * (C / 8) + c8) * HW + pix] = pk.u;
@@ -419,11 +520,11 @@ __global__ void tc_pack_nchw_kernel(const float* __restrict__ in, __nv_bfloat16*
 }
 
 // InstanceNorm from accumulated sums on fp32 planes; one thread = 8 channels of a pixel.
+template <bool FP16>
 __global__ void __launch_bounds__(256)
 tc_norm_split_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                     const float* __restrict__ residual, float* __restrict__ out_f32,
-                     __nv_bfloat16* __restrict__ out_ap, int C, size_t HW, int S) {
+                     const uint16_t* res_ap, uint16_t* out_ap, int C, size_t HW, int S) {
   const int c8 = blockIdx.y, n = blockIdx.z;
   __shared__ float sc[8], sh[8];
   if (threadIdx.x < 8) {
@@ -442,33 +543,31 @@ tc_norm_split_kernel(const float* __restrict__ y, const double* __restrict__ sta
     g[e] = gamma[c8 * 8 + e]; b[e] = beta[c8 * 8 + e]; m[e] = sc[e]; r[e] = sh[e];
   }
   const float4* y4 = reinterpret_cast<const float4*>(y) + ((size_t)n * (C / 4) + 2 * c8) * HW;
-  const float4* r4 = residual ? reinterpret_cast<const float4*>(residual) + ((size_t)n * (C / 4) + 2 * c8) * HW : nullptr;
-  float4* o4 = out_f32 ? reinterpret_cast<float4*>(out_f32) + ((size_t)n * (C / 4) + 2 * c8) * HW : nullptr;
   for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < HW;
        pix += (size_t)gridDim.x * blockDim.x) {
     const float4 a = y4[pix], c = y4[HW + pix];
     float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = (v[e] - m[e]) * r[e] * g[e] + b[e];
-    if (r4) {
-      const float4 ra = r4[pix], rc = r4[HW + pix];
-      v[0] += ra.x; v[1] += ra.y; v[2] += ra.z; v[3] += ra.w;
-      v[4] += rc.x; v[5] += rc.y; v[6] += rc.z; v[7] += rc.w;
-    }
-    if (o4) {
-      o4[pix] = make_float4(v[0], v[1], v[2], v[3]);
-      o4[HW + pix] = make_float4(v[4], v[5], v[6], v[7]);
-    }
-    if (out_ap) {
-      __nv_bfloat16 t[8][3];
+    if (res_ap) {
+      float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int s = S - 1; s >= 0; --s) {   // smallest term first
+        union { uint16_t h[8]; uint4 u; } pk;
+        pk.u = reinterpret_cast<const uint4*>(res_ap)[((size_t)(n * S + s) * (C / 8) + c8) * HW + pix];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) split_bf16(v[e], S, t[e]);
-      for (int s = 0; s < S; ++s) {
-        union { __nv_bfloat16 h[8]; uint4 u; } pk;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) pk.h[e] = t[e][s];
-        reinterpret_cast<uint4*>(out_ap)[((size_t)(n * S + s) * (C / 8) + c8) * HW + pix] = pk.u;
+        for (int e = 0; e < 8; ++e) res[e] += term_value<FP16>(pk.h[e]);
       }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += res[e];
+    }
+    uint16_t t[8][3];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
+    for (int s = 0; s < S; ++s) {
+      union { uint16_t h[8]; uint4 u; } pk;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pk.h[e] = t[e][s];
+      reinterpret_cast<uint4*>(out_ap)[((size_t)(n * S + s) * (C / 8) + c8) * HW + pix] = pk.u;
     }
   }
 }
@@ -494,7 +593,8 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// AP tensor viewed as (8 ch, W_eff, H, planes) with row pitch W.
+// AP tensor viewed as (8 ch, W_eff, H, planes) with row pitch W.  (The element
+// type only sets the element size: fp16 and bf16 planes use the same map.)
 int encode_ap_map(CUtensorMap* map, const void* base, int W_eff, int W, int H, size_t planes,
                   int PW) {
   const cuuint64_t dims[4] = {8, (cuuint64_t)W_eff, (cuuint64_t)H, (cuuint64_t)planes};
@@ -513,43 +613,59 @@ int encode_ap_map(CUtensorMap* map, const void* base, int W_eff, int W, int H, s
   return PDS_OK;
 }
 
-template <int NT>
+constexpr size_t kTailBytes = 8 * (2 * kMaxStages + 5) + 32 + 64 * sizeof(float) + 256;
+
+template <int S, int NT, int N, bool WRES>
 int launch_tc(TcKernelParams& p, cudaStream_t st) {
   constexpr int PW = 8 * NT + 2;
-  p.a_plane_bytes = 2 * kPH * PW * 16;
-  p.w_plane_bytes = 9 * 2 * p.N * 16;
-  p.stage_bytes = (uint32_t)align_up((size_t)p.S * (p.a_plane_bytes + p.w_plane_bytes), 128);
-  const size_t tail = 8 * (2 * kMaxStages + 4) + 16 + 64 * sizeof(float) + 256;
-  const size_t budget = 227 * 1024 - tail;
+  constexpr uint32_t A_TERM_BYTES = 2 * kPH * PW * 16;
+  constexpr uint32_t W_CHUNK_BYTES = 9 * 2 * S * N * 16;
+  p.wres_bytes = WRES ? (uint32_t)p.nchunks * W_CHUNK_BYTES : 0;
+  p.stage_bytes = (uint32_t)align_up((size_t)S * A_TERM_BYTES + (WRES ? 0 : W_CHUNK_BYTES), 128);
+  const size_t budget = 227 * 1024 - kTailBytes - p.wres_bytes;
   int stages = (int)(budget / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
-    set_error("conv3x3_tc: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
+    set_error("conv3x3_tc: stage of %u bytes (+ %u resident) does not fit twice in shared memory",
+              p.stage_bytes, p.wres_bytes);
     return PDS_ERR_UNSUPPORTED;
   }
   p.stages = stages;
-  const size_t smem = (size_t)stages * p.stage_bytes + tail;
-  PDS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = p.wres_bytes + (size_t)stages * p.stage_bytes + kTailBytes;
+  static bool configured = false;
+  if (!configured) {
+    PDS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<S, NT, N, WRES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
   const int total = p.tiles_x * p.tiles_y * p.n_slices;
   const int grid = total < num_sms() ? total : num_sms();
-  static const std::string name = "conv3x3_tc<NT=" + std::to_string(NT) + ">";
+  static const std::string name = "conv3x3_tc<S=" + std::to_string(S) + ",NT=" + std::to_string(NT) +
+                                  ",N=" + std::to_string(N) + (WRES ? ",Wres>" : ",Wstream>");
   PDS_KERNEL(name.c_str(), st);
-  conv3x3_tc_kernel<NT><<<grid, kThreads, smem, st>>>(p);
+  conv3x3_tc_kernel<S, NT, N, WRES><<<grid, kThreads, smem, st>>>(p);
   PDS_LAUNCH_CHECK("conv3x3_tc_kernel");
   return PDS_OK;
 }
+
+// MMA tiles per CTA tile for S terms (double-buffered accumulators: 2*NT*S*64 <= 512 columns)
+int nt_for(int S) { return S == 1 ? 4 : (S == 2 ? 2 : 1); }
 
 }  // namespace
 
 bool tc_available() { return encode_fn() != nullptr; }
 
-size_t tc_conv_max_maps(int n_div) { return (size_t)1 + (n_div > 0 ? n_div : 0); }
+size_t tc_conv_max_maps(int n_div) { return (size_t)(n_div > 0 ? n_div : 0) + 1; }
 
 int tc_prepare_weights(const TcLayer& l, const float* w_oihw, const float* bias, cudaStream_t st) {
-  const size_t per_split = l.w_elems() / l.S;
+  const size_t per_term = l.w_elems() / l.S;
   {
     PDS_KERNEL("tc_prepare_weights", st);
-    tc_prepare_weights_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(w_oihw, l.w, l.Cout, l.Cin, l.N, l.S);
+    const unsigned g = (unsigned)((per_term + 255) / 256);
+    if (l.fp16)
+      tc_prepare_weights_kernel<true><<<g, 256, 0, st>>>(w_oihw, l.w, l.Cout, l.Cin, l.N, l.S, l.wscale);
+    else
+      tc_prepare_weights_kernel<false><<<g, 256, 0, st>>>(w_oihw, l.w, l.Cout, l.Cin, l.N, l.S, l.wscale);
     PDS_LAUNCH_CHECK("tc_prepare_weights_kernel");
   }
   PDS_KERNEL("tc_pad_bias", st);
@@ -558,25 +674,28 @@ int tc_prepare_weights(const TcLayer& l, const float* w_oihw, const float* bias,
   return PDS_OK;
 }
 
-int tc_pack_nchw(const float* in, __nv_bfloat16* ap, int B, int C, int H, int W, int S, cudaStream_t st) {
+int tc_pack_nchw(const float* in, uint16_t* ap, int B, int C, int H, int W, int S, int fp16, cudaStream_t st) {
   const size_t HW = (size_t)H * W, total = (size_t)B * (C / 8) * HW;
   if (total == 0) return PDS_OK;
   PDS_KERNEL("tc_pack_nchw", st);
-  tc_pack_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, ap, C, HW, S, total);
+  const unsigned g = (unsigned)((total + 255) / 256);
+  if (fp16) tc_pack_nchw_kernel<true><<<g, 256, 0, st>>>(in, ap, C, HW, S, total);
+  else tc_pack_nchw_kernel<false><<<g, 256, 0, st>>>(in, ap, C, HW, S, total);
   PDS_LAUNCH_CHECK("tc_pack_nchw_kernel");
   return PDS_OK;
 }
 
 int tc_norm_split(const float* y, const double* stats, const float* gamma, const float* beta,
-                  const float* residual, float* out_f32, __nv_bfloat16* out_ap, int n_slices, int C,
-                  int H, int W, int S, cudaStream_t st) {
+                  const uint16_t* res_ap, uint16_t* out_ap, int n_slices, int C, int H, int W, int S,
+                  int fp16, cudaStream_t st) {
   const size_t HW = (size_t)H * W;
   if (n_slices == 0 || HW == 0) return PDS_OK;
   unsigned gx = (unsigned)((HW + 255) / 256);
   if (gx > 64) gx = 64;
   dim3 grid(gx, (unsigned)(C / 8), (unsigned)n_slices);
-  PDS_KERNEL("tc_norm_split", st);
-  tc_norm_split_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, residual, out_f32, out_ap, C, HW, S);
+  PDS_KERNEL(res_ap ? "tc_norm_residual_split" : "tc_norm_split", st);
+  if (fp16) tc_norm_split_kernel<true><<<grid, 256, 0, st>>>(y, stats, gamma, beta, res_ap, out_ap, C, HW, S);
+  else tc_norm_split_kernel<false><<<grid, 256, 0, st>>>(y, stats, gamma, beta, res_ap, out_ap, C, HW, S);
   PDS_LAUNCH_CHECK("tc_norm_split_kernel");
   return PDS_OK;
 }
@@ -589,58 +708,56 @@ int tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   }
   if (a.n_slices == 0) return PDS_OK;
   TcKernelParams p = {};
-  p.maps = a.maps_dev;
+  p.maps_d = a.in2 ? a.maps_dev : nullptr;
   p.w = l.w; p.bias = l.bias;
   p.out_f32 = a.out_f32; p.out_ap = a.out_ap; p.out_sig = a.out_sig; p.stats = a.stats;
-  p.n_slices = a.n_slices; p.n_div = a.n_div > 0 ? a.n_div : 1; p.H = a.H; p.W = a.W;
-  p.S = l.S;
-  static const unsigned char pa[3][6] = {{0}, {0, 0, 1}, {0, 0, 1, 1, 0, 2}};
-  static const unsigned char pb[3][6] = {{0}, {0, 1, 0}, {0, 1, 0, 1, 2, 0}};
-  p.nprod = l.S == 1 ? 1 : (l.S == 2 ? 3 : 6);
-  for (int i = 0; i < p.nprod; ++i) { p.prod_a[i] = pa[l.S - 1][i]; p.prod_b[i] = pb[l.S - 1][i]; }
+  p.n_slices = a.n_slices; p.n0 = a.n0; p.n_div = a.n_div > 0 ? a.n_div : 1; p.H = a.H; p.W = a.W;
   p.nchunks = l.Cin / 16;
   p.nchunks1 = a.in_C / 16;
   p.planes1 = a.in_C / 8;
   p.planes2 = a.in2 ? a.in2_C / 8 : 0;
-  p.N = l.N; p.Cout = l.Cout; p.epilogue = a.epilogue;
-  p.sig_D = a.epilogue == TC_EPI_SIG ? (a.n_div > 0 ? a.n_div : 1) : 1;
-  if (a.epilogue == TC_EPI_SIG) p.n_div = 1;   // sig_D only drives the output indexing
-  if ((a.in2 ? a.in_C + a.in2_C : a.in_C) != l.Cin || l.Cin % 16 || l.N % 16 || l.N > 64 ||
-      (a.epilogue != TC_EPI_SIG && l.N % 32)) {
-    set_error("conv3x3_tc: unsupported channel configuration (Cin=%d, N=%d)", l.Cin, l.N);
+  p.in_global = a.in2 ? 1 : 0;
+  p.Cout = l.Cout; p.epilogue = a.epilogue; p.fp16 = l.fp16;
+  p.inv_wscale = 1.0f / l.wscale;
+  static const int dbg = getenv("PDS_B200_TC_DEBUG") ? atoi(getenv("PDS_B200_TC_DEBUG")) : 0;
+  p.dbg = dbg;
+  if ((a.in2 ? a.in_C + a.in2_C : a.in_C) != l.Cin || l.Cin % 16 || (l.N != 16 && l.N != 64) ||
+      l.S < 1 || l.S > 3 || (a.epilogue == TC_EPI_SIG) != (l.N == 16)) {
+    set_error("conv3x3_tc: unsupported configuration (Cin=%d, N=%d, S=%d)", l.Cin, l.N, l.S);
     return PDS_ERR_UNSUPPORTED;
   }
-  // tile width: the widest NT in {3, 2, 1} that wastes the fewest columns; the split
-  // planes of a stage must fit shared memory at least twice (S=3 -> NT <= 3)
-  const int w8 = (a.W + 7) / 8;
-  int NT = 1, best_waste = 1 << 30;
-  for (int nt = 3; nt >= 1; --nt) {
-    const int waste = ((w8 + nt - 1) / nt) * nt - w8;
-    if (waste < best_waste) { best_waste = waste; NT = nt; }
-  }
-  p.tiles_x = (w8 + NT - 1) / NT;
+  const int NT = nt_for(l.S);
+  p.tiles_x = (a.W + 8 * NT - 1) / (8 * NT);
   p.tiles_y = (a.H + 15) / 16;
   const int PW = 8 * NT + 2;
-  // tensor maps: [0] = primary input; [1 + d] = right descriptors, width W - d so that
-  // columns at or beyond the shifted image's right edge read as zero padding
-  int rc = encode_ap_map(&a.maps_host[0], a.in, a.W, a.W, a.H, (size_t)a.in_slices * l.S * (a.in_C / 8), PW);
+  int rc = encode_ap_map(&p.map0, a.in, a.W, a.W, a.H, (size_t)a.in_slices * l.S * (a.in_C / 8), PW);
   if (rc != PDS_OK) return rc;
-  size_t nmaps = 1;
-  if (a.in2) {
-    for (int d = 0; d < p.n_div; ++d) {
-      const int weff = a.W - d > 0 ? a.W - d : 1;
-      rc = encode_ap_map(&a.maps_host[1 + d], a.in2, weff, a.W, a.H,
-                         (size_t)a.in_slices * l.S * (a.in2_C / 8), PW);
-      if (rc != PDS_OK) return rc;
-    }
-    nmaps += p.n_div;
+  // weights resident when the whole layer fits beside >= 3 activation stages
+  const size_t w_bytes = l.w_elems() * 2;
+  const size_t a_stage = (size_t)l.S * 2 * kPH * PW * 16;
+  const bool wres = w_bytes + 3 * a_stage + kTailBytes <= 227 * 1024;
+#define PDS_TC_CASE(SS, NN)                                                       \
+  if (l.S == SS && l.N == NN)                                                     \
+    return wres ? launch_tc<SS, (SS == 1 ? 4 : (SS == 2 ? 2 : 1)), NN, true>(p, st) \
+                : launch_tc<SS, (SS == 1 ? 4 : (SS == 2 ? 2 : 1)), NN, false>(p, st);
+  PDS_TC_CASE(1, 64) PDS_TC_CASE(1, 16) PDS_TC_CASE(2, 64) PDS_TC_CASE(2, 16)
+  PDS_TC_CASE(3, 64) PDS_TC_CASE(3, 16)
+#undef PDS_TC_CASE
+  set_error("conv3x3_tc: no kernel for S=%d N=%d", l.S, l.N);
+  return PDS_ERR_UNSUPPORTED;
+}
+
+// Right-descriptor maps of the first convolution: map d views the planes with width
+// W - d so that columns at or beyond the shifted image's right edge read as zero.
+int tc_encode_shift_maps(CUtensorMap* maps_host, const uint16_t* in2, int in_slices, int S, int C,
+                         int H, int W, int D) {
+  const int PW = 8 * nt_for(S) + 2;
+  for (int d = 0; d < D; ++d) {
+    const int weff = W - d > 0 ? W - d : 1;
+    int rc = encode_ap_map(&maps_host[d], in2, weff, W, H, (size_t)in_slices * S * (C / 8), PW);
+    if (rc != PDS_OK) return rc;
   }
-  PDS_CUDA(cudaMemcpyAsync(a.maps_dev, a.maps_host, nmaps * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
-  switch (NT) {
-    case 1: return launch_tc<1>(p, st);
-    case 2: return launch_tc<2>(p, st);
-    default: return launch_tc<3>(p, st);
-  }
+  return PDS_OK;
 }
 
 }  // namespace pds

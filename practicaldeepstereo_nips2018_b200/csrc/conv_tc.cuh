@@ -1,58 +1,66 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM 3x3 convolution for the matching
-// operation, with split-bf16 operands ("bf16xS": every fp32 value is carried as
-// S bf16 terms, hi + mid + lo; the products of the leading terms are
-// accumulated in fp32 in TMEM -- S=3 gives fp32-equivalent products, S=1 is
-// plain bf16).  See conv_tc.cu for the kernel and DESIGN.md for the data layout.
+// tcgen05 (5th-gen tensor core) implicit-GEMM 3x3 convolution with split
+// 16-bit operands: every fp32 value x is carried as S terms t0 + t1 (+ t2) of
+// fp16 (11-bit significands, "fp16x2" = 22 bits) or bf16 (8-bit significands,
+// "bf16x3" = 24 bits); the products whose orders of magnitude sum to < S are
+// accumulated in fp32 in TMEM, ONE ACCUMULATOR PER ORDER OF MAGNITUDE, and added
+// in fp32 registers in the epilogue.  See conv_tc.cu for the kernel and
+// DESIGN.md for the data layout and the measured tensor-pipe model behind it.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "pds_common.cuh"
 
 namespace pds {
 
-// Activation planes ("AP"): [slice][split s][C/8][H][W][8] bf16 -- every
-// 8-channel group of every pixel is one 16-byte vector, pixels of an image row
-// are contiguous.  This is exactly the K-major no-swizzle core-matrix layout of
-// a UMMA operand, so a TMA box (8 ch, x, y, planes) lands in shared memory ready
-// for tcgen05.mma, and a tap shift is just a start-address offset.
+// Activation planes ("AP"): [slice][term s][C/8][H][W][8] 16-bit -- every
+// 8-channel group of every pixel is one 16-byte vector and the pixels of an
+// image row are contiguous.  This is exactly the K-major no-swizzle core-matrix
+// layout of a UMMA operand: a TMA box (8 ch, x, y, 2 planes) lands in shared
+// memory ready for tcgen05.mma, and a convolution tap is a start-address offset.
 struct TcLayer {
-  int Cin = 0;     // input channels (multiple of 16)
-  int Cout = 0;    // real output channels
-  int N = 0;       // Cout padded to a multiple of 16 (UMMA N)
-  int S = 1;       // split terms
-  __nv_bfloat16* w = nullptr;   // [s][chunk][tap 9][2][N][8]
+  int Cin = 0;       // input channels (multiple of 16)
+  int Cout = 0;      // real output channels
+  int N = 0;         // Cout padded to 16 or 64: rows of ONE term of the B operand
+  int S = 1;         // terms per value
+  int fp16 = 0;      // term type: 1 = IEEE half, 0 = bfloat16
+  float wscale = 1;  // weights are stored multiplied by this power of two
+  uint16_t* w = nullptr;        // [chunk][tap 9][K-half 2][term][N][8]
   float* bias = nullptr;        // [N]
   const float* gamma = nullptr; // InstanceNorm affine of the block (may be null)
   const float* beta = nullptr;
-  size_t w_elems() const { return (size_t)S * (Cin / 16) * 9 * 2 * N * 8; }
+  size_t w_elems() const { return (size_t)(Cin / 16) * 9 * 2 * S * N * 8; }
 };
 
 enum TcEpilogue {
   TC_EPI_ACT = 0,   // bias + LeakyReLU + InstanceNorm sums -> fp32 planes
-  TC_EPI_PLAIN = 1, // bias -> fp32 planes + split bf16 planes (conv0)
-  TC_EPI_SIG = 2    // bias -> (B, Cout, D, H, W) fp32 signatures (last conv)
+  TC_EPI_PLAIN = 1, // bias -> split AP planes (first convolution, no activation)
+  TC_EPI_SIG = 2    // bias -> (B, Cout, D, H, W) fp32 signatures (last convolution)
 };
 
 struct TcConvArgs {
   const TcLayer* layer;
   int epilogue;
-  int n_slices;            // output slices (B * D)
-  int n_div;               // conv0: input slice = n / n_div, disparity = n % n_div; else 1
+  int n_slices;            // output slices of THIS launch
+  int n0;                  // global index (b * D + d) of the first of them
+  int n_div;               // D: disparity = global slice % n_div, sample = global slice / n_div
   int H, W;
-  // inputs: AP tensors; `in2` only for conv0 (right descriptors, read at x - d)
-  const __nv_bfloat16* in;
-  int in_slices;           // number of slices in `in`
-  int in_C;                // channels of `in`
-  const __nv_bfloat16* in2;
+  // inputs: AP tensors.  With `in2` (first convolution) `in` holds one slice per
+  // SAMPLE (left descriptors) and `in2` the right descriptors, read at x - d;
+  // otherwise `in` holds the n_slices slices of this launch.
+  const uint16_t* in;
+  int in_slices;           // slices stored in `in` (and `in2`)
+  int in_C;
+  const uint16_t* in2;
   int in2_C;
-  // outputs (by epilogue)
+  // outputs (by epilogue), indexed by the LOCAL slice except out_sig / stats
   float* out_f32;          // [n][N/4][H][W][4]
-  __nv_bfloat16* out_ap;   // [n][S][N/8][H][W][8]
-  float* out_sig;          // (B, Cout, D, H, W)
-  double* stats;           // [n][N][2], pre-zeroed
-  // scratch: device array of CUtensorMap (>= 1 + n_div entries), 64-byte aligned
+  uint16_t* out_ap;        // [n][S][N/8][H][W][8]
+  float* out_sig;          // (B, Cout, D, H, W), global indexing
+  double* stats;           // [global n][N][2], pre-zeroed
+  // scratch: device array of CUtensorMap (>= 1 + n_div entries, 64-byte aligned) + host staging
   CUtensorMap* maps_dev;
-  CUtensorMap* maps_host;  // host staging of the same size
+  CUtensorMap* maps_host;
 };
 
 size_t tc_conv_max_maps(int n_div);
@@ -61,16 +69,23 @@ size_t tc_conv_max_maps(int n_div);
 int tc_prepare_weights(const TcLayer& l, const float* w_oihw, const float* bias, cudaStream_t st);
 
 // (B, C, H, W) fp32 -> AP [B][S][C/8][H][W][8]
-int tc_pack_nchw(const float* in, __nv_bfloat16* ap, int B, int C, int H, int W, int S,
+int tc_pack_nchw(const float* in, uint16_t* ap, int B, int C, int H, int W, int S, int fp16,
                  cudaStream_t st);
 
 int tc_conv3x3(const TcConvArgs& a, cudaStream_t st);
 
-// InstanceNorm apply on fp32 planes [n][C/4][H][W][4] (+ optional residual, same
-// layout), writing fp32 planes (optional) and split AP planes (optional).
+// Host-side encoding of the D tensor maps the first convolution reads the right
+// descriptors through (map d: width W - d, so the shifted image's right edge
+// reads as zero padding).  The caller copies them to TcConvArgs::maps_dev.
+int tc_encode_shift_maps(CUtensorMap* maps_host, const uint16_t* in2, int in_slices, int S, int C,
+                         int H, int W, int D);
+
+// InstanceNorm apply on fp32 planes y [n][C/4][H][W][4] with the sums of
+// stats[n][C][2]; the optional residual is READ FROM AP planes (sum of its
+// terms) and the result is written as AP planes (out_ap may alias res_ap).
 int tc_norm_split(const float* y, const double* stats, const float* gamma, const float* beta,
-                  const float* residual, float* out_f32, __nv_bfloat16* out_ap, int n_slices,
-                  int C, int H, int W, int S, cudaStream_t st);
+                  const uint16_t* res_ap, uint16_t* out_ap, int n_slices, int C, int H, int W,
+                  int S, int fp16, cudaStream_t st);
 
 bool tc_available();  // driver entry point for cuTensorMapEncodeTiled resolved?
 

@@ -1,0 +1,144 @@
+// Tail of the hourglass (reference regularization.py:90-92, 125-126):
+// _upsample_to_fullsize = ConvTranspose3d(F/2 = 4 -> 1, kernel (3,4,4), stride
+// (1,2,2), padding 1) without activation / normalisation, fused with the
+// InstanceNorm3d of the block that produces its input.
+//
+// The layer has ONE output channel: it is not a tensor-core shape but a
+// bandwidth kernel -- read the half-size volume (4 ch, channels-last) once,
+// write the (B, 2D, 4H, 4W) cost volume once.  Algorithmic bytes per pair at
+// C2: 212 MB in + 212 MB out.
+//
+//   out[z, 2y+cy, 2x+cx] = bias + sum over tz in 0..2, ty, tx in {0,1}, ci of
+//       in[z+tz-1, y+cy-ty, x+cx-tx][ci] * W[ci][0][2-tz][1-cy+2ty][1-cx+2tx]
+//
+// One thread owns one (y, x) column of the input grid and marches along z with
+// three running 2x2 output patches (out z-1, z, z+1); the 3x3 neighbourhood of
+// the current input plane is read through L1 (neighbouring threads share it).
+// The 192 weights live in the kernel parameter (constant bank): every FFMA takes
+// its weight as a constant operand, no shared-memory or register traffic.
+#include "conv_layers.cuh"
+
+namespace pds {
+namespace {
+
+struct TailParams {
+  const float4* in;      // [B][D][H][W][4] post-LeakyReLU, pre-InstanceNorm
+  float* out;            // [B][D][2H][2W]
+  const double* stats;   // [B][4][2] sum, sum of squares of `in` (null: input already normalised)
+  int B, D, H, W, zseg, nseg;
+  float gamma[4], beta[4];
+  float w[3][4][4][4];   // [kd][kh][kw][ci]
+  float bias;
+};
+
+__device__ __forceinline__ float dot4(const float4& v, const float* w) {
+  return fmaf(v.x, w[0], fmaf(v.y, w[1], fmaf(v.z, w[2], v.w * w[3])));
+}
+
+__global__ void __launch_bounds__(256)
+hourglass_tail_kernel(const __grid_constant__ TailParams p) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  const int b = blockIdx.z / p.nseg, seg = blockIdx.z - b * p.nseg;
+  const int z0 = seg * p.zseg, z1 = min(p.D, z0 + p.zseg);
+  if (x >= p.W || y >= p.H) return;
+  // InstanceNorm of the input as one multiply-add per channel
+  float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.stats) {
+    const double n = (double)p.D * p.H * p.W;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double s = p.stats[(b * 4 + c) * 2], q = p.stats[(b * 4 + c) * 2 + 1];
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+      sc[c] = rstd * p.gamma[c];
+      sh[c] = p.beta[c] - (float)mean * sc[c];
+    }
+  }
+  const size_t plane = (size_t)p.H * p.W;
+  const float4* base = p.in + (size_t)b * p.D * plane;
+  const int OW = 2 * p.W;
+  const size_t oplane = (size_t)4 * plane;
+  float* obase = p.out + (size_t)b * p.D * oplane + (size_t)(2 * y) * OW + 2 * x;
+  bool okx[3], oky[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { okx[d] = x + d - 1 >= 0 && x + d - 1 < p.W; oky[d] = y + d - 1 >= 0 && y + d - 1 < p.H; }
+
+  float acc[3][4];   // [out z - zi + 1][cy*2+cx]
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[k][c] = 0.f;
+
+  for (int zi = z0 - 1; zi <= z1; ++zi) {
+    if (zi >= 0 && zi < p.D) {
+      float4 v[3][3];
+      const float4* pl = base + (size_t)zi * plane + (size_t)y * p.W + x;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          if (oky[dy] && okx[dx]) {
+            float4 t = __ldg(pl + (dy - 1) * p.W + (dx - 1));
+            t.x = fmaf(t.x, sc[0], sh[0]); t.y = fmaf(t.y, sc[1], sh[1]);
+            t.z = fmaf(t.z, sc[2], sh[2]); t.w = fmaf(t.w, sc[3], sh[3]);
+            v[dy][dx] = t;
+          } else {
+            v[dy][dx] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero padding of the NORMALISED tensor
+          }
+        }
+      // input plane zi feeds out z = zi - tz + 1 with kd = 2 - tz
+#pragma unroll
+      for (int tz = 0; tz < 3; ++tz) {
+        const int kd = 2 - tz, slot = 2 - tz;   // slot 0: out zi-1, 1: out zi, 2: out zi+1
+#pragma unroll
+        for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+          for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+            for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+              for (int tx = 0; tx < 2; ++tx)
+                acc[slot][cy * 2 + cx] +=
+                    dot4(v[1 + cy - ty][1 + cx - tx], p.w[kd][1 - cy + 2 * ty][1 - cx + 2 * tx]);
+      }
+    }
+    const int zo = zi - 1;
+    if (zo >= z0 && zo < z1) {
+      float* o = obase + (size_t)zo * oplane;
+      *reinterpret_cast<float2*>(o) = make_float2(acc[0][0] + p.bias, acc[0][1] + p.bias);
+      *reinterpret_cast<float2*>(o + OW) = make_float2(acc[0][2] + p.bias, acc[0][3] + p.bias);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[0][c] = acc[1][c]; acc[1][c] = acc[2][c]; acc[2][c] = 0.f; }
+  }
+}
+
+}  // namespace
+
+// w_host: the layer's weight in PyTorch layout (Cin = 4, Cout = 1, 3, 4, 4), on the HOST.
+int hourglass_tail_forward(const float* in, float* out, const double* stats, const float* gamma_host,
+                           const float* beta_host, const float* w_host, float bias, int B, int D,
+                           int H, int W, cudaStream_t st) {
+  if (B == 0 || D == 0 || H == 0 || W == 0) return PDS_OK;
+  TailParams p;
+  p.in = reinterpret_cast<const float4*>(in); p.out = out; p.stats = stats;
+  p.B = B; p.D = D; p.H = H; p.W = W;
+  p.zseg = D > 48 ? 48 : D;
+  p.nseg = (D + p.zseg - 1) / p.zseg;
+  for (int c = 0; c < 4; ++c) { p.gamma[c] = gamma_host ? gamma_host[c] : 1.f; p.beta[c] = beta_host ? beta_host[c] : 0.f; }
+  for (int ci = 0; ci < 4; ++ci)
+    for (int kd = 0; kd < 3; ++kd)
+      for (int kh = 0; kh < 4; ++kh)
+        for (int kw = 0; kw < 4; ++kw) p.w[kd][kh][kw][ci] = w_host[((ci * 3 + kd) * 4 + kh) * 4 + kw];
+  p.bias = bias;
+  dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8), (unsigned)(B * p.nseg));
+  if (grid.z > 65535) { set_error("hourglass_tail: batch too large"); return PDS_ERR_UNSUPPORTED; }
+  PDS_KERNEL("hourglass_tail(tconv 4->1 + IN)", st);
+  hourglass_tail_kernel<<<grid, dim3(32, 8), 0, st>>>(p);
+  PDS_LAUNCH_CHECK("hourglass_tail_kernel");
+  return PDS_OK;
+}
+
+}  // namespace pds

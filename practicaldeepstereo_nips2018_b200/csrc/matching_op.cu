@@ -23,12 +23,17 @@ struct pds_matching_op {
   std::vector<pds::ConvLayer> layers;  // conv0, 2 per residual block, conv_last
   float* blob = nullptr;               // all parameters, kernel layout (fp32 path)
   // tensor-core path (precision != fp32)
-  int split = 0;                       // bf16 terms per value (1, 2 or 3)
+  int split = 0;                       // 16-bit terms per value (1, 2 or 3)
+  int fp16 = 0;                        // term type (1 = half, 0 = bfloat16)
+  int group = 0;                       // disparity slices per pass (0 = all of them)
   std::vector<pds::TcLayer> tc;
   void* tc_blob = nullptr;
+  // tensor maps of the shifted right descriptors, cached per (buffer, shape)
   CUtensorMap* maps_dev = nullptr;
   CUtensorMap* maps_host = nullptr;
   int maps_cap = 0;
+  const void* maps_key_ptr = nullptr;
+  int maps_key[4] = {0, 0, 0, 0};
 };
 
 namespace pds {
@@ -48,7 +53,7 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
   PDS_CHECK_ARG(C >= 1 && F >= 1 && S >= 1 && n_res >= 0, "pds_matching_op_create: bad sizes");
   PDS_CHECK_ARG(n_params == 4 + 8 * n_res,
                 "pds_matching_op_create: expected %d parameter tensors, got %d", 4 + 8 * n_res, n_params);
-  PDS_CHECK_ARG(precision >= PDS_PRECISION_FP32 && precision <= PDS_PRECISION_BF16,
+  PDS_CHECK_ARG(precision >= PDS_PRECISION_FP32 && precision <= PDS_PRECISION_FP16,
                 "pds_matching_op_create: bad precision");
   cudaStream_t st = (cudaStream_t)stream;
   if (precision != PDS_PRECISION_FP32) {
@@ -65,7 +70,10 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
   PDS_CHECK_ARG(op, "out of host memory");
   op->C = C; op->F = F; op->S = S; op->n_res = n_res; op->precision = precision;
   if (precision != PDS_PRECISION_FP32) {
-    op->split = precision == PDS_PRECISION_BF16X3 ? 3 : (precision == PDS_PRECISION_BF16X2 ? 2 : 1);
+    op->split = precision == PDS_PRECISION_BF16X3 ? 3
+                : (precision == PDS_PRECISION_BF16X2 || precision == PDS_PRECISION_FP16X2) ? 2 : 1;
+    op->fp16 = (precision == PDS_PRECISION_FP16X2 || precision == PDS_PRECISION_FP16) ? 1 : 0;
+    if (const char* g = getenv("PDS_B200_MATCH_GROUP")) op->group = atoi(g);
     const int nl = 2 + 2 * n_res;
     op->tc.resize(nl);
     size_t bytes = 0;
@@ -73,8 +81,12 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
       TcLayer& l = op->tc[i];
       l.Cin = i == 0 ? 2 * C : F;
       l.Cout = i == nl - 1 ? S : F;
-      l.N = (int)align_up(l.Cout, 16);
+      l.N = l.Cout <= 16 ? 16 : 64;
       l.S = op->split;
+      l.fp16 = op->fp16;
+      // fp16 terms: scale the weights by 2^8 so that the low term of typical (|w| << 1)
+      // weights stays a normal half; undone exactly in the epilogue
+      l.wscale = op->fp16 ? 256.f : 1.f;
       bytes += align_up(l.w_elems() * 2, 256) + align_up(l.N * 4, 256) + 2 * align_up(F * 4, 256);
     }
     cudaError_t e = cudaMalloc(&op->tc_blob, bytes);
@@ -83,7 +95,7 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
     int pi = 0, rc = PDS_OK;
     for (int i = 0; i < nl && rc == PDS_OK; ++i) {
       TcLayer& l = op->tc[i];
-      l.w = (__nv_bfloat16*)cur; cur += align_up(l.w_elems() * 2, 256);
+      l.w = (uint16_t*)cur; cur += align_up(l.w_elems() * 2, 256);
       l.bias = (float*)cur; cur += align_up(l.N * 4, 256);
       rc = tc_prepare_weights(l, params[pi], params[pi + 1], st);
       pi += 2;
@@ -140,33 +152,44 @@ extern "C" void pds_matching_op_destroy(pds_matching_op* op) {
 namespace pds {
 namespace {
 
-// Tensor-core pipeline buffers (all sizes in bytes, 256-aligned).
+// Tensor-core pipeline buffers (all sizes in bytes, 256-aligned).  The disparity
+// slices n = b * D + d are processed in groups of `G`: the three activation
+// buffers of a group (residual stream planes, fp32 convolution output,
+// normalised planes) are sized to stay resident in the 126 MB L2 between the
+// convolution that writes them and the pass that reads them.
 struct TcPlan {
-  size_t lap, rap, x, y, xap, aap, stats, total;
+  int G;
+  size_t lap, rap, xa, t, ya, stats, total;
 };
 
 TcPlan tc_plan(const pds_matching_op* op, int B, int H, int W, int D) {
   const size_t hw = (size_t)H * W, n = (size_t)B * D, S = op->split;
   TcPlan p;
+  const size_t per_slice = (size_t)op->F * hw * (2 * S + 4 + 2 * S);
+  (void)per_slice;
+  // Measured on B200 (C2, fp16x2): one pass over all 48 slices 3.3 ms, groups of 12 / 3 / 1
+  // slices 4.4 / 7.9 / 12.2 ms -- per-launch fill/drain and the tail wave cost more than L2
+  // residency returns, so the default is a single group; PDS_B200_MATCH_GROUP overrides.
+  int G = op->group > 0 ? op->group : (int)n;
+  if ((size_t)G > n) G = (int)n;
+  p.G = G;
   p.lap = align_up((size_t)B * S * op->C * hw * 2, 256);
   p.rap = p.lap;
-  p.x = align_up(n * op->F * hw * 4, 256);
-  p.y = p.x;
-  p.xap = align_up(n * S * op->F * hw * 2, 256);
-  p.aap = p.xap;
+  p.xa = align_up((size_t)G * S * op->F * hw * 2, 256);
+  p.ya = p.xa;
+  p.t = align_up((size_t)G * op->F * hw * 4, 256);
   p.stats = align_up(n * op->F * 2 * sizeof(double) * 2 * (op->n_res > 0 ? op->n_res : 1), 256);
-  p.total = p.lap + p.rap + p.x + p.y + p.xap + p.aap + p.stats + 1024;
+  p.total = p.lap + p.rap + p.xa + p.t + p.ya + p.stats + 1024;
   return p;
 }
 
 int tc_forward(pds_matching_op* op, const float* left, const float* right, float* signatures, int B,
                int H, int W, int D, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  const size_t hw = (size_t)H * W;
-  const int N = B * D, S = op->split;
-  if (op->maps_cap < 1 + D) {
+  const int N = B * D, S = op->split, fp16 = op->fp16;
+  if (op->maps_cap < D) {
     cudaFree(op->maps_dev); free(op->maps_host);
-    op->maps_dev = nullptr; op->maps_host = nullptr; op->maps_cap = 0;
-    const int cap = 1 + (D > 64 ? D : 64);
+    op->maps_dev = nullptr; op->maps_host = nullptr; op->maps_cap = 0; op->maps_key_ptr = nullptr;
+    const int cap = D > 64 ? D : 64;
     PDS_CUDA(cudaMalloc(&op->maps_dev, cap * sizeof(CUtensorMap)));
     if (posix_memalign((void**)&op->maps_host, 64, cap * sizeof(CUtensorMap)) != 0) {
       set_error("out of host memory"); return PDS_ERR_CUDA;
@@ -175,45 +198,56 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
   }
   Workspace ws(workspace, workspace_bytes);
   const TcPlan pl = tc_plan(op, B, H, W, D);
-  __nv_bfloat16* lap = (__nv_bfloat16*)ws.take<char>(pl.lap);
-  __nv_bfloat16* rap = (__nv_bfloat16*)ws.take<char>(pl.rap);
-  float* x = (float*)ws.take<char>(pl.x);
-  float* y = (float*)ws.take<char>(pl.y);
-  __nv_bfloat16* xap = (__nv_bfloat16*)ws.take<char>(pl.xap);
-  __nv_bfloat16* aap = (__nv_bfloat16*)ws.take<char>(pl.aap);
+  uint16_t* lap = (uint16_t*)ws.take<char>(pl.lap);
+  uint16_t* rap = (uint16_t*)ws.take<char>(pl.rap);
+  uint16_t* xa = (uint16_t*)ws.take<char>(pl.xa);
+  float* t = (float*)ws.take<char>(pl.t);
+  uint16_t* ya = (uint16_t*)ws.take<char>(pl.ya);
   double* stats = (double*)ws.take<char>(pl.stats);
   if (ws.overflow) { set_error("pds_matching_op_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
   const size_t stat_elems = (size_t)N * op->F * 2;
   PDS_CUDA(cudaMemsetAsync(stats, 0, pl.stats, st));
   int rc;
-  if ((rc = tc_pack_nchw(left, lap, B, op->C, H, W, S, st)) != PDS_OK) return rc;
-  if ((rc = tc_pack_nchw(right, rap, B, op->C, H, W, S, st)) != PDS_OK) return rc;
-
-  TcConvArgs a = {};
-  a.maps_dev = op->maps_dev; a.maps_host = op->maps_host;
-  a.H = H; a.W = W; a.n_slices = N;
-  // conv0: cat[left, shift_d(right)] gathered straight from the descriptors
-  a.layer = &op->tc[0]; a.epilogue = TC_EPI_PLAIN; a.n_div = D;
-  a.in = lap; a.in_slices = B; a.in_C = op->C; a.in2 = rap; a.in2_C = op->C;
-  a.out_f32 = x; a.out_ap = xap;
-  if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
-  a.in2 = nullptr; a.in2_C = 0; a.n_div = 1; a.in_slices = N; a.in_C = op->F;
-  for (int r = 0; r < op->n_res; ++r) {
-    const TcLayer& c1 = op->tc[1 + 2 * r];
-    const TcLayer& c2 = op->tc[2 + 2 * r];
-    double* s1 = stats + stat_elems * (2 * r);
-    double* s2 = stats + stat_elems * (2 * r + 1);
-    a.layer = &c1; a.epilogue = TC_EPI_ACT; a.in = xap; a.out_f32 = y; a.out_ap = nullptr; a.stats = s1;
-    if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
-    if ((rc = tc_norm_split(y, s1, c1.gamma, c1.beta, nullptr, nullptr, aap, N, op->F, H, W, S, st)) != PDS_OK) return rc;
-    a.layer = &c2; a.in = aap; a.stats = s2;
-    if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
-    // x = IN(t) + x (ResidualBlock.forward, network_blocks.py:143-144)
-    if ((rc = tc_norm_split(y, s2, c2.gamma, c2.beta, x, x, xap, N, op->F, H, W, S, st)) != PDS_OK) return rc;
+  if ((rc = tc_pack_nchw(left, lap, B, op->C, H, W, S, fp16, st)) != PDS_OK) return rc;
+  if ((rc = tc_pack_nchw(right, rap, B, op->C, H, W, S, fp16, st)) != PDS_OK) return rc;
+  // shifted-read tensor maps of the right descriptors: re-encoded only when the buffer or shape changes
+  if (op->maps_key_ptr != rap || op->maps_key[0] != B || op->maps_key[1] != H || op->maps_key[2] != W ||
+      op->maps_key[3] != D) {
+    if ((rc = tc_encode_shift_maps(op->maps_host, rap, B, S, op->C, H, W, D)) != PDS_OK) return rc;
+    PDS_CUDA(cudaMemcpyAsync(op->maps_dev, op->maps_host, D * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+    op->maps_key_ptr = rap; op->maps_key[0] = B; op->maps_key[1] = H; op->maps_key[2] = W; op->maps_key[3] = D;
   }
-  a.layer = &op->tc.back(); a.epilogue = TC_EPI_SIG; a.in = xap; a.n_div = D;
-  a.out_f32 = nullptr; a.out_ap = nullptr; a.stats = nullptr; a.out_sig = signatures;
-  return tc_conv3x3(a, st);
+
+  for (int n0 = 0; n0 < N; n0 += pl.G) {
+    const int g = N - n0 < pl.G ? N - n0 : pl.G;
+    TcConvArgs a = {};
+    a.maps_dev = op->maps_dev; a.maps_host = op->maps_host;
+    a.H = H; a.W = W; a.n_slices = g; a.n0 = n0; a.n_div = D;
+    // conv0: cat[left, shift_d(right)] gathered straight from the descriptors
+    a.layer = &op->tc[0]; a.epilogue = TC_EPI_PLAIN;
+    a.in = lap; a.in_slices = B; a.in_C = op->C; a.in2 = rap; a.in2_C = op->C;
+    a.out_ap = xa;
+    if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
+    a.in2 = nullptr; a.in2_C = 0; a.in_slices = g; a.in_C = op->F; a.out_ap = nullptr;
+    for (int r = 0; r < op->n_res; ++r) {
+      const TcLayer& c1 = op->tc[1 + 2 * r];
+      const TcLayer& c2 = op->tc[2 + 2 * r];
+      double* s1 = stats + stat_elems * (2 * r);
+      double* s2 = stats + stat_elems * (2 * r + 1);
+      const size_t soff = (size_t)n0 * op->F * 2;
+      a.layer = &c1; a.epilogue = TC_EPI_ACT; a.in = xa; a.out_f32 = t; a.stats = s1;
+      if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
+      if ((rc = tc_norm_split(t, s1 + soff, c1.gamma, c1.beta, nullptr, ya, g, op->F, H, W, S, fp16, st)) != PDS_OK) return rc;
+      a.layer = &c2; a.in = ya; a.stats = s2;
+      if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
+      // x = IN(t) + x (ResidualBlock.forward, network_blocks.py:143-144), in place on the planes
+      if ((rc = tc_norm_split(t, s2 + soff, c2.gamma, c2.beta, xa, xa, g, op->F, H, W, S, fp16, st)) != PDS_OK) return rc;
+    }
+    a.layer = &op->tc.back(); a.epilogue = TC_EPI_SIG; a.in = xa;
+    a.out_f32 = nullptr; a.out_ap = nullptr; a.stats = nullptr; a.out_sig = signatures;
+    if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
+  }
+  return PDS_OK;
 }
 
 }  // namespace

@@ -15,6 +15,10 @@ struct pds_regularization {
   int F, precision;
   std::vector<pds::ConvLayer> layers;
   float* blob = nullptr;
+  // host copies for the fused tail kernel (F == 8): last layer's weight (4,1,3,4,4) and bias,
+  // InstanceNorm affine of _upsample_to_halfsize
+  bool fused_tail = false;
+  float tail_w[192], tail_bias = 0.f, tail_gamma[4], tail_beta[4];
 };
 
 namespace pds {
@@ -96,7 +100,7 @@ extern "C" int pds_regularization_create(pds_regularization** out, const float* 
   using namespace pds;
   PDS_CHECK_ARG(out && params, "pds_regularization_create: null pointer");
   PDS_CHECK_ARG(F >= 2 && F % 2 == 0, "pds_regularization_create: number_of_features must be even");
-  PDS_CHECK_ARG(precision >= PDS_PRECISION_FP32 && precision <= PDS_PRECISION_BF16,
+  PDS_CHECK_ARG(precision >= PDS_PRECISION_FP32 && precision <= PDS_PRECISION_FP16,
                 "pds_regularization_create: bad precision");
   pds_regularization* reg = new (std::nothrow) pds_regularization();
   PDS_CHECK_ARG(reg, "out of host memory");
@@ -111,6 +115,19 @@ extern "C" int pds_regularization_create(pds_regularization** out, const float* 
   cudaError_t e = cudaMalloc(&reg->blob, blob_elems(reg->layers) * sizeof(float));
   if (e != cudaSuccess) { delete reg; return cuda_fail(e, "cudaMalloc(regularization weights)"); }
   int rc = load_layers(reg->layers, params, reg->blob, (cudaStream_t)stream);
+  if (rc == PDS_OK && F == 8) {
+    // parameter order (state_dict): ..., _upsample_to_halfsize.{0.weight, 0.bias, 2.weight, 2.bias},
+    // _upsample_to_fullsize.{weight, bias}
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e1 = cudaMemcpyAsync(reg->tail_gamma, params[n_params - 4], 4 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaMemcpyAsync(reg->tail_beta, params[n_params - 3], 4 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    cudaError_t e3 = cudaMemcpyAsync(reg->tail_w, params[n_params - 2], 192 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    cudaError_t e4 = cudaMemcpyAsync(&reg->tail_bias, params[n_params - 1], sizeof(float), cudaMemcpyDeviceToHost, st);
+    cudaError_t e5 = cudaStreamSynchronize(st);
+    for (cudaError_t e : {e1, e2, e3, e4, e5})
+      if (e != cudaSuccess && rc == PDS_OK) rc = cuda_fail(e, "copy of the hourglass tail parameters");
+    reg->fused_tail = rc == PDS_OK;
+  }
   if (rc != PDS_OK) { cudaFree(reg->blob); delete reg; return rc; }
   *out = reg;
   return PDS_OK;
@@ -214,6 +231,15 @@ extern "C" int pds_regularization_forward(pds_regularization* reg, const float* 
   }
   float* half = ws.take<float>((size_t)B * vox * 8 * (F / 2));
   if (ws.overflow) { set_error("pds_regularization_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
+  if (reg->fused_tail) {
+    // _upsample_to_halfsize: convolution + LeakyReLU + sums; its InstanceNorm is applied by the
+    // tail kernel while it reads the volume (saves one 424 MB pass at C2)
+    PDS_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * L[li].Cout * 2 * sizeof(double), st));
+    if ((rc = conv_forward_simt(L[li++], g, out, nullptr, 0, half, stats, st)) != PDS_OK) return rc;
+    g.D *= 2; g.H *= 2; g.W *= 2;
+    return hourglass_tail_forward(half, cost, stats, reg->tail_gamma, reg->tail_beta, reg->tail_w,
+                                  reg->tail_bias, B, g.D, g.H, g.W, st);
+  }
   if ((rc = conv_block(L[li++], g, out, half, stats, nullptr, nullptr, half, nullptr, 0, st)) != PDS_OK) return rc;
   g.D *= 2; g.H *= 2; g.W *= 2;
   // _upsample_to_fullsize: 1 output channel, channels-last == (B, 2D, 4H, 4W) after squeeze(1)

@@ -35,7 +35,7 @@ class PdsNetwork(nn.Module):
         stacks themselves run in reduced precision, so that the fp32 pipeline is
         fp32 end to end."""
         precision = getattr(getattr(self._matching, '_operation', None), 'precision', 'fp32')
-        exact = left_image.is_cuda and precision in ('fp32', 'bf16x3', 'bf16x2')
+        exact = left_image.is_cuda and precision in ('fp32', 'bf16x3', 'bf16x2', 'fp16x2')
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=not exact):
             left_descriptor, shortcut_from_left = self._embedding(left_image)
             right_descriptor = self._embedding(right_image)[0]

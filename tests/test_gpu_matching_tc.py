@@ -1,0 +1,63 @@
+"""a2 parity of the tcgen05 path: MatchingOperation over all disparities on the
+tensor cores (split 16-bit operands) vs the ATen restatement (B200 only).
+
+Tolerances (signature scale ~10): the fp32-grade modes (fp16x2: 22 significand
+bits, bf16x3: 24) must stay within 2e-4 max-abs -- the bound the fp32 CUDA-core
+path is held to in test_gpu_matching.py; bf16x2 (16 bits) 1e-3; single-term
+modes are only checked for gross errors."""
+import pytest
+import torch
+
+from oracle import synth, torch_port
+from practicaldeepstereo_nips2018_b200 import matching
+from gpu_util import cuda, load_module, max_abs, tdict
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'fp16x2': 2e-4, 'bf16x3': 2e-4, 'bf16x2': 1e-3, 'bf16': 0.5, 'fp16': 0.1}
+
+
+def _reference(l, r, params, md, n_res=2):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    p = tdict(params)
+    return torch_port.matching(l, r, lambda x: torch_port.matching_operation(x, p, n_res), md)
+
+
+@pytest.mark.parametrize('precision', sorted(TOL))
+@pytest.mark.parametrize('B,H,W,md', [(1, 16, 16, 0), (2, 21, 37, 9), (1, 48, 80, 23)])
+def test_tc_matching_vs_torch_port(precision, B, H, W, md):
+    params = synth.make_params(synth.matching_operation_specs(), 35)
+    op = load_module(matching.MatchingOperation(precision=precision), params)
+    l, r = cuda(synth.tensor((B, 64, H, W), 36)), cuda(synth.tensor((B, 64, H, W), 37))
+    with torch.no_grad():
+        out = matching.Matching(md, op)(l, r)
+        ref = _reference(l, r, params, md)
+    assert out.shape == ref.shape == (B, 8, md + 1, H, W)
+    assert max_abs(out, ref) <= TOL[precision]
+
+
+@pytest.mark.parametrize('precision', ['fp16x2', 'bf16x3'])
+def test_tc_disparity_beyond_width_and_groups(precision, monkeypatch):
+    """More disparities than columns (fully shifted-out right image) and a slice
+    count that is not a multiple of the L2 group size."""
+    monkeypatch.setenv('PDS_B200_MATCH_GROUP', '3')
+    params = synth.make_params(synth.matching_operation_specs(), 38)
+    op = load_module(matching.MatchingOperation(precision=precision), params)
+    l, r = cuda(synth.tensor((2, 64, 18, 11), 39)), cuda(synth.tensor((2, 64, 18, 11), 40))
+    with torch.no_grad():
+        out = matching.Matching(12, op)(l, r)            # 26 slices, groups of 3
+        ref = _reference(l, r, params, 12)
+    assert max_abs(out, ref) <= TOL[precision]
+
+
+def test_tc_full_width_slice():
+    """One C2-sized disparity group (144 x 240, 3 disparities): every tile column,
+    the weight-resident kernel and the InstanceNorm sums at full size."""
+    params = synth.make_params(synth.matching_operation_specs(), 41)
+    op = load_module(matching.MatchingOperation(precision='fp16x2'), params)
+    l, r = cuda(synth.tensor((1, 64, 144, 240), 42)), cuda(synth.tensor((1, 64, 144, 240), 43))
+    with torch.no_grad():
+        out = matching.Matching(2, op)(l, r)
+        ref = _reference(l, r, params, 2)
+    assert max_abs(out, ref) <= 2e-4

@@ -55,8 +55,23 @@ def test_hourglass_golden(golden):
     with torch.no_grad():
         out = reg(cuda(sig), cuda(sc))
     assert out.shape == (1, 32, 64, 128)
-    # fp32 noise floor of this tiny-bottleneck config: reference vs fp64 = 1.8e-4
-    assert max_abs(out, golden('regularization')['out']) <= 1e-3
+    # fp32 noise floor of this tiny-bottleneck config (1x1x2 voxels under InstanceNorm):
+    # reference vs its own fp64 run = 1.8e-4, amplified up to 316x by the 2-voxel normalisation
+    assert max_abs(out, golden('regularization')['out']) <= 3e-3
+
+
+def test_hourglass_well_conditioned_vs_torch_port():
+    """Bottleneck of 2x2x4 voxels: the hourglass (incl. the fused InstanceNorm + transposed
+    convolution tail) against ATen fp32 on the same device at the fp32 noise floor."""
+    torch.backends.cudnn.allow_tf32 = False
+    params = synth.make_params(synth.regularization_specs(), 48)
+    reg = load_module(regularization.Regularization(), params)
+    sig, sc = cuda(synth.tensor((2, 8, 32, 32, 64), 49)), cuda(synth.tensor((2, 8, 32, 64), 50))
+    with torch.no_grad():
+        out = reg(sig, sc)
+        ref = torch_port.regularization(sig, sc, tdict(params))
+    assert out.shape == ref.shape == (2, 64, 128, 256)
+    assert max_abs(out, ref) <= 2e-4
 
 
 def test_hourglass_output_size():

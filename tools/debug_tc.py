@@ -77,5 +77,6 @@ run('random conv0+last, one tile', 0, 1, 16, 8, 1, prec)
 run('random conv0+last, NT=3 ragged', 0, 2, 21, 37, 5, prec)
 run('full op, one tile', 2, 1, 16, 8, 1, prec)
 run('full op, 48x80 D=6', 2, 1, 48, 80, 6, prec)
-for pr in ('bf16x3', 'bf16x2', 'bf16'):
+run('full op, B=2 33x50 D=7 (ragged)', 2, 2, 33, 50, 7, prec)
+for pr in ('fp16x2', 'bf16x3', 'bf16x2', 'bf16', 'fp16'):
     run('full op, 144x240 D=4', 2, 1, 144, 240, 4, pr)

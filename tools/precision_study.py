@@ -24,7 +24,7 @@ from practicaldeepstereo_nips2018_b200 import PdsNetwork  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--workload', default='C2')
 ap.add_argument('--json', default=None)
-ap.add_argument('--precisions', default='fp32,bf16x3,bf16x2,bf16')
+ap.add_argument('--precisions', default='fp32,fp16x2,bf16x3,bf16x2,bf16,fp16')
 args = ap.parse_args()
 H, W, md = {'C1': (64, 128, 63), 'C2': (540, 960, 191), 'C3': (540, 960, 255),
             'C4': (375, 1242, 191), 'S': (256, 512, 127)}[args.workload]
