@@ -2,7 +2,7 @@
 """Benchmark of the PdsNetwork.forward hot path (stereo pairs / second).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--precision fp32|bf16x3|bf16x2|bf16] [--workload C2|C3|C4|C1]
+                    [--precision fp16x2|fp32|bf16x3|bf16x2|bf16|fp16] [--workload C2|C3|C4|C1]
 
 One process per GPU (torchrun for N > 1: ranks are independent replicas, one
 NCCL broadcast of the weights at start-up, NO collective in the timed region).
@@ -112,33 +112,29 @@ def load_peaks():
             'source': 'fallback'}
 
 
-def kernel_rooflines(report, steps, batch, Hp, Wp, md, precision, peaks):
+def kernel_rooflines(report, steps, peaks):
     """Per-kernel-class roofline from the live CUDA-event profile of `steps` steps.
-    Algorithmic bytes / flops per launch are the DESIGN.md figures."""
-    Hq, Wq, Dq, Dc = Hp // 4, Wp // 4, (md + 1) // 4, (md + 1) // 2
+    Algorithmic FLOPs / bytes per launch come from the library's own accounting
+    (pds_profiler_read_work: reference FLOP count of the layer, minimum HBM bytes;
+    DESIGN.md section 4); a class is graded on the roof it is closer to."""
     out = []
-    n_slices = batch * Dq
-    conv64_flops = 2.0 * 9 * 64 * 64 * Hq * Wq * n_slices        # one 64->64 3x3 layer
-    for name, (launches, ms) in sorted(report.items(), key=lambda kv: -kv[1][1]):
-        if launches == 0:
+    for name, (launches, ms, flops, nbytes) in sorted(report.items(), key=lambda kv: -kv[1][1]):
+        if launches == 0 or ms <= 0:
             continue
-        avg_s = ms / launches / 1e3
+        sec = ms / 1e3
         entry = {'kernel': name, 'launches_per_step': launches / steps,
-                 'ms_per_step': ms / steps, 'avg_us': avg_s * 1e6}
-        if name == 'subpixel_map':
-            by = batch * (Dc * (Hp - (Hp - 0)) * 0 + Dc * Hp * Wp * 4 + Hp * Wp * 4)
-            entry.update(bound='hbm', unit='GB/s', achieved=by / avg_s / 1e9, peak=peaks['hbm_gbs'])
-        elif name == 'matching_concat':
-            by = batch * (2 * 64 * Hq * Wq * 4 + 128 * Dq * Hq * Wq * 4)
-            entry.update(bound='hbm', unit='GB/s', achieved=by / avg_s / 1e9, peak=peaks['hbm_gbs'])
-        elif name.startswith('conv_igemm_f32<8,8,8') or name.startswith('conv3x3_tc'):
-            # the matching 64->64 layers dominate this class (4 of its launches per step
-            # at C2 are exactly conv64_flops; conv0 is 2x that) -> use the class total
-            fl = conv64_flops * (4 + 2) / max(launches / steps, 1) if launches / steps >= 5 else conv64_flops
-            entry.update(bound='tensor', unit='TFLOP/s', achieved=fl / avg_s / 1e12,
-                         peak=peaks['bf16_tflops_sustained'])
-        if 'achieved' in entry:
-            entry['frac'] = entry['achieved'] / entry['peak']
+                 'ms_per_step': ms / steps, 'avg_us': ms / launches * 1e3}
+        tensor = flops / sec / 1e12 / peaks['bf16_tflops_sustained'] if flops else 0.0
+        hbm = nbytes / sec / 1e9 / peaks['hbm_gbs'] if nbytes else 0.0
+        if flops or nbytes:
+            entry['tflops'] = flops / sec / 1e12
+            entry['gbs'] = nbytes / sec / 1e9
+            if tensor >= hbm:
+                entry.update(bound='tensor', unit='TFLOP/s', achieved=entry['tflops'],
+                             peak=peaks['bf16_tflops_sustained'], frac=tensor)
+            else:
+                entry.update(bound='hbm', unit='GB/s', achieved=entry['gbs'],
+                             peak=peaks['hbm_gbs'], frac=hbm)
         out.append(entry)
     return out
 
@@ -214,7 +210,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('PDS_B200_PRECISION', 'fp32'))
+    ap.add_argument('--precision', default=os.environ.get('PDS_B200_PRECISION', 'fp16x2'))
     ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=1, help='stereo pairs per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -315,7 +311,7 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         total_pairs = args.steps * args.batch * world
-        kernels = kernel_rooflines(report, args.steps, args.batch, Hp, Wp, md, args.precision, peaks)
+        kernels = kernel_rooflines(report, args.steps, peaks)
         dominant = next((k for k in kernels if 'achieved' in k), None)
         roofline = None
         if dominant:

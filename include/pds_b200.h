@@ -76,6 +76,11 @@ void pds_profiler_enable(int on);
 void pds_profiler_reset(void);
 int pds_profiler_read(int index, char* name, int name_len,
                       unsigned long long* launches, double* milliseconds);
+/* Algorithmic work of the same kernel class, summed over its launches: FLOPs
+ * counted as the reference's dense contraction (2 * taps * Cin * Cout * outputs,
+ * whatever the executed precision) and the minimum HBM bytes (each input read
+ * once, each output written once).                                            */
+int pds_profiler_read_work(int index, double* flops, double* bytes);
 
 /* ---- a1: Matching.forward, data movement (matching.py:50-63) -------------
  * Builds, for every disparity d in [0, D), the tensor the reference hands to

@@ -29,6 +29,7 @@ SIGNATURES = {
     'pds_profiler_reset': (None, []),
     'pds_profiler_read': (_i, [_i, ctypes.c_char_p, _i, ctypes.POINTER(ctypes.c_ulonglong),
                                ctypes.POINTER(ctypes.c_double)]),
+    'pds_profiler_read_work': (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'pds_matching_concat': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'pds_matching_stack': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'pds_matching_op_create': (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp]),
@@ -120,11 +121,15 @@ def profiler_reset():
 
 
 def profiler_report():
-    """{kernel class: (launches, total device ms)} since the last reset."""
+    """{kernel class: (launches, total device ms, algorithmic FLOPs, algorithmic HBM bytes)}
+    since the last reset."""
     out, i = {}, 0
     name = ctypes.create_string_buffer(128)
     n, ms = ctypes.c_ulonglong(), ctypes.c_double()
+    fl, by = ctypes.c_double(), ctypes.c_double()
     while lib().pds_profiler_read(i, name, 128, ctypes.byref(n), ctypes.byref(ms)):
-        out[name.value.decode()] = (int(n.value), float(ms.value))
+        lib().pds_profiler_read_work(i, ctypes.byref(fl), ctypes.byref(by))
+        out[name.value.decode()] = (int(n.value), float(ms.value), float(fl.value),
+                                    float(by.value))
         i += 1
     return out

@@ -204,6 +204,7 @@ int launch_k3s1(const ConvLayer& l, const ConvGeom& g, const float* in, float* o
   if (grid.z > 65535) { set_error("conv3d_direct: grid too large"); return PDS_ERR_UNSUPPORTED; }
   static const std::string name = "conv3d_k3s1_direct<" + std::to_string(CIN) + "," + std::to_string(COUT) + ">";
   PDS_KERNEL(name.c_str(), st);
+  PDS_KERNEL_WORK(2.0 * 27 * CIN * COUT * g.N * g.D * g.H * g.W, 4.0 * g.N * g.D * g.H * g.W * (CIN + COUT));
   conv3d_k3s1_direct_kernel<CIN, COUT, PX><<<grid, 128, smem, st>>>(p);
   PDS_LAUNCH_CHECK("conv3d_k3s1_direct_kernel");
   return PDS_OK;

@@ -64,6 +64,9 @@ struct ConvLayer {
   int ntaps() const { return dim[0].ntaps() * dim[1].ntaps() * dim[2].ntaps(); }
   int nclass() const { return dim[0].nclass() * dim[1].nclass() * dim[2].nclass(); }
   size_t weight_elems() const { return (size_t)nclass() * ntaps() * Cin * Cout; }
+  size_t weight_elems_pytorch() const {
+    return (size_t)Cin * Cout * dim[0].ksize() * dim[1].ksize() * dim[2].ksize();
+  }
 };
 
 inline ConvLayer make_layer(int cin, int cout, DimSpec d, DimSpec h, DimSpec w, bool transposed,
@@ -91,6 +94,11 @@ int relayout_weights(const ConvLayer& l, const float* src, float* dst, cudaStrea
 // output per (n, cout) into stats[n][cout][2] (double), which must be zeroed.
 int conv_forward_simt(const ConvLayer& l, const ConvGeom& g, const float* in, const float* in2,
                       int Cin1, float* out, double* stats, cudaStream_t st);
+
+// Direct fp32 kernels for the few-channel 3x3x3 stride-1 layers (conv3d_direct.cu); *handled is
+// false when the layer is not one of them (nothing is launched then).
+int conv_forward_direct(const ConvLayer& l, const ConvGeom& g, const float* in, float* out,
+                        double* stats, cudaStream_t st, bool* handled);
 
 // InstanceNorm (biased variance, eps 1e-5) applied from accumulated statistics,
 // fused with the additions that follow it in the reference:

@@ -254,6 +254,11 @@ int launch_conv(const ConvParams& p, cudaStream_t st) {
   static const std::string name = "conv_igemm_f32<" + std::to_string(TN) + "," + std::to_string(NG) + "," +
                                   std::to_string(TM) + "," + std::to_string(KC) + ">";
   PDS_KERNEL(name.c_str(), st);
+  {
+    const double zvox = (double)Mz * ncls * p.N, taps = p.dim[0].ntaps() * p.dim[1].ntaps() * p.dim[2].ntaps();
+    PDS_KERNEL_WORK(2.0 * taps * p.Cin * p.Cout * zvox,
+                    4.0 * ((double)p.N / p.n_div * p.D * p.H * p.W * p.Cin + zvox * p.Cout));
+  }
   conv_igemm_f32<TN, NG, TM, KC><<<grid, 128, 0, st>>>(q);
   PDS_LAUNCH_CHECK("conv_igemm_f32");
   return PDS_OK;
@@ -387,6 +392,7 @@ int launch_layout(const float* in, float* out, int N, int C, size_t S, cudaStrea
   }
   dim3 grid((unsigned)((S + 31) / 32), (unsigned)N);
   PDS_KERNEL(TO_CL ? "layout_to_channels_last" : "layout_to_channels_first", st);
+  PDS_KERNEL_WORK(0, 8.0 * N * C * S);
   layout_kernel<TO_CL><<<grid, 256, smem, st>>>(in, out, C, S);
   PDS_LAUNCH_CHECK("layout_kernel");
   return PDS_OK;
@@ -450,6 +456,7 @@ int instance_norm_apply(const float* y, const double* stats, const float* gamma,
   if (gx > cap) gx = cap;
   dim3 grid(gx, (unsigned)N);
   PDS_KERNEL("instance_norm_apply", st);
+  PDS_KERNEL_WORK(0, 4.0 * N * S * C * (1 + (out ? 1 : 0) + (out2 ? 1 : 0) + (add ? 1 : 0)));
   if (v4)
     instance_norm_apply_kernel<4><<<grid, 256, smem, st>>>(y, stats, gamma, beta, add, add_bcast, out, out2, S, HW, C);
   else

@@ -643,6 +643,12 @@ int launch_tc(TcKernelParams& p, cudaStream_t st) {
   static const std::string name = "conv3x3_tc<S=" + std::to_string(S) + ",NT=" + std::to_string(NT) +
                                   ",N=" + std::to_string(N) + (WRES ? ",Wres>" : ",Wstream>");
   PDS_KERNEL(name.c_str(), st);
+  {
+    // reference FLOPs of the layer (real Cout, all Cin); bytes: AP terms in (both inputs), output as written
+    const double px = (double)p.H * p.W * p.n_slices;
+    const double out_b = p.epilogue == TC_EPI_SIG ? 4.0 * p.Cout : (p.epilogue == TC_EPI_PLAIN ? 2.0 * S * N : 4.0 * N);
+    PDS_KERNEL_WORK(2.0 * 9 * 16 * p.nchunks * p.Cout * px, px * out_b + (p.in_global ? 0.0 : px * 2.0 * S * 16 * p.nchunks));
+  }
   conv3x3_tc_kernel<S, NT, N, WRES><<<grid, kThreads, smem, st>>>(p);
   PDS_LAUNCH_CHECK("conv3x3_tc_kernel");
   return PDS_OK;
@@ -678,6 +684,7 @@ int tc_pack_nchw(const float* in, uint16_t* ap, int B, int C, int H, int W, int 
   const size_t HW = (size_t)H * W, total = (size_t)B * (C / 8) * HW;
   if (total == 0) return PDS_OK;
   PDS_KERNEL("tc_pack_nchw", st);
+  PDS_KERNEL_WORK(0, (double)B * C * HW * (4 + 2 * S));
   const unsigned g = (unsigned)((total + 255) / 256);
   if (fp16) tc_pack_nchw_kernel<true><<<g, 256, 0, st>>>(in, ap, C, HW, S, total);
   else tc_pack_nchw_kernel<false><<<g, 256, 0, st>>>(in, ap, C, HW, S, total);
@@ -694,6 +701,7 @@ int tc_norm_split(const float* y, const double* stats, const float* gamma, const
   if (gx > 64) gx = 64;
   dim3 grid(gx, (unsigned)(C / 8), (unsigned)n_slices);
   PDS_KERNEL(res_ap ? "tc_norm_residual_split" : "tc_norm_split", st);
+  PDS_KERNEL_WORK(0, (double)n_slices * C * HW * (4 + 2 * S + (res_ap ? 2 * S : 0)));
   if (fp16) tc_norm_split_kernel<true><<<grid, 256, 0, st>>>(y, stats, gamma, beta, res_ap, out_ap, C, HW, S);
   else tc_norm_split_kernel<false><<<grid, 256, 0, st>>>(y, stats, gamma, beta, res_ap, out_ap, C, HW, S);
   PDS_LAUNCH_CHECK("tc_norm_split_kernel");

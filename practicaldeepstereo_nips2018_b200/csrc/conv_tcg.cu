@@ -1,0 +1,645 @@
+// Generic tcgen05 implicit-GEMM convolution kernel: interprets the programs planned by
+// conv_tcg_plan.cu (see conv_tcg.cuh for the model).  sm_100a only.
+//
+// Warp roles (192 threads, one CTA per SM, persistent over a contiguous range of CTA tiles):
+//   warp 0    TMA producer: per unit, the unit's boxes (cp.async.bulk.tensor.5d, zero fill ==
+//             the convolution's padding) for every operand term, plus the unit's weight slab
+//             when the layer's weights are not resident;
+//   warp 1    MMA issuer (one elected lane): per entry, NACC x S tcgen05.mma -- activation term
+//             s against the weight terms 0 .. S-1-s concatenated along N, one TMEM accumulator
+//             per order of magnitude (conv_tc.cu explains the scheme);
+//   warps 2-5 epilogue: TMEM -> registers, sum of the orders, bias, LeakyReLU, fp32
+//             channels-last store, InstanceNorm sums (double atomics once per sample).
+// Accumulators are double-buffered in TMEM whenever 2 * NACC * S * N <= 512 columns.
+#include <string.h>
+
+#include <string>
+
+#include "conv_tcg.cuh"
+#include "tc_ptx.cuh"
+
+namespace pds {
+namespace {
+
+using namespace ptx;
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 6;
+
+struct alignas(64) TcgParams {
+  CUtensorMap map;
+  const unsigned char* tables;   // units | boxes | entries | tile offsets (device copy of the plan)
+  const uint16_t* w;
+  const float* bias;
+  float* out;
+  double* stats;
+  int n_samples, lrelu, fp16;
+  int nacc, ntx, ntz, ncls, upi;
+  int GZ, GY, GX, OZ, OY, OX, Cout, mul, nd3;
+  int tiles_x, tiles_y, tiles_z;
+  int BX, planes_per_term;
+  int resident, stages, reuse;
+  uint32_t box_bytes, box_tx_bytes, term_bytes, a_bytes, stage_bytes, wres_bytes, w_total_bytes;
+  uint32_t off_boxes, off_entries, off_tiles, table_bytes;
+  float inv_wscale;
+};
+
+constexpr uint32_t pow2_cols(uint32_t c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+template <int S, int N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tcg_kernel(const __grid_constant__ TcgParams p) {
+  constexpr int CH = N < 32 ? N : 32;            // accumulator columns handled per epilogue step
+  constexpr int NCH = N / CH;
+  constexpr uint32_t ACC_COLS = S * N;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  const uint32_t wres_base = smem_u32(smem);
+  const uint32_t stage_base = wres_base + p.wres_bytes;
+  unsigned char* tab = smem + p.wres_bytes + (size_t)p.stages * p.stage_bytes;
+  const TcgUnit* units = (const TcgUnit*)tab;
+  const TcgBox* boxes = (const TcgBox*)(tab + p.off_boxes);
+  const TcgEntry* entries = (const TcgEntry*)(tab + p.off_entries);
+  const int* tile_off = (const int*)(tab + p.off_tiles);
+  unsigned char* tail = tab + p.table_bytes;
+  const uint32_t bar_base = smem_u32(tail);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * kMaxStages + 4);
+  uint32_t* tmem_slot = (uint32_t*)(tail + 8 * (2 * kMaxStages + 5) + 8);
+  float* sbias = (float*)(tail + 8 * (2 * kMaxStages + 5) + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t buf_cols = (uint32_t)p.nacc * ACC_COLS;
+  const int nbuf = 2 * buf_cols <= 512 ? 2 : 1;
+  const uint32_t tmem_cols = pow2_cols(nbuf * buf_cols);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (uint32_t i = threadIdx.x; i < p.table_bytes / 4; i += kThreads)
+    ((uint32_t*)tab)[i] = ((const uint32_t*)p.tables)[i];
+  for (int i = threadIdx.x; i < N; i += kThreads) sbias[i] = p.bias[i];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // contiguous range of CTA tiles per CTA (all classes of a tile stay together)
+  const int tiles_per_sample = p.tiles_x * p.tiles_y * p.tiles_z;
+  const int total_tiles = tiles_per_sample * p.n_samples;
+  const int tiles_per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_begin = min((int)blockIdx.x * tiles_per_cta, total_tiles);
+  const int tile_end = min(tile_begin + tiles_per_cta, total_tiles);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      if (p.resident) {
+        mbar_expect_tx(wfull_bar, p.w_total_bytes);
+        for (uint32_t o = 0; o < p.w_total_bytes; o += 32768) {
+          const uint32_t n = min(32768u, p.w_total_bytes - o);
+          bulk_load(wres_base + o, (const unsigned char*)p.w + o, n, wfull_bar);
+        }
+      }
+      uint32_t stage = 0, phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int n = tile / tiles_per_sample;
+        int r = tile - n * tiles_per_sample;
+        const int tz = r / (p.tiles_x * p.tiles_y);
+        r -= tz * p.tiles_x * p.tiles_y;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int x0 = tx * 8 * p.ntx, y0 = ty * 16, z0 = tz * p.ntz;
+        for (int cls = 0; cls < (p.reuse ? 1 : p.ncls); ++cls) {
+          for (int u = 0; u < p.upi; ++u) {
+            const TcgUnit un = units[cls * p.upi + u];
+            const int nb = un.box_end - un.box_beg;
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), (uint32_t)nb * S * p.box_tx_bytes + (p.resident ? 0u : un.w_bytes));
+            const uint32_t sa = stage_base + stage * p.stage_bytes;
+            for (int j = 0; j < nb; ++j) {
+              const TcgBox b = boxes[un.box_beg + j];
+#pragma unroll
+              for (int s = 0; s < S; ++s)
+                tma_load_5d(sa + s * p.term_bytes + j * p.box_bytes, &p.map, 0, x0 + b.dx, y0 + b.dy,
+                            z0 + b.dz, (n * S + s) * p.planes_per_term + b.plane, full_bar(stage));
+            }
+            if (!p.resident)
+              bulk_load(sa + p.a_bytes, (const unsigned char*)p.w + (size_t)un.w_off16 * 16, un.w_bytes,
+                        full_bar(stage));
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t fmt = (1u << 4) | (p.fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(128 >> 4) << 24);
+    // activation term s multiplies the N * (S - s) concatenated weight rows; an MMA is at most 256
+    // columns wide, so the widest case (S = 3, N = 128) takes a second instruction for the rest
+    uint32_t idesc[S], idesc_rest[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int cols = N * (S - s), first = cols > 256 ? 256 : cols;
+      idesc[s] = fmt | ((uint32_t)(first >> 3) << 17);
+      idesc_rest[s] = fmt | ((uint32_t)((cols - first) >> 3) << 17);
+    }
+    const uint32_t a_hi = umma_desc_hi((uint32_t)p.BX * 16);
+    const uint32_t b_hi = umma_desc_hi(128);
+    const uint32_t b_lbo = ((uint32_t)(S * N) & 0x3fff) << 16;     // K-half stride of the B operand, 16-byte units
+    const uint32_t term16 = p.term_bytes >> 4;
+    if (p.resident) { mbar_wait(wfull_bar, 0); tc_fence_after(); }
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      for (int cls = 0; cls < p.ncls; ++cls) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + acc * buf_cols;
+        const bool hold = p.reuse && cls + 1 < p.ncls;      // the stage serves the next class too
+        for (int u = 0; u < p.upi; ++u) {
+          const TcgUnit un = units[cls * p.upi + u];
+          if (!(p.reuse && cls > 0)) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+          }
+          const uint32_t sa16 = (stage_base + stage * p.stage_bytes) >> 4;
+          const uint32_t sw16 = p.resident ? (wres_base >> 4) : sa16;
+          if (elect_one()) {
+            for (int e = un.ent_beg; e < un.ent_end; ++e) {
+              const TcgEntry en = entries[e];
+              const uint32_t a_lo = en.a + sa16;
+              const uint64_t bd = umma_desc((en.b + sw16) | b_lbo, b_hi);
+              const uint32_t accumulate = (u == 0 && e == un.ent_beg) ? 0u : 1u;
+              for (int i = 0; i < p.nacc; ++i) {
+                const uint32_t a_i = a_lo + (uint32_t)tile_off[i];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                  const uint64_t ad = umma_desc(a_i + s * term16, a_hi);
+                  tc_mma(d_base + i * ACC_COLS + s * N, ad, bd, idesc[s], s == 0 ? accumulate : 1u);
+                  if (N * (S - s) > 256)   // B rows 256.. (16 bytes each), accumulator columns 256..
+                    tc_mma(d_base + i * ACC_COLS + s * N + 256, ad, bd + 256, idesc_rest[s],
+                           s == 0 ? accumulate : 1u);
+                }
+              }
+            }
+            if (!hold) tc_commit(empty_bar(stage));
+            if (u == p.upi - 1) tc_commit(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (!hold && ++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (nbuf == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps (2..5): TMEM lanes 32*(warp%4) .. +31 =====
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const int px = row & 7, py = row >> 3;
+    uint32_t acc = 0, acc_phase = 0;
+    double s1[NCH], s2[NCH];        // InstanceNorm sums of the current sample: channel ch*CH + lane % CH
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
+    int stat_n = -1;
+    auto flush_stats = [&]() {
+      if (stat_n >= 0 && p.stats && lane < CH) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int ch = c * CH + lane;
+          if (ch < p.Cout) {
+            double* dst = p.stats + ((size_t)stat_n * p.Cout + ch) * 2;
+            atomicAdd(dst, s1[c]); atomicAdd(dst + 1, s2[c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
+    };
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int n = tile / tiles_per_sample;
+      int r = tile - n * tiles_per_sample;
+      const int tz = r / (p.tiles_x * p.tiles_y);
+      r -= tz * p.tiles_x * p.tiles_y;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      if (n != stat_n) { flush_stats(); stat_n = n; }
+      for (int cls = 0; cls < p.ncls; ++cls) {
+        const int cz = (cls >> 2) & 1, cy = (cls >> 1) & 1, cx = cls & 1;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + ((uint32_t)(32 * q) << 16) + acc * buf_cols;
+#pragma unroll 1
+        for (int i = 0; i < p.nacc; ++i) {
+          const int ix = i % p.ntx, iz = i / p.ntx;
+          const int gx = tx * 8 * p.ntx + 8 * ix + px, gy = ty * 16 + py, gz = tz * p.ntz + iz;
+          const bool valid = gx < p.GX && gy < p.GY && gz < p.GZ;
+          const int oz = p.nd3 ? p.mul * gz + cz : 0, oy = p.mul * gy + cy, ox = p.mul * gx + cx;
+          float* o = p.out + ((((size_t)n * p.OZ + oz) * p.OY + oy) * p.OX + ox) * p.Cout;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            float v[CH];
+            tmem_ld<CH>(t_base + i * ACC_COLS + (S - 1) * N + c * CH, v);   // smallest terms first
+#pragma unroll
+            for (int s = S - 2; s >= 0; --s) {
+              float t[CH];
+              tmem_ld<CH>(t_base + i * ACC_COLS + s * N + c * CH, t);
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] += t[j];
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+              float t = fmaf(v[j], p.inv_wscale, sbias[c * CH + j]);
+              if (p.lrelu) t = t > 0.f ? t : 0.1f * t;
+              v[j] = valid ? t : 0.f;
+            }
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4)
+                if (c * CH + j < p.Cout)
+                  *reinterpret_cast<float4*>(o + c * CH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.stats) {
+              float sq[CH];
+#pragma unroll
+              for (int j = 0; j < CH; ++j) sq[j] = v[j] * v[j];
+              s1[c] += (double)warp_transpose_reduce<CH>(v, lane);
+              s2[c] += (double)warp_transpose_reduce<CH>(sq, lane);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        if (nbuf == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
+      }
+    }
+    flush_stats();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---- weights: PyTorch layout fp32 -> per entry [K half][term][N][8] 16-bit ------------------------
+template <bool FP16>
+__global__ void tcg_prepare_weights_kernel(const float* __restrict__ w, const TcgWeightSrc* __restrict__ src,
+                                           uint16_t* __restrict__ out, int n_entries, int Cin, int Cout,
+                                           int N, int S, int KZ, int KY, int KX, int transposed,
+                                           float wscale) {
+  const size_t per_entry = (size_t)2 * N * 8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_entry * n_entries) return;
+  const int e = (int)(i / per_entry);
+  const int r = (int)(i % per_entry);
+  const int c = r % 8, co = (r / 8) % N, h = r / (8 * N);
+  const TcgWeightSrc ws = src[e];
+  float x = 0.f;
+  if (ws.group[h] >= 0 && co < Cout) {
+    const int ci = 8 * ws.group[h] + c;
+    const size_t a = transposed ? ((size_t)ci * Cout + co) : ((size_t)co * Cin + ci);
+    x = w[((a * KZ + ws.kz[h]) * KY + ws.ky[h]) * KX + ws.kx[h]] * wscale;
+  }
+  uint16_t t[3];
+  split_terms<FP16>(x, t);
+  for (int s = 0; s < S; ++s)
+    out[(size_t)e * (2 * S * N * 8) + ((size_t)(h * S + s) * N + co) * 8 + c] = t[s];
+}
+
+__global__ void tcg_pad_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int Cout, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] = i < Cout ? b[i] : 0.f;
+}
+
+// ---- normalisation pass: fp32 channels-last -> split AP planes ------------------------------------
+struct NormParams {
+  const float* ya; const double* sa; const float* ga; const float* ba;
+  const float* yb; const double* sb; const float* gb; const float* bb;
+  const float* bcast;
+  uint16_t* out;
+  int C, Z, Y, X, S, phases;
+};
+
+template <bool FP16>
+__global__ void __launch_bounds__(256)
+tcg_norm_to_ap_kernel(const NormParams p) {
+  extern __shared__ float sm[];          // scale_a[C], shift_a[C], scale_b[C], shift_b[C]
+  const int n = blockIdx.y;
+  const size_t V = (size_t)p.Z * p.Y * p.X;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    float sc = 1.f, sh = 0.f;
+    if (p.sa) {
+      const double s = p.sa[((size_t)n * p.C + c) * 2], q = p.sa[((size_t)n * p.C + c) * 2 + 1];
+      const double mean = s / (double)V;
+      double var = q / (double)V - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+      sc = rstd * (p.ga ? p.ga[c] : 1.f);
+      sh = (p.ba ? p.ba[c] : 0.f) - (float)mean * sc;
+    }
+    sm[c] = sc; sm[p.C + c] = sh;
+    sc = 1.f; sh = 0.f;
+    if (p.yb && p.sb) {
+      const double s = p.sb[((size_t)n * p.C + c) * 2], q = p.sb[((size_t)n * p.C + c) * 2 + 1];
+      const double mean = s / (double)V;
+      double var = q / (double)V - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+      sc = rstd * (p.gb ? p.gb[c] : 1.f);
+      sh = (p.bb ? p.bb[c] : 0.f) - (float)mean * sc;
+    }
+    sm[2 * p.C + c] = sc; sm[3 * p.C + c] = sh;
+  }
+  __syncthreads();
+  const int G = p.C / 8;
+  const size_t total = V * G;
+  const int sep = p.phases > 1;
+  const int sepz = p.phases == 8;
+  const int IZ = sepz ? p.Z / 2 : p.Z, IY = sep ? p.Y / 2 : p.Y, IX = sep ? p.X / 2 : p.X;
+  const size_t plane = (size_t)IZ * IY * IX;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const size_t vox = i / G;
+    const int x = (int)(vox % p.X), y = (int)((vox / p.X) % p.Y), z = (int)(vox / ((size_t)p.X * p.Y));
+    const float4* pa = reinterpret_cast<const float4*>(p.ya + ((size_t)n * V + vox) * p.C + 8 * g);
+    const float4 a0 = pa[0], a1 = pa[1];
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sm[8 * g + e], sm[p.C + 8 * g + e]);
+    if (p.yb) {
+      const float4* pb = reinterpret_cast<const float4*>(p.yb + ((size_t)n * V + vox) * p.C + 8 * g);
+      const float4 b0 = pb[0], b1 = pb[1];
+      const float w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += fmaf(w[e], sm[2 * p.C + 8 * g + e], sm[3 * p.C + 8 * g + e]);
+    }
+    if (p.bcast) {
+      const float4* pc = reinterpret_cast<const float4*>(p.bcast + (((size_t)n * p.Y + y) * p.X + x) * p.C + 8 * g);
+      const float4 c0 = pc[0], c1 = pc[1];
+      v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w;
+      v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
+    }
+    uint16_t t[8][3];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
+    const int ph = sep ? ((sepz ? (z & 1) * 4 : 0) + (y & 1) * 2 + (x & 1)) : 0;
+    const int zz = sepz ? z >> 1 : z, yy = sep ? y >> 1 : y, xx = sep ? x >> 1 : x;
+    const size_t pos = ((size_t)zz * IY + yy) * IX + xx;
+    for (int s = 0; s < p.S; ++s) {
+      union { uint16_t h[8]; uint4 u; } pk;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pk.h[e] = t[e][s];
+      reinterpret_cast<uint4*>(p.out)[((((size_t)n * p.S + s) * p.phases + ph) * G + g) * plane + pos] = pk.u;
+    }
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult res;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &res) == cudaSuccess &&
+        res == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+constexpr size_t kTailBytes = 8 * (2 * kMaxStages + 5) + 32 + 128 * sizeof(float) + 256;
+
+struct TableLayout { uint32_t off_boxes, off_entries, off_tiles, table_bytes, off_wsrc, total; };
+
+TableLayout table_layout(const TcgPlan& pl) {
+  TableLayout t;
+  uint32_t o = (uint32_t)(pl.units.size() * sizeof(TcgUnit));
+  o = (uint32_t)align_up(o, 16); t.off_boxes = o; o += (uint32_t)(pl.boxes.size() * sizeof(TcgBox));
+  o = (uint32_t)align_up(o, 16); t.off_entries = o; o += (uint32_t)(pl.entries.size() * sizeof(TcgEntry));
+  o = (uint32_t)align_up(o, 16); t.off_tiles = o; o += (uint32_t)(pl.tile_off16.size() * 4);
+  t.table_bytes = (uint32_t)align_up(o, 128);
+  t.off_wsrc = t.table_bytes;
+  t.total = t.off_wsrc + (uint32_t)(pl.wsrc.size() * sizeof(TcgWeightSrc));
+  return t;
+}
+
+template <int S, int N>
+int launch_tcg(const TcgParams& p, size_t smem, int grid, cudaStream_t st, double flops, double bytes) {
+  static bool configured = false;
+  if (!configured) {
+    PDS_CUDA(cudaFuncSetAttribute(conv_tcg_kernel<S, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  static const std::string name = "conv_tcg<S=" + std::to_string(S) + ",N=" + std::to_string(N) + ">";
+  PDS_KERNEL(name.c_str(), st);
+  PDS_KERNEL_WORK(flops, bytes);
+  conv_tcg_kernel<S, N><<<grid, kThreads, smem, st>>>(p);
+  PDS_LAUNCH_CHECK("conv_tcg_kernel");
+  return PDS_OK;
+}
+
+}  // namespace
+
+bool tcg_available() { return encode_fn() != nullptr; }
+
+size_t TcgLayer::prog_bytes() const { return table_layout(plan).total; }
+
+size_t tcg_layer_bytes(const TcgLayer& l) {
+  return align_up(l.plan.w_total_bytes, 256) + align_up((size_t)l.plan.N * 4, 256) + align_up(l.prog_bytes(), 256);
+}
+
+int tcg_layer_init(TcgLayer& l, char* blob, const float* w_src, const float* bias_src, cudaStream_t st,
+                   size_t* consumed) {
+  const TcgPlan& pl = l.plan;
+  const TableLayout tl = table_layout(pl);
+  char* cur = blob;
+  l.w = (uint16_t*)cur; cur += align_up(pl.w_total_bytes, 256);
+  l.bias = (float*)cur; cur += align_up((size_t)pl.N * 4, 256);
+  l.prog = cur; cur += align_up(tl.total, 256);
+  *consumed = (size_t)(cur - blob);
+  std::vector<unsigned char> host(tl.total, 0);
+  memcpy(host.data(), pl.units.data(), pl.units.size() * sizeof(TcgUnit));
+  memcpy(host.data() + tl.off_boxes, pl.boxes.data(), pl.boxes.size() * sizeof(TcgBox));
+  memcpy(host.data() + tl.off_entries, pl.entries.data(), pl.entries.size() * sizeof(TcgEntry));
+  memcpy(host.data() + tl.off_tiles, pl.tile_off16.data(), pl.tile_off16.size() * 4);
+  memcpy(host.data() + tl.off_wsrc, pl.wsrc.data(), pl.wsrc.size() * sizeof(TcgWeightSrc));
+  PDS_CUDA(cudaMemcpyAsync(l.prog, host.data(), tl.total, cudaMemcpyHostToDevice, st));
+  PDS_CUDA(cudaStreamSynchronize(st));   // `host` goes out of scope
+  const int k = pl.shape.kind == TCG_TCONV4_S2 ? 4 : (pl.shape.kind == TCG_CONV5_S2 ? 5 : 3);
+  const int KZ = pl.shape.nd == 3 ? k : 1;
+  const size_t total = (size_t)2 * pl.N * 8 * pl.entries.size();
+  {
+    PDS_KERNEL("tcg_prepare_weights", st);
+    const unsigned g = (unsigned)((total + 255) / 256);
+    const TcgWeightSrc* src = (const TcgWeightSrc*)((const char*)l.prog + tl.off_wsrc);
+    if (l.fp16)
+      tcg_prepare_weights_kernel<true><<<g, 256, 0, st>>>(w_src, src, l.w, (int)pl.entries.size(), pl.shape.Cin,
+                                                          pl.shape.Cout, pl.N, pl.shape.S, KZ, k, k,
+                                                          l.transposed, l.wscale);
+    else
+      tcg_prepare_weights_kernel<false><<<g, 256, 0, st>>>(w_src, src, l.w, (int)pl.entries.size(), pl.shape.Cin,
+                                                           pl.shape.Cout, pl.N, pl.shape.S, KZ, k, k,
+                                                           l.transposed, l.wscale);
+    PDS_LAUNCH_CHECK("tcg_prepare_weights_kernel");
+  }
+  PDS_KERNEL("tcg_pad_bias", st);
+  tcg_pad_bias_kernel<<<1, 128, 0, st>>>(bias_src, l.bias, pl.shape.Cout, pl.N);
+  PDS_LAUNCH_CHECK("tcg_pad_bias_kernel");
+  return PDS_OK;
+}
+
+int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, float* out, double* stats,
+                     int lrelu, cudaStream_t st) {
+  const TcgPlan& pl = l.plan;
+  if (n_samples == 0) return PDS_OK;
+  if (!encode_fn()) {
+    set_error("conv_tcg: cuTensorMapEncodeTiled is not available from this driver");
+    return PDS_ERR_UNSUPPORTED;
+  }
+  const TableLayout tl = table_layout(pl);
+  TcgParams p = {};
+  {
+    const cuuint64_t dims[5] = {8, (cuuint64_t)pl.IX, (cuuint64_t)pl.IY, (cuuint64_t)pl.IZ,
+                                (cuuint64_t)pl.in_planes(n_samples)};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)pl.IX * 16, (cuuint64_t)pl.IY * pl.IX * 16,
+                                   (cuuint64_t)pl.IZ * pl.IY * pl.IX * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)pl.BX, (cuuint32_t)pl.BY, (cuuint32_t)pl.BZ, (cuuint32_t)pl.PB};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode_fn()(&p.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(in_ap), dims,
+                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv_tcg: cuTensorMapEncodeTiled failed with CUresult %d (dims %d x %d x %d x %zu, box %d x %d x %d x %d)",
+                (int)r, pl.IX, pl.IY, pl.IZ, pl.in_planes(n_samples), pl.BX, pl.BY, pl.BZ, pl.PB);
+      return PDS_ERR_CUDA;
+    }
+  }
+  p.tables = (const unsigned char*)l.prog; p.w = l.w; p.bias = l.bias; p.out = out; p.stats = stats;
+  p.n_samples = n_samples; p.lrelu = lrelu; p.fp16 = l.fp16;
+  p.nacc = pl.nacc; p.ntx = pl.ntx; p.ntz = pl.ntz; p.ncls = pl.ncls; p.upi = pl.units_per_item;
+  p.GZ = pl.GZ; p.GY = pl.GY; p.GX = pl.GX; p.OZ = pl.OZ; p.OY = pl.OY; p.OX = pl.OX;
+  p.Cout = pl.shape.Cout; p.mul = pl.ncls > 1 ? 2 : 1; p.nd3 = pl.shape.nd == 3;
+  p.tiles_x = (pl.GX + 8 * pl.ntx - 1) / (8 * pl.ntx);
+  p.tiles_y = (pl.GY + 15) / 16;
+  p.tiles_z = (pl.GZ + pl.ntz - 1) / pl.ntz;
+  p.BX = pl.BX; p.planes_per_term = pl.nph * pl.P;
+  p.resident = pl.resident; p.stages = pl.stages;
+  p.reuse = pl.ncls > 1 && pl.units_per_item == 1 && pl.resident;
+  p.box_tx_bytes = (uint32_t)pl.PB * pl.BZ * pl.BY * pl.BX * 16;   // what TMA delivers (box_bytes is its 128-aligned slot)
+  p.box_bytes = pl.box_bytes; p.term_bytes = (uint32_t)pl.max_boxes * pl.box_bytes;
+  p.a_bytes = p.term_bytes * pl.shape.S; p.stage_bytes = pl.stage_bytes; p.wres_bytes = pl.wres_bytes;
+  p.w_total_bytes = pl.w_total_bytes;
+  p.off_boxes = tl.off_boxes; p.off_entries = tl.off_entries; p.off_tiles = tl.off_tiles;
+  p.table_bytes = tl.table_bytes;
+  p.inv_wscale = 1.0f / l.wscale;
+  if (pl.shape.Cout % 4) { set_error("conv_tcg: Cout must be a multiple of 4"); return PDS_ERR_UNSUPPORTED; }
+  const size_t smem = (size_t)pl.wres_bytes + (size_t)pl.stages * pl.stage_bytes + tl.table_bytes + kTailBytes + 128;
+  if (smem > 227 * 1024) {
+    set_error("conv_tcg: plan needs %zu bytes of shared memory", smem);
+    return PDS_ERR_UNSUPPORTED;
+  }
+  const int total = p.tiles_x * p.tiles_y * p.tiles_z * n_samples;
+  const int grid = total < num_sms() ? total : num_sms();
+  const int k = pl.shape.kind == TCG_TCONV4_S2 ? 2 : (pl.shape.kind == TCG_CONV5_S2 ? 5 : 3);
+  const double taps = (double)k * k * (pl.shape.nd == 3 ? k : 1);
+  const double rows = (double)n_samples * pl.GZ * pl.GY * pl.GX * pl.ncls;
+  const double flops = 2.0 * taps * pl.shape.Cin * pl.shape.Cout * rows;
+  const double bytes = (double)pl.in_ap_bytes(n_samples) + 4.0 * pl.out_elems(n_samples);
+#define PDS_TCG_CASE(SS, NN) \
+  if (pl.shape.S == SS && pl.N == NN) return launch_tcg<SS, NN>(p, smem, grid, st, flops, bytes);
+  PDS_TCG_CASE(2, 16) PDS_TCG_CASE(2, 32) PDS_TCG_CASE(2, 64) PDS_TCG_CASE(2, 128)
+  PDS_TCG_CASE(3, 16) PDS_TCG_CASE(3, 32) PDS_TCG_CASE(3, 64) PDS_TCG_CASE(3, 128)
+  PDS_TCG_CASE(1, 16) PDS_TCG_CASE(1, 32) PDS_TCG_CASE(1, 64) PDS_TCG_CASE(1, 128)
+#undef PDS_TCG_CASE
+  set_error("conv_tcg: no kernel for S=%d N=%d", pl.shape.S, pl.N);
+  return PDS_ERR_UNSUPPORTED;
+}
+
+int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast, uint16_t* out_ap,
+                   int n, int C, int Z, int Y, int X, int S, int fp16, int phases, cudaStream_t st) {
+  if (n == 0) return PDS_OK;
+  if (C % 8 || C > 128 || (phases != 1 && phases != 4 && phases != 8) ||
+      (phases > 1 && ((X | Y) & 1)) || (phases == 8 && (Z & 1))) {
+    set_error("tcg_norm_to_ap: unsupported shape (C=%d, %d x %d x %d, phases %d)", C, Z, Y, X, phases);
+    return PDS_ERR_UNSUPPORTED;
+  }
+  NormParams p;
+  p.ya = a.y; p.sa = a.stats; p.ga = a.gamma; p.ba = a.beta;
+  p.yb = b ? b->y : nullptr; p.sb = b ? b->stats : nullptr; p.gb = b ? b->gamma : nullptr; p.bb = b ? b->beta : nullptr;
+  p.bcast = bcast; p.out = out_ap;
+  p.C = C; p.Z = Z; p.Y = Y; p.X = X; p.S = S; p.phases = phases;
+  const size_t total = (size_t)Z * Y * X * (C / 8);
+  unsigned gx = (unsigned)((total + 255) / 256);
+  const unsigned cap = (unsigned)(num_sms() * 8);
+  if (gx > cap) gx = cap;
+  dim3 grid(gx, (unsigned)n);
+  PDS_KERNEL(b ? "tcg_norm2_to_ap" : "tcg_norm_to_ap", st);
+  PDS_KERNEL_WORK(0, (double)n * Z * Y * X * C * (4.0 + 2.0 * S + (b ? 4.0 : 0.0)));
+  const size_t smem = (size_t)4 * C * sizeof(float);
+  if (fp16) tcg_norm_to_ap_kernel<true><<<grid, 256, smem, st>>>(p);
+  else tcg_norm_to_ap_kernel<false><<<grid, 256, smem, st>>>(p);
+  PDS_LAUNCH_CHECK("tcg_norm_to_ap_kernel");
+  return PDS_OK;
+}
+
+}  // namespace pds
+
+// ---- test hook (tests/test_gpu_tcg.py): one layer, PyTorch layouts in and out ---------------------
+// x (n, Cin, Z, Y, X), w / bias in PyTorch layout, out (n, Cout, OZ, OY, OX), stats (n, Cout, 2) double
+// or null; all device pointers.  Allocates its own scratch (test use only).
+#include "conv_layers.cuh"
+extern "C" int pds_tcg_conv_debug(int kind, int nd, int Cin, int Cout, int Z, int Y, int X, int S, int fp16,
+                                  int n, const float* x, const float* w, const float* bias, float* out,
+                                  double* stats, int lrelu, void* stream) {
+  using namespace pds;
+  cudaStream_t st = (cudaStream_t)stream;
+  TcgLayer l;
+  TcgShape sh;
+  sh.kind = kind; sh.nd = nd; sh.Cin = Cin; sh.Cout = Cout; sh.Z = Z; sh.Y = Y; sh.X = X; sh.S = S;
+  int rc = tcg_plan(sh, &l.plan);
+  if (rc != PDS_OK) return rc;
+  l.transposed = kind == TCG_TCONV4_S2; l.fp16 = fp16; l.wscale = fp16 ? 256.f : 1.f;
+  const TcgPlan& pl = l.plan;
+  const size_t vin = (size_t)Z * Y * X, vout = (size_t)pl.OZ * pl.OY * pl.OX;
+  char *blob = nullptr, *scratch = nullptr;
+  const size_t b_xcl = align_up(n * vin * Cin * 4, 256), b_ap = align_up(pl.in_ap_bytes(n), 256),
+               b_ycl = align_up(n * vout * Cout * 4, 256);
+  PDS_CUDA(cudaMalloc(&blob, tcg_layer_bytes(l)));
+  if (cudaMalloc(&scratch, b_xcl + b_ap + b_ycl) != cudaSuccess) { cudaFree(blob); set_error("out of memory"); return PDS_ERR_CUDA; }
+  float* x_cl = (float*)scratch;
+  uint16_t* ap = (uint16_t*)(scratch + b_xcl);
+  float* y_cl = (float*)(scratch + b_xcl + b_ap);
+  size_t used = 0;
+  rc = tcg_layer_init(l, blob, w, bias, st, &used);
+  if (rc == PDS_OK) rc = nchw_to_nhwc(x, x_cl, n, Cin, vin, st);
+  TcgNormSrc src; src.y = x_cl;
+  if (rc == PDS_OK) rc = tcg_norm_to_ap(src, nullptr, nullptr, ap, n, Cin, Z, Y, X, S, fp16, pl.nph, st);
+  if (rc == PDS_OK && stats) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)n * Cout * 2 * sizeof(double), st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync");
+  }
+  if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, stats, lrelu, st);
+  if (rc == PDS_OK) rc = nhwc_to_nchw(y_cl, out, n, Cout, vout, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == PDS_OK && e != cudaSuccess) rc = cuda_fail(e, "pds_tcg_conv_debug");
+  cudaFree(blob); cudaFree(scratch);
+  return rc;
+}

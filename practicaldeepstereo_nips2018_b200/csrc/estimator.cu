@@ -204,6 +204,8 @@ int launch(const T* cost, float* disparity, int64_t* argmax, int B, int D, int H
   const int quads = (W + V - 1) / V;
   dim3 grid((unsigned)(((size_t)quads * Hc + 63) / 64), (unsigned)B);
   PDS_KERNEL("subpixel_map", st);
+  // rows above crop_top are never loaded; every other cost element is read once
+  PDS_KERNEL_WORK(0, (double)B * Hc * ((double)D * W * sizeof(T) + (double)(W - crop_left) * 4));
 #define PDS_EST(RR)                                                                  \
   subpixel_map_kernel<T, V, RR, 8><<<grid, 64, 0, st>>>(cost, disparity, argmax, D, H, W, \
                                                         step, crop_top, crop_left, quads)

@@ -136,6 +136,7 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
   dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8), (unsigned)(B * p.nseg));
   if (grid.z > 65535) { set_error("hourglass_tail: batch too large"); return PDS_ERR_UNSUPPORTED; }
   PDS_KERNEL("hourglass_tail(tconv 4->1 + IN)", st);
+  PDS_KERNEL_WORK(2.0 * 192 * B * D * H * W, (double)B * D * H * W * (16 + 16));
   hourglass_tail_kernel<<<grid, dim3(32, 8), 0, st>>>(p);
   PDS_LAUNCH_CHECK("hourglass_tail_kernel");
   return PDS_OK;

@@ -91,6 +91,7 @@ extern "C" int pds_matching_concat(const void* left, const void* right, void* vo
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)H, (unsigned)(2 * C), (unsigned)B);
   PDS_KERNEL("matching_concat", st);
+  PDS_KERNEL_WORK(0, (double)B * H * W * esz * (2.0 * C + 2.0 * C * D));
   if (dtype == PDS_F32) {
     if (smem > 48 * 1024)
       PDS_CUDA(cudaFuncSetAttribute(matching_concat_kernel<float>,
@@ -121,6 +122,7 @@ extern "C" int pds_matching_stack(const void* in, void* out, int B, int F, int D
   const unsigned gx = (unsigned)((plane / 4 + 255) / 256 > 8 ? 8 : (plane / 4 + 255) / 256);
   dim3 grid(gx ? gx : 1, (unsigned)(F * D), (unsigned)B);
   PDS_KERNEL("matching_stack", st);
+  PDS_KERNEL_WORK(0, 2.0 * B * F * D * plane * (dtype == PDS_F32 ? 4 : 2));
   if (dtype == PDS_F32)
     matching_stack_kernel<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, F, D, plane);
   else

@@ -26,9 +26,9 @@ namespace {
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_profiling{0};
 std::mutex g_prof_mutex;
-struct Pending { const char* name; cudaEvent_t start, stop; };
+struct Pending { const char* name; cudaEvent_t start, stop; double flops, bytes; };
 std::vector<Pending> g_pending;
-struct Total { unsigned long long launches = 0; double ms = 0.0; };
+struct Total { unsigned long long launches = 0; double ms = 0.0, flops = 0.0, bytes = 0.0; };
 std::map<std::string, Total> g_totals;
 
 void drain_pending() {  // caller holds g_prof_mutex
@@ -38,6 +38,8 @@ void drain_pending() {  // caller holds g_prof_mutex
       Total& t = g_totals[p.name];
       t.launches += 1;
       t.ms += ms;
+      t.flops += p.flops;
+      t.bytes += p.bytes;
     }
     cudaEventDestroy(p.start);
     cudaEventDestroy(p.stop);
@@ -60,7 +62,7 @@ KernelScope::~KernelScope() {
   if (cudaEventCreate(&stop) != cudaSuccess) { cudaEventDestroy(start_); return; }
   cudaEventRecord(stop, st_);
   std::lock_guard<std::mutex> lock(g_prof_mutex);
-  g_pending.push_back({name_, start_, stop});
+  g_pending.push_back({name_, start_, stop, flops_, bytes_});
 }
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -107,5 +109,16 @@ extern "C" int pds_profiler_read(int index, char* name, int name_len, unsigned l
   }
   if (launches) *launches = it->second.launches;
   if (milliseconds) *milliseconds = it->second.ms;
+  return 1;
+}
+
+extern "C" int pds_profiler_read_work(int index, double* flops, double* bytes) {
+  std::lock_guard<std::mutex> lock(pds::g_prof_mutex);
+  pds::drain_pending();
+  if (index < 0 || index >= (int)pds::g_totals.size()) return 0;
+  auto it = pds::g_totals.begin();
+  std::advance(it, index);
+  if (flops) *flops = it->second.flops;
+  if (bytes) *bytes = it->second.bytes;
   return 1;
 }

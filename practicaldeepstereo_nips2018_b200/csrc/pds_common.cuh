@@ -39,11 +39,15 @@ int cuda_fail(cudaError_t e, const char* what);
 struct KernelScope {
   KernelScope(const char* name, cudaStream_t st);
   ~KernelScope();
+  // algorithmic work of this launch (reference FLOPs / minimum HBM bytes), summed per kernel class
+  void work(double flops, double bytes) { flops_ = flops; bytes_ = bytes; }
   const char* name_;
   cudaStream_t st_;
   cudaEvent_t start_ = nullptr;
+  double flops_ = 0.0, bytes_ = 0.0;
 };
 #define PDS_KERNEL(name, st) ::pds::KernelScope pds_kernel_scope__(name, st)
+#define PDS_KERNEL_WORK(flops, bytes) pds_kernel_scope__.work((double)(flops), (double)(bytes))
 
 inline int num_sms() {
   static int n = 0;

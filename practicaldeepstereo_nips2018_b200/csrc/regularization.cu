@@ -6,15 +6,27 @@
 // LeakyReLU and accumulates the InstanceNorm sums, followed by one
 // normalise(+add) pass that also produces the sums the reference forms right
 // after (shortcut + output, up-sampled + skip).
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
 
 #include "conv_layers.cuh"
+#include "conv_tc.cuh"
+#include "conv_tcg.cuh"
 
 struct pds_regularization {
   int F, precision;
   std::vector<pds::ConvLayer> layers;
   float* blob = nullptr;
+  // tensor-core path (precision != fp32): raw parameters in PyTorch layout (the programs and the
+  // weight images depend on the volume extent, so they are (re)built by the first forward of a shape)
+  int split = 0, fp16 = 0;
+  float* raw = nullptr;
+  std::vector<const float*> raw_params;
+  std::vector<pds::TcgLayer> tcg;       // all layers but _upsample_to_fullsize
+  char* tcg_blob = nullptr;
+  int tcg_shape[3] = {0, 0, 0};
   // host copies for the fused tail kernel (F == 8): last layer's weight (4,1,3,4,4) and bias,
   // InstanceNorm affine of _upsample_to_halfsize
   bool fused_tail = false;
@@ -86,10 +98,177 @@ int conv_block(const ConvLayer& l, const ConvGeom& g, const float* in, float* y,
                cudaStream_t st) {
   const size_t S = (size_t)l.dim[0].out_size(g.D) * l.dim[1].out_size(g.H) * l.dim[2].out_size(g.W);
   PDS_CUDA(cudaMemsetAsync(stats, 0, (size_t)g.N * l.Cout * 2 * sizeof(double), st));
-  int rc = conv_forward_simt(l, g, in, nullptr, 0, y, stats, st);
+  static const bool direct = getenv("PDS_B200_DIRECT3D") && atoi(getenv("PDS_B200_DIRECT3D"));
+  bool handled = false;
+  int rc = PDS_OK;
+  if (direct) rc = conv_forward_direct(l, g, in, y, stats, st, &handled);
+  if (rc == PDS_OK && !handled) rc = conv_forward_simt(l, g, in, nullptr, 0, y, stats, st);
   if (rc != PDS_OK) return rc;
   return instance_norm_apply(y, stats, l.gamma, l.beta, add, add_bcast, out, out2, g.N, S,
                              bcast_hw ? bcast_hw : S, l.Cout, st);
+}
+
+// Device copy of the parameters in PyTorch layout (state_dict order) for the tensor-core path.
+int copy_raw_params(pds_regularization* reg, const float* const* params, cudaStream_t st) {
+  size_t total = 0;
+  std::vector<size_t> sizes;
+  for (auto& l : reg->layers) {
+    sizes.push_back(l.weight_elems_pytorch()); sizes.push_back(l.Cout);
+    if (l.lrelu) { sizes.push_back(l.Cout); sizes.push_back(l.Cout); }
+  }
+  for (size_t n : sizes) total += align_up(n, 64);
+  PDS_CUDA(cudaMalloc(&reg->raw, total * sizeof(float)));
+  float* cur = reg->raw;
+  for (size_t i = 0; i < sizes.size(); ++i) {
+    PDS_CUDA(cudaMemcpyAsync(cur, params[i], sizes[i] * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    reg->raw_params.push_back(cur);
+    cur += align_up(sizes[i], 64);
+  }
+  return PDS_OK;
+}
+
+// Shapes of the 18 tensor-core layers for a (D, H, W) signature volume, in layer order.
+std::vector<TcgShape> hourglass_shapes(int F, int S, int D, int H, int W) {
+  std::vector<TcgShape> v;
+  auto add = [&](int kind, int cin, int cout, int z, int y, int x) {
+    TcgShape s; s.kind = kind; s.nd = 3; s.Cin = cin; s.Cout = cout; s.Z = z; s.Y = y; s.X = x; s.S = S;
+    v.push_back(s);
+  };
+  int c = F, z = D, y = H, x = W;
+  add(TCG_CONV3_S1, c, c, z, y, x);
+  for (int k = 0; k < 4; ++k) {
+    add(TCG_CONV3_S2, c, 2 * c, z, y, x);
+    c *= 2; z /= 2; y /= 2; x /= 2;
+    add(TCG_CONV3_S1, c, c, z, y, x);
+  }
+  for (int k = 0; k < 4; ++k) {
+    add(TCG_TCONV4_S2, c, c / 2, z, y, x);
+    c /= 2; z *= 2; y *= 2; x *= 2;
+    add(TCG_CONV3_S1, c, c, z, y, x);
+  }
+  add(TCG_TCONV4_S2, c, c / 2, z, y, x);
+  return v;
+}
+
+// (Re)plans the layers and rebuilds their weight images for a new volume extent.
+int prepare_tcg(pds_regularization* reg, int D, int H, int W, cudaStream_t st) {
+  if (reg->tcg_shape[0] == D && reg->tcg_shape[1] == H && reg->tcg_shape[2] == W && !reg->tcg.empty())
+    return PDS_OK;
+  const std::vector<TcgShape> shapes = hourglass_shapes(reg->F, reg->split, D, H, W);
+  std::vector<TcgLayer> layers(shapes.size());
+  size_t bytes = 0;
+  for (size_t i = 0; i < shapes.size(); ++i) {
+    int rc = tcg_plan(shapes[i], &layers[i].plan);
+    if (rc != PDS_OK) return rc;
+    layers[i].transposed = shapes[i].kind == TCG_TCONV4_S2;
+    layers[i].fp16 = reg->fp16;
+    layers[i].wscale = reg->fp16 ? 256.f : 1.f;
+    bytes += tcg_layer_bytes(layers[i]);
+  }
+  PDS_CUDA(cudaStreamSynchronize(st));      // the previous shape's buffers may still be in use
+  cudaFree(reg->tcg_blob); reg->tcg_blob = nullptr; reg->tcg.clear();
+  PDS_CUDA(cudaMalloc(&reg->tcg_blob, bytes));
+  char* cur = reg->tcg_blob;
+  for (size_t i = 0; i < layers.size(); ++i) {
+    size_t used = 0;
+    const float* const* pp = &reg->raw_params[4 * i];   // weight, bias, gamma, beta
+    int rc = tcg_layer_init(layers[i], cur, pp[0], pp[1], st, &used);
+    if (rc != PDS_OK) return rc;
+    layers[i].gamma = pp[2]; layers[i].beta = pp[3];
+    cur += used;
+  }
+  reg->tcg = layers;
+  reg->tcg_shape[0] = D; reg->tcg_shape[1] = H; reg->tcg_shape[2] = W;
+  return PDS_OK;
+}
+
+struct TcgBuffers {
+  size_t sc_cl, ap, y_l0, y_d[4], y_s[4], y_u[4], y_e[4], y_half, stats, total;
+};
+
+TcgBuffers tcg_buffers(const pds_regularization* reg, int B, int D, int H, int W) {
+  TcgBuffers b;
+  const size_t vox = (size_t)D * H * W, F = reg->F, S = reg->split;
+  auto buf = [&](size_t bytes) { return align_up(bytes, 256); };
+  b.sc_cl = buf((size_t)B * H * W * F * 4);
+  b.ap = buf((size_t)B * S * vox * F * 2);          // the widest AP tensor: F channels at full extent
+  b.y_l0 = buf(B * vox * F * 4);
+  size_t c = F, v = vox;
+  for (int k = 0; k < 4; ++k) { c *= 2; v /= 8; b.y_d[k] = b.y_s[k] = buf(B * v * c * 4); }
+  for (int k = 0; k < 4; ++k) { c /= 2; v *= 8; b.y_u[k] = b.y_e[k] = buf(B * v * c * 4); }
+  b.y_half = buf(B * vox * 8 * (F / 2) * 4);
+  b.stats = buf((size_t)18 * B * 16 * F * 2 * sizeof(double));
+  b.total = b.sc_cl + 2 * b.ap + b.y_l0 + b.y_half + b.stats + 1024;
+  for (int k = 0; k < 4; ++k) b.total += b.y_d[k] + b.y_s[k] + b.y_u[k] + b.y_e[k];
+  return b;
+}
+
+// Regularization.forward on the tcgen05 engine.  Every Conv -> LeakyReLU -> InstanceNorm block is one
+// convolution launch (fp32 channels-last output + sums) and one normalisation pass that writes the
+// NEXT layer's operand planes, fused with the additions the reference performs in between
+// (regularization.py:117-123); skip tensors are never materialised: the pass that needs one
+// re-normalises the stored convolution output.
+int tcg_forward(pds_regularization* reg, const float* signatures, const float* shortcut, float* cost, int B,
+                int D, int H, int W, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  int rc = prepare_tcg(reg, D, H, W, st);
+  if (rc != PDS_OK) return rc;
+  const int F = reg->F, S = reg->split, fp16 = reg->fp16;
+  const TcgBuffers bs = tcg_buffers(reg, B, D, H, W);
+  Workspace ws(workspace, workspace_bytes);
+  float* sc_cl = (float*)ws.take<char>(bs.sc_cl);
+  uint16_t* ap[2] = {(uint16_t*)ws.take<char>(bs.ap), (uint16_t*)ws.take<char>(bs.ap)};
+  float* y_l0 = (float*)ws.take<char>(bs.y_l0);
+  float *y_d[4], *y_s[4], *y_u[4], *y_e[4];
+  for (int k = 0; k < 4; ++k) { y_d[k] = (float*)ws.take<char>(bs.y_d[k]); y_s[k] = (float*)ws.take<char>(bs.y_s[k]); }
+  for (int k = 0; k < 4; ++k) { y_u[k] = (float*)ws.take<char>(bs.y_u[k]); y_e[k] = (float*)ws.take<char>(bs.y_e[k]); }
+  float* y_half = (float*)ws.take<char>(bs.y_half);
+  double* stats = (double*)ws.take<char>(bs.stats);
+  if (ws.overflow) { set_error("pds_regularization_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
+  PDS_CUDA(cudaMemsetAsync(stats, 0, bs.stats, st));
+  const size_t stat_stride = (size_t)B * 16 * F * 2;
+  auto st_of = [&](int layer) { return stats + stat_stride * layer; };
+  const std::vector<TcgLayer>& L = reg->tcg;
+  auto src = [&](int layer, const float* y) {
+    TcgNormSrc s; s.y = y; s.stats = st_of(layer); s.gamma = L[layer].gamma; s.beta = L[layer].beta;
+    return s;
+  };
+
+  if ((rc = nchw_to_nhwc(shortcut, sc_cl, B, F, (size_t)H * W, st)) != PDS_OK) return rc;
+  if ((rc = tc_pack_nchw(signatures, ap[0], B, F, 1, (int)((size_t)D * H * W), S, fp16, st)) != PDS_OK) return rc;
+  // layer 0: output = smoothing(signatures); level-0 input = shortcut (broadcast over D) + output
+  if ((rc = tcg_conv_forward(L[0], B, ap[0], y_l0, st_of(0), 1, st)) != PDS_OK) return rc;
+  if ((rc = tcg_norm_to_ap(src(0, y_l0), nullptr, sc_cl, ap[1], B, F, D, H, W, S, fp16, 8, st)) != PDS_OK) return rc;
+  int c = F, z = D, y = H, x = W, li = 1;
+  for (int k = 0; k < 4; ++k) {
+    // ContractionBlock3d (regularization.py:28-31): down = block_s2(in); smooth = block(down)
+    const int ld = li++, lsm = li++;
+    if ((rc = tcg_conv_forward(L[ld], B, ap[1], y_d[k], st_of(ld), 1, st)) != PDS_OK) return rc;
+    c *= 2; z /= 2; y /= 2; x /= 2;
+    if ((rc = tcg_norm_to_ap(src(ld, y_d[k]), nullptr, nullptr, ap[0], B, c, z, y, x, S, fp16, 1, st)) != PDS_OK) return rc;
+    if ((rc = tcg_conv_forward(L[lsm], B, ap[0], y_s[k], st_of(lsm), 1, st)) != PDS_OK) return rc;
+    if (k < 3) {   // next level input = down_k + smooth_k, phase-separated for the stride-2 layer
+      const TcgNormSrc d = src(ld, y_d[k]);
+      if ((rc = tcg_norm_to_ap(src(lsm, y_s[k]), &d, nullptr, ap[1], B, c, z, y, x, S, fp16, 8, st)) != PDS_OK) return rc;
+    } else {
+      if ((rc = tcg_norm_to_ap(src(lsm, y_s[k]), nullptr, nullptr, ap[1], B, c, z, y, x, S, fp16, 1, st)) != PDS_OK) return rc;
+    }
+  }
+  for (int k = 0; k < 4; ++k) {
+    // ExpansionBlock3d (regularization.py:54-57): smoothing(up(out) + skip); skip = the smoothing
+    // output pushed before contraction 3 - k (layer 2 * (3 - k) of the contraction part, 0 for k = 3)
+    const int lu = li++, lsm = li++;
+    if ((rc = tcg_conv_forward(L[lu], B, ap[1], y_u[k], st_of(lu), 1, st)) != PDS_OK) return rc;
+    c /= 2; z *= 2; y *= 2; x *= 2;
+    const int skip_layer = k < 3 ? 2 * (3 - k) : 0;
+    const TcgNormSrc skip = src(skip_layer, k < 3 ? y_s[2 - k] : y_l0);
+    if ((rc = tcg_norm_to_ap(src(lu, y_u[k]), &skip, nullptr, ap[0], B, c, z, y, x, S, fp16, 1, st)) != PDS_OK) return rc;
+    if ((rc = tcg_conv_forward(L[lsm], B, ap[0], y_e[k], st_of(lsm), 1, st)) != PDS_OK) return rc;
+    if ((rc = tcg_norm_to_ap(src(lsm, y_e[k]), nullptr, nullptr, ap[1], B, c, z, y, x, S, fp16, 1, st)) != PDS_OK) return rc;
+  }
+  // _upsample_to_halfsize (its InstanceNorm is applied by the tail kernel) + _upsample_to_fullsize
+  if ((rc = tcg_conv_forward(L[li], B, ap[1], y_half, st_of(li), 1, st)) != PDS_OK) return rc;
+  return hourglass_tail_forward(y_half, cost, st_of(li), reg->tail_gamma, reg->tail_beta, reg->tail_w,
+                                reg->tail_bias, B, 2 * D, 2 * H, 2 * W, st);
 }
 
 }  // namespace
@@ -128,7 +307,13 @@ extern "C" int pds_regularization_create(pds_regularization** out, const float* 
       if (e != cudaSuccess && rc == PDS_OK) rc = cuda_fail(e, "copy of the hourglass tail parameters");
     reg->fused_tail = rc == PDS_OK;
   }
-  if (rc != PDS_OK) { cudaFree(reg->blob); delete reg; return rc; }
+  if (rc == PDS_OK && precision != PDS_PRECISION_FP32 && F == 8 && tcg_available()) {
+    reg->split = precision == PDS_PRECISION_BF16X3 ? 3
+                 : (precision == PDS_PRECISION_BF16X2 || precision == PDS_PRECISION_FP16X2) ? 2 : 1;
+    reg->fp16 = (precision == PDS_PRECISION_FP16X2 || precision == PDS_PRECISION_FP16) ? 1 : 0;
+    rc = copy_raw_params(reg, params, (cudaStream_t)stream);
+  }
+  if (rc != PDS_OK) { cudaFree(reg->blob); cudaFree(reg->raw); delete reg; return rc; }
   *out = reg;
   return PDS_OK;
 }
@@ -136,6 +321,8 @@ extern "C" int pds_regularization_create(pds_regularization** out, const float* 
 extern "C" void pds_regularization_destroy(pds_regularization* reg) {
   if (!reg) return;
   cudaFree(reg->blob);
+  cudaFree(reg->raw);
+  cudaFree(reg->tcg_blob);
   delete reg;
 }
 
@@ -144,6 +331,7 @@ extern "C" size_t pds_regularization_workspace_bytes(const pds_regularization* r
   using namespace pds;
   if (!reg || B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
   const size_t vox = (size_t)D * H * W, F = reg->F;
+  if (reg->raw) return tcg_buffers(reg, B, D, H, W).total;
   auto buf = [&](size_t elems) { return align_up(elems * 4, 256); };
   size_t bytes = buf(B * vox * F) + buf((size_t)B * H * W * F);      // sig_cl, shortcut_cl
   bytes += 2 * buf(B * vox * F);                                     // out0 (skip), sum0
@@ -176,6 +364,7 @@ extern "C" int pds_regularization_forward(pds_regularization* reg, const float* 
     return PDS_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (reg->raw) return tcg_forward(reg, signatures, shortcut, cost, B, D, H, W, workspace, workspace_bytes, st);
   const int F = reg->F;
   const size_t vox = (size_t)D * H * W, hw = (size_t)H * W;
   Workspace ws(workspace, workspace_bytes);

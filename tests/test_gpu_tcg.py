@@ -1,0 +1,141 @@
+"""Generic tcgen05 convolution engine (csrc/conv_tcg.cu) on B200: every layer kind against the
+ATen operator the reference layer calls (network_blocks.py:61-85, 106-131), then the whole
+hourglass (regularization.py:94-126) in the tensor-core precisions against the torch port.
+
+Tolerances: fp16x2 / bf16x3 carry 22 / 24 significand bits per operand with fp32 accumulation
+-> relative error of a K-term dot product ~ 1e-6 * sqrt(K) of the operand scale; bf16x2 (16
+bits) ~ 1e-4; single-term fp16 ~ 1e-3."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import synth, torch_port
+from practicaldeepstereo_nips2018_b200 import _capi, regularization
+from gpu_util import cuda, load_module, max_abs, tdict
+
+pytestmark = pytest.mark.gpu
+
+CONV3_S1, CONV3_S2, TCONV4_S2, CONV5_S2 = 0, 1, 2, 3
+
+
+def run_layer(kind, nd, x, w, b, S=2, fp16=1, lrelu=0):
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    fn = lib.pds_tcg_conv_debug
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int] * 10 + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p]
+    n, cin = x.shape[:2]
+    cout = w.shape[1] if kind == TCONV4_S2 else w.shape[0]
+    Z, Y, X = (x.shape[2:] if nd == 3 else (1,) + tuple(x.shape[2:]))
+    if kind in (CONV3_S2, CONV5_S2):
+        oshape = tuple(s // 2 for s in x.shape[2:])
+    elif kind == TCONV4_S2:
+        oshape = tuple(s * 2 for s in x.shape[2:])
+    else:
+        oshape = tuple(x.shape[2:])
+    out = torch.empty((n, cout) + oshape, device='cuda')
+    stats = torch.zeros((n, cout, 2), dtype=torch.float64, device='cuda')
+    rc = fn(kind, nd, cin, cout, Z, Y, X, S, fp16, n, x.data_ptr(), w.data_ptr(), b.data_ptr(),
+            out.data_ptr(), stats.data_ptr(), lrelu, torch.cuda.current_stream().cuda_stream)
+    _capi.check(rc)
+    return out, stats
+
+
+def aten(kind, nd, x, w, b):
+    conv = F.conv3d if nd == 3 else F.conv2d
+    if kind == CONV3_S1:
+        return conv(x, w, b, padding=1)
+    if kind == CONV3_S2:
+        return conv(x, w, b, padding=1, stride=2)
+    if kind == CONV5_S2:
+        return F.conv2d(x, w, b, padding=2, stride=2)
+    return F.conv_transpose3d(x, w, b, padding=1, stride=2)
+
+
+CASES = [
+    # kind, nd, Cin, Cout, n, spatial
+    (CONV3_S1, 3, 8, 8, 2, (5, 18, 19)),
+    (CONV3_S1, 3, 8, 8, 1, (16, 48, 80)),
+    (CONV3_S1, 3, 16, 16, 2, (8, 24, 40)),
+    (CONV3_S1, 3, 32, 32, 1, (4, 12, 20)),
+    (CONV3_S1, 3, 64, 64, 2, (2, 6, 10)),
+    (CONV3_S1, 3, 128, 128, 1, (3, 9, 15)),
+    (CONV3_S2, 3, 8, 16, 2, (16, 48, 80)),
+    (CONV3_S2, 3, 16, 32, 1, (8, 24, 40)),
+    (CONV3_S2, 3, 32, 64, 2, (4, 12, 20)),
+    (CONV3_S2, 3, 64, 128, 1, (6, 18, 30)),
+    (TCONV4_S2, 3, 128, 64, 1, (3, 9, 15)),
+    (TCONV4_S2, 3, 64, 32, 2, (2, 6, 10)),
+    (TCONV4_S2, 3, 32, 16, 1, (4, 12, 20)),
+    (TCONV4_S2, 3, 16, 8, 2, (8, 24, 40)),
+    (TCONV4_S2, 3, 8, 4, 1, (16, 48, 80)),
+    (TCONV4_S2, 3, 8, 4, 2, (5, 17, 17)),
+    (CONV5_S2, 2, 64, 64, 2, (72, 120)),
+    (CONV3_S1, 2, 64, 8, 2, (36, 130)),
+    (CONV3_S1, 2, 64, 64, 1, (40, 50)),
+]
+
+
+@pytest.mark.parametrize('kind,nd,cin,cout,n,spatial', CASES)
+def test_layer_vs_aten(kind, nd, cin, cout, n, spatial):
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device='cpu').manual_seed(kind * 977 + cin * 31 + cout + sum(spatial))
+    k = {CONV3_S1: 3, CONV3_S2: 3, TCONV4_S2: 4, CONV5_S2: 5}[kind]
+    ks = (k,) * nd
+    x = torch.randn((n, cin) + spatial, generator=g).cuda()
+    wshape = ((cin, cout) if kind == TCONV4_S2 else (cout, cin)) + ks
+    w = (torch.randn(wshape, generator=g) / np.sqrt(cin * k ** nd)).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    ref = aten(kind, nd, x.double(), w.double(), b.double())
+    out, stats = run_layer(kind, nd, x, w, b)
+    assert out.shape == ref.shape
+    assert max_abs(out, ref) <= 2e-5 * float(ref.abs().max())
+    # InstanceNorm sums of the stored values (fp32 partial sums over 32 voxels, then double)
+    flat = out.double().flatten(2)
+    assert torch.allclose(stats[..., 0], flat.sum(-1), rtol=2e-6, atol=1e-6 * flat.abs().sum(-1).max())
+    assert torch.allclose(stats[..., 1], (flat * flat).sum(-1), rtol=2e-6)
+    # LeakyReLU epilogue
+    out2, _ = run_layer(kind, nd, x, w, b, lrelu=1)
+    assert max_abs(out2, F.leaky_relu(ref, 0.1)) <= 2e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('S,fp16,tol', [(3, 0, 2e-5), (2, 0, 2e-3), (1, 1, 2e-2), (1, 0, 1e-1)])
+def test_layer_other_precisions(S, fp16, tol):
+    g = torch.Generator(device='cpu').manual_seed(5)
+    x = torch.randn((1, 16, 6, 20, 24), generator=g).cuda()
+    w = (torch.randn((16, 16, 3, 3, 3), generator=g) / np.sqrt(16 * 27)).cuda()
+    b = torch.randn(16, generator=g).cuda()
+    ref = aten(CONV3_S1, 3, x.double(), w.double(), b.double())
+    out, _ = run_layer(CONV3_S1, 3, x, w, b, S=S, fp16=fp16)
+    assert max_abs(out, ref) <= tol * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('precision,tol', [('fp16x2', 2e-4), ('bf16x3', 2e-4), ('bf16x2', 2e-2)])
+def test_hourglass_tensor_core_vs_torch_port(precision, tol):
+    """Whole hourglass on the tcgen05 engine (bottleneck 2x3x4 voxels, batch 2)."""
+    torch.backends.cudnn.allow_tf32 = False
+    params = synth.make_params(synth.regularization_specs(), 48)
+    reg = load_module(regularization.Regularization(precision=precision), params)
+    sig, sc = cuda(synth.tensor((2, 8, 32, 48, 64), 49)), cuda(synth.tensor((2, 8, 48, 64), 50))
+    with torch.no_grad():
+        out = reg(sig, sc)
+        ref = torch_port.regularization(sig.double(), sc.double(),
+                                        {k: v.double() for k, v in tdict(params).items()})
+        out_b = reg(sig[:1, :, :16, :32].contiguous(), sc[:1, :, :32].contiguous())        # second shape: layers are re-planned
+        ref_b = torch_port.regularization(sig[:1, :, :16, :32].double(), sc[:1, :, :32].double(),
+                                          {k: v.double() for k, v in tdict(params).items()})
+    scale = float(ref.abs().max())
+    assert max_abs(out, ref) <= tol * max(scale, 1.0)
+    assert max_abs(out_b, ref_b) <= 10 * tol * max(float(ref_b.abs().max()), 1.0)
+
+
+def test_hourglass_tensor_core_golden(golden):
+    params = synth.make_params(synth.regularization_specs(), 45)
+    reg = load_module(regularization.Regularization(precision='fp16x2'), params)
+    sig, sc = synth.tensor((1, 8, 16, 16, 32), 46), synth.tensor((1, 8, 16, 32), 47)
+    with torch.no_grad():
+        out = reg(cuda(sig), cuda(sc))
+    # same bound as the fp32 path (tests/test_gpu_regularization.py::test_hourglass_golden)
+    assert max_abs(out, golden('regularization')['out']) <= 3e-3
