@@ -154,6 +154,31 @@ int pds_expansion_block_forward(const float* const* params, const float* in,
                                 int D, int H, int W, void* workspace,
                                 size_t workspace_bytes, void* stream);
 
+/* ---- a6: Embedding.forward (embedding.py:46-65) ----------------------------
+ * InstanceNorm2d(3) -> 2 x [conv5x5 s2 + LeakyReLU + IN] -> residual blocks ->
+ * descriptor; shortcut = conv3x3 block of the descriptor.  params: state_dict()
+ * order of Embedding (28 tensors by default).  Tensor-core precisions only
+ * (PDS_ERR_UNSUPPORTED for PDS_PRECISION_FP32: callers keep their own fp32 path).
+ * images (n, in_features, H, W), H and W multiples of 4 -> descriptor
+ * (n, features, H/4, W/4); shortcut (n_shortcut, shortcut_features, H/4, W/4) is
+ * computed for the first n_shortcut samples only (the reference computes and
+ * discards it for the right image, network.py:40); shortcut may be NULL when
+ * n_shortcut == 0.  Left and right images are simply samples of one batch.     */
+typedef struct pds_embedding pds_embedding;
+
+int pds_embedding_create(pds_embedding** emb, const float* const* params,
+                         int n_params, int in_features /* 3 */,
+                         int features /* 64 */, int shortcut_features /* 8 */,
+                         int residual_blocks /* 2 */, int precision,
+                         void* stream);
+void pds_embedding_destroy(pds_embedding* emb);
+size_t pds_embedding_workspace_bytes(const pds_embedding* emb, int n, int H,
+                                     int W);
+int pds_embedding_forward(pds_embedding* emb, const float* images,
+                          float* descriptor, float* shortcut, int n,
+                          int n_shortcut, int H, int W, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- a4: SubpixelMap.__call__ (estimator.py:45-91) -----------------------
  * cost (B, D, H, W) of `dtype` -> disparity (B, H-crop_top, W-crop_left)
  * float32; the crop is SizeAdapter.unpad (size_adapter.py:51-52) fused into

@@ -44,6 +44,10 @@ SIGNATURES = {
     'pds_contraction_block_forward': (_i, [ctypes.POINTER(_vp), _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     'pds_expansion_block_workspace_bytes': (_sz, [_i, _i, _i, _i, _i]),
     'pds_expansion_block_forward': (_i, [ctypes.POINTER(_vp), _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    'pds_embedding_create': (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp]),
+    'pds_embedding_destroy': (None, [_vp]),
+    'pds_embedding_workspace_bytes': (_sz, [_vp, _i, _i, _i]),
+    'pds_embedding_forward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     'pds_subpixel_map': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

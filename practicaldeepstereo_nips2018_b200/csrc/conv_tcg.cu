@@ -297,7 +297,7 @@ template <bool FP16>
 __global__ void tcg_prepare_weights_kernel(const float* __restrict__ w, const TcgWeightSrc* __restrict__ src,
                                            uint16_t* __restrict__ out, int n_entries, int Cin, int Cout,
                                            int N, int S, int KZ, int KY, int KX, int transposed,
-                                           float wscale) {
+                                           float wscale) {   // Cin: channels of the SOURCE tensor (<= the layer's)
   const size_t per_entry = (size_t)2 * N * 8;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_entry * n_entries) return;
@@ -306,7 +306,7 @@ __global__ void tcg_prepare_weights_kernel(const float* __restrict__ w, const Tc
   const int c = r % 8, co = (r / 8) % N, h = r / (8 * N);
   const TcgWeightSrc ws = src[e];
   float x = 0.f;
-  if (ws.group[h] >= 0 && co < Cout) {
+  if (ws.group[h] >= 0 && co < Cout && 8 * ws.group[h] + c < Cin) {
     const int ci = 8 * ws.group[h] + c;
     const size_t a = transposed ? ((size_t)ci * Cout + co) : ((size_t)co * Cin + ci);
     x = w[((a * KZ + ws.kz[h]) * KY + ws.ky[h]) * KX + ws.kx[h]] * wscale;
@@ -328,6 +328,7 @@ struct NormParams {
   const float* yb; const double* sb; const float* gb; const float* bb;
   const float* bcast;
   uint16_t* out;
+  float* out_f32;
   int C, Z, Y, X, S, phases;
 };
 
@@ -389,6 +390,11 @@ tcg_norm_to_ap_kernel(const NormParams p) {
       const float4 c0 = pc[0], c1 = pc[1];
       v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w;
       v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
+    }
+    if (p.out_f32) {
+      float4* po = reinterpret_cast<float4*>(p.out_f32 + ((size_t)n * V + vox) * p.C + 8 * g);
+      po[0] = make_float4(v[0], v[1], v[2], v[3]);
+      po[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
     uint16_t t[8][3];
 #pragma unroll
@@ -486,16 +492,17 @@ int tcg_layer_init(TcgLayer& l, char* blob, const float* w_src, const float* bia
   const int k = pl.shape.kind == TCG_TCONV4_S2 ? 4 : (pl.shape.kind == TCG_CONV5_S2 ? 5 : 3);
   const int KZ = pl.shape.nd == 3 ? k : 1;
   const size_t total = (size_t)2 * pl.N * 8 * pl.entries.size();
+  const int cin_src = l.cin_src > 0 ? l.cin_src : pl.shape.Cin;
   {
     PDS_KERNEL("tcg_prepare_weights", st);
     const unsigned g = (unsigned)((total + 255) / 256);
     const TcgWeightSrc* src = (const TcgWeightSrc*)((const char*)l.prog + tl.off_wsrc);
     if (l.fp16)
-      tcg_prepare_weights_kernel<true><<<g, 256, 0, st>>>(w_src, src, l.w, (int)pl.entries.size(), pl.shape.Cin,
+      tcg_prepare_weights_kernel<true><<<g, 256, 0, st>>>(w_src, src, l.w, (int)pl.entries.size(), cin_src,
                                                           pl.shape.Cout, pl.N, pl.shape.S, KZ, k, k,
                                                           l.transposed, l.wscale);
     else
-      tcg_prepare_weights_kernel<false><<<g, 256, 0, st>>>(w_src, src, l.w, (int)pl.entries.size(), pl.shape.Cin,
+      tcg_prepare_weights_kernel<false><<<g, 256, 0, st>>>(w_src, src, l.w, (int)pl.entries.size(), cin_src,
                                                            pl.shape.Cout, pl.N, pl.shape.S, KZ, k, k,
                                                            l.transposed, l.wscale);
     PDS_LAUNCH_CHECK("tcg_prepare_weights_kernel");
@@ -574,7 +581,8 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
 }
 
 int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast, uint16_t* out_ap,
-                   int n, int C, int Z, int Y, int X, int S, int fp16, int phases, cudaStream_t st) {
+                   int n, int C, int Z, int Y, int X, int S, int fp16, int phases, cudaStream_t st,
+                   float* out_f32) {
   if (n == 0) return PDS_OK;
   if (C % 8 || C > 128 || (phases != 1 && phases != 4 && phases != 8) ||
       (phases > 1 && ((X | Y) & 1)) || (phases == 8 && (Z & 1))) {
@@ -584,7 +592,7 @@ int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast,
   NormParams p;
   p.ya = a.y; p.sa = a.stats; p.ga = a.gamma; p.ba = a.beta;
   p.yb = b ? b->y : nullptr; p.sb = b ? b->stats : nullptr; p.gb = b ? b->gamma : nullptr; p.bb = b ? b->beta : nullptr;
-  p.bcast = bcast; p.out = out_ap;
+  p.bcast = bcast; p.out = out_ap; p.out_f32 = out_f32;
   p.C = C; p.Z = Z; p.Y = Y; p.X = X; p.S = S; p.phases = phases;
   const size_t total = (size_t)Z * Y * X * (C / 8);
   unsigned gx = (unsigned)((total + 255) / 256);
@@ -592,7 +600,7 @@ int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast,
   if (gx > cap) gx = cap;
   dim3 grid(gx, (unsigned)n);
   PDS_KERNEL(b ? "tcg_norm2_to_ap" : "tcg_norm_to_ap", st);
-  PDS_KERNEL_WORK(0, (double)n * Z * Y * X * C * (4.0 + 2.0 * S + (b ? 4.0 : 0.0)));
+  PDS_KERNEL_WORK(0, (double)n * Z * Y * X * C * (4.0 + 2.0 * S + (b ? 4.0 : 0.0) + (out_f32 ? 4.0 : 0.0)));
   const size_t smem = (size_t)4 * C * sizeof(float);
   if (fp16) tcg_norm_to_ap_kernel<true><<<grid, 256, smem, st>>>(p);
   else tcg_norm_to_ap_kernel<false><<<grid, 256, smem, st>>>(p);

@@ -98,6 +98,7 @@ int tcg_plan(const TcgShape& shape, TcgPlan* plan);
 struct TcgLayer {
   TcgPlan plan;
   int transposed = 0;          // PyTorch weight layout (Cin, Cout, k...) instead of (Cout, Cin, k...)
+  int cin_src = 0;             // input channels of the SOURCE weight tensor when fewer than the layer's (zero-padded)
   int fp16 = 1;
   float wscale = 256.f;
   // device buffers (owned by the caller's blob)
@@ -133,8 +134,10 @@ struct TcgNormSrc {
 // out_ap = IN(a) [+ IN(b)] [+ bcast] as split AP planes; bcast: fp32 channels-last
 // [n][Y][X][C] added to every z.  phases: 1 (plain), 4 or 8 (phase-separated for a stride-2
 // consumer).
+// out_f32 (optional): the same sum as fp32 channels-last (a later pass adds it as a residual).
 int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast, uint16_t* out_ap,
-                   int n, int C, int Z, int Y, int X, int S, int fp16, int phases, cudaStream_t st);
+                   int n, int C, int Z, int Y, int X, int S, int fp16, int phases, cudaStream_t st,
+                   float* out_f32 = nullptr);
 
 bool tcg_available();   // driver entry point for cuTensorMapEncodeTiled resolved?
 

@@ -1,0 +1,311 @@
+// a6 -- Embedding.forward (reference embedding.py:46-65) on the tcgen05 convolution engine:
+//   InstanceNorm2d(3, non-affine) -> 2 x [conv5x5 stride 2 + LeakyReLU + IN] -> residual blocks
+//   -> descriptor; shortcut = conv3x3(64 -> 8) + LeakyReLU + IN of the descriptor.
+//
+// The image is normalised and written straight into phase-separated operand planes with its 3
+// channels zero-padded to one 8-channel group, so the first convolution runs on the tensor cores
+// as well (25 taps paired two per K=16 MMA).  Every later block is one convolution launch (fp32
+// channels-last + InstanceNorm sums) and one normalisation pass that produces the next operand
+// planes, fused with the residual additions (network_blocks.py:143-144).  Left and right images
+// are just samples of one batch; the shortcut block runs on the first `n_shortcut` samples only
+// (the reference computes and discards the right image's, network.py:40).
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "conv_layers.cuh"
+#include "conv_tcg.cuh"
+#include "tc_ptx.cuh"
+
+struct pds_embedding {
+  int Cin, F, Fs, n_res, precision, split, fp16;
+  float* raw = nullptr;                    // parameters, PyTorch layout, state_dict order
+  std::vector<const float*> raw_params;
+  std::vector<pds::TcgLayer> layers;       // conv1, conv2, 2 per residual block, shortcut
+  char* blob = nullptr;
+  int shape[2] = {0, 0};
+};
+
+namespace pds {
+namespace {
+
+using namespace ptx;
+
+// sum / sum of squares of every (sample, channel) plane of an NCHW image
+__global__ void __launch_bounds__(256)
+image_stats_kernel(const float* __restrict__ img, double* __restrict__ stats, size_t HW) {
+  const int plane = blockIdx.y;
+  const float* p = img + (size_t)plane * HW;
+  double s = 0.0, q = 0.0;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < HW; i += (size_t)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < HW) {
+      const float4 v = *reinterpret_cast<const float4*>(p + i);
+      s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+      q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    } else {
+      for (size_t j = i; j < HW; ++j) { s += p[j]; q += (double)p[j] * p[j]; }
+    }
+  }
+  __shared__ double rs[8], rq[8];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rq[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { s += rs[w]; q += rq[w]; }
+    atomicAdd(stats + 2 * plane, s);
+    atomicAdd(stats + 2 * plane + 1, q);
+  }
+}
+
+// InstanceNorm2d(C <= 8, affine=False, eps 1e-5) of an NCHW image -> phase-separated AP planes
+// [n][S][4 phases][1 plane][H/2][W/2][8] with channels C..7 zero.  One thread = one pixel.
+template <bool FP16>
+__global__ void __launch_bounds__(256)
+image_norm_to_ap_kernel(const float* __restrict__ img, const double* __restrict__ stats,
+                        uint16_t* __restrict__ out, int C, int H, int W, int S) {
+  const int n = blockIdx.y;
+  const size_t HW = (size_t)H * W;
+  __shared__ float sc[8], sh[8];
+  if (threadIdx.x < 8) {
+    float a = 0.f, b = 0.f;
+    if ((int)threadIdx.x < C) {
+      const double s = stats[((size_t)n * C + threadIdx.x) * 2], q = stats[((size_t)n * C + threadIdx.x) * 2 + 1];
+      const double mean = s / (double)HW;
+      double var = q / (double)HW - mean * mean;
+      if (var < 0.0) var = 0.0;
+      a = (float)(1.0 / sqrt(var + 1e-5));
+      b = -(float)mean * a;
+    }
+    sc[threadIdx.x] = a; sh[threadIdx.x] = b;
+  }
+  __syncthreads();
+  const int IY = H / 2, IX = W / 2;
+  const size_t plane = (size_t)IY * IX;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)(i / W);
+    uint16_t t[8][3];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float v = c < C ? fmaf(img[((size_t)n * C + c) * HW + i], sc[c], sh[c]) : 0.f;
+      split_terms<FP16>(v, t[c]);
+    }
+    const int ph = (y & 1) * 2 + (x & 1);
+    const size_t pos = (size_t)(y >> 1) * IX + (x >> 1);
+    for (int s = 0; s < S; ++s) {
+      union { uint16_t h[8]; uint4 u; } pk;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) pk.h[c] = t[c][s];
+      reinterpret_cast<uint4*>(out)[(((size_t)n * S + s) * 4 + ph) * plane + pos] = pk.u;
+    }
+  }
+}
+
+std::vector<TcgShape> embedding_shapes(const pds_embedding* e, int H, int W) {
+  std::vector<TcgShape> v;
+  auto add = [&](int kind, int cin, int cout, int y, int x) {
+    TcgShape s; s.kind = kind; s.nd = 2; s.Cin = cin; s.Cout = cout; s.Z = 1; s.Y = y; s.X = x; s.S = e->split;
+    v.push_back(s);
+  };
+  add(TCG_CONV5_S2, 8, e->F, H, W);
+  add(TCG_CONV5_S2, e->F, e->F, H / 2, W / 2);
+  for (int r = 0; r < 2 * e->n_res; ++r) add(TCG_CONV3_S1, e->F, e->F, H / 4, W / 4);
+  add(TCG_CONV3_S1, e->F, e->Fs, H / 4, W / 4);
+  return v;
+}
+
+int prepare(pds_embedding* e, int H, int W, cudaStream_t st) {
+  if (e->shape[0] == H && e->shape[1] == W && !e->layers.empty()) return PDS_OK;
+  const std::vector<TcgShape> shapes = embedding_shapes(e, H, W);
+  std::vector<TcgLayer> layers(shapes.size());
+  size_t bytes = 0;
+  for (size_t i = 0; i < shapes.size(); ++i) {
+    int rc = tcg_plan(shapes[i], &layers[i].plan);
+    if (rc != PDS_OK) return rc;
+    layers[i].fp16 = e->fp16;
+    layers[i].wscale = e->fp16 ? 256.f : 1.f;
+    if (i == 0) layers[i].cin_src = e->Cin;
+    bytes += tcg_layer_bytes(layers[i]);
+  }
+  PDS_CUDA(cudaStreamSynchronize(st));
+  cudaFree(e->blob); e->blob = nullptr; e->layers.clear();
+  PDS_CUDA(cudaMalloc(&e->blob, bytes));
+  char* cur = e->blob;
+  for (size_t i = 0; i < layers.size(); ++i) {
+    size_t used = 0;
+    const float* const* pp = &e->raw_params[4 * i];   // weight, bias, gamma, beta
+    int rc = tcg_layer_init(layers[i], cur, pp[0], pp[1], st, &used);
+    if (rc != PDS_OK) return rc;
+    layers[i].gamma = pp[2]; layers[i].beta = pp[3];
+    cur += used;
+  }
+  e->layers = layers;
+  e->shape[0] = H; e->shape[1] = W;
+  return PDS_OK;
+}
+
+struct Buffers { size_t ap, y1, yq, stats, total; };
+
+Buffers buffers(const pds_embedding* e, int n, int H, int W) {
+  Buffers b;
+  auto buf = [&](size_t bytes) { return align_up(bytes, 256); };
+  const size_t S = e->split, F = e->F;
+  // operand planes: the image (8 ch at full size) and the half-size F-channel tensor are the largest
+  b.ap = buf(std::max((size_t)n * S * H * W * 16, (size_t)n * S * (H / 2) * (W / 2) * F * 2));
+  b.y1 = buf((size_t)n * (H / 2) * (W / 2) * F * 4);
+  b.yq = buf((size_t)n * (H / 4) * (W / 4) * F * 4);
+  b.stats = buf((size_t)(4 + 2 * e->n_res) * n * 64 * 2 * sizeof(double));
+  b.total = 2 * b.ap + b.y1 + 5 * b.yq + b.stats + 1024;
+  return b;
+}
+
+}  // namespace
+}  // namespace pds
+
+extern "C" int pds_embedding_create(pds_embedding** out, const float* const* params, int n_params,
+                                    int in_features, int features, int shortcut_features,
+                                    int residual_blocks, int precision, void* stream) {
+  using namespace pds;
+  PDS_CHECK_ARG(out && params, "pds_embedding_create: null pointer");
+  PDS_CHECK_ARG(in_features >= 1 && features >= 1 && shortcut_features >= 1 && residual_blocks >= 0,
+                "pds_embedding_create: bad sizes");
+  PDS_CHECK_ARG(n_params == 4 * (3 + 2 * residual_blocks),
+                "pds_embedding_create: expected %d parameter tensors, got %d", 4 * (3 + 2 * residual_blocks), n_params);
+  if (precision == PDS_PRECISION_FP32 || precision < 0 || precision > PDS_PRECISION_FP16) {
+    set_error("pds_embedding_create: the embedding kernels are tensor-core only (precision != fp32)");
+    return PDS_ERR_UNSUPPORTED;
+  }
+  if (!tcg_available() || in_features > 8 || features != 64 || shortcut_features % 4 || shortcut_features > 16) {
+    set_error("pds_embedding_create: needs <= 8 input channels, 64 features, shortcut features in {4, 8, 12, 16}");
+    return PDS_ERR_UNSUPPORTED;
+  }
+  pds_embedding* e = new (std::nothrow) pds_embedding();
+  PDS_CHECK_ARG(e, "out of host memory");
+  e->Cin = in_features; e->F = features; e->Fs = shortcut_features; e->n_res = residual_blocks;
+  e->precision = precision;
+  e->split = precision == PDS_PRECISION_BF16X3 ? 3
+             : (precision == PDS_PRECISION_BF16X2 || precision == PDS_PRECISION_FP16X2) ? 2 : 1;
+  e->fp16 = (precision == PDS_PRECISION_FP16X2 || precision == PDS_PRECISION_FP16) ? 1 : 0;
+  // parameter sizes, state_dict order: [w, b, gamma, beta] per block
+  std::vector<size_t> sizes;
+  auto block = [&](int cin, int cout, int k) {
+    sizes.push_back((size_t)cout * cin * k * k); sizes.push_back(cout); sizes.push_back(cout); sizes.push_back(cout);
+  };
+  block(in_features, features, 5);
+  block(features, features, 5);
+  for (int r = 0; r < 2 * residual_blocks; ++r) block(features, features, 3);
+  block(features, shortcut_features, 3);
+  size_t total = 0;
+  for (size_t s : sizes) total += align_up(s, 64);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t err = cudaMalloc(&e->raw, total * sizeof(float));
+  if (err != cudaSuccess) { delete e; return cuda_fail(err, "cudaMalloc(embedding parameters)"); }
+  float* cur = e->raw;
+  for (size_t i = 0; i < sizes.size(); ++i) {
+    err = cudaMemcpyAsync(cur, params[i], sizes[i] * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (err != cudaSuccess) { cudaFree(e->raw); delete e; return cuda_fail(err, "cudaMemcpyAsync(parameters)"); }
+    e->raw_params.push_back(cur);
+    cur += align_up(sizes[i], 64);
+  }
+  *out = e;
+  return PDS_OK;
+}
+
+extern "C" void pds_embedding_destroy(pds_embedding* e) {
+  if (!e) return;
+  cudaFree(e->raw);
+  cudaFree(e->blob);
+  delete e;
+}
+
+extern "C" size_t pds_embedding_workspace_bytes(const pds_embedding* e, int n, int H, int W) {
+  if (!e || n <= 0 || H <= 0 || W <= 0) return 0;
+  return pds::buffers(e, n, H, W).total;
+}
+
+extern "C" int pds_embedding_forward(pds_embedding* e, const float* images, float* descriptor,
+                                     float* shortcut, int n, int n_shortcut, int H, int W,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace pds;
+  PDS_CHECK_ARG(e && images && descriptor, "pds_embedding_forward: null pointer");
+  PDS_CHECK_ARG(n >= 0 && n_shortcut >= 0 && n_shortcut <= n && (shortcut || n_shortcut == 0),
+                "pds_embedding_forward: bad sample counts");
+  PDS_CHECK_ARG(H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0,
+                "pds_embedding_forward: height and width must be multiples of 4");
+  if (n == 0) return PDS_OK;
+  if (!workspace || workspace_bytes < pds_embedding_workspace_bytes(e, n, H, W) || ((uintptr_t)workspace & 255)) {
+    set_error("pds_embedding_forward: workspace too small or not 256-byte aligned");
+    return PDS_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = prepare(e, H, W, st);
+  if (rc != PDS_OK) return rc;
+  const Buffers bs = buffers(e, n, H, W);
+  Workspace ws(workspace, workspace_bytes);
+  uint16_t* ap[2] = {(uint16_t*)ws.take<char>(bs.ap), (uint16_t*)ws.take<char>(bs.ap)};
+  float* y1 = (float*)ws.take<char>(bs.y1);
+  float* y2 = (float*)ws.take<char>(bs.yq);
+  float* t = (float*)ws.take<char>(bs.yq);
+  float* u = (float*)ws.take<char>(bs.yq);
+  float* xres[2] = {(float*)ws.take<char>(bs.yq), (float*)ws.take<char>(bs.yq)};
+  double* stats = (double*)ws.take<char>(bs.stats);
+  if (ws.overflow) { set_error("pds_embedding_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
+  PDS_CUDA(cudaMemsetAsync(stats, 0, bs.stats, st));
+  const size_t stat_stride = (size_t)n * 64 * 2;
+  auto st_of = [&](int i) { return stats + stat_stride * i; };
+  const std::vector<TcgLayer>& L = e->layers;
+  const int S = e->split, fp16 = e->fp16, F = e->F, Hh = H / 2, Wh = W / 2, Hq = H / 4, Wq = W / 4;
+  auto src = [&](int layer, const float* y) {
+    TcgNormSrc s; s.y = y; s.stats = st_of(layer); s.gamma = L[layer].gamma; s.beta = L[layer].beta;
+    return s;
+  };
+  const int n_layers = (int)L.size();
+  double* img_stats = st_of(n_layers);          // slot after the layers'
+
+  // InstanceNorm2d of the image -> phase-separated planes (embedding.py:32)
+  {
+    const size_t HW = (size_t)H * W;
+    {
+      PDS_KERNEL("image_stats", st);
+      PDS_KERNEL_WORK(0, 4.0 * n * e->Cin * HW);
+      dim3 grid((unsigned)std::min<size_t>((HW / 4 + 255) / 256, 64), (unsigned)(n * e->Cin));
+      image_stats_kernel<<<grid, 256, 0, st>>>(images, img_stats, HW);
+      PDS_LAUNCH_CHECK("image_stats_kernel");
+    }
+    PDS_KERNEL("image_norm_to_ap", st);
+    PDS_KERNEL_WORK(0, (double)n * HW * (4.0 * e->Cin + 16.0 * S));
+    dim3 grid((unsigned)std::min<size_t>((HW + 255) / 256, (size_t)num_sms() * 8), (unsigned)n);
+    if (fp16) image_norm_to_ap_kernel<true><<<grid, 256, 0, st>>>(images, img_stats, ap[0], e->Cin, H, W, S);
+    else image_norm_to_ap_kernel<false><<<grid, 256, 0, st>>>(images, img_stats, ap[0], e->Cin, H, W, S);
+    PDS_LAUNCH_CHECK("image_norm_to_ap_kernel");
+  }
+  // two stride-2 5x5 blocks
+  if ((rc = tcg_conv_forward(L[0], n, ap[0], y1, st_of(0), 1, st)) != PDS_OK) return rc;
+  if ((rc = tcg_norm_to_ap(src(0, y1), nullptr, nullptr, ap[1], n, F, 1, Hh, Wh, S, fp16, 4, st)) != PDS_OK) return rc;
+  if ((rc = tcg_conv_forward(L[1], n, ap[1], y2, st_of(1), 1, st)) != PDS_OK) return rc;
+  // residual stream x = IN(y2); every block: x <- IN(conv(IN(conv(x)))) + x
+  if ((rc = tcg_norm_to_ap(src(1, y2), nullptr, nullptr, ap[0], n, F, 1, Hq, Wq, S, fp16, 1, st,
+                           e->n_res == 0 ? xres[0] : nullptr)) != PDS_OK) return rc;
+  TcgNormSrc x = src(1, y2);
+  float* x_final = xres[0];
+  for (int r = 0; r < e->n_res; ++r) {
+    const int l1 = 2 + 2 * r, l2 = 3 + 2 * r;
+    if ((rc = tcg_conv_forward(L[l1], n, ap[0], t, st_of(l1), 1, st)) != PDS_OK) return rc;
+    if ((rc = tcg_norm_to_ap(src(l1, t), nullptr, nullptr, ap[1], n, F, 1, Hq, Wq, S, fp16, 1, st)) != PDS_OK) return rc;
+    if ((rc = tcg_conv_forward(L[l2], n, ap[1], u, st_of(l2), 1, st)) != PDS_OK) return rc;
+    float* xn = xres[r & 1];
+    if ((rc = tcg_norm_to_ap(src(l2, u), &x, nullptr, ap[0], n, F, 1, Hq, Wq, S, fp16, 1, st, xn)) != PDS_OK) return rc;
+    x = TcgNormSrc(); x.y = xn;          // materialised sum: added as is by the next block
+    x_final = xn;
+  }
+  if ((rc = nhwc_to_nchw(x_final, descriptor, n, F, (size_t)Hq * Wq, st)) != PDS_OK) return rc;
+  if (n_shortcut > 0) {
+    // _shortcut block on the descriptor planes (embedding.py:43-44,65)
+    const int ls = n_layers - 1;
+    if ((rc = tcg_conv_forward(L[ls], n_shortcut, ap[0], t, st_of(ls), 1, st)) != PDS_OK) return rc;
+    if ((rc = instance_norm_apply(t, st_of(ls), L[ls].gamma, L[ls].beta, nullptr, nullptr, t, nullptr,
+                                  n_shortcut, (size_t)Hq * Wq, (size_t)Hq * Wq, e->Fs, st)) != PDS_OK) return rc;
+    if ((rc = nhwc_to_nchw(t, shortcut, n_shortcut, e->Fs, (size_t)Hq * Wq, st)) != PDS_OK) return rc;
+  }
+  return PDS_OK;
+}

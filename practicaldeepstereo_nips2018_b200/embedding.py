@@ -1,31 +1,83 @@
-"""Embedding tower (reference embedding.py:11-65).
+"""Embedding tower (reference embedding.py:11-65) on the tcgen05 convolution
+engine (csrc/embedding.cu).  Structure and state_dict keys are the reference's.
 
-Adjacent to the hot path (SURVEY.md 8 row a6, 4.6 % of the FLOPs, not named by
-the north star): it is kept on stock ATen/cuDNN operators in this round and is
-listed as "next" (f2) in DESIGN.md.  Structure and state_dict keys are the
-reference's."""
+Eval / no-grad CUDA calls in a tensor-core precision run the kernels; the fp32
+precision and gradient-enabled calls (training, outside the inference hot path)
+run the plain ATen composition of the same modules."""
+import ctypes
+
+import torch
 from torch import nn
 
-from . import network_blocks
+from . import _capi, network_blocks
+from .matching import _KernelHandle, _needs_autograd
 
 
 class Embedding(nn.Module):
     def __init__(self, number_of_input_features=3, number_of_embedding_features=64,
-                 number_of_shortcut_features=8, number_of_residual_blocks=2):
+                 number_of_shortcut_features=8, number_of_residual_blocks=2, precision='fp32'):
         super().__init__()
+        if precision not in _capi.PRECISIONS:
+            raise ValueError(f'precision should be one of {sorted(_capi.PRECISIONS)}')
         f = number_of_embedding_features
+        self._shape = (number_of_input_features, f, number_of_shortcut_features,
+                       number_of_residual_blocks)
+        self.precision = precision
         tower = [nn.InstanceNorm2d(number_of_input_features),
                  network_blocks.convolutional_block_5x5_stride_2(number_of_input_features, f),
                  network_blocks.convolutional_block_5x5_stride_2(f, f)]
         tower += [network_blocks.ResidualBlock(f) for _ in range(number_of_residual_blocks)]
         self._embedding_modules = nn.ModuleList(tower)
         self._shortcut = network_blocks.convolutional_block_3x3(f, number_of_shortcut_features)
+        self.__dict__['_kernel'] = _KernelHandle(self._create_handle, self._destroy_handle)
+
+    # -- C-ABI plumbing -------------------------------------------------------
+    def _create_handle(self, handle, params, precision, device):
+        cin, f, fs, n_res = self._shape
+        _capi.check(_capi.lib().pds_embedding_create(
+            ctypes.byref(handle), _capi.pointer_array(params), len(params), cin, f, fs, n_res,
+            _capi.PRECISIONS[precision], _capi.stream_ptr(device)))
+        torch.cuda.current_stream(device).synchronize()   # params may be temporaries
+
+    @staticmethod
+    def _destroy_handle(handle):
+        _capi.lib().pds_embedding_destroy(handle)
+
+    def uses_kernels(self, image):
+        cin, f, fs, _ = self._shape
+        return (self.precision != 'fp32' and image.is_cuda and not _needs_autograd(image, self)
+                and cin <= 8 and f == 64 and fs in (4, 8, 12, 16)
+                and image.dim() == 4 and image.size(2) % 4 == 0 and image.size(3) % 4 == 0)
+
+    def embed(self, images, number_of_shortcuts):
+        """images (N,3,H,W) -> descriptors (N,64,H/4,W/4) and the shortcut
+        (number_of_shortcuts,8,H/4,W/4) of the first `number_of_shortcuts` images."""
+        cin, f, fs, _ = self._shape
+        images = images.detach().contiguous().float()
+        n, c, H, W = images.shape
+        if c != cin:
+            raise ValueError(f'images should have {cin} channels')
+        lib = _capi.lib()
+        handle = self._kernel.get(list(self.parameters()), self.precision, images.device)
+        descriptor = images.new_empty((n, f, H // 4, W // 4))
+        shortcut = images.new_empty((number_of_shortcuts, fs, H // 4, W // 4))
+        with torch.cuda.device(images.device):
+            nbytes = lib.pds_embedding_workspace_bytes(handle, n, H, W)
+            ws = self._kernel.workspace(nbytes, images.device)
+            _capi.check(lib.pds_embedding_forward(
+                handle, _capi.ptr(images), _capi.ptr(descriptor),
+                _capi.ptr(shortcut) if number_of_shortcuts else None, n, number_of_shortcuts,
+                H, W, _capi.ptr(ws), ws.numel(), _capi.stream_ptr(images.device)))
+        return descriptor, shortcut
 
     def forward(self, image, with_shortcut=True):
         """image (B,3,H,W) -> descriptor (B,64,H/4,W/4), shortcut (B,8,H/4,W/4).
 
         ``with_shortcut=False`` skips the shortcut block, whose result the
         reference computes for the right image and throws away (network.py:40)."""
+        if self.uses_kernels(image):
+            descriptor, shortcut = self.embed(image, image.size(0) if with_shortcut else 0)
+            return descriptor, (shortcut if with_shortcut else None)
         descriptor = image
         for module in self._embedding_modules:
             descriptor = module(descriptor)

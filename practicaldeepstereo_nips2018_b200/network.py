@@ -30,15 +30,23 @@ class PdsNetwork(nn.Module):
         self._matching.set_maximum_disparity((maximum_disparity + 1) // 4 - 1)
 
     def _embed(self, left_image, right_image):
-        """Embedding of both images.  It still runs on ATen/cuDNN operators (row a6
-        of SURVEY.md 8, "next"); TF32 is switched off for it unless the convolution
-        stacks themselves run in reduced precision, so that the fp32 pipeline is
-        fp32 end to end."""
+        """Embedding of both images.  With the kernel embedding the two images are
+        samples of ONE batch and the shortcut block runs on the left image only (the
+        reference computes the right image's and discards it, network.py:40).  A
+        foreign / fp32 embedding module is called as the reference does, on ATen
+        operators, with TF32 switched off while the convolution stacks are fp32-grade
+        so that the pipeline is fp32 end to end."""
+        emb = self._embedding
+        if isinstance(emb, embedding.Embedding) and emb.uses_kernels(left_image) \
+                and left_image.shape == right_image.shape:
+            batch = left_image.size(0)
+            descriptors, shortcut_from_left = emb.embed(torch.cat([left_image, right_image]), batch)
+            return descriptors[:batch], descriptors[batch:], shortcut_from_left
         precision = getattr(getattr(self._matching, '_operation', None), 'precision', 'fp32')
         exact = left_image.is_cuda and precision in ('fp32', 'bf16x3', 'bf16x2', 'fp16x2')
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=not exact):
-            left_descriptor, shortcut_from_left = self._embedding(left_image)
-            right_descriptor = self._embedding(right_image)[0]
+            left_descriptor, shortcut_from_left = emb(left_image)
+            right_descriptor = emb(right_image)[0]
         return left_descriptor, right_descriptor, shortcut_from_left
 
     def pass_through_network(self, left_image, right_image):
@@ -67,7 +75,7 @@ class PdsNetwork(nn.Module):
         the convolution stacks (see include/pds_b200.h, enum pds_precision)."""
         network = PdsNetwork(
             size_adapter_module=size_adapter.SizeAdapter(),
-            embedding_module=embedding.Embedding(),
+            embedding_module=embedding.Embedding(precision=precision),
             matching_module=matching.Matching(
                 operation=matching.MatchingOperation(precision=precision),
                 maximum_disparity=0),

@@ -1,0 +1,80 @@
+"""a6 parity: the embedding tower on the tcgen05 engine (csrc/embedding.cu) against the golden
+vectors of the unmodified reference and the torch port in fp64 (B200 only), and the whole
+network in the fp32-grade tensor-core precision."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, torch_port
+from practicaldeepstereo_nips2018_b200 import PdsNetwork, embedding
+from gpu_util import cuda, load_module, max_abs, tdict
+from test_gpu_network import margin_aware
+
+pytestmark = pytest.mark.gpu
+
+
+def _f64(params):
+    return {k: v.double() for k, v in tdict(params).items()}
+
+
+@pytest.mark.parametrize('precision,tol', [('fp16x2', 2e-4), ('bf16x3', 2e-4)])
+def test_embedding_golden(golden, precision, tol):
+    g = golden('embedding')
+    params = synth.make_params(synth.embedding_specs(), 51)
+    emb = load_module(embedding.Embedding(precision=precision), params)
+    img = cuda(synth.tensor((1, 3, 64, 128), 52, scale=255.0, uniform=True))
+    with torch.no_grad():
+        assert emb.uses_kernels(img)
+        d, s = emb(img)
+    assert d.shape == (1, 64, 16, 32) and s.shape == (1, 8, 16, 32)
+    assert max_abs(d, g['descriptor']) <= tol * float(np.abs(g['descriptor']).max())
+    assert max_abs(s, g['shortcut']) <= tol * float(np.abs(g['shortcut']).max())
+
+
+def test_embedding_vs_torch_port_ragged_batch():
+    """Quarter-resolution extent 25 x 33 (partial tiles everywhere), batch 3, shortcut for 2."""
+    params = synth.make_params(synth.embedding_specs(), 53)
+    emb = load_module(embedding.Embedding(precision='fp16x2'), params)
+    img = cuda(synth.tensor((3, 3, 100, 132), 54, scale=255.0, uniform=True))
+    with torch.no_grad():
+        d, s = emb.embed(img, 2)
+        rd, rs = torch_port.embedding(img.double(), _f64(params))
+        d_all, s_all = emb(img)                      # module call: shortcut for every sample
+        d_no, s_no = emb(img, with_shortcut=False)
+    assert d.shape == (3, 64, 25, 33) and s.shape == (2, 8, 25, 33) and s_no is None
+    assert max_abs(d, rd) <= 2e-4 * float(rd.abs().max())
+    assert max_abs(s, rs[:2]) <= 2e-4 * float(rs.abs().max())
+    assert torch.equal(d_all, d) and torch.equal(d_no, d) and torch.equal(s_all[:2], s)
+    assert max_abs(s_all, rs) <= 2e-4 * float(rs.abs().max())
+    with torch.no_grad():                            # extents that are not multiples of 4: ATen path
+        d5, _ = emb(img[..., :98, :130])
+        r5, _ = torch_port.embedding(img[..., :98, :130], tdict(params))
+    assert not emb.uses_kernels(img[..., :98, :130]) and max_abs(d5, r5) <= 1e-3
+
+
+def test_network_fp16x2_vs_torch_port():
+    """PdsNetwork.forward with every stage on the tensor-core kernels (the bench precision):
+    margin-aware parity against the fp32 torch port on the same device."""
+    torch.backends.cudnn.allow_tf32 = False
+    params = synth.make_params(synth.network_specs(), 71)
+    net = load_module(PdsNetwork.default(63, precision='fp16x2'), params)
+    left = cuda(synth.tensor((2, 3, 100, 310), 72, scale=255.0, uniform=True))
+    right = cuda(synth.tensor((2, 3, 100, 310), 73, scale=255.0, uniform=True))
+    right[..., :-9] = 0.7 * left[..., 9:] + 0.3 * right[..., :-9]
+    with torch.no_grad():
+        disp = net(left, right)
+        pl, pr = net._size_adapter.pad(left), net._size_adapter.pad(right)
+        ld, rd, sc = net._embed(pl, pr)
+        cost = net.pass_through_network(pl, pr)[0]
+        _, idx = net._estimator(cost, crop_top=28, crop_left=10, return_argmax=True)
+        st = torch_port.network_stages(left.double(), right.double(), _f64(params), 63)
+    assert disp.shape == (2, 100, 310)
+    assert max_abs(ld, st['left_descriptor']) <= 2e-4 * float(st['left_descriptor'].abs().max())
+    assert max_abs(rd, st['right_descriptor']) <= 2e-4 * float(st['right_descriptor'].abs().max())
+    assert max_abs(sc, st['shortcut']) <= 2e-4 * float(st['shortcut'].abs().max())
+    cost_err = max_abs(cost, st['cost'])
+    assert cost_err <= 1e-3
+    flips, err, safe = margin_aware(disp.cpu().numpy(), idx.cpu().numpy(),
+                                    st['disparity'].float().cpu().numpy(),
+                                    st['cost'].float().cpu().numpy(), (28, 10), cost_err)
+    assert safe > 0.9 and flips < 1e-2 and err <= 1e-3 + 50 * cost_err
