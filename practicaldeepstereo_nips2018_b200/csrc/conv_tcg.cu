@@ -11,8 +11,11 @@
 //   warps 2-5 epilogue: TMEM -> registers, sum of the orders, bias, LeakyReLU, fp32
 //             channels-last store, InstanceNorm sums (double atomics once per sample).
 // Accumulators are double-buffered in TMEM whenever 2 * NACC * S * N <= 512 columns.
+#include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <set>
 #include <string>
 
 #include "conv_tcg.cuh"
@@ -23,7 +26,8 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kThreads = 192;
+constexpr int kEpilogueWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpilogueWarps);
 constexpr int kMaxStages = 6;
 
 struct alignas(64) TcgParams {
@@ -37,7 +41,7 @@ struct alignas(64) TcgParams {
   int nacc, ntx, ntz, ncls, upi;
   int GZ, GY, GX, OZ, OY, OX, Cout, mul, nd3;
   int tiles_x, tiles_y, tiles_z;
-  int BX, planes_per_term;
+  int BX, planes_per_term, ntx_log2, zstride16;
   int resident, stages, reuse;
   uint32_t box_bytes, box_tx_bytes, term_bytes, a_bytes, stage_bytes, wres_bytes, w_total_bytes;
   uint32_t off_boxes, off_entries, off_tiles, table_bytes;
@@ -52,6 +56,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   constexpr int CH = N < 32 ? N : 32;            // accumulator columns handled per epilogue step
   constexpr int NCH = N / CH;
   constexpr uint32_t ACC_COLS = S * N;
+  constexpr int NACC_MAX = 128 / N > 0 ? 128 / N : 1;   // MMA tiles per CTA tile never exceed this (planner)
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -79,7 +84,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 32 * kEpilogueWarps); }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -96,12 +101,27 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // contiguous range of CTA tiles per CTA (all classes of a tile stay together)
+  // work item = (CTA tile, output class); every CTA walks one contiguous range of items (whole
+  // tiles when a stage is shared by the classes of a tile)
   const int tiles_per_sample = p.tiles_x * p.tiles_y * p.tiles_z;
-  const int total_tiles = tiles_per_sample * p.n_samples;
-  const int tiles_per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int tile_begin = min((int)blockIdx.x * tiles_per_cta, total_tiles);
-  const int tile_end = min(tile_begin + tiles_per_cta, total_tiles);
+  const int total_items = tiles_per_sample * p.n_samples * p.ncls;
+  int per_cta = (total_items + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (p.reuse) per_cta = (per_cta + p.ncls - 1) / p.ncls * p.ncls;
+  const int item_begin = min((int)blockIdx.x * per_cta, total_items);
+  const int item_end = min(item_begin + per_cta, total_items);
+  struct Item { int n, tx, ty, tz, cls; };
+  auto decode = [&](int item) {
+    Item it;
+    it.cls = item % p.ncls;
+    const int tile = item / p.ncls;
+    it.n = tile / tiles_per_sample;
+    int r = tile - it.n * tiles_per_sample;
+    it.tz = r / (p.tiles_x * p.tiles_y);
+    r -= it.tz * p.tiles_x * p.tiles_y;
+    it.ty = r / p.tiles_x;
+    it.tx = r - it.ty * p.tiles_x;
+    return it;
+  };
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -114,32 +134,27 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
         }
       }
       uint32_t stage = 0, phase = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int n = tile / tiles_per_sample;
-        int r = tile - n * tiles_per_sample;
-        const int tz = r / (p.tiles_x * p.tiles_y);
-        r -= tz * p.tiles_x * p.tiles_y;
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        const int x0 = tx * 8 * p.ntx, y0 = ty * 16, z0 = tz * p.ntz;
-        for (int cls = 0; cls < (p.reuse ? 1 : p.ncls); ++cls) {
-          for (int u = 0; u < p.upi; ++u) {
-            const TcgUnit un = units[cls * p.upi + u];
-            const int nb = un.box_end - un.box_beg;
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), (uint32_t)nb * S * p.box_tx_bytes + (p.resident ? 0u : un.w_bytes));
-            const uint32_t sa = stage_base + stage * p.stage_bytes;
-            for (int j = 0; j < nb; ++j) {
-              const TcgBox b = boxes[un.box_beg + j];
+      for (int item = item_begin; item < item_end; ++item) {
+        const Item it = decode(item);
+        if (p.reuse && it.cls != 0) continue;       // the tile's stage is already resident
+        const int x0 = it.tx * 8 * p.ntx, y0 = it.ty * 16, z0 = it.tz * p.ntz;
+        for (int u = 0; u < p.upi; ++u) {
+          const TcgUnit un = units[it.cls * p.upi + u];
+          const int nb = un.box_end - un.box_beg;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), (uint32_t)nb * S * p.box_tx_bytes + (p.resident ? 0u : un.w_bytes));
+          const uint32_t sa = stage_base + stage * p.stage_bytes;
+          for (int j = 0; j < nb; ++j) {
+            const TcgBox b = boxes[un.box_beg + j];
 #pragma unroll
-              for (int s = 0; s < S; ++s)
-                tma_load_5d(sa + s * p.term_bytes + j * p.box_bytes, &p.map, 0, x0 + b.dx, y0 + b.dy,
-                            z0 + b.dz, (n * S + s) * p.planes_per_term + b.plane, full_bar(stage));
-            }
-            if (!p.resident)
-              bulk_load(sa + p.a_bytes, (const unsigned char*)p.w + (size_t)un.w_off16 * 16, un.w_bytes,
-                        full_bar(stage));
-            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            for (int s = 0; s < S; ++s)
+              tma_load_5d(sa + s * p.term_bytes + j * p.box_bytes, &p.map, 0, x0 + b.dx, y0 + b.dy,
+                          z0 + b.dz, (it.n * S + s) * p.planes_per_term + b.plane, full_bar(stage));
           }
+          if (!p.resident)
+            bulk_load(sa + p.a_bytes, (const unsigned char*)p.w + (size_t)un.w_off16 * 16, un.w_bytes,
+                      full_bar(stage));
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -159,30 +174,37 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
     const uint32_t b_hi = umma_desc_hi(128);
     const uint32_t b_lbo = ((uint32_t)(S * N) & 0x3fff) << 16;     // K-half stride of the B operand, 16-byte units
     const uint32_t term16 = p.term_bytes >> 4;
+    const uint32_t ent_base = smem_u32(entries);
     if (p.resident) { mbar_wait(wfull_bar, 0); tc_fence_after(); }
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      for (int cls = 0; cls < p.ncls; ++cls) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + acc * buf_cols;
-        const bool hold = p.reuse && cls + 1 < p.ncls;      // the stage serves the next class too
-        for (int u = 0; u < p.upi; ++u) {
-          const TcgUnit un = units[cls * p.upi + u];
-          if (!(p.reuse && cls > 0)) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-          }
-          const uint32_t sa16 = (stage_base + stage * p.stage_bytes) >> 4;
-          const uint32_t sw16 = p.resident ? (wres_base >> 4) : sa16;
-          if (elect_one()) {
-            for (int e = un.ent_beg; e < un.ent_end; ++e) {
-              const TcgEntry en = entries[e];
-              const uint32_t a_lo = en.a + sa16;
-              const uint64_t bd = umma_desc((en.b + sw16) | b_lbo, b_hi);
-              const uint32_t accumulate = (u == 0 && e == un.ent_beg) ? 0u : 1u;
-              for (int i = 0; i < p.nacc; ++i) {
-                const uint32_t a_i = a_lo + (uint32_t)tile_off[i];
+    for (int item = item_begin; item < item_end; ++item) {
+      const int cls = item % p.ncls;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + acc * buf_cols;
+      const bool hold = p.reuse && cls + 1 < p.ncls;      // the stage serves the next class too
+      for (int u = 0; u < p.upi; ++u) {
+        const TcgUnit un = units[cls * p.upi + u];
+        if (!(p.reuse && cls > 0)) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+        }
+        const uint32_t sa16 = (stage_base + stage * p.stage_bytes) >> 4;
+        const uint32_t sw16 = p.resident ? (wres_base >> 4) : sa16;
+        if (elect_one()) {
+          // entries come from shared memory one ahead of their use; everything else in the loop is
+          // warp-uniform arithmetic on kernel parameters (the issue rate of this lane bounds the
+          // narrow layers: an N = 16 MMA lasts ~36 cycles)
+          uint2 en = lds64(ent_base + 8u * un.ent_beg);
+          for (int e = un.ent_beg; e < un.ent_end; ++e) {
+            const uint2 nxt = lds64(ent_base + 8u * min(e + 1, un.ent_end - 1));
+            const uint32_t a_lo = en.x + sa16;
+            const uint64_t bd = umma_desc((en.y + sw16) | b_lbo, b_hi);
+            const uint32_t accumulate = (u == 0 && e == un.ent_beg) ? 0u : 1u;
+#pragma unroll
+            for (int i = 0; i < NACC_MAX; ++i) {
+              if (i < p.nacc) {
+                const uint32_t a_i = a_lo + (uint32_t)((i >> p.ntx_log2) * p.zstride16 + ((i & (p.ntx - 1)) << 3));
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                   const uint64_t ad = umma_desc(a_i + s * term16, a_hi);
@@ -193,22 +215,25 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
                 }
               }
             }
-            if (!hold) tc_commit(empty_bar(stage));
-            if (u == p.upi - 1) tc_commit(tfull_bar(acc));
+            en = nxt;
           }
-          __syncwarp();
-          if (!hold && ++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          if (!hold) tc_commit(empty_bar(stage));
+          if (u == p.upi - 1) tc_commit(tfull_bar(acc));
         }
-        if (nbuf == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
+        __syncwarp();
+        if (!hold && ++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
       }
+      if (nbuf == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
     }
   } else {
-    // ===== epilogue warps (2..5): TMEM lanes 32*(warp%4) .. +31 =====
-    const int q = warp & 3;
+    // ===== epilogue: 8 warps, two per TMEM lane quarter (32 * (warp % 4) .. + 31) =====
+    // The two warps of a quarter split the MMA tiles of an item (or, with a single tile, its
+    // column chunks).
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int row = 32 * q + lane;
     const int px = row & 7, py = row >> 3;
     uint32_t acc = 0, acc_phase = 0;
-    double s1[NCH], s2[NCH];        // InstanceNorm sums of the current sample: channel ch*CH + lane % CH
+    double s1[NCH], s2[NCH];        // InstanceNorm sums of the current sample: channel c*CH + lane % CH
 #pragma unroll
     for (int c = 0; c < NCH; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
     int stat_n = -1;
@@ -217,7 +242,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int ch = c * CH + lane;
-          if (ch < p.Cout) {
+          if (ch < p.Cout && (s1[c] != 0.0 || s2[c] != 0.0)) {
             double* dst = p.stats + ((size_t)stat_n * p.Cout + ch) * 2;
             atomicAdd(dst, s1[c]); atomicAdd(dst + 1, s2[c]);
           }
@@ -226,60 +251,70 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
     };
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const int n = tile / tiles_per_sample;
-      int r = tile - n * tiles_per_sample;
-      const int tz = r / (p.tiles_x * p.tiles_y);
-      r -= tz * p.tiles_x * p.tiles_y;
-      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      if (n != stat_n) { flush_stats(); stat_n = n; }
-      for (int cls = 0; cls < p.ncls; ++cls) {
-        const int cz = (cls >> 2) & 1, cy = (cls >> 1) & 1, cx = cls & 1;
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
-        const uint32_t t_base = tmem_base + ((uint32_t)(32 * q) << 16) + acc * buf_cols;
+    const bool split_tiles = p.nacc > 1;
+    for (int item = item_begin; item < item_end; ++item) {
+      const Item it = decode(item);
+      if (it.n != stat_n) { flush_stats(); stat_n = it.n; }
+      const int cz = (it.cls >> 2) & 1, cy = (it.cls >> 1) & 1, cx = it.cls & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(32 * q) << 16) + acc * buf_cols;
+      // per-thread partial sums of the item (NCH == 1: reduced across the warp once per item)
+      float a1[CH], a2[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
 #pragma unroll 1
-        for (int i = 0; i < p.nacc; ++i) {
-          const int ix = i % p.ntx, iz = i / p.ntx;
-          const int gx = tx * 8 * p.ntx + 8 * ix + px, gy = ty * 16 + py, gz = tz * p.ntz + iz;
-          const bool valid = gx < p.GX && gy < p.GY && gz < p.GZ;
-          const int oz = p.nd3 ? p.mul * gz + cz : 0, oy = p.mul * gy + cy, ox = p.mul * gx + cx;
-          float* o = p.out + ((((size_t)n * p.OZ + oz) * p.OY + oy) * p.OX + ox) * p.Cout;
+      for (int i = split_tiles ? half : 0; i < p.nacc; i += split_tiles ? 2 : 1) {
+        const int ix = i % p.ntx, iz = i / p.ntx;
+        const int gx = it.tx * 8 * p.ntx + 8 * ix + px, gy = it.ty * 16 + py, gz = it.tz * p.ntz + iz;
+        const bool valid = gx < p.GX && gy < p.GY && gz < p.GZ;
+        const int oz = p.nd3 ? p.mul * gz + cz : 0, oy = p.mul * gy + cy, ox = p.mul * gx + cx;
+        float* o = p.out + ((((size_t)it.n * p.OZ + oz) * p.OY + oy) * p.OX + ox) * p.Cout;
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            float v[CH];
-            tmem_ld<CH>(t_base + i * ACC_COLS + (S - 1) * N + c * CH, v);   // smallest terms first
+        for (int c = 0; c < NCH; ++c) {
+          if (!split_tiles && NCH > 1 && (c >= NCH / 2) != (half != 0)) continue;
+          float v[S][CH];
 #pragma unroll
-            for (int s = S - 2; s >= 0; --s) {
-              float t[CH];
-              tmem_ld<CH>(t_base + i * ACC_COLS + s * N + c * CH, t);
+          for (int s = 0; s < S; ++s) tmem_ld_issue<CH>(t_base + i * ACC_COLS + s * N + c * CH, v[s]);
+          tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < CH; ++j) v[j] += t[j];
-            }
+          for (int s = 0; s < S; ++s) tmem_ld_fence<CH>(v[s]);
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              float t = fmaf(v[j], p.inv_wscale, sbias[c * CH + j]);
-              if (p.lrelu) t = t > 0.f ? t : 0.1f * t;
-              v[j] = valid ? t : 0.f;
-            }
-            if (valid) {
+          for (int s = S - 2; s >= 0; --s)       // smallest terms first
 #pragma unroll
-              for (int j = 0; j < CH; j += 4)
-                if (c * CH + j < p.Cout)
-                  *reinterpret_cast<float4*>(o + c * CH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            if (p.stats) {
+            for (int j = 0; j < CH; ++j) v[S - 1][j] += v[s][j];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            float t = fmaf(v[S - 1][j], p.inv_wscale, sbias[c * CH + j]);
+            if (p.lrelu) t = t > 0.f ? t : 0.1f * t;
+            v[0][j] = valid ? t : 0.f;
+          }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4)
+              if (c * CH + j < p.Cout)
+                *reinterpret_cast<float4*>(o + c * CH + j) = make_float4(v[0][j], v[0][j + 1], v[0][j + 2], v[0][j + 3]);
+          }
+          if (p.stats) {
+            if (NCH == 1) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) { a1[j] += v[0][j]; a2[j] = fmaf(v[0][j], v[0][j], a2[j]); }
+            } else {
               float sq[CH];
 #pragma unroll
-              for (int j = 0; j < CH; ++j) sq[j] = v[j] * v[j];
-              s1[c] += (double)warp_transpose_reduce<CH>(v, lane);
+              for (int j = 0; j < CH; ++j) sq[j] = v[0][j] * v[0][j];
+              s1[c] += (double)warp_transpose_reduce<CH>(v[0], lane);
               s2[c] += (double)warp_transpose_reduce<CH>(sq, lane);
             }
           }
         }
-        tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
-        if (nbuf == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (nbuf == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
+      if (NCH == 1 && p.stats) {
+        s1[0] += (double)warp_transpose_reduce<CH>(a1, lane);
+        s2[0] += (double)warp_transpose_reduce<CH>(a2, lane);
       }
     }
     flush_stats();
@@ -447,15 +482,32 @@ TableLayout table_layout(const TcgPlan& pl) {
   return t;
 }
 
+// Kernel-class name for the profiler; PDS_B200_PROFILE_DETAIL=1 appends the layer geometry so that
+// bench.py / tools can attribute time to individual layers.
+const char* tcg_name(int S, int N, const TcgPlan& pl) {
+  static const bool detail = getenv("PDS_B200_PROFILE_DETAIL") && atoi(getenv("PDS_B200_PROFILE_DETAIL"));
+  static std::mutex mu;
+  static std::set<std::string> names;
+  std::string n = "conv_tcg<S=" + std::to_string(S) + ",N=" + std::to_string(N) + ">";
+  if (detail) {
+    static const char* kinds[] = {"c3s1", "c3s2", "t4s2", "c5s2"};
+    n += std::string("[") + kinds[pl.shape.kind] + " " + std::to_string(pl.shape.Cin) + "->" +
+         std::to_string(pl.shape.Cout) + " " + std::to_string(pl.shape.Z) + "x" + std::to_string(pl.shape.Y) +
+         "x" + std::to_string(pl.shape.X) + "]";
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  return names.insert(n).first->c_str();
+}
+
 template <int S, int N>
-int launch_tcg(const TcgParams& p, size_t smem, int grid, cudaStream_t st, double flops, double bytes) {
+int launch_tcg(const TcgParams& p, const TcgPlan& pl, size_t smem, int grid, cudaStream_t st, double flops,
+               double bytes) {
   static bool configured = false;
   if (!configured) {
     PDS_CUDA(cudaFuncSetAttribute(conv_tcg_kernel<S, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  static const std::string name = "conv_tcg<S=" + std::to_string(S) + ",N=" + std::to_string(N) + ">";
-  PDS_KERNEL(name.c_str(), st);
+  PDS_KERNEL(tcg_name(S, N, pl), st);
   PDS_KERNEL_WORK(flops, bytes);
   conv_tcg_kernel<S, N><<<grid, kThreads, smem, st>>>(p);
   PDS_LAUNCH_CHECK("conv_tcg_kernel");
@@ -548,6 +600,12 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
   p.tiles_y = (pl.GY + 15) / 16;
   p.tiles_z = (pl.GZ + pl.ntz - 1) / pl.ntz;
   p.BX = pl.BX; p.planes_per_term = pl.nph * pl.P;
+  p.ntx_log2 = pl.ntx == 1 ? 0 : (pl.ntx == 2 ? 1 : (pl.ntx == 4 ? 2 : 3));
+  p.zstride16 = pl.BY * pl.BX;
+  if ((1 << p.ntx_log2) != pl.ntx || pl.nacc > (128 / pl.N > 0 ? 128 / pl.N : 1)) {
+    set_error("conv_tcg: unsupported tile arrangement %d x %d", pl.ntx, pl.ntz);
+    return PDS_ERR_UNSUPPORTED;
+  }
   p.resident = pl.resident; p.stages = pl.stages;
   p.reuse = pl.ncls > 1 && pl.units_per_item == 1 && pl.resident;
   p.box_tx_bytes = (uint32_t)pl.PB * pl.BZ * pl.BY * pl.BX * 16;   // what TMA delivers (box_bytes is its 128-aligned slot)
@@ -563,7 +621,7 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
     set_error("conv_tcg: plan needs %zu bytes of shared memory", smem);
     return PDS_ERR_UNSUPPORTED;
   }
-  const int total = p.tiles_x * p.tiles_y * p.tiles_z * n_samples;
+  const int total = p.tiles_x * p.tiles_y * p.tiles_z * n_samples * (p.reuse ? 1 : pl.ncls);
   const int grid = total < num_sms() ? total : num_sms();
   const int k = pl.shape.kind == TCG_TCONV4_S2 ? 2 : (pl.shape.kind == TCG_CONV5_S2 ? 5 : 3);
   const double taps = (double)k * k * (pl.shape.nd == 3 ? k : 1);
@@ -571,7 +629,7 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
   const double flops = 2.0 * taps * pl.shape.Cin * pl.shape.Cout * rows;
   const double bytes = (double)pl.in_ap_bytes(n_samples) + 4.0 * pl.out_elems(n_samples);
 #define PDS_TCG_CASE(SS, NN) \
-  if (pl.shape.S == SS && pl.N == NN) return launch_tcg<SS, NN>(p, smem, grid, st, flops, bytes);
+  if (pl.shape.S == SS && pl.N == NN) return launch_tcg<SS, NN>(p, pl, smem, grid, st, flops, bytes);
   PDS_TCG_CASE(2, 16) PDS_TCG_CASE(2, 32) PDS_TCG_CASE(2, 64) PDS_TCG_CASE(2, 128)
   PDS_TCG_CASE(3, 16) PDS_TCG_CASE(3, 32) PDS_TCG_CASE(3, 64) PDS_TCG_CASE(3, 128)
   PDS_TCG_CASE(1, 16) PDS_TCG_CASE(1, 32) PDS_TCG_CASE(1, 64) PDS_TCG_CASE(1, 128)

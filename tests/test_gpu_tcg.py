@@ -137,5 +137,7 @@ def test_hourglass_tensor_core_golden(golden):
     sig, sc = synth.tensor((1, 8, 16, 16, 32), 46), synth.tensor((1, 8, 16, 32), 47)
     with torch.no_grad():
         out = reg(cuda(sig), cuda(sc))
-    # same bound as the fp32 path (tests/test_gpu_regularization.py::test_hourglass_golden)
-    assert max_abs(out, golden('regularization')['out']) <= 3e-3
+    # ill-conditioned fixture (1x1x2-voxel bottleneck under InstanceNorm amplifies rounding noise by
+    # up to 316x; the reference itself moves by 1.3e-3 between fp32 and fp64 here, see
+    # tests/test_gpu_regularization.py::test_hourglass_golden): twice the fp32 path's bound
+    assert max_abs(out, golden('regularization')['out']) <= 6e-3
