@@ -139,6 +139,24 @@ int pds_regularization_forward(pds_regularization* reg,
                                void* workspace, size_t workspace_bytes,
                                void* stream);
 
+/* Regularization.forward + SubpixelMap.__call__ + SizeAdapter.unpad in one call
+ * (regularization.py:125-126 -> estimator.py:59-91 -> size_adapter.py:51-52, the
+ * tail of PdsNetwork.forward in eval mode, network.py:49-52): the last layer of
+ * the hourglass feeds the estimator's running arg-max state directly and the
+ * (B, 2D, 4H, 4W) cost volume is never written.  Results are bit-identical to
+ * pds_regularization_forward followed by pds_subpixel_map.
+ * disparity (B, 4H - crop_top, 4W - crop_left) float32; argmax may be NULL.
+ * half_support_window / disparity_step as in pds_subpixel_map (window radius
+ * hsw / step <= 4, else PDS_ERR_UNSUPPORTED).                                 */
+int pds_regularization_forward_disparity(pds_regularization* reg,
+                                         const float* signatures,
+                                         const float* shortcut, float* disparity,
+                                         int64_t* argmax, int B, int D, int H,
+                                         int W, int half_support_window,
+                                         int disparity_step, int crop_top,
+                                         int crop_left, void* workspace,
+                                         size_t workspace_bytes, void* stream);
+
 /* Individually tested reference blocks (test/test_regularization.py:13-28):
  * ContractionBlock3d.forward (regularization.py:28-31) and
  * ExpansionBlock3d.forward (regularization.py:54-57); params = the block's

@@ -40,6 +40,8 @@ SIGNATURES = {
     'pds_regularization_destroy': (None, [_vp]),
     'pds_regularization_workspace_bytes': (_sz, [_vp, _i, _i, _i, _i]),
     'pds_regularization_forward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    'pds_regularization_forward_disparity': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i,
+                                                  _vp, _sz, _vp]),
     'pds_contraction_block_workspace_bytes': (_sz, [_i, _i, _i, _i, _i]),
     'pds_contraction_block_forward': (_i, [ctypes.POINTER(_vp), _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     'pds_expansion_block_workspace_bytes': (_sz, [_i, _i, _i, _i, _i]),

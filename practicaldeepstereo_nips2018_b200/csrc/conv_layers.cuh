@@ -113,10 +113,14 @@ int instance_norm_apply(const float* y, const double* stats, const float* gamma,
 // Hourglass tail (hourglass_tail.cu): InstanceNorm of the 4-channel half-size volume
 // fused into ConvTranspose3d(4 -> 1, (3,4,4), stride (1,2,2), padding 1).  in:
 // [B][D][H][W][4] post-LeakyReLU; stats [B][4][2] (null: already normalised);
-// gamma / beta / w (PyTorch layout) are HOST pointers; out: (B, D, 2H, 2W).
+// gamma / beta / w (PyTorch layout) are HOST pointers; out: (B, D, 2H, 2W).  With `disparity`
+// the layer is fused with SubpixelMap (estimator.py:59-91, window radius R, disparity step) and
+// the SizeAdapter crop: the cost volume is never written, `out` is ignored.
 int hourglass_tail_forward(const float* in, float* out, const double* stats, const float* gamma_host,
                            const float* beta_host, const float* w_host, float bias, int B, int D,
-                           int H, int W, cudaStream_t st);
+                           int H, int W, cudaStream_t st, float* disparity = nullptr,
+                           int64_t* argmax = nullptr, int R = 0, int step = 1, int crop_top = 0,
+                           int crop_left = 0);
 
 // [N][C][S] <-> [N][S][C]
 int nchw_to_nhwc(const float* in, float* out, int N, int C, size_t S, cudaStream_t st);

@@ -519,12 +519,27 @@ __global__ void tc_pack_nchw_kernel(const float* __restrict__ in, uint16_t* __re
   }
 }
 
-// InstanceNorm from accumulated sums on fp32 planes; one thread = 8 channels of a pixel.
-template <bool FP16>
-__global__ void __launch_bounds__(256)
+// InstanceNorm from accumulated sums on fp32 planes; one thread = 8 channels of a pixel, two
+// pixels per iteration with every load issued before the first use (the pass is a pure HBM
+// stream: 4 B read (+ 2S B residual) and 2S B written per element).
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+  uint4 r;
+  // not .nc: the residual planes are updated in place by this very kernel
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg_stream_u4(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <bool FP16, int S, bool RES>
+__global__ void __launch_bounds__(256, 3)
 tc_norm_split_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                     const uint16_t* res_ap, uint16_t* out_ap, int C, size_t HW, int S) {
+                     const uint16_t* res_ap, uint16_t* out_ap, int C, size_t HW) {
+  constexpr int U = 2;   // pixels per thread per iteration
   const int c8 = blockIdx.y, n = blockIdx.z;
   __shared__ float sc[8], sh[8];
   if (threadIdx.x < 8) {
@@ -533,41 +548,61 @@ tc_norm_split_kernel(const float* __restrict__ y, const double* __restrict__ sta
     const double mean = s / (double)HW;
     double var = q / (double)HW - mean * mean;
     if (var < 0.0) var = 0.0;
-    sc[threadIdx.x] = (float)mean;
-    sh[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+    const float scale = (float)(1.0 / sqrt(var + 1e-5)) * gamma[c];
+    sc[threadIdx.x] = scale;
+    sh[threadIdx.x] = beta[c] - (float)mean * scale;
   }
   __syncthreads();
-  float g[8], b[8], m[8], r[8];
+  float a[8], b[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    g[e] = gamma[c8 * 8 + e]; b[e] = beta[c8 * 8 + e]; m[e] = sc[e]; r[e] = sh[e];
-  }
+  for (int e = 0; e < 8; ++e) { a[e] = sc[e]; b[e] = sh[e]; }
   const float4* y4 = reinterpret_cast<const float4*>(y) + ((size_t)n * (C / 4) + 2 * c8) * HW;
-  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < HW;
-       pix += (size_t)gridDim.x * blockDim.x) {
-    const float4 a = y4[pix], c = y4[HW + pix];
-    float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  const uint4* r4 = reinterpret_cast<const uint4*>(res_ap);
+  uint4* o4 = reinterpret_cast<uint4*>(out_ap);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < HW; p0 += U * stride) {
+    float4 lo[U], hi[U];
+    uint4 rr[U][S];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (v[e] - m[e]) * r[e] * g[e] + b[e];
-    if (res_ap) {
-      float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int s = S - 1; s >= 0; --s) {   // smallest term first
-        union { uint16_t h[8]; uint4 u; } pk;
-        pk.u = reinterpret_cast<const uint4*>(res_ap)[((size_t)(n * S + s) * (C / 8) + c8) * HW + pix];
+    for (int u = 0; u < U; ++u) {
+      const size_t pix = p0 + u * stride;
+      if (pix < HW) {
+        lo[u] = ldg_stream(y4 + pix);
+        hi[u] = ldg_stream(y4 + HW + pix);
+        if (RES) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) res[e] += term_value<FP16>(pk.h[e]);
+          for (int s = 0; s < S; ++s) rr[u][s] = ldg_stream_u4(r4 + ((size_t)(n * S + s) * (C / 8) + c8) * HW + pix);
+        }
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] += res[e];
     }
-    uint16_t t[8][3];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
-    for (int s = 0; s < S; ++s) {
-      union { uint16_t h[8]; uint4 u; } pk;
+    for (int u = 0; u < U; ++u) {
+      const size_t pix = p0 + u * stride;
+      if (pix >= HW) continue;
+      float v[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) pk.h[e] = t[e][s];
-      reinterpret_cast<uint4*>(out_ap)[((size_t)(n * S + s) * (C / 8) + c8) * HW + pix] = pk.u;
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], a[e], b[e]);
+      if (RES) {
+        float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = S - 1; s >= 0; --s) {   // smallest term first
+          const uint32_t w[4] = {rr[u][s].x, rr[u][s].y, rr[u][s].z, rr[u][s].w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) res[e] += term_value<FP16>((uint16_t)(w[e >> 1] >> (16 * (e & 1))));
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += res[e];
+      }
+      uint16_t t[8][3];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        uint4 pk;
+        pk.x = t[0][s] | ((uint32_t)t[1][s] << 16); pk.y = t[2][s] | ((uint32_t)t[3][s] << 16);
+        pk.z = t[4][s] | ((uint32_t)t[5][s] << 16); pk.w = t[6][s] | ((uint32_t)t[7][s] << 16);
+        stg_stream_u4(o4 + ((size_t)(n * S + s) * (C / 8) + c8) * HW + pix, pk);
+      }
     }
   }
 }
@@ -697,13 +732,19 @@ int tc_norm_split(const float* y, const double* stats, const float* gamma, const
                   int fp16, cudaStream_t st) {
   const size_t HW = (size_t)H * W;
   if (n_slices == 0 || HW == 0) return PDS_OK;
-  unsigned gx = (unsigned)((HW + 255) / 256);
-  if (gx > 64) gx = 64;
+  unsigned gx = (unsigned)((HW + 511) / 512);      // two pixels per thread per iteration
+  if (gx > 128) gx = 128;
   dim3 grid(gx, (unsigned)(C / 8), (unsigned)n_slices);
   PDS_KERNEL(res_ap ? "tc_norm_residual_split" : "tc_norm_split", st);
   PDS_KERNEL_WORK(0, (double)n_slices * C * HW * (4 + 2 * S + (res_ap ? 2 * S : 0)));
-  if (fp16) tc_norm_split_kernel<true><<<grid, 256, 0, st>>>(y, stats, gamma, beta, res_ap, out_ap, C, HW, S);
-  else tc_norm_split_kernel<false><<<grid, 256, 0, st>>>(y, stats, gamma, beta, res_ap, out_ap, C, HW, S);
+#define PDS_NORM_CASE(FF, SS)                                                                              \
+  if ((fp16 != 0) == FF && S == SS) {                                                                      \
+    if (res_ap) tc_norm_split_kernel<FF, SS, true><<<grid, 256, 0, st>>>(y, stats, gamma, beta, res_ap, out_ap, C, HW); \
+    else tc_norm_split_kernel<FF, SS, false><<<grid, 256, 0, st>>>(y, stats, gamma, beta, res_ap, out_ap, C, HW);       \
+  }
+  PDS_NORM_CASE(true, 1) PDS_NORM_CASE(true, 2) PDS_NORM_CASE(true, 3)
+  PDS_NORM_CASE(false, 1) PDS_NORM_CASE(false, 2) PDS_NORM_CASE(false, 3)
+#undef PDS_NORM_CASE
   PDS_LAUNCH_CHECK("tc_norm_split_kernel");
   return PDS_OK;
 }

@@ -367,8 +367,8 @@ struct NormParams {
   int C, Z, Y, X, S, phases;
 };
 
-template <bool FP16>
-__global__ void __launch_bounds__(256)
+template <bool FP16, int S>
+__global__ void __launch_bounds__(256, 3)
 tcg_norm_to_ap_kernel(const NormParams p) {
   extern __shared__ float sm[];          // scale_a[C], shift_a[C], scale_b[C], shift_b[C]
   const int n = blockIdx.y;
@@ -398,50 +398,63 @@ tcg_norm_to_ap_kernel(const NormParams p) {
     sm[2 * p.C + c] = sc; sm[3 * p.C + c] = sh;
   }
   __syncthreads();
-  const int G = p.C / 8;
-  const size_t total = V * G;
+  // one CTA per image row (z, y) (grid-stride over rows); threads walk the row's (x, channel
+  // group) items -- no per-item division: G is a power of two
+  const int G = p.C / 8, gshift = 31 - __clz(G);
   const int sep = p.phases > 1;
   const int sepz = p.phases == 8;
   const int IZ = sepz ? p.Z / 2 : p.Z, IY = sep ? p.Y / 2 : p.Y, IX = sep ? p.X / 2 : p.X;
   const size_t plane = (size_t)IZ * IY * IX;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    const size_t vox = i / G;
-    const int x = (int)(vox % p.X), y = (int)((vox / p.X) % p.Y), z = (int)(vox / ((size_t)p.X * p.Y));
-    const float4* pa = reinterpret_cast<const float4*>(p.ya + ((size_t)n * V + vox) * p.C + 8 * g);
-    const float4 a0 = pa[0], a1 = pa[1];
-    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const int rows = p.Z * p.Y, items = p.X * G;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int z = row / p.Y, y = row - z * p.Y;
+    const size_t vox0 = (size_t)row * p.X;
+    const int zz = sepz ? z >> 1 : z, yy = sep ? y >> 1 : y;
+    const int ph_zy = sep ? ((sepz ? (z & 1) * 4 : 0) + (y & 1) * 2) : 0;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      const int g = i & (G - 1), x = i >> gshift;
+      const size_t off = ((size_t)n * V + vox0 + x) * p.C + 8 * g;
+      const float4* pa = reinterpret_cast<const float4*>(p.ya + off);
+      const float4 a0 = ldg_stream(pa), a1 = ldg_stream(pa + 1);
+      float4 b0, b1, c0, c1;
+      if (p.yb) {
+        const float4* pb = reinterpret_cast<const float4*>(p.yb + off);
+        b0 = ldg_stream(pb); b1 = ldg_stream(pb + 1);
+      }
+      if (p.bcast) {
+        const float4* pc = reinterpret_cast<const float4*>(p.bcast + (((size_t)n * p.Y + y) * p.X + x) * p.C + 8 * g);
+        c0 = __ldg(pc); c1 = __ldg(pc + 1);
+      }
+      float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float* sa = sm + 8 * g;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sm[8 * g + e], sm[p.C + 8 * g + e]);
-    if (p.yb) {
-      const float4* pb = reinterpret_cast<const float4*>(p.yb + ((size_t)n * V + vox) * p.C + 8 * g);
-      const float4 b0 = pb[0], b1 = pb[1];
-      const float w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sa[e], sa[p.C + e]);
+      if (p.yb) {
+        const float w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] += fmaf(w[e], sm[2 * p.C + 8 * g + e], sm[3 * p.C + 8 * g + e]);
-    }
-    if (p.bcast) {
-      const float4* pc = reinterpret_cast<const float4*>(p.bcast + (((size_t)n * p.Y + y) * p.X + x) * p.C + 8 * g);
-      const float4 c0 = pc[0], c1 = pc[1];
-      v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w;
-      v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
-    }
-    if (p.out_f32) {
-      float4* po = reinterpret_cast<float4*>(p.out_f32 + ((size_t)n * V + vox) * p.C + 8 * g);
-      po[0] = make_float4(v[0], v[1], v[2], v[3]);
-      po[1] = make_float4(v[4], v[5], v[6], v[7]);
-    }
-    uint16_t t[8][3];
+        for (int e = 0; e < 8; ++e) v[e] += fmaf(w[e], sa[2 * p.C + e], sa[3 * p.C + e]);
+      }
+      if (p.bcast) {
+        v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w;
+        v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
+      }
+      if (p.out_f32) {
+        float4* po = reinterpret_cast<float4*>(p.out_f32 + off);
+        po[0] = make_float4(v[0], v[1], v[2], v[3]);
+        po[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      uint16_t t[8][3];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
-    const int ph = sep ? ((sepz ? (z & 1) * 4 : 0) + (y & 1) * 2 + (x & 1)) : 0;
-    const int zz = sepz ? z >> 1 : z, yy = sep ? y >> 1 : y, xx = sep ? x >> 1 : x;
-    const size_t pos = ((size_t)zz * IY + yy) * IX + xx;
-    for (int s = 0; s < p.S; ++s) {
-      union { uint16_t h[8]; uint4 u; } pk;
+      for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
+      const int ph = ph_zy + (sep ? (x & 1) : 0);
+      const size_t pos = ((size_t)zz * IY + yy) * IX + (sep ? x >> 1 : x);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) pk.h[e] = t[e][s];
-      reinterpret_cast<uint4*>(p.out)[((((size_t)n * p.S + s) * p.phases + ph) * G + g) * plane + pos] = pk.u;
+      for (int s = 0; s < S; ++s) {
+        float4 pk;
+        pk.x = __uint_as_float(t[0][s] | ((uint32_t)t[1][s] << 16)); pk.y = __uint_as_float(t[2][s] | ((uint32_t)t[3][s] << 16));
+        pk.z = __uint_as_float(t[4][s] | ((uint32_t)t[5][s] << 16)); pk.w = __uint_as_float(t[6][s] | ((uint32_t)t[7][s] << 16));
+        stg_stream(reinterpret_cast<float4*>(p.out) + ((((size_t)n * S + s) * p.phases + ph) * G + g) * plane + pos, pk);
+      }
     }
   }
 }
@@ -652,16 +665,19 @@ int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast,
   p.yb = b ? b->y : nullptr; p.sb = b ? b->stats : nullptr; p.gb = b ? b->gamma : nullptr; p.bb = b ? b->beta : nullptr;
   p.bcast = bcast; p.out = out_ap; p.out_f32 = out_f32;
   p.C = C; p.Z = Z; p.Y = Y; p.X = X; p.S = S; p.phases = phases;
-  const size_t total = (size_t)Z * Y * X * (C / 8);
-  unsigned gx = (unsigned)((total + 255) / 256);
-  const unsigned cap = (unsigned)(num_sms() * 8);
+  if (C & (C - 1)) { set_error("tcg_norm_to_ap: channel count must be a power of two"); return PDS_ERR_UNSUPPORTED; }
+  unsigned gx = (unsigned)(Z * Y);                   // one CTA per row, grid-stride beyond the cap
+  const unsigned cap = (unsigned)(num_sms() * 32);
   if (gx > cap) gx = cap;
   dim3 grid(gx, (unsigned)n);
   PDS_KERNEL(b ? "tcg_norm2_to_ap" : "tcg_norm_to_ap", st);
   PDS_KERNEL_WORK(0, (double)n * Z * Y * X * C * (4.0 + 2.0 * S + (b ? 4.0 : 0.0) + (out_f32 ? 4.0 : 0.0)));
   const size_t smem = (size_t)4 * C * sizeof(float);
-  if (fp16) tcg_norm_to_ap_kernel<true><<<grid, 256, smem, st>>>(p);
-  else tcg_norm_to_ap_kernel<false><<<grid, 256, smem, st>>>(p);
+#define PDS_TCG_NORM_CASE(FF, SS) \
+  if ((fp16 != 0) == FF && S == SS) tcg_norm_to_ap_kernel<FF, SS><<<grid, 256, smem, st>>>(p);
+  PDS_TCG_NORM_CASE(true, 1) PDS_TCG_NORM_CASE(true, 2) PDS_TCG_NORM_CASE(true, 3)
+  PDS_TCG_NORM_CASE(false, 1) PDS_TCG_NORM_CASE(false, 2) PDS_TCG_NORM_CASE(false, 3)
+#undef PDS_TCG_NORM_CASE
   PDS_LAUNCH_CHECK("tcg_norm_to_ap_kernel");
   return PDS_OK;
 }

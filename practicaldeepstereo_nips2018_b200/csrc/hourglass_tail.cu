@@ -35,12 +35,80 @@ __device__ __forceinline__ float dot4(const float4& v, const float* w) {
   return fmaf(v.x, w[0], fmaf(v.y, w[1], fmaf(v.z, w[2], v.w * w[3])));
 }
 
+// th.max semantics (estimator.cu): strictly greater keeps the lowest index; the first NaN wins.
+__device__ __forceinline__ bool takes_over(float v, float best) {
+  return (v > best) || ((v != v) && (best == best));
+}
+
+// Running state of SubpixelMap for one output pixel (estimator.py:59-91, same scheme as
+// subpixel_map_kernel): maximum with its index, the R values before it (from a rolling
+// history) and the R values after it (captured as the scan passes them).
+template <int R>
+struct MapState {
+  float best, before[R], after[R], hist[R];
+  int idx;
+  __device__ __forceinline__ void init() {
+    best = 0.f; idx = -1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { before[r] = 0.f; after[r] = 0.f; hist[r] = 0.f; }
+  }
+  __device__ __forceinline__ void push(float x, int d) {
+    if (d == 0) {
+      best = x; idx = 0; hist[0] = x;
+      return;
+    }
+    const int off = d - idx;
+    if (takes_over(x, best)) {
+      best = x; idx = d;
+#pragma unroll
+      for (int r = 0; r < R; ++r) before[r] = hist[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) if (off == r + 1) after[r] = x;
+    }
+#pragma unroll
+    for (int r = R - 1; r > 0; --r) hist[r] = hist[r - 1];
+    hist[0] = x;
+  }
+  // softmax over the window, max-subtracted, summation in shift order (estimator.py:66-90)
+  __device__ __forceinline__ float disparity(int D, int step) const {
+    float e[2 * R + 1], sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; ++k) {
+      const int j = idx + k - R;
+      const float s = k < R ? before[R - 1 - k] : (k == R ? best : after[k - R - 1]);
+      const bool valid = (j >= 0) && (j < D);
+      e[k] = valid ? expf(s - best) : 0.f;
+      sum += e[k];
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; ++k) {
+      const int j = idx + k - R;
+      const bool valid = (j >= 0) && (j < D);
+      acc += (e[k] / sum) * (valid ? (float)(step * j) : 0.f);
+    }
+    return acc;
+  }
+};
+
+struct FusedParams {
+  float* disparity;      // (B, 2H - crop_top, 2W - crop_left)
+  int64_t* argmax;       // same shape or null
+  int step, crop_top, crop_left;
+};
+
+// R == 0: writes the cost volume (B, D, 2H, 2W).  R >= 1: the volume is never written -- every
+// thread feeds the four output pixels it owns into the SubpixelMap state (window radius R) and
+// stores their disparities, cropped (SizeAdapter.unpad), at the end of its march along z.
+template <int R>
 __global__ void __launch_bounds__(256)
-hourglass_tail_kernel(const __grid_constant__ TailParams p) {
+hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f) {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   const int b = blockIdx.z / p.nseg, seg = blockIdx.z - b * p.nseg;
   const int z0 = seg * p.zseg, z1 = min(p.D, z0 + p.zseg);
   if (x >= p.W || y >= p.H) return;
+  if (R > 0 && (2 * y + 1 < f.crop_top || 2 * x + 1 < f.crop_left)) return;   // all four pixels cropped
   // InstanceNorm of the input as one multiply-add per channel
   float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
   if (p.stats) {
@@ -60,7 +128,7 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p) {
   const float4* base = p.in + (size_t)b * p.D * plane;
   const int OW = 2 * p.W;
   const size_t oplane = (size_t)4 * plane;
-  float* obase = p.out + (size_t)b * p.D * oplane + (size_t)(2 * y) * OW + 2 * x;
+  float* obase = R == 0 ? p.out + (size_t)b * p.D * oplane + (size_t)(2 * y) * OW + 2 * x : nullptr;
   bool okx[3], oky[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) { okx[d] = x + d - 1 >= 0 && x + d - 1 < p.W; oky[d] = y + d - 1 >= 0 && y + d - 1 < p.H; }
@@ -70,6 +138,11 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p) {
   for (int k = 0; k < 3; ++k)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[k][c] = 0.f;
+  MapState<(R > 0 ? R : 1)> state[4];
+  if (R > 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) state[c].init();
+  }
 
   for (int zi = z0 - 1; zi <= z1; ++zi) {
     if (zi >= 0 && zi < p.D) {
@@ -106,26 +179,46 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p) {
     }
     const int zo = zi - 1;
     if (zo >= z0 && zo < z1) {
-      float* o = obase + (size_t)zo * oplane;
-      *reinterpret_cast<float2*>(o) = make_float2(acc[0][0] + p.bias, acc[0][1] + p.bias);
-      *reinterpret_cast<float2*>(o + OW) = make_float2(acc[0][2] + p.bias, acc[0][3] + p.bias);
+      if (R == 0) {
+        float* o = obase + (size_t)zo * oplane;
+        *reinterpret_cast<float2*>(o) = make_float2(acc[0][0] + p.bias, acc[0][1] + p.bias);
+        *reinterpret_cast<float2*>(o + OW) = make_float2(acc[0][2] + p.bias, acc[0][3] + p.bias);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) state[c].push(acc[0][c] + p.bias, zo);
+      }
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) { acc[0][c] = acc[1][c]; acc[1][c] = acc[2][c]; acc[2][c] = 0.f; }
+  }
+  if (R > 0) {
+    const int Hc = 2 * p.H - f.crop_top, Wc = OW - f.crop_left;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int oy = 2 * y + (c >> 1) - f.crop_top, ox = 2 * x + (c & 1) - f.crop_left;
+      if (oy < 0 || ox < 0) continue;
+      const size_t o = ((size_t)b * Hc + oy) * Wc + ox;
+      f.disparity[o] = state[c].disparity(p.D, f.step);
+      if (f.argmax) f.argmax[o] = state[c].idx;
+    }
   }
 }
 
 }  // namespace
 
 // w_host: the layer's weight in PyTorch layout (Cin = 4, Cout = 1, 3, 4, 4), on the HOST.
+// disparity != null: fused with SubpixelMap (window radius R = half_support_window / step in
+// 1..4) and the SizeAdapter crop; `out` is not written.
 int hourglass_tail_forward(const float* in, float* out, const double* stats, const float* gamma_host,
                            const float* beta_host, const float* w_host, float bias, int B, int D,
-                           int H, int W, cudaStream_t st) {
+                           int H, int W, cudaStream_t st, float* disparity, int64_t* argmax, int R,
+                           int step, int crop_top, int crop_left) {
   if (B == 0 || D == 0 || H == 0 || W == 0) return PDS_OK;
   TailParams p;
   p.in = reinterpret_cast<const float4*>(in); p.out = out; p.stats = stats;
   p.B = B; p.D = D; p.H = H; p.W = W;
-  p.zseg = D > 48 ? 48 : D;
+  const bool fused = disparity != nullptr;
+  p.zseg = fused ? D : (D > 48 ? 48 : D);
   p.nseg = (D + p.zseg - 1) / p.zseg;
   for (int c = 0; c < 4; ++c) { p.gamma[c] = gamma_host ? gamma_host[c] : 1.f; p.beta[c] = beta_host ? beta_host[c] : 0.f; }
   for (int ci = 0; ci < 4; ++ci)
@@ -133,11 +226,25 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
       for (int kh = 0; kh < 4; ++kh)
         for (int kw = 0; kw < 4; ++kw) p.w[kd][kh][kw][ci] = w_host[((ci * 3 + kd) * 4 + kh) * 4 + kw];
   p.bias = bias;
+  FusedParams f;
+  f.disparity = disparity; f.argmax = argmax; f.step = step; f.crop_top = crop_top; f.crop_left = crop_left;
   dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8), (unsigned)(B * p.nseg));
   if (grid.z > 65535) { set_error("hourglass_tail: batch too large"); return PDS_ERR_UNSUPPORTED; }
-  PDS_KERNEL("hourglass_tail(tconv 4->1 + IN)", st);
-  PDS_KERNEL_WORK(2.0 * 192 * B * D * H * W, (double)B * D * H * W * (16 + 16));
-  hourglass_tail_kernel<<<grid, dim3(32, 8), 0, st>>>(p);
+  if (fused && (R < 1 || R > 4 || crop_top < 0 || crop_left < 0 || crop_top > 2 * H || crop_left > 2 * W)) {
+    set_error("hourglass_tail: fused estimator needs a window radius in 1..4 and a crop inside the image");
+    return PDS_ERR_UNSUPPORTED;
+  }
+  PDS_KERNEL(fused ? "hourglass_tail+subpixel_map" : "hourglass_tail(tconv 4->1 + IN)", st);
+  PDS_KERNEL_WORK(2.0 * 192 * B * D * H * W,
+                  (double)B * D * H * W * 16 + (fused ? 4.0 * B * (2 * H - crop_top) * (2 * W - crop_left)
+                                                       : (double)B * D * H * W * 16));
+  switch (fused ? R : 0) {
+    case 0: hourglass_tail_kernel<0><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
+    case 1: hourglass_tail_kernel<1><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
+    case 2: hourglass_tail_kernel<2><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
+    case 3: hourglass_tail_kernel<3><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
+    default: hourglass_tail_kernel<4><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
+  }
   PDS_LAUNCH_CHECK("hourglass_tail_kernel");
   return PDS_OK;
 }

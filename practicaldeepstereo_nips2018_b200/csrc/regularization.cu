@@ -182,6 +182,13 @@ int prepare_tcg(pds_regularization* reg, int D, int H, int W, cudaStream_t st) {
   return PDS_OK;
 }
 
+// SubpixelMap + SizeAdapter.unpad fused into the last layer (disparity == null: plain cost volume)
+struct TailFusion {
+  float* disparity = nullptr;
+  int64_t* argmax = nullptr;
+  int R = 0, step = 1, crop_top = 0, crop_left = 0;
+};
+
 struct TcgBuffers {
   size_t sc_cl, ap, y_l0, y_d[4], y_s[4], y_u[4], y_e[4], y_half, stats, total;
 };
@@ -209,7 +216,8 @@ TcgBuffers tcg_buffers(const pds_regularization* reg, int B, int D, int H, int W
 // (regularization.py:117-123); skip tensors are never materialised: the pass that needs one
 // re-normalises the stored convolution output.
 int tcg_forward(pds_regularization* reg, const float* signatures, const float* shortcut, float* cost, int B,
-                int D, int H, int W, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                int D, int H, int W, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                const TailFusion& tf) {
   int rc = prepare_tcg(reg, D, H, W, st);
   if (rc != PDS_OK) return rc;
   const int F = reg->F, S = reg->split, fp16 = reg->fp16;
@@ -268,7 +276,8 @@ int tcg_forward(pds_regularization* reg, const float* signatures, const float* s
   // _upsample_to_halfsize (its InstanceNorm is applied by the tail kernel) + _upsample_to_fullsize
   if ((rc = tcg_conv_forward(L[li], B, ap[1], y_half, st_of(li), 1, st)) != PDS_OK) return rc;
   return hourglass_tail_forward(y_half, cost, st_of(li), reg->tail_gamma, reg->tail_beta, reg->tail_w,
-                                reg->tail_bias, B, 2 * D, 2 * H, 2 * W, st);
+                                reg->tail_bias, B, 2 * D, 2 * H, 2 * W, st, tf.disparity, tf.argmax, tf.R,
+                                tf.step, tf.crop_top, tf.crop_left);
 }
 
 }  // namespace
@@ -349,12 +358,12 @@ extern "C" size_t pds_regularization_workspace_bytes(const pds_regularization* r
   return bytes + 1024;
 }
 
-extern "C" int pds_regularization_forward(pds_regularization* reg, const float* signatures,
-                                          const float* shortcut, float* cost, int B, int D, int H,
-                                          int W, void* workspace, size_t workspace_bytes,
-                                          void* stream) {
-  using namespace pds;
-  PDS_CHECK_ARG(reg && signatures && shortcut && cost, "pds_regularization_forward: null pointer");
+namespace pds {
+namespace {
+int regularization_forward(pds_regularization* reg, const float* signatures, const float* shortcut,
+                           float* cost, int B, int D, int H, int W, void* workspace,
+                           size_t workspace_bytes, void* stream, const TailFusion& tf) {
+  PDS_CHECK_ARG(reg && signatures && shortcut && (cost || tf.disparity), "pds_regularization_forward: null pointer");
   PDS_CHECK_ARG(B >= 0 && D >= 16 && H >= 16 && W >= 16 && D % 16 == 0 && H % 16 == 0 && W % 16 == 0,
                 "pds_regularization_forward: D, H, W must be positive multiples of 16");
   if (B == 0) return PDS_OK;
@@ -364,7 +373,11 @@ extern "C" int pds_regularization_forward(pds_regularization* reg, const float* 
     return PDS_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (reg->raw) return tcg_forward(reg, signatures, shortcut, cost, B, D, H, W, workspace, workspace_bytes, st);
+  if (tf.disparity && !reg->fused_tail) {
+    set_error("pds_regularization_forward_disparity: needs the 8-feature hourglass");
+    return PDS_ERR_UNSUPPORTED;
+  }
+  if (reg->raw) return tcg_forward(reg, signatures, shortcut, cost, B, D, H, W, workspace, workspace_bytes, st, tf);
   const int F = reg->F;
   const size_t vox = (size_t)D * H * W, hw = (size_t)H * W;
   Workspace ws(workspace, workspace_bytes);
@@ -427,12 +440,49 @@ extern "C" int pds_regularization_forward(pds_regularization* reg, const float* 
     if ((rc = conv_forward_simt(L[li++], g, out, nullptr, 0, half, stats, st)) != PDS_OK) return rc;
     g.D *= 2; g.H *= 2; g.W *= 2;
     return hourglass_tail_forward(half, cost, stats, reg->tail_gamma, reg->tail_beta, reg->tail_w,
-                                  reg->tail_bias, B, g.D, g.H, g.W, st);
+                                  reg->tail_bias, B, g.D, g.H, g.W, st, tf.disparity, tf.argmax, tf.R,
+                                  tf.step, tf.crop_top, tf.crop_left);
   }
   if ((rc = conv_block(L[li++], g, out, half, stats, nullptr, nullptr, half, nullptr, 0, st)) != PDS_OK) return rc;
   g.D *= 2; g.H *= 2; g.W *= 2;
   // _upsample_to_fullsize: 1 output channel, channels-last == (B, 2D, 4H, 4W) after squeeze(1)
   return conv_forward_simt(L[li], g, half, nullptr, 0, cost, nullptr, st);
+}
+}  // namespace
+}  // namespace pds
+
+extern "C" int pds_regularization_forward(pds_regularization* reg, const float* signatures,
+                                          const float* shortcut, float* cost, int B, int D, int H,
+                                          int W, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  return pds::regularization_forward(reg, signatures, shortcut, cost, B, D, H, W, workspace,
+                                     workspace_bytes, stream, pds::TailFusion());
+}
+
+extern "C" int pds_regularization_forward_disparity(pds_regularization* reg, const float* signatures,
+                                                    const float* shortcut, float* disparity,
+                                                    int64_t* argmax, int B, int D, int H, int W,
+                                                    int half_support_window, int disparity_step,
+                                                    int crop_top, int crop_left, void* workspace,
+                                                    size_t workspace_bytes, void* stream) {
+  using namespace pds;
+  PDS_CHECK_ARG(disparity, "pds_regularization_forward_disparity: null pointer");
+  // estimator.py:34-41
+  PDS_CHECK_ARG(disparity_step >= 1, "\"disparity_step\" should be positive integer.");
+  PDS_CHECK_ARG(half_support_window >= 1, "\"half_support_window\" should be positive integer.");
+  PDS_CHECK_ARG(half_support_window % disparity_step == 0,
+                "\"half_support_window\" should be multiple of the\"disparity_step\"");
+  PDS_CHECK_ARG(crop_top >= 0 && crop_top < 4 * H && crop_left >= 0 && crop_left < 4 * W,
+                "pds_regularization_forward_disparity: crop outside the image");
+  TailFusion tf;
+  tf.disparity = disparity; tf.argmax = argmax; tf.R = half_support_window / disparity_step;
+  tf.step = disparity_step; tf.crop_top = crop_top; tf.crop_left = crop_left;
+  if (tf.R > 4) {
+    set_error("pds_regularization_forward_disparity: window radius above 4 is not fused");
+    return PDS_ERR_UNSUPPORTED;
+  }
+  return regularization_forward(reg, signatures, shortcut, nullptr, B, D, H, W, workspace,
+                                workspace_bytes, stream, tf);
 }
 
 // ---- individually tested blocks ------------------------------------------------

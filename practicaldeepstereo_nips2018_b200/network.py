@@ -1,9 +1,17 @@
 """PdsNetwork: drop-in for practical_deep_stereo.network.PdsNetwork
 (reference network.py:14-65) wired to the B200 kernel modules."""
+import os
+
 import torch
 from torch import nn
 
 from . import embedding, estimator, matching, regularization, size_adapter
+
+
+# Regularization.forward_disparity (hourglass tail + estimator + crop in one kernel, bit-identical)
+# is built and tested but, with its serial scan along the full disparity axis, currently slower
+# than the two separate kernels at C2 (0.70 ms vs 0.28 + 0.11 ms): off unless asked for.
+FUSE_TAIL_AND_ESTIMATOR = os.environ.get('PDS_B200_FUSE_TAIL', '0') == '1'
 
 
 class PdsNetwork(nn.Module):
@@ -58,16 +66,28 @@ class PdsNetwork(nn.Module):
     def forward(self, left_image, right_image):
         """Sub-pixel disparity [B, H, W] in eval mode, matching cost
         [B, (md + 1) / 2, H, W] in training mode."""
-        cost = self.pass_through_network(self._size_adapter.pad(left_image),
-                                         self._size_adapter.pad(right_image))[0]
+        left, right = self._size_adapter.pad(left_image), self._size_adapter.pad(right_image)
+        reg, est = self._regularization, self._estimator
+        if (FUSE_TAIL_AND_ESTIMATOR and not self.training and left.is_cuda
+                and isinstance(est, estimator.SubpixelMap)
+                and isinstance(reg, regularization.Regularization) and reg.can_fuse_estimator(est)
+                and not matching._needs_autograd(left, right, self)):
+            # hourglass tail, estimator and SizeAdapter.unpad as one pipeline: the cost volume
+            # (212 MB at 960x540) is never written (bit-identical to the separate calls below)
+            left_descriptor, right_descriptor, shortcut = self._embed(left, right)
+            signatures = self._matching(left_descriptor, right_descriptor)
+            return reg.forward_disparity(signatures, shortcut, est._half_support_window,
+                                         est._disparity_step,
+                                         crop_top=self._size_adapter._pixels_pad_to_height,
+                                         crop_left=self._size_adapter._pixels_pad_to_width)
+        cost = self.pass_through_network(left, right)[0]
         if self.training:
             return self._size_adapter.unpad(cost)
-        if isinstance(self._estimator, estimator.SubpixelMap) and cost.is_cuda:
+        if isinstance(est, estimator.SubpixelMap) and cost.is_cuda:
             # SizeAdapter.unpad fused into the estimator's store
-            return self._estimator(cost,
-                                   crop_top=self._size_adapter._pixels_pad_to_height,
-                                   crop_left=self._size_adapter._pixels_pad_to_width)
-        return self._size_adapter.unpad(self._estimator(cost))
+            return est(cost, crop_top=self._size_adapter._pixels_pad_to_height,
+                       crop_left=self._size_adapter._pixels_pad_to_width)
+        return self._size_adapter.unpad(est(cost))
 
     @staticmethod
     def default(maximum_disparity=255, precision='fp32'):

@@ -118,6 +118,41 @@ class Regularization(nn.Module):
             output = block(output, skips.pop())
         return self._upsample_to_fullsize(self._upsample_to_halfsize(output)).squeeze(1)
 
+    def forward_disparity(self, matching_signatures, shortcut_from_left_image,
+                          half_support_window, disparity_step, crop_top=0, crop_left=0,
+                          return_argmax=False):
+        """Regularization.forward followed by SubpixelMap and SizeAdapter.unpad as ONE
+        pipeline whose cost volume is never written (bit-identical to the separate calls):
+        signatures [B, F, D, H, W], shortcut [B, F, H, W] -> disparity
+        [B, 4H - crop_top, 4W - crop_left]."""
+        _capi.require_cuda(matching_signatures, shortcut_from_left_image)
+        sig, sc = _f32(matching_signatures), _f32(shortcut_from_left_image)
+        B, F, D, H, W = sig.shape
+        if F != self._number_of_features or tuple(sc.shape) != (B, F, H, W):
+            raise ValueError('expected signatures [B, F, D, H, W] and shortcut [B, F, H, W]')
+        if D % 16 or H % 16 or W % 16:
+            raise ValueError('D, H and W of the signature volume should be multiples of 16')
+        lib = _capi.lib()
+        handle = self._kernel.get(list(self.parameters()), self.precision, sig.device)
+        out = sig.new_empty((B, 4 * H - crop_top, 4 * W - crop_left))
+        idx = torch.empty_like(out, dtype=torch.int64) if return_argmax else None
+        with torch.cuda.device(sig.device):
+            nbytes = lib.pds_regularization_workspace_bytes(handle, B, D, H, W)
+            ws = self._kernel.workspace(nbytes, sig.device)
+            _capi.check(lib.pds_regularization_forward_disparity(
+                handle, _capi.ptr(sig), _capi.ptr(sc), _capi.ptr(out),
+                _capi.ptr(idx) if idx is not None else None, B, D, H, W, half_support_window,
+                disparity_step, crop_top, crop_left, _capi.ptr(ws), ws.numel(),
+                _capi.stream_ptr(sig.device)))
+        return (out, idx) if return_argmax else out
+
+    def can_fuse_estimator(self, estimator_module):
+        """True when forward_disparity serves this estimator (window radius <= 4)."""
+        hsw = getattr(estimator_module, '_half_support_window', None)
+        step = getattr(estimator_module, '_disparity_step', None)
+        return (self._number_of_features == 8 and hsw is not None and step is not None
+                and hsw // step <= 4)
+
     def forward(self, matching_signatures, shortcut_from_left_image):
         """signatures [B, F, D, H, W], shortcut [B, F, H, W] -> cost [B, 2D, 4H, 4W]."""
         if _needs_autograd(matching_signatures, shortcut_from_left_image, self):

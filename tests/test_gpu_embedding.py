@@ -66,9 +66,10 @@ def test_network_fp16x2_vs_torch_port():
         pl, pr = net._size_adapter.pad(left), net._size_adapter.pad(right)
         ld, rd, sc = net._embed(pl, pr)
         cost = net.pass_through_network(pl, pr)[0]
-        _, idx = net._estimator(cost, crop_top=28, crop_left=10, return_argmax=True)
+        d2, idx = net._estimator(cost, crop_top=28, crop_left=10, return_argmax=True)
         st = torch_port.network_stages(left.double(), right.double(), _f64(params), 63)
     assert disp.shape == (2, 100, 310)
+    assert torch.equal(disp, d2)     # forward() fuses hourglass tail + estimator + crop: bit-identical
     assert max_abs(ld, st['left_descriptor']) <= 2e-4 * float(st['left_descriptor'].abs().max())
     assert max_abs(rd, st['right_descriptor']) <= 2e-4 * float(st['right_descriptor'].abs().max())
     assert max_abs(sc, st['shortcut']) <= 2e-4 * float(st['shortcut'].abs().max())

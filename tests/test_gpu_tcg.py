@@ -141,3 +141,23 @@ def test_hourglass_tensor_core_golden(golden):
     # up to 316x; the reference itself moves by 1.3e-3 between fp32 and fp64 here, see
     # tests/test_gpu_regularization.py::test_hourglass_golden): twice the fp32 path's bound
     assert max_abs(out, golden('regularization')['out']) <= 6e-3
+
+
+@pytest.mark.parametrize('precision', ['fp16x2', 'fp32'])
+@pytest.mark.parametrize('hsw,step,crop', [(4, 2, (36, 0)), (2, 1, (0, 0)), (8, 2, (5, 7)), (3, 3, (64, 129))])
+def test_fused_tail_estimator_is_bit_identical(precision, hsw, step, crop):
+    """pds_regularization_forward_disparity == pds_regularization_forward + pds_subpixel_map
+    (+ SizeAdapter.unpad), bit for bit, indices included."""
+    from practicaldeepstereo_nips2018_b200 import estimator
+    params = synth.make_params(synth.regularization_specs(), 48)
+    reg = load_module(regularization.Regularization(precision=precision), params)
+    est = estimator.SubpixelMap(hsw, step)
+    sig, sc = cuda(synth.tensor((2, 8, 16, 32, 48), 59)), cuda(synth.tensor((2, 8, 32, 48), 60))
+    with torch.no_grad():
+        cost = reg(sig, sc)
+        d_ref, i_ref = est(cost, crop_top=crop[0], crop_left=crop[1], return_argmax=True)
+        d, i = reg.forward_disparity(sig, sc, hsw, step, crop_top=crop[0], crop_left=crop[1],
+                                     return_argmax=True)
+    assert d.shape == d_ref.shape == (2, 128 - crop[0], 192 - crop[1])
+    assert torch.equal(i, i_ref)
+    assert torch.equal(d, d_ref)
