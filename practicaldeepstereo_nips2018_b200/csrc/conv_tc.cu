@@ -443,6 +443,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
               for (int k = 0; k < 8; ++k)
                 o[(size_t)k * HW] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             }
+            if (p.epilogue != TC_EPI_ACT) continue;
             // InstanceNorm partial sums over this warp's 32 pixels, one channel per lane
             float sq[32];
 #pragma unroll
@@ -474,10 +475,14 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
 
 // ---- auxiliary kernels ------------------------------------------------------------------
 
-// (Cout, Cin, 3, 3) fp32 -> [chunk][tap][2][S][N][8] terms of w * wscale (zero rows for cout >= Cout)
+// (Cout, src_cin, 3, 3) fp32 -> [chunk][tap][2][S][N][8] terms of w * wscale (zero rows for
+// cout >= Cout).  The layer's input channels are the source channels [ci_off, ci_off + Cin).
+// qmode: only the kx = 2 column of the kernel survives, moved to the centre column (the
+// "right-neighbour taps applied in place" operator of the factorised first convolution).
 template <bool FP16>
 __global__ void tc_prepare_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out,
-                                          int Cout, int Cin, int N, int S, float wscale) {
+                                          int Cout, int Cin, int N, int S, float wscale, int src_cin,
+                                          int ci_off, int qmode) {
   const size_t total = (size_t)(Cin / 16) * 9 * 2 * N * 8;   // per term
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -487,7 +492,13 @@ __global__ void tc_prepare_weights_kernel(const float* __restrict__ w, uint16_t*
   const int tap = (i / (16 * (size_t)N)) % 9;
   const int c = i / (144 * (size_t)N);
   const int ci = c * 16 + j * 8 + e;
-  const float x = co < Cout ? w[((size_t)co * Cin + ci) * 9 + tap] * wscale : 0.f;
+  int tap_src = tap;
+  bool live = co < Cout;
+  if (qmode) {
+    live = live && (tap % 3 == 1);
+    tap_src = tap + 1;
+  }
+  const float x = live ? w[((size_t)co * src_cin + ci_off + ci) * 9 + tap_src] * wscale : 0.f;
   uint16_t t[3];
   split_terms<FP16>(x, t);
   for (int s = 0; s < S; ++s)
@@ -496,7 +507,53 @@ __global__ void tc_prepare_weights_kernel(const float* __restrict__ w, uint16_t*
 
 __global__ void tc_pad_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int Cout, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) out[i] = i < Cout ? b[i] : 0.f;
+  if (i < N) out[i] = (b && i < Cout) ? b[i] : 0.f;
+}
+
+// First convolution of the matching operation, factorised (it is linear in the concatenation):
+//   conv0(cat[L, shift_d R]) = A + shift_d(Bf) + edge terms,   A = conv(L; W_left) + bias,
+//   Bf = conv(R; W_right),  Q = the kx = 2 taps of W_right applied in place.
+// shift_d(Bf)[x] = Bf[x - d]; the zero-filled columns x < d see only R's column 0 through the
+// right-neighbour taps (x = d - 1 -> Q[0]); at the image's last column those taps read the zero
+// padding in the reference but R[W - d] in Bf -> subtract Q[W - d] (d >= 1).
+// A / Bf / Q: fp32 planes [b][C/4][H][W][4]; out: split AP planes [b*D + d][S][C/8][H][W][8].
+template <bool FP16, int S>
+__global__ void __launch_bounds__(256)
+tc_compose_first_kernel(const float* __restrict__ A, const float* __restrict__ Bf,
+                        const float* __restrict__ Q, uint16_t* __restrict__ out, int C, int H, int W,
+                        int D) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int b = n / D, d = n - b * D;
+  const size_t HW = (size_t)H * W;
+  const size_t base = ((size_t)b * (C / 4) + 2 * c8) * HW;
+  const float4* a4 = reinterpret_cast<const float4*>(A) + base;
+  const float4* b4 = reinterpret_cast<const float4*>(Bf) + base;
+  const float4* q4 = reinterpret_cast<const float4*>(Q) + base;
+  float4* o4 = reinterpret_cast<float4*>(out);
+  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % W);
+    const size_t row = pix - x;
+    float4 lo = __ldg(a4 + pix), hi = __ldg(a4 + HW + pix);
+    float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    auto add = [&](const float4* src, size_t at, float sign) {
+      const float4 l = __ldg(src + at), h = __ldg(src + HW + at);
+      v[0] = fmaf(sign, l.x, v[0]); v[1] = fmaf(sign, l.y, v[1]); v[2] = fmaf(sign, l.z, v[2]); v[3] = fmaf(sign, l.w, v[3]);
+      v[4] = fmaf(sign, h.x, v[4]); v[5] = fmaf(sign, h.y, v[5]); v[6] = fmaf(sign, h.z, v[6]); v[7] = fmaf(sign, h.w, v[7]);
+    };
+    if (x >= d) add(b4, pix - d, 1.f);
+    else if (x == d - 1) add(q4, row, 1.f);
+    if (x == W - 1 && d >= 1 && d <= W) add(q4, row + (W - d), -1.f);
+    uint16_t t[8][3];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      float4 pk;
+      pk.x = __uint_as_float(t[0][s] | ((uint32_t)t[1][s] << 16)); pk.y = __uint_as_float(t[2][s] | ((uint32_t)t[3][s] << 16));
+      pk.z = __uint_as_float(t[4][s] | ((uint32_t)t[5][s] << 16)); pk.w = __uint_as_float(t[6][s] | ((uint32_t)t[7][s] << 16));
+      stg_stream(o4 + ((size_t)(n * S + s) * (C / 8) + c8) * HW + pix, pk);
+    }
+  }
 }
 
 // (B, C, H, W) fp32 -> AP [B][S][C/8][H][W][8]
@@ -698,20 +755,40 @@ bool tc_available() { return encode_fn() != nullptr; }
 
 size_t tc_conv_max_maps(int n_div) { return (size_t)(n_div > 0 ? n_div : 0) + 1; }
 
-int tc_prepare_weights(const TcLayer& l, const float* w_oihw, const float* bias, cudaStream_t st) {
+int tc_prepare_weights(const TcLayer& l, const float* w_oihw, const float* bias, cudaStream_t st,
+                       int src_cin, int ci_off, int qmode) {
+  if (src_cin <= 0) src_cin = l.Cin;
   const size_t per_term = l.w_elems() / l.S;
   {
     PDS_KERNEL("tc_prepare_weights", st);
     const unsigned g = (unsigned)((per_term + 255) / 256);
     if (l.fp16)
-      tc_prepare_weights_kernel<true><<<g, 256, 0, st>>>(w_oihw, l.w, l.Cout, l.Cin, l.N, l.S, l.wscale);
+      tc_prepare_weights_kernel<true><<<g, 256, 0, st>>>(w_oihw, l.w, l.Cout, l.Cin, l.N, l.S, l.wscale, src_cin, ci_off, qmode);
     else
-      tc_prepare_weights_kernel<false><<<g, 256, 0, st>>>(w_oihw, l.w, l.Cout, l.Cin, l.N, l.S, l.wscale);
+      tc_prepare_weights_kernel<false><<<g, 256, 0, st>>>(w_oihw, l.w, l.Cout, l.Cin, l.N, l.S, l.wscale, src_cin, ci_off, qmode);
     PDS_LAUNCH_CHECK("tc_prepare_weights_kernel");
   }
   PDS_KERNEL("tc_pad_bias", st);
   tc_pad_bias_kernel<<<1, 256, 0, st>>>(bias, l.bias, l.Cout, l.N);
   PDS_LAUNCH_CHECK("tc_pad_bias_kernel");
+  return PDS_OK;
+}
+
+int tc_compose_first(const float* A, const float* Bf, const float* Q, uint16_t* out_ap, int B, int C, int H,
+                     int W, int D, int S, int fp16, cudaStream_t st) {
+  const size_t HW = (size_t)H * W;
+  if (B == 0 || HW == 0 || D == 0) return PDS_OK;
+  unsigned gx = (unsigned)((HW + 255) / 256);
+  if (gx > 128) gx = 128;
+  dim3 grid(gx, (unsigned)(C / 8), (unsigned)(B * D));
+  PDS_KERNEL("tc_compose_first", st);
+  PDS_KERNEL_WORK(0, (double)B * C * HW * (12.0 + 2.0 * S * D));
+#define PDS_COMPOSE_CASE(FF, SS) \
+  if ((fp16 != 0) == FF && S == SS) tc_compose_first_kernel<FF, SS><<<grid, 256, 0, st>>>(A, Bf, Q, out_ap, C, H, W, D);
+  PDS_COMPOSE_CASE(true, 1) PDS_COMPOSE_CASE(true, 2) PDS_COMPOSE_CASE(true, 3)
+  PDS_COMPOSE_CASE(false, 1) PDS_COMPOSE_CASE(false, 2) PDS_COMPOSE_CASE(false, 3)
+#undef PDS_COMPOSE_CASE
+  PDS_LAUNCH_CHECK("tc_compose_first_kernel");
   return PDS_OK;
 }
 

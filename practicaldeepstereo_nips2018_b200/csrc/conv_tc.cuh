@@ -35,7 +35,8 @@ struct TcLayer {
 enum TcEpilogue {
   TC_EPI_ACT = 0,   // bias + LeakyReLU + InstanceNorm sums -> fp32 planes
   TC_EPI_PLAIN = 1, // bias -> split AP planes (first convolution, no activation)
-  TC_EPI_SIG = 2    // bias -> (B, Cout, D, H, W) fp32 signatures (last convolution)
+  TC_EPI_SIG = 2,   // bias -> (B, Cout, D, H, W) fp32 signatures (last convolution)
+  TC_EPI_F32 = 3    // bias -> fp32 planes, no activation, no sums (factorised first convolution)
 };
 
 struct TcConvArgs {
@@ -66,7 +67,16 @@ struct TcConvArgs {
 size_t tc_conv_max_maps(int n_div);
 
 // weights (Cout, Cin, 3, 3) fp32 + bias (Cout) -> TcLayer buffers (pre-allocated)
-int tc_prepare_weights(const TcLayer& l, const float* w_oihw, const float* bias, cudaStream_t st);
+// src_cin / ci_off: the layer reads input channels [ci_off, ci_off + l.Cin) of a source tensor
+// with src_cin channels (0: the source has exactly l.Cin); bias may be null (zeros); qmode: see
+// tc_compose_first.
+int tc_prepare_weights(const TcLayer& l, const float* w_oihw, const float* bias, cudaStream_t st,
+                       int src_cin = 0, int ci_off = 0, int qmode = 0);
+
+// Factorised first convolution of the matching operation (conv_tc.cu, tc_compose_first_kernel):
+// x0[b*D + d] = A[b] + shift_d(Bf[b]) + edge terms from Q[b], written as split AP planes.
+int tc_compose_first(const float* A, const float* Bf, const float* Q, uint16_t* out_ap, int B, int C, int H,
+                     int W, int D, int S, int fp16, cudaStream_t st);
 
 // (B, C, H, W) fp32 -> AP [B][S][C/8][H][W][8]
 int tc_pack_nchw(const float* in, uint16_t* ap, int B, int C, int H, int W, int S, int fp16,

@@ -27,6 +27,10 @@ struct pds_matching_op {
   int fp16 = 0;                        // term type (1 = half, 0 = bfloat16)
   int group = 0;                       // disparity slices per pass (0 = all of them)
   std::vector<pds::TcLayer> tc;
+  // factorised first convolution (conv_tc.cu, tc_compose_first): left half + bias, right half,
+  // right half's kx = 2 taps in place
+  pds::TcLayer first[3];
+  int factor = 0;
   void* tc_blob = nullptr;
   // tensor maps of the shifted right descriptors, cached per (buffer, shape)
   CUtensorMap* maps_dev = nullptr;
@@ -89,6 +93,12 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
       l.wscale = op->fp16 ? 256.f : 1.f;
       bytes += align_up(l.w_elems() * 2, 256) + align_up(l.N * 4, 256) + 2 * align_up(F * 4, 256);
     }
+    op->factor = !(getenv("PDS_B200_MATCH_FACTOR") && atoi(getenv("PDS_B200_MATCH_FACTOR")) == 0);
+    for (int i = 0; i < 3; ++i) {
+      TcLayer& l = op->first[i];
+      l.Cin = C; l.Cout = F; l.N = 64; l.S = op->split; l.fp16 = op->fp16; l.wscale = op->fp16 ? 256.f : 1.f;
+      bytes += align_up(l.w_elems() * 2, 256) + align_up(l.N * 4, 256);
+    }
     cudaError_t e = cudaMalloc(&op->tc_blob, bytes);
     if (e != cudaSuccess) { delete op; return cuda_fail(e, "cudaMalloc(matching tensor-core weights)"); }
     char* cur = (char*)op->tc_blob;
@@ -108,6 +118,12 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
         l.gamma = g; l.beta = b;
         pi += 2;
       }
+    }
+    for (int i = 0; i < 3 && rc == PDS_OK; ++i) {
+      TcLayer& l = op->first[i];
+      l.w = (uint16_t*)cur; cur += align_up(l.w_elems() * 2, 256);
+      l.bias = (float*)cur; cur += align_up(l.N * 4, 256);
+      rc = tc_prepare_weights(l, params[0], i == 0 ? params[1] : nullptr, st, 2 * C, i == 0 ? 0 : C, i == 2);
     }
     if (rc != PDS_OK) { cudaFree(op->tc_blob); delete op; return rc; }
     *out = op;
@@ -159,7 +175,7 @@ namespace {
 // convolution that writes them and the pass that reads them.
 struct TcPlan {
   int G;
-  size_t lap, rap, xa, t, ya, stats, total;
+  size_t lap, rap, xa, t, ya, stats, first, total;
 };
 
 TcPlan tc_plan(const pds_matching_op* op, int B, int H, int W, int D) {
@@ -179,7 +195,8 @@ TcPlan tc_plan(const pds_matching_op* op, int B, int H, int W, int D) {
   p.ya = p.xa;
   p.t = align_up((size_t)G * op->F * hw * 4, 256);
   p.stats = align_up(n * op->F * 2 * sizeof(double) * 2 * (op->n_res > 0 ? op->n_res : 1), 256);
-  p.total = p.lap + p.rap + p.xa + p.t + p.ya + p.stats + 1024;
+  p.first = align_up((size_t)B * op->F * hw * 4, 256);     // A, Bf, Q of the factorised first convolution
+  p.total = p.lap + p.rap + p.xa + p.t + p.ya + p.stats + 3 * p.first + 1024;
   return p;
 }
 
@@ -204,6 +221,9 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
   float* t = (float*)ws.take<char>(pl.t);
   uint16_t* ya = (uint16_t*)ws.take<char>(pl.ya);
   double* stats = (double*)ws.take<char>(pl.stats);
+  float* fa = (float*)ws.take<char>(pl.first);
+  float* fb = (float*)ws.take<char>(pl.first);
+  float* fq = (float*)ws.take<char>(pl.first);
   if (ws.overflow) { set_error("pds_matching_op_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
   const size_t stat_elems = (size_t)N * op->F * 2;
   PDS_CUDA(cudaMemsetAsync(stats, 0, pl.stats, st));
@@ -223,11 +243,25 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
     TcConvArgs a = {};
     a.maps_dev = op->maps_dev; a.maps_host = op->maps_host;
     a.H = H; a.W = W; a.n_slices = g; a.n0 = n0; a.n_div = D;
-    // conv0: cat[left, shift_d(right)] gathered straight from the descriptors
-    a.layer = &op->tc[0]; a.epilogue = TC_EPI_PLAIN;
-    a.in = lap; a.in_slices = B; a.in_C = op->C; a.in2 = rap; a.in2_C = op->C;
-    a.out_ap = xa;
-    if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
+    if (op->factor && pl.G == N) {
+      // conv0 is linear in the concatenation: three convolutions over the B descriptors (instead
+      // of one over B * D slices) and one composition pass that writes every slice's planes
+      TcConvArgs f = a;
+      f.n_slices = B; f.n0 = 0; f.n_div = 1; f.epilogue = TC_EPI_F32; f.in_slices = B; f.in_C = op->C;
+      f.layer = &op->first[0]; f.in = lap; f.out_f32 = fa;
+      if ((rc = tc_conv3x3(f, st)) != PDS_OK) return rc;
+      f.layer = &op->first[1]; f.in = rap; f.out_f32 = fb;
+      if ((rc = tc_conv3x3(f, st)) != PDS_OK) return rc;
+      f.layer = &op->first[2]; f.out_f32 = fq;
+      if ((rc = tc_conv3x3(f, st)) != PDS_OK) return rc;
+      if ((rc = tc_compose_first(fa, fb, fq, xa, B, op->F, H, W, D, S, fp16, st)) != PDS_OK) return rc;
+    } else {
+      // conv0: cat[left, shift_d(right)] gathered straight from the descriptors
+      a.layer = &op->tc[0]; a.epilogue = TC_EPI_PLAIN;
+      a.in = lap; a.in_slices = B; a.in_C = op->C; a.in2 = rap; a.in2_C = op->C;
+      a.out_ap = xa;
+      if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
+    }
     a.in2 = nullptr; a.in2_C = 0; a.in_slices = g; a.in_C = op->F; a.out_ap = nullptr;
     for (int r = 0; r < op->n_res; ++r) {
       const TcLayer& c1 = op->tc[1 + 2 * r];
