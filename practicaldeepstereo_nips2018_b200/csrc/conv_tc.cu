@@ -732,9 +732,16 @@ int launch_tc(TcKernelParams& p, cudaStream_t st) {
   }
   const int total = p.tiles_x * p.tiles_y * p.n_slices;
   const int grid = total < num_sms() ? total : num_sms();
-  static const std::string name = "conv3x3_tc<S=" + std::to_string(S) + ",NT=" + std::to_string(NT) +
+  static const std::string base = "conv3x3_tc<S=" + std::to_string(S) + ",NT=" + std::to_string(NT) +
                                   ",N=" + std::to_string(N) + (WRES ? ",Wres>" : ",Wstream>");
-  PDS_KERNEL(name.c_str(), st);
+  // PDS_B200_PROFILE_DETAIL=1: one profiler class per epilogue variant and slice count
+  static const bool detail = getenv("PDS_B200_PROFILE_DETAIL") && atoi(getenv("PDS_B200_PROFILE_DETAIL"));
+  static std::string names[8][2];
+  std::string& nm = names[p.epilogue & 7][p.n_slices > 8 ? 1 : 0];
+  if (nm.empty())
+    nm = detail ? base + "[epi " + std::to_string(p.epilogue) + (p.n_slices > 8 ? ", all slices]" : ", descriptors]")
+                : base;
+  PDS_KERNEL(nm.c_str(), st);
   {
     // reference FLOPs of the layer (real Cout, all Cin); bytes: AP terms in (both inputs), output as written
     const double px = (double)p.H * p.W * p.n_slices;

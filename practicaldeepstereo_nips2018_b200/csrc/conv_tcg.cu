@@ -42,7 +42,7 @@ struct alignas(64) TcgParams {
   int GZ, GY, GX, OZ, OY, OX, Cout, mul, nd3;
   int tiles_x, tiles_y, tiles_z;
   int BX, planes_per_term, ntx_log2, zstride16;
-  int resident, stages, reuse;
+  int resident, stages, reuse, merged;
   uint32_t box_bytes, box_tx_bytes, term_bytes, a_bytes, stage_bytes, wres_bytes, w_total_bytes;
   uint32_t off_boxes, off_entries, off_tiles, table_bytes;
   float inv_wscale;
@@ -241,8 +241,9 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
       if (stat_n >= 0 && p.stats && lane < CH) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const int ch = c * CH + lane;
-          if (ch < p.Cout && (s1[c] != 0.0 || s2[c] != 0.0)) {
+          const int col = c * CH + lane;
+          const int ch = p.merged ? col % p.Cout : col;       // merged: 8 columns (classes) per channel
+          if (col < (p.merged ? 8 * p.Cout : p.Cout) && (s1[c] != 0.0 || s2[c] != 0.0)) {
             double* dst = p.stats + ((size_t)stat_n * p.Cout + ch) * 2;
             atomicAdd(dst, s1[c]); atomicAdd(dst + 1, s2[c]);
           }
@@ -290,10 +291,24 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
             v[0][j] = valid ? t : 0.f;
           }
           if (valid) {
+            if (p.merged) {
+              // column = class * Cout + channel: scatter the 8 parity classes of this input voxel
 #pragma unroll
-            for (int j = 0; j < CH; j += 4)
-              if (c * CH + j < p.Cout)
-                *reinterpret_cast<float4*>(o + c * CH + j) = make_float4(v[0][j], v[0][j + 1], v[0][j + 2], v[0][j + 3]);
+              for (int j = 0; j < CH; j += 4) {
+                const int col = c * CH + j;
+                if (col < 8 * p.Cout) {
+                  const int mc = col / p.Cout, co = col - mc * p.Cout;
+                  float* om = p.out + ((((size_t)it.n * p.OZ + 2 * gz + ((mc >> 2) & 1)) * p.OY + 2 * gy + ((mc >> 1) & 1)) * p.OX +
+                                       2 * gx + (mc & 1)) * p.Cout + co;
+                  *reinterpret_cast<float4*>(om) = make_float4(v[0][j], v[0][j + 1], v[0][j + 2], v[0][j + 3]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4)
+                if (c * CH + j < p.Cout)
+                  *reinterpret_cast<float4*>(o + c * CH + j) = make_float4(v[0][j], v[0][j + 1], v[0][j + 2], v[0][j + 3]);
+            }
           }
           if (p.stats) {
             if (NCH == 1) {
@@ -332,7 +347,7 @@ template <bool FP16>
 __global__ void tcg_prepare_weights_kernel(const float* __restrict__ w, const TcgWeightSrc* __restrict__ src,
                                            uint16_t* __restrict__ out, int n_entries, int Cin, int Cout,
                                            int N, int S, int KZ, int KY, int KX, int transposed,
-                                           float wscale) {   // Cin: channels of the SOURCE tensor (<= the layer's)
+                                           float wscale, int merged) {   // Cin: channels of the SOURCE tensor (<= the layer's)
   const size_t per_entry = (size_t)2 * N * 8;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_entry * n_entries) return;
@@ -341,7 +356,25 @@ __global__ void tcg_prepare_weights_kernel(const float* __restrict__ w, const Tc
   const int c = r % 8, co = (r / 8) % N, h = r / (8 * N);
   const TcgWeightSrc ws = src[e];
   float x = 0.f;
-  if (ws.group[h] >= 0 && co < Cout && 8 * ws.group[h] + c < Cin) {
+  if (merged) {
+    // column = class * Cout + channel; tap offset o = k - 1 per dimension; class bit c uses input
+    // offsets c (kernel index 1 - c) and c - 1 (kernel index 3 - c) -- ConvTranspose k4 s2 p1
+    const int mc = co / Cout, ch = co - mc * Cout;
+    const int cb[3] = {(mc >> 2) & 1, (mc >> 1) & 1, mc & 1};
+    const int off[3] = {ws.kz[h] - 1, ws.ky[h] - 1, ws.kx[h] - 1};
+    int k[3];
+    bool live = ws.group[h] >= 0 && mc < 8 && 8 * ws.group[h] + c < Cin;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int t = cb[d] - off[d];
+      live = live && (t == 0 || t == 1);
+      k[d] = 1 - cb[d] + 2 * t;
+    }
+    if (live) {
+      const int ci = 8 * ws.group[h] + c;
+      x = w[((((size_t)ci * Cout + ch) * 4 + k[0]) * 4 + k[1]) * 4 + k[2]] * wscale;
+    }
+  } else if (ws.group[h] >= 0 && co < Cout && 8 * ws.group[h] + c < Cin) {
     const int ci = 8 * ws.group[h] + c;
     const size_t a = transposed ? ((size_t)ci * Cout + co) : ((size_t)co * Cin + ci);
     x = w[((a * KZ + ws.kz[h]) * KY + ws.ky[h]) * KX + ws.kx[h]] * wscale;
@@ -352,9 +385,10 @@ __global__ void tcg_prepare_weights_kernel(const float* __restrict__ w, const Tc
     out[(size_t)e * (2 * S * N * 8) + ((size_t)(h * S + s) * N + co) * 8 + c] = t[s];
 }
 
-__global__ void tcg_pad_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int Cout, int N) {
+__global__ void tcg_pad_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int Cout, int N,
+                                    int merged) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) out[i] = i < Cout ? b[i] : 0.f;
+  if (i < N) out[i] = merged ? (i < 8 * Cout ? b[i % Cout] : 0.f) : (i < Cout ? b[i] : 0.f);
 }
 
 // ---- normalisation pass: fp32 channels-last -> split AP planes ------------------------------------
@@ -503,7 +537,7 @@ const char* tcg_name(int S, int N, const TcgPlan& pl) {
   static std::set<std::string> names;
   std::string n = "conv_tcg<S=" + std::to_string(S) + ",N=" + std::to_string(N) + ">";
   if (detail) {
-    static const char* kinds[] = {"c3s1", "c3s2", "t4s2", "c5s2"};
+    static const char* kinds[] = {"c3s1", "c3s2", "t4s2", "c5s2", "t4s2m"};
     n += std::string("[") + kinds[pl.shape.kind] + " " + std::to_string(pl.shape.Cin) + "->" +
          std::to_string(pl.shape.Cout) + " " + std::to_string(pl.shape.Z) + "x" + std::to_string(pl.shape.Y) +
          "x" + std::to_string(pl.shape.X) + "]";
@@ -565,15 +599,15 @@ int tcg_layer_init(TcgLayer& l, char* blob, const float* w_src, const float* bia
     if (l.fp16)
       tcg_prepare_weights_kernel<true><<<g, 256, 0, st>>>(w_src, src, l.w, (int)pl.entries.size(), cin_src,
                                                           pl.shape.Cout, pl.N, pl.shape.S, KZ, k, k,
-                                                          l.transposed, l.wscale);
+                                                          l.transposed, l.wscale, pl.merged);
     else
       tcg_prepare_weights_kernel<false><<<g, 256, 0, st>>>(w_src, src, l.w, (int)pl.entries.size(), cin_src,
                                                            pl.shape.Cout, pl.N, pl.shape.S, KZ, k, k,
-                                                           l.transposed, l.wscale);
+                                                           l.transposed, l.wscale, pl.merged);
     PDS_LAUNCH_CHECK("tcg_prepare_weights_kernel");
   }
   PDS_KERNEL("tcg_pad_bias", st);
-  tcg_pad_bias_kernel<<<1, 128, 0, st>>>(bias_src, l.bias, pl.shape.Cout, pl.N);
+  tcg_pad_bias_kernel<<<1, 128, 0, st>>>(bias_src, l.bias, pl.shape.Cout, pl.N, pl.merged);
   PDS_LAUNCH_CHECK("tcg_pad_bias_kernel");
   return PDS_OK;
 }
@@ -608,7 +642,7 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
   p.n_samples = n_samples; p.lrelu = lrelu; p.fp16 = l.fp16;
   p.nacc = pl.nacc; p.ntx = pl.ntx; p.ntz = pl.ntz; p.ncls = pl.ncls; p.upi = pl.units_per_item;
   p.GZ = pl.GZ; p.GY = pl.GY; p.GX = pl.GX; p.OZ = pl.OZ; p.OY = pl.OY; p.OX = pl.OX;
-  p.Cout = pl.shape.Cout; p.mul = pl.ncls > 1 ? 2 : 1; p.nd3 = pl.shape.nd == 3;
+  p.Cout = pl.shape.Cout; p.mul = (pl.ncls > 1 || pl.merged) ? 2 : 1; p.nd3 = pl.shape.nd == 3;
   p.tiles_x = (pl.GX + 8 * pl.ntx - 1) / (8 * pl.ntx);
   p.tiles_y = (pl.GY + 15) / 16;
   p.tiles_z = (pl.GZ + pl.ntz - 1) / pl.ntz;
@@ -619,7 +653,7 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
     set_error("conv_tcg: unsupported tile arrangement %d x %d", pl.ntx, pl.ntz);
     return PDS_ERR_UNSUPPORTED;
   }
-  p.resident = pl.resident; p.stages = pl.stages;
+  p.resident = pl.resident; p.stages = pl.stages; p.merged = pl.merged;
   p.reuse = pl.ncls > 1 && pl.units_per_item == 1 && pl.resident;
   p.box_tx_bytes = (uint32_t)pl.PB * pl.BZ * pl.BY * pl.BX * 16;   // what TMA delivers (box_bytes is its 128-aligned slot)
   p.box_bytes = pl.box_bytes; p.term_bytes = (uint32_t)pl.max_boxes * pl.box_bytes;
@@ -636,9 +670,9 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
   }
   const int total = p.tiles_x * p.tiles_y * p.tiles_z * n_samples * (p.reuse ? 1 : pl.ncls);
   const int grid = total < num_sms() ? total : num_sms();
-  const int k = pl.shape.kind == TCG_TCONV4_S2 ? 2 : (pl.shape.kind == TCG_CONV5_S2 ? 5 : 3);
+  const int k = (pl.shape.kind == TCG_TCONV4_S2 || pl.merged) ? 2 : (pl.shape.kind == TCG_CONV5_S2 ? 5 : 3);
   const double taps = (double)k * k * (pl.shape.nd == 3 ? k : 1);
-  const double rows = (double)n_samples * pl.GZ * pl.GY * pl.GX * pl.ncls;
+  const double rows = (double)n_samples * pl.GZ * pl.GY * pl.GX * (pl.merged ? 8 : pl.ncls);
   const double flops = 2.0 * taps * pl.shape.Cin * pl.shape.Cout * rows;
   const double bytes = (double)pl.in_ap_bytes(n_samples) + 4.0 * pl.out_elems(n_samples);
 #define PDS_TCG_CASE(SS, NN) \
@@ -700,7 +734,7 @@ extern "C" int pds_tcg_conv_debug(int kind, int nd, int Cin, int Cout, int Z, in
   if (rc != PDS_OK) return rc;
   l.transposed = kind == TCG_TCONV4_S2; l.fp16 = fp16; l.wscale = fp16 ? 256.f : 1.f;
   const TcgPlan& pl = l.plan;
-  const size_t vin = (size_t)Z * Y * X, vout = (size_t)pl.OZ * pl.OY * pl.OX;
+  const size_t vin = (size_t)Z * Y * X, vout = (size_t)pl.OZ * pl.OY * pl.OX;   // (merged: OZ = 2Z ...)
   char *blob = nullptr, *scratch = nullptr;
   const size_t b_xcl = align_up(n * vin * Cin * 4, 256), b_ap = align_up(pl.in_ap_bytes(n), 256),
                b_ycl = align_up(n * vout * Cout * 4, 256);

@@ -33,7 +33,12 @@
 
 namespace pds {
 
-enum TcgKind { TCG_CONV3_S1 = 0, TCG_CONV3_S2 = 1, TCG_TCONV4_S2 = 2, TCG_CONV5_S2 = 3 };
+// TCG_TCONV4_S2M: the transposed layer with its 8 output parity classes MERGED along N: one
+// 3x3x3-tap convolution over the input grid with 8 * Cout output columns (column = class * Cout +
+// channel; a tap a class does not use has zero weights).  An MMA with N <= 64 is operand-fetch
+// bound, so the wider N is free and the 27 merged taps replace 8 x 8 class taps: chosen by the
+// callers for Cout <= 8.
+enum TcgKind { TCG_CONV3_S1 = 0, TCG_CONV3_S2 = 1, TCG_TCONV4_S2 = 2, TCG_CONV5_S2 = 3, TCG_TCONV4_S2M = 4 };
 
 struct TcgShape {
   int kind = TCG_CONV3_S1;
@@ -66,7 +71,8 @@ struct TcgWeightSrc { int kz[2], ky[2], kx[2], group[2]; };
 
 struct TcgPlan {
   TcgShape shape;
-  int N = 16;                 // accumulator columns per weight term (Cout padded to 16/32/64/128)
+  int N = 16;                 // accumulator columns per weight term (Cout, or 8 * Cout when merged, padded to 16/32/64/128)
+  int merged = 0;             // TCG_TCONV4_S2M
   int nacc = 1, ntx = 1, ntz = 1;   // MMA tiles per CTA tile
   int ncls = 1;               // output parity classes (8 for the 3-D transposed layer)
   int nph = 1;                // phase sub-volumes of the input (1, 4 or 8)

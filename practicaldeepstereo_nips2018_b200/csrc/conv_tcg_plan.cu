@@ -17,7 +17,7 @@ struct DimTap { int k, phase, off; };
 //   TCONV4_S2 out = 2z + cls; in = z + cls - t, kernel index 1 - cls + 2t  (t = 0, 1)
 std::vector<DimTap> dim_taps(int kind, int cls) {
   switch (kind) {
-    case TCG_CONV3_S1: return {{0, 0, -1}, {1, 0, 0}, {2, 0, 1}};
+    case TCG_CONV3_S1: case TCG_TCONV4_S2M: return {{0, 0, -1}, {1, 0, 0}, {2, 0, 1}};   // merged: k = offset + 1
     case TCG_CONV3_S2: return {{0, 1, -1}, {1, 0, 0}, {2, 1, 0}};
     case TCG_CONV5_S2: return {{0, 0, -1}, {1, 1, -1}, {2, 0, 0}, {3, 1, 0}, {4, 0, 1}};
     default: return {{1 - cls, 0, cls}, {3 - cls, 0, cls - 1}};
@@ -36,6 +36,7 @@ int tcg_plan(const TcgShape& sh, TcgPlan* out) {
   TcgPlan p;
   p.shape = sh;
   const bool strided = sh.kind == TCG_CONV3_S2 || sh.kind == TCG_CONV5_S2;
+  const bool merged = sh.kind == TCG_TCONV4_S2M;
   const bool transposed = sh.kind == TCG_TCONV4_S2;
   if (sh.nd != 2 && sh.nd != 3) { set_error("tcg_plan: nd must be 2 or 3"); return PDS_ERR_UNSUPPORTED; }
   if (sh.nd == 2 && sh.Z != 1) { set_error("tcg_plan: 2-D layers need Z == 1"); return PDS_ERR_UNSUPPORTED; }
@@ -48,18 +49,23 @@ int tcg_plan(const TcgShape& sh, TcgPlan* out) {
     set_error("tcg_plan: stride-2 layers need even extents");
     return PDS_ERR_UNSUPPORTED;
   }
+  if (merged && (sh.nd != 3 || 8 * sh.Cout > 128)) {
+    set_error("tcg_plan: merged transposed layers are 3-D with Cout <= 16");
+    return PDS_ERR_UNSUPPORTED;
+  }
   if (transposed && sh.nd != 3) { set_error("tcg_plan: transposed layers are 3-D only"); return PDS_ERR_UNSUPPORTED; }
   const int nd = sh.nd;
   const int div = strided ? 2 : 1;
   p.IZ = nd == 3 ? sh.Z / div : 1; p.IY = sh.Y / div; p.IX = sh.X / div;
   p.GZ = p.IZ; p.GY = p.IY; p.GX = p.IX;
-  const int mul = transposed ? 2 : 1;
+  const int mul = (transposed || merged) ? 2 : 1;
   p.OZ = p.GZ * (nd == 3 ? mul : 1); p.OY = p.GY * mul; p.OX = p.GX * mul;
   p.ncls = transposed ? 8 : 1;
   p.nph = strided ? (nd == 3 ? 8 : 4) : 1;
   p.P = sh.Cin / 8;
   p.PB = sh.Cin >= 16 ? 2 : 1;
-  p.N = pad_n(sh.Cout);
+  p.N = pad_n(merged ? 8 * sh.Cout : sh.Cout);
+  p.merged = merged ? 1 : 0;
   const int S = sh.S;
   const int nchunks = sh.Cin >= 16 ? sh.Cin / 16 : 1;
   const unsigned ent16 = 2u * S * p.N;          // 16-byte units of one entry's B operand
@@ -241,7 +247,7 @@ extern "C" int pds_tcg_plan_describe(int kind, int nd, int Cin, int Cout, int Z,
   const int hdr[32] = {p.N, p.nacc, p.ntx, p.ntz, p.ncls, p.nph, p.P, p.GZ, p.GY, p.GX, p.OZ, p.OY, p.OX,
                        p.IZ, p.IY, p.IX, p.BX, p.BY, p.BZ, p.PB, p.units_per_item, p.resident, p.stages,
                        (int)p.box_bytes, (int)p.stage_bytes, (int)p.wres_bytes, (int)p.w_total_bytes,
-                       nu, nb, ne, p.max_boxes, 0};
+                       nu, nb, ne, p.max_boxes, p.merged};
   int* w = buf;
   for (int i = 0; i < 32; ++i) *w++ = hdr[i];
   for (const TcgUnit& u : p.units) {

@@ -18,7 +18,7 @@ from gpu_util import cuda, load_module, max_abs, tdict
 
 pytestmark = pytest.mark.gpu
 
-CONV3_S1, CONV3_S2, TCONV4_S2, CONV5_S2 = 0, 1, 2, 3
+CONV3_S1, CONV3_S2, TCONV4_S2, CONV5_S2, TCONV4_S2M = 0, 1, 2, 3, 4
 
 
 def run_layer(kind, nd, x, w, b, S=2, fp16=1, lrelu=0):
@@ -27,11 +27,11 @@ def run_layer(kind, nd, x, w, b, S=2, fp16=1, lrelu=0):
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_int] * 10 + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p]
     n, cin = x.shape[:2]
-    cout = w.shape[1] if kind == TCONV4_S2 else w.shape[0]
+    cout = w.shape[1] if kind in (TCONV4_S2, TCONV4_S2M) else w.shape[0]
     Z, Y, X = (x.shape[2:] if nd == 3 else (1,) + tuple(x.shape[2:]))
     if kind in (CONV3_S2, CONV5_S2):
         oshape = tuple(s // 2 for s in x.shape[2:])
-    elif kind == TCONV4_S2:
+    elif kind in (TCONV4_S2, TCONV4_S2M):
         oshape = tuple(s * 2 for s in x.shape[2:])
     else:
         oshape = tuple(x.shape[2:])
@@ -72,6 +72,9 @@ CASES = [
     (TCONV4_S2, 3, 16, 8, 2, (8, 24, 40)),
     (TCONV4_S2, 3, 8, 4, 1, (16, 48, 80)),
     (TCONV4_S2, 3, 8, 4, 2, (5, 17, 17)),
+    (TCONV4_S2M, 3, 8, 4, 2, (5, 17, 17)),
+    (TCONV4_S2M, 3, 8, 4, 1, (16, 48, 80)),
+    (TCONV4_S2M, 3, 16, 8, 2, (8, 24, 40)),
     (CONV5_S2, 2, 64, 64, 2, (72, 120)),
     (CONV3_S1, 2, 64, 8, 2, (36, 130)),
     (CONV3_S1, 2, 64, 64, 1, (40, 50)),
@@ -82,10 +85,10 @@ CASES = [
 def test_layer_vs_aten(kind, nd, cin, cout, n, spatial):
     torch.backends.cudnn.allow_tf32 = False
     g = torch.Generator(device='cpu').manual_seed(kind * 977 + cin * 31 + cout + sum(spatial))
-    k = {CONV3_S1: 3, CONV3_S2: 3, TCONV4_S2: 4, CONV5_S2: 5}[kind]
+    k = {CONV3_S1: 3, CONV3_S2: 3, TCONV4_S2: 4, CONV5_S2: 5, TCONV4_S2M: 4}[kind]
     ks = (k,) * nd
     x = torch.randn((n, cin) + spatial, generator=g).cuda()
-    wshape = ((cin, cout) if kind == TCONV4_S2 else (cout, cin)) + ks
+    wshape = ((cin, cout) if kind in (TCONV4_S2, TCONV4_S2M) else (cout, cin)) + ks
     w = (torch.randn(wshape, generator=g) / np.sqrt(cin * k ** nd)).cuda()
     b = torch.randn(cout, generator=g).cuda()
     ref = aten(kind, nd, x.double(), w.double(), b.double())

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from practicaldeepstereo_nips2018_b200 import _capi
 
-CONV3_S1, CONV3_S2, TCONV4_S2, CONV5_S2 = 0, 1, 2, 3
+CONV3_S1, CONV3_S2, TCONV4_S2, CONV5_S2, TCONV4_S2M = 0, 1, 2, 3, 4
 
 
 def describe(kind, nd, cin, cout, Z, Y, X, S=2):
@@ -41,7 +41,8 @@ def emulate(p, kind, nd, x, w, S=2):
     """x (n, Cin, Z, Y, X) float64, w in PyTorch layout -> (n, Cout, OZ, OY, OX) as the kernel
     computes it from the plan (single exact term; the split only changes rounding)."""
     n, cin = x.shape[:2]
-    cout = w.shape[1] if kind == TCONV4_S2 else w.shape[0]
+    cout = w.shape[1] if kind in (TCONV4_S2, TCONV4_S2M) else w.shape[0]
+    merged = kind == TCONV4_S2M
     N, P, nph = p['N'], p['P'], p['nph']
     IZ, IY, IX, BX, BY, BZ, PB = (p[k] for k in ('IZ', 'IY', 'IX', 'BX', 'BY', 'BZ', 'PB'))
     box16 = p['box_bytes'] // 16
@@ -84,21 +85,38 @@ def emulate(p, kind, nd, x, w, S=2):
                             kz, ky, kx, g = p['wsrc'][e, h]
                             if g < 0:
                                 continue
-                            if kind == TCONV4_S2:
+                            if merged:
+                                # column = class * cout + channel; tap offset o = k - 1; class bit c uses
+                                # offsets c (kernel index 1 - c) and c - 1 (kernel index 3 - c)
+                                wm = np.zeros((8 * cout, 8))
+                                for mc in range(8):
+                                    ks = []
+                                    for cb, off in zip(((mc >> 2) & 1, (mc >> 1) & 1, mc & 1),
+                                                       (kz - 1, ky - 1, kx - 1)):
+                                        t = cb - off
+                                        ks.append(1 - cb + 2 * t if t in (0, 1) else None)
+                                    if None not in ks:
+                                        wm[mc * cout:(mc + 1) * cout] = w[8 * g:8 * g + 8, :, ks[0], ks[1], ks[2]].T
+                            elif kind == TCONV4_S2:
                                 wm = w[8 * g:8 * g + 8, :, kz, ky, kx].T          # (cout, 8)
                             else:
                                 wm = w[:, 8 * g:8 * g + 8, kz, ky, kx]
                             for i in range(p['nacc']):
                                 A = image[a16 + int(p['tile_off'][i]) + h * lbo + row_off]   # (128, 8)
-                                D[i, :, :cout] += A @ wm.T
+                                D[i, :, :wm.shape[0]] += A @ wm.T
                 cz, cy, cx = (cls >> 2) & 1, (cls >> 1) & 1, cls & 1
-                m = 2 if kind == TCONV4_S2 else 1
+                m = 2 if kind in (TCONV4_S2, TCONV4_S2M) else 1
                 for i in range(p['nacc']):
                     ix, iz = i % ntx, i // ntx
                     for r in range(128):
                         gz, gy, gx = z0 + iz, y0 + (r >> 3), x0 + 8 * ix + (r & 7)
                         if gz < p['GZ'] and gy < p['GY'] and gx < p['GX']:
-                            out[b, :, m * gz + cz if nd == 3 else 0, m * gy + cy, m * gx + cx] = D[i, r, :cout]
+                            if merged:
+                                for mc in range(8):
+                                    out[b, :, 2 * gz + ((mc >> 2) & 1), 2 * gy + ((mc >> 1) & 1),
+                                        2 * gx + (mc & 1)] = D[i, r, mc * cout:(mc + 1) * cout]
+                            else:
+                                out[b, :, m * gz + cz if nd == 3 else 0, m * gy + cy, m * gx + cx] = D[i, r, :cout]
     return out
 
 
@@ -112,7 +130,7 @@ def reference(kind, nd, x, w):
         y = (F.conv3d if nd == 3 else F.conv2d)(xt, wt, padding=1, stride=2)
     elif kind == CONV5_S2:
         y = F.conv2d(xt, wt, padding=2, stride=2)
-    else:
+    else:      # TCONV4_S2 and its merged-class variant
         y = F.conv_transpose3d(xt, wt, padding=1, stride=2)
     y = y.numpy()
     return y[:, :, None] if nd == 2 else y
@@ -132,6 +150,8 @@ CASES = [
     (TCONV4_S2, 3, 32, 16, 3, 6, 9),
     (TCONV4_S2, 3, 16, 8, 3, 18, 10),
     (TCONV4_S2, 3, 8, 4, 5, 17, 17),
+    (TCONV4_S2M, 3, 8, 4, 5, 17, 17),     # parity classes merged along N
+    (TCONV4_S2M, 3, 16, 8, 3, 18, 10),
     (CONV5_S2, 2, 64, 64, 1, 36, 20),
     (CONV3_S1, 2, 64, 8, 1, 20, 70),
     (CONV3_S1, 2, 64, 64, 1, 17, 12),
@@ -142,9 +162,9 @@ CASES = [
 def test_plan_emulation_matches_aten(kind, nd, cin, cout, Z, Y, X):
     rng = np.random.RandomState(kind * 1000 + cin + cout + Z + Y + X)
     x = rng.randn(2 if cin <= 16 else 1, cin, Z, Y, X)
-    k = {CONV3_S1: 3, CONV3_S2: 3, TCONV4_S2: 4, CONV5_S2: 5}[kind]
+    k = {CONV3_S1: 3, CONV3_S2: 3, TCONV4_S2: 4, CONV5_S2: 5, TCONV4_S2M: 4}[kind]
     kz = k if nd == 3 else 1
-    w = rng.randn(*((cin, cout) if kind == TCONV4_S2 else (cout, cin)), kz, k, k) / np.sqrt(cin * k * k * kz)
+    w = rng.randn(*((cin, cout) if kind in (TCONV4_S2, TCONV4_S2M) else (cout, cin)), kz, k, k) / np.sqrt(cin * k * k * kz)
     p = describe(kind, nd, cin, cout, Z, Y, X)
     # structural invariants the kernel relies on
     assert p['nacc'] * 2 * p['N'] <= 512 and p['stages'] >= 2
@@ -166,10 +186,10 @@ def test_plan_full_size_layers_fit():
             c, z, y, x = 2 * c, z // 2, y // 2, x // 2
             assert describe(CONV3_S1, 3, c, c, z, y, x)['stages'] >= 2
         for _ in range(4):
-            assert describe(TCONV4_S2, 3, c, c // 2, z, y, x)['stages'] >= 2
+            assert describe(TCONV4_S2M if c // 2 <= 8 else TCONV4_S2, 3, c, c // 2, z, y, x)['stages'] >= 2
             c, z, y, x = c // 2, z * 2, y * 2, x * 2
             assert describe(CONV3_S1, 3, c, c, z, y, x)['stages'] >= 2
-        assert describe(TCONV4_S2, 3, 8, 4, z, y, x)['stages'] >= 2
+        assert describe(TCONV4_S2M, 3, 8, 4, z, y, x)['stages'] >= 2
     assert describe(CONV5_S2, 2, 64, 64, 1, 288, 480)['stages'] >= 2
     assert describe(CONV3_S1, 2, 64, 8, 1, 144, 240)['stages'] >= 2
 

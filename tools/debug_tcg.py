@@ -15,10 +15,10 @@ import test_gpu_tcg as T  # noqa: E402
 kind, nd, cin, cout, n, spatial = T.CASES[int(sys.argv[1])]
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 fp16 = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-k = {0: 3, 1: 3, 2: 4, 3: 5}[kind]
+k = {0: 3, 1: 3, 2: 4, 3: 5, 4: 4}[kind]
 g = torch.Generator(device='cpu').manual_seed(1)
 x = torch.randn((n, cin) + spatial, generator=g).cuda()
-wshape = ((cin, cout) if kind == 2 else (cout, cin)) + (k,) * nd
+wshape = ((cin, cout) if kind in (2, 4) else (cout, cin)) + (k,) * nd
 w = (torch.randn(wshape, generator=g) / np.sqrt(cin * k ** nd)).cuda()
 b = torch.randn(cout, generator=g).cuda()
 t0 = time.time()

@@ -20,6 +20,8 @@ METRICS = [
     ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ_%', 1),
     ('launch__registers_per_thread', 'regs', 1),
     ('launch__grid_size', 'grid', 1),
+    ('smsp__cycles_active.avg', 'act_cyc', 1),
+    ('sm__cycles_elapsed.max', 'ela_cyc', 1),
 ]
 UNIT_SCALE = {'ns': 1.0, 'us': 1e3, 'ms': 1e6, 's': 1e9, 'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6,
               'Gbyte': 1e9}
