@@ -56,7 +56,7 @@ class ClockSampler(threading.Thread):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self._stop_evt.is_set():
@@ -265,7 +265,10 @@ def main():
         sampler = ClockSampler(local) if rank == 0 else None
         if sampler:
             sampler.start()
-            time.sleep(0.3)
+            t_wait = time.time()
+            while not sampler.samples and time.time() - t_wait < 3.0:   # nvidia-smi takes a moment to start
+                net(*pairs[0])
+                time.sleep(0.02)
 
         # ---- value: inputs resident in HBM ------------------------------------------
         barrier()
@@ -314,10 +317,16 @@ def main():
         kernels = kernel_rooflines(report, args.steps, peaks)
         dominant = next((k for k in kernels if 'achieved' in k), None)
         roofline = None
+        traffic = {}
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))
         if dominant:
             roofline = {'bound': dominant['bound'], 'achieved': dominant['achieved'],
                         'peak': dominant['peak'], 'unit': dominant['unit'],
-                        'frac': dominant['frac'], 'traffic': None, 'kernel': dominant['kernel'],
+                        'frac': dominant['frac'], 'traffic': traffic.get(dominant['kernel']),
+                        'traffic_source': traffic.get('_source') if dominant['kernel'] in traffic else None,
+                        'kernel': dominant['kernel'],
                         'peak_source': peaks['source'],
                         'timing': 'CUDA events around every launch, separate instrumented pass of '
                                   f'{args.steps} steps'}
@@ -331,7 +340,8 @@ def main():
             'config': {'workload': desc, 'batch_per_gpu': args.batch, 'maximum_disparity': md,
                        'precision': args.precision, 'parallelism': f'replicas x{world}',
                        'l2': 'per-step working set > 1 GB (>> 126 MB L2); 4 rotating input pairs',
-                       'embedding': 'ATen/cuDNN fp32 (TF32 off)'},
+                       'embedding': ('own tcgen05 kernels' if args.precision != 'fp32'
+                                     else 'ATen/cuDNN fp32 (TF32 off)')},
             'e2e': {'value': total_pairs / (e2e_ms / 1e3), 'unit': 'pairs/s',
                     'h2d_bytes_per_step': 2 * args.batch * 3 * H * W * 4,
                     'd2h_bytes_per_step': args.batch * H * W * 4},
