@@ -249,6 +249,12 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pdl_trigger();
+    if (WRES) {   // constant data: may be fetched while the previous kernel is still running
+      mbar_expect_tx(wfull_bar, (uint32_t)p.nchunks * W_CHUNK_BYTES);
+      for (int c = 0; c < p.nchunks; ++c)
+        bulk_load(wres_base + c * W_CHUNK_BYTES, p.w + (size_t)c * (W_CHUNK_BYTES / 2), W_CHUNK_BYTES, wfull_bar);
+    }
   }
   for (int i = threadIdx.x; i < N; i += kThreads) sbias[i] = p.bias[i];
   if (warp == 1) {
@@ -260,6 +266,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything below reads / writes tensors of the stream's earlier kernels
 
   // every CTA walks ONE contiguous range of tiles: consecutive tiles share halo rows in L2 and
   // stay within one or two slices, so the InstanceNorm sums are flushed once per slice change
@@ -272,11 +279,6 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      if (WRES) {
-        mbar_expect_tx(wfull_bar, (uint32_t)p.nchunks * W_CHUNK_BYTES);
-        for (int c = 0; c < p.nchunks; ++c)
-          bulk_load(wres_base + c * W_CHUNK_BYTES, p.w + (size_t)c * (W_CHUNK_BYTES / 2), W_CHUNK_BYTES, wfull_bar);
-      }
       uint32_t stage = 0, phase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int nl = tile / tiles_per_slice, r = tile - nl * tiles_per_slice;
@@ -526,6 +528,8 @@ tc_compose_first_kernel(const float* __restrict__ A, const float* __restrict__ B
   const int b = n / D, d = n - b * D;
   const size_t HW = (size_t)H * W;
   const size_t base = ((size_t)b * (C / 4) + 2 * c8) * HW;
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   const float4* a4 = reinterpret_cast<const float4*>(A) + base;
   const float4* b4 = reinterpret_cast<const float4*>(Bf) + base;
   const float4* q4 = reinterpret_cast<const float4*>(Q) + base;
@@ -599,6 +603,8 @@ tc_norm_split_kernel(const float* __restrict__ y, const double* __restrict__ sta
   constexpr int U = 2;   // pixels per thread per iteration
   const int c8 = blockIdx.y, n = blockIdx.z;
   __shared__ float sc[8], sh[8];
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   if (threadIdx.x < 8) {
     const int c = c8 * 8 + threadIdx.x;
     const double s = stats[((size_t)n * C + c) * 2], q = stats[((size_t)n * C + c) * 2 + 1];
@@ -748,8 +754,7 @@ int launch_tc(TcKernelParams& p, cudaStream_t st) {
     const double out_b = p.epilogue == TC_EPI_SIG ? 4.0 * p.Cout : (p.epilogue == TC_EPI_PLAIN ? 2.0 * S * N : 4.0 * N);
     PDS_KERNEL_WORK(2.0 * 9 * 16 * p.nchunks * p.Cout * px, px * out_b + (p.in_global ? 0.0 : px * 2.0 * S * 16 * p.nchunks));
   }
-  conv3x3_tc_kernel<S, NT, N, WRES><<<grid, kThreads, smem, st>>>(p);
-  PDS_LAUNCH_CHECK("conv3x3_tc_kernel");
+  PDS_CUDA(launch_pdl(conv3x3_tc_kernel<S, NT, N, WRES>, dim3(grid), dim3(kThreads), smem, st, p));
   return PDS_OK;
 }
 
@@ -791,7 +796,7 @@ int tc_compose_first(const float* A, const float* Bf, const float* Q, uint16_t* 
   PDS_KERNEL("tc_compose_first", st);
   PDS_KERNEL_WORK(0, (double)B * C * HW * (12.0 + 2.0 * S * D));
 #define PDS_COMPOSE_CASE(FF, SS) \
-  if ((fp16 != 0) == FF && S == SS) tc_compose_first_kernel<FF, SS><<<grid, 256, 0, st>>>(A, Bf, Q, out_ap, C, H, W, D);
+  if ((fp16 != 0) == FF && S == SS) PDS_CUDA(launch_pdl(tc_compose_first_kernel<FF, SS>, grid, dim3(256), 0, st, A, Bf, Q, out_ap, C, H, W, D));
   PDS_COMPOSE_CASE(true, 1) PDS_COMPOSE_CASE(true, 2) PDS_COMPOSE_CASE(true, 3)
   PDS_COMPOSE_CASE(false, 1) PDS_COMPOSE_CASE(false, 2) PDS_COMPOSE_CASE(false, 3)
 #undef PDS_COMPOSE_CASE
@@ -823,8 +828,8 @@ int tc_norm_split(const float* y, const double* stats, const float* gamma, const
   PDS_KERNEL_WORK(0, (double)n_slices * C * HW * (4 + 2 * S + (res_ap ? 2 * S : 0)));
 #define PDS_NORM_CASE(FF, SS)                                                                              \
   if ((fp16 != 0) == FF && S == SS) {                                                                      \
-    if (res_ap) tc_norm_split_kernel<FF, SS, true><<<grid, 256, 0, st>>>(y, stats, gamma, beta, res_ap, out_ap, C, HW); \
-    else tc_norm_split_kernel<FF, SS, false><<<grid, 256, 0, st>>>(y, stats, gamma, beta, res_ap, out_ap, C, HW);       \
+    if (res_ap) PDS_CUDA(launch_pdl(tc_norm_split_kernel<FF, SS, true>, grid, dim3(256), 0, st, y, stats, gamma, beta, res_ap, out_ap, C, HW)); \
+    else PDS_CUDA(launch_pdl(tc_norm_split_kernel<FF, SS, false>, grid, dim3(256), 0, st, y, stats, gamma, beta, res_ap, out_ap, C, HW)); \
   }
   PDS_NORM_CASE(true, 1) PDS_NORM_CASE(true, 2) PDS_NORM_CASE(true, 3)
   PDS_NORM_CASE(false, 1) PDS_NORM_CASE(false, 2) PDS_NORM_CASE(false, 3)

@@ -46,6 +46,7 @@ struct alignas(64) TcgParams {
   uint32_t box_bytes, box_tx_bytes, term_bytes, a_bytes, stage_bytes, wres_bytes, w_total_bytes;
   uint32_t off_boxes, off_entries, off_tiles, table_bytes;
   float inv_wscale;
+  long long* trace;              // optional per-CTA cycle stamps (debug): [cta][8]
 };
 
 constexpr uint32_t pow2_cols(uint32_t c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
@@ -83,10 +84,18 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   const uint32_t tmem_cols = pow2_cols(nbuf * buf_cols);
 
   if (threadIdx.x == 0) {
+    pdl_trigger();
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 32 * kEpilogueWarps); }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (p.resident) {   // constant data: may be fetched while the previous kernel is still running
+      mbar_expect_tx(wfull_bar, p.w_total_bytes);
+      for (uint32_t o = 0; o < p.w_total_bytes; o += 32768) {
+        const uint32_t n = min(32768u, p.w_total_bytes - o);
+        bulk_load(wres_base + o, (const unsigned char*)p.w + o, n, wfull_bar);
+      }
+    }
   }
   for (uint32_t i = threadIdx.x; i < p.table_bytes / 4; i += kThreads)
     ((uint32_t*)tab)[i] = ((const uint32_t*)p.tables)[i];
@@ -100,6 +109,9 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything below reads / writes tensors of the stream's earlier kernels
+  const long long t_start = clock64();
+  auto stamp = [&](int k) { if (p.trace) p.trace[(size_t)blockIdx.x * 8 + k] = clock64() - t_start; };
 
   // work item = (CTA tile, output class); every CTA walks one contiguous range of items (whole
   // tiles when a stage is shared by the classes of a tile)
@@ -126,14 +138,8 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      if (p.resident) {
-        mbar_expect_tx(wfull_bar, p.w_total_bytes);
-        for (uint32_t o = 0; o < p.w_total_bytes; o += 32768) {
-          const uint32_t n = min(32768u, p.w_total_bytes - o);
-          bulk_load(wres_base + o, (const unsigned char*)p.w + o, n, wfull_bar);
-        }
-      }
       uint32_t stage = 0, phase = 0;
+      stamp(0);
       for (int item = item_begin; item < item_end; ++item) {
         const Item it = decode(item);
         if (p.reuse && it.cls != 0) continue;       // the tile's stage is already resident
@@ -157,6 +163,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
+      stamp(1);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -176,7 +183,9 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
     const uint32_t term16 = p.term_bytes >> 4;
     const uint32_t ent_base = smem_u32(entries);
     if (p.resident) { mbar_wait(wfull_bar, 0); tc_fence_after(); }
+    if (lane == 0) stamp(2);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    bool first_full = true;
     for (int item = item_begin; item < item_end; ++item) {
       const int cls = item % p.ncls;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -188,6 +197,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
         if (!(p.reuse && cls > 0)) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (first_full && lane == 0) { stamp(3); first_full = false; }
         }
         const uint32_t sa16 = (stage_base + stage * p.stage_bytes) >> 4;
         const uint32_t sw16 = p.resident ? (wres_base >> 4) : sa16;
@@ -225,6 +235,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
       }
       if (nbuf == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
     }
+    if (lane == 0) stamp(4);
   } else {
     // ===== epilogue: 8 warps, two per TMEM lane quarter (32 * (warp % 4) .. + 31) =====
     // The two warps of a quarter split the MMA tiles of an item (or, with a single tile, its
@@ -332,10 +343,13 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
         s2[0] += (double)warp_transpose_reduce<CH>(a2, lane);
       }
     }
+    if (warp == 2 && lane == 0) stamp(5);
     flush_stats();
+    if (warp == 2 && lane == 0) stamp(6);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(7);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -407,6 +421,8 @@ tcg_norm_to_ap_kernel(const NormParams p) {
   extern __shared__ float sm[];          // scale_a[C], shift_a[C], scale_b[C], shift_b[C]
   const int n = blockIdx.y;
   const size_t V = (size_t)p.Z * p.Y * p.X;
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
     float sc = 1.f, sh = 0.f;
     if (p.sa) {
@@ -556,8 +572,7 @@ int launch_tcg(const TcgParams& p, const TcgPlan& pl, size_t smem, int grid, cud
   }
   PDS_KERNEL(tcg_name(S, N, pl), st);
   PDS_KERNEL_WORK(flops, bytes);
-  conv_tcg_kernel<S, N><<<grid, kThreads, smem, st>>>(p);
-  PDS_LAUNCH_CHECK("conv_tcg_kernel");
+  PDS_CUDA(launch_pdl(conv_tcg_kernel<S, N>, dim3(grid), dim3(kThreads), smem, st, p));
   return PDS_OK;
 }
 
@@ -612,6 +627,8 @@ int tcg_layer_init(TcgLayer& l, char* blob, const float* w_src, const float* bia
   return PDS_OK;
 }
 
+long long* g_tcg_trace = nullptr;   // set by the debug hook (PDS_B200_TCG_TRACE)
+
 int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, float* out, double* stats,
                      int lrelu, cudaStream_t st) {
   const TcgPlan& pl = l.plan;
@@ -662,6 +679,7 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
   p.off_boxes = tl.off_boxes; p.off_entries = tl.off_entries; p.off_tiles = tl.off_tiles;
   p.table_bytes = tl.table_bytes;
   p.inv_wscale = 1.0f / l.wscale;
+  p.trace = g_tcg_trace;
   if (pl.shape.Cout % 4) { set_error("conv_tcg: Cout must be a multiple of 4"); return PDS_ERR_UNSUPPORTED; }
   const size_t smem = (size_t)pl.wres_bytes + (size_t)pl.stages * pl.stage_bytes + tl.table_bytes + kTailBytes + 128;
   if (smem > 227 * 1024) {
@@ -708,7 +726,7 @@ int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast,
   PDS_KERNEL_WORK(0, (double)n * Z * Y * X * C * (4.0 + 2.0 * S + (b ? 4.0 : 0.0) + (out_f32 ? 4.0 : 0.0)));
   const size_t smem = (size_t)4 * C * sizeof(float);
 #define PDS_TCG_NORM_CASE(FF, SS) \
-  if ((fp16 != 0) == FF && S == SS) tcg_norm_to_ap_kernel<FF, SS><<<grid, 256, smem, st>>>(p);
+  if ((fp16 != 0) == FF && S == SS) PDS_CUDA(launch_pdl(tcg_norm_to_ap_kernel<FF, SS>, grid, dim3(256), smem, st, p));
   PDS_TCG_NORM_CASE(true, 1) PDS_TCG_NORM_CASE(true, 2) PDS_TCG_NORM_CASE(true, 3)
   PDS_TCG_NORM_CASE(false, 1) PDS_TCG_NORM_CASE(false, 2) PDS_TCG_NORM_CASE(false, 3)
 #undef PDS_TCG_NORM_CASE
@@ -752,7 +770,48 @@ extern "C" int pds_tcg_conv_debug(int kind, int nd, int Cin, int Cout, int Z, in
     cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)n * Cout * 2 * sizeof(double), st);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync");
   }
+  const bool trace = getenv("PDS_B200_TCG_TRACE") != nullptr;
+  if (trace) {
+    cudaMalloc(&g_tcg_trace, 148 * 8 * sizeof(long long));
+    cudaMemset(g_tcg_trace, 0, 148 * 8 * sizeof(long long));
+    if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, nullptr, lrelu, st);   // warm (instruction cache, L2)
+  }
   if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, stats, lrelu, st);
+  if (trace) {
+    cudaStreamSynchronize(st);
+    long long h[148 * 8];
+    cudaMemcpy(h, g_tcg_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    const char* names[8] = {"producer start", "producer done", "weights ready", "first stage full", "MMA issue done",
+                            "epilogue done", "stats flushed", "CTA end"};
+    for (int k = 0; k < 8; ++k) {
+      long long mx = 0, sum = 0; int cnt = 0;
+      for (int c = 0; c < 148; ++c) if (h[c * 8 + 7]) { mx = mx > h[c * 8 + k] ? mx : h[c * 8 + k]; sum += h[c * 8 + k]; ++cnt; }
+      printf("trace %-18s avg %8lld max %8lld cycles (%d CTAs)\n", names[k], cnt ? sum / cnt : 0, mx, cnt);
+    }
+    cudaFree(g_tcg_trace); g_tcg_trace = nullptr;
+  }
+  if (trace && rc == PDS_OK) {
+    // kernel duration back to back vs alternating with a small-shared-memory kernel (the
+    // normalisation pass that precedes every convolution in the pipelines)
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms_a = 0.f, ms_b = 0.f, ms_n = 0.f;
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < 10; ++i) tcg_conv_forward(l, n, ap, y_cl, nullptr, lrelu, st);
+    cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_a, e0, e1);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < 10; ++i) tcg_norm_to_ap(src, nullptr, nullptr, ap, n, Cin, Z, Y, X, S, fp16, pl.nph, st);
+    cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_n, e0, e1);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < 10; ++i) {
+      tcg_norm_to_ap(src, nullptr, nullptr, ap, n, Cin, Z, Y, X, S, fp16, pl.nph, st);
+      tcg_conv_forward(l, n, ap, y_cl, nullptr, lrelu, st);
+    }
+    cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_b, e0, e1);
+    printf("timing: conv back-to-back %.1f us, norm alone %.1f us, norm+conv alternating %.1f us per pair\n",
+           ms_a * 100, ms_n * 100, ms_b * 100);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   if (rc == PDS_OK) rc = nhwc_to_nchw(y_cl, out, n, Cout, vout, st);
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == PDS_OK && e != cudaSuccess) rc = cuda_fail(e, "pds_tcg_conv_debug");

@@ -1,6 +1,8 @@
 // a6 -- Embedding.forward (reference embedding.py:46-65) on the tcgen05 convolution engine:
 //   InstanceNorm2d(3, non-affine) -> 2 x [conv5x5 stride 2 + LeakyReLU + IN] -> residual blocks
 //   -> descriptor; shortcut = conv3x3(64 -> 8) + LeakyReLU + IN of the descriptor.
+// The residual blocks are the same 64 -> 64 blocks as the matching operation's and run on its
+// kernel (conv_tc.cu) with the images as slices; the other layers run on the generic engine.
 //
 // The image is normalised and written straight into phase-separated operand planes with its 3
 // channels zero-padded to one 8-channel group, so the first convolution runs on the tensor cores
@@ -14,6 +16,7 @@
 #include <vector>
 
 #include "conv_layers.cuh"
+#include "conv_tc.cuh"
 #include "conv_tcg.cuh"
 #include "tc_ptx.cuh"
 
@@ -21,7 +24,9 @@ struct pds_embedding {
   int Cin, F, Fs, n_res, precision, split, fp16;
   float* raw = nullptr;                    // parameters, PyTorch layout, state_dict order
   std::vector<const float*> raw_params;
-  std::vector<pds::TcgLayer> layers;       // conv1, conv2, 2 per residual block, shortcut
+  std::vector<pds::TcgLayer> layers;       // conv1, conv2, shortcut (generic engine; planned per extent)
+  std::vector<pds::TcLayer> res;           // 2 per residual block: the matching operation's 3x3 kernel
+  char* res_blob = nullptr;
   char* blob = nullptr;
   int shape[2] = {0, 0};
 };
@@ -101,6 +106,27 @@ image_norm_to_ap_kernel(const float* __restrict__ img, const double* __restrict_
   }
 }
 
+// split AP planes [n][S][C/8][HW][8] -> (n, C, HW) fp32 (terms summed smallest first)
+template <bool FP16>
+__global__ void __launch_bounds__(256)
+ap_to_nchw_kernel(const uint16_t* __restrict__ ap, float* __restrict__ out, int C, size_t HW, int S) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += (size_t)gridDim.x * blockDim.x) {
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = S - 1; s >= 0; --s) {
+      const uint4 q = reinterpret_cast<const uint4*>(ap)[((size_t)(n * S + s) * (C / 8) + c8) * HW + pix];
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint16_t h = (uint16_t)(w[e >> 1] >> (16 * (e & 1)));
+        v[e] += FP16 ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[((size_t)n * C + c8 * 8 + e) * HW + pix] = v[e];
+  }
+}
+
 std::vector<TcgShape> embedding_shapes(const pds_embedding* e, int H, int W) {
   std::vector<TcgShape> v;
   auto add = [&](int kind, int cin, int cout, int y, int x) {
@@ -109,7 +135,6 @@ std::vector<TcgShape> embedding_shapes(const pds_embedding* e, int H, int W) {
   };
   add(TCG_CONV5_S2, 8, e->F, H, W);
   add(TCG_CONV5_S2, e->F, e->F, H / 2, W / 2);
-  for (int r = 0; r < 2 * e->n_res; ++r) add(TCG_CONV3_S1, e->F, e->F, H / 4, W / 4);
   add(TCG_CONV3_S1, e->F, e->Fs, H / 4, W / 4);
   return v;
 }
@@ -133,7 +158,8 @@ int prepare(pds_embedding* e, int H, int W, cudaStream_t st) {
   char* cur = e->blob;
   for (size_t i = 0; i < layers.size(); ++i) {
     size_t used = 0;
-    const float* const* pp = &e->raw_params[4 * i];   // weight, bias, gamma, beta
+    const size_t block = i < 2 ? i : (size_t)(2 + 2 * e->n_res);     // parameter block of this layer
+    const float* const* pp = &e->raw_params[4 * block];   // weight, bias, gamma, beta
     int rc = tcg_layer_init(layers[i], cur, pp[0], pp[1], st, &used);
     if (rc != PDS_OK) return rc;
     layers[i].gamma = pp[2]; layers[i].beta = pp[3];
@@ -154,8 +180,8 @@ Buffers buffers(const pds_embedding* e, int n, int H, int W) {
   b.ap = buf(std::max((size_t)n * S * H * W * 16, (size_t)n * S * (H / 2) * (W / 2) * F * 2));
   b.y1 = buf((size_t)n * (H / 2) * (W / 2) * F * 4);
   b.yq = buf((size_t)n * (H / 4) * (W / 4) * F * 4);
-  b.stats = buf((size_t)(4 + 2 * e->n_res) * n * 64 * 2 * sizeof(double));
-  b.total = 2 * b.ap + b.y1 + 5 * b.yq + b.stats + 1024;
+  b.stats = buf((size_t)(4 + 2 * e->n_res) * n * 64 * 2 * sizeof(double));   // conv1, conv2, residual convs, shortcut, image
+  b.total = 2 * b.ap + b.y1 + 2 * b.yq + b.stats + 1024;
   return b;
 }
 
@@ -207,6 +233,27 @@ extern "C" int pds_embedding_create(pds_embedding** out, const float* const* par
     e->raw_params.push_back(cur);
     cur += align_up(sizes[i], 64);
   }
+  // residual-block convolutions: weight images of the matching kernel (independent of the extent)
+  e->res.resize(2 * residual_blocks);
+  size_t rbytes = 0;
+  for (TcLayer& l : e->res) {
+    l.Cin = features; l.Cout = features; l.N = 64; l.S = e->split; l.fp16 = e->fp16; l.wscale = e->fp16 ? 256.f : 1.f;
+    rbytes += align_up(l.w_elems() * 2, 256) + align_up(l.N * 4, 256);
+  }
+  if (rbytes) {
+    err = cudaMalloc(&e->res_blob, rbytes);
+    if (err != cudaSuccess) { cudaFree(e->raw); delete e; return cuda_fail(err, "cudaMalloc(embedding weights)"); }
+    char* rc_cur = e->res_blob;
+    for (size_t i = 0; i < e->res.size(); ++i) {
+      TcLayer& l = e->res[i];
+      const float* const* pp = &e->raw_params[4 * (2 + i)];
+      l.w = (uint16_t*)rc_cur; rc_cur += align_up(l.w_elems() * 2, 256);
+      l.bias = (float*)rc_cur; rc_cur += align_up(l.N * 4, 256);
+      l.gamma = pp[2]; l.beta = pp[3];
+      int rc = tc_prepare_weights(l, pp[0], pp[1], st);
+      if (rc != PDS_OK) { cudaFree(e->raw); cudaFree(e->res_blob); delete e; return rc; }
+    }
+  }
   *out = e;
   return PDS_OK;
 }
@@ -214,6 +261,7 @@ extern "C" int pds_embedding_create(pds_embedding** out, const float* const* par
 extern "C" void pds_embedding_destroy(pds_embedding* e) {
   if (!e) return;
   cudaFree(e->raw);
+  cudaFree(e->res_blob);
   cudaFree(e->blob);
   delete e;
 }
@@ -246,8 +294,6 @@ extern "C" int pds_embedding_forward(pds_embedding* e, const float* images, floa
   float* y1 = (float*)ws.take<char>(bs.y1);
   float* y2 = (float*)ws.take<char>(bs.yq);
   float* t = (float*)ws.take<char>(bs.yq);
-  float* u = (float*)ws.take<char>(bs.yq);
-  float* xres[2] = {(float*)ws.take<char>(bs.yq), (float*)ws.take<char>(bs.yq)};
   double* stats = (double*)ws.take<char>(bs.stats);
   if (ws.overflow) { set_error("pds_embedding_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
   PDS_CUDA(cudaMemsetAsync(stats, 0, bs.stats, st));
@@ -260,7 +306,7 @@ extern "C" int pds_embedding_forward(pds_embedding* e, const float* images, floa
     return s;
   };
   const int n_layers = (int)L.size();
-  double* img_stats = st_of(n_layers);          // slot after the layers'
+  double* img_stats = st_of(3 + 2 * e->n_res);   // slot after the layers'
 
   // InstanceNorm2d of the image -> phase-separated planes (embedding.py:32)
   {
@@ -283,27 +329,38 @@ extern "C" int pds_embedding_forward(pds_embedding* e, const float* images, floa
   if ((rc = tcg_conv_forward(L[0], n, ap[0], y1, st_of(0), 1, st)) != PDS_OK) return rc;
   if ((rc = tcg_norm_to_ap(src(0, y1), nullptr, nullptr, ap[1], n, F, 1, Hh, Wh, S, fp16, 4, st)) != PDS_OK) return rc;
   if ((rc = tcg_conv_forward(L[1], n, ap[1], y2, st_of(1), 1, st)) != PDS_OK) return rc;
-  // residual stream x = IN(y2); every block: x <- IN(conv(IN(conv(x)))) + x
-  if ((rc = tcg_norm_to_ap(src(1, y2), nullptr, nullptr, ap[0], n, F, 1, Hq, Wq, S, fp16, 1, st,
-                           e->n_res == 0 ? xres[0] : nullptr)) != PDS_OK) return rc;
-  TcgNormSrc x = src(1, y2);
-  float* x_final = xres[0];
+  // residual stream x = IN(y2) as operand planes; every block: x <- IN(conv(IN(conv(x)))) + x, on
+  // the matching operation's kernels with the images as slices (network_blocks.py:134-144)
+  if ((rc = tcg_norm_to_ap(src(1, y2), nullptr, nullptr, ap[0], n, F, 1, Hq, Wq, S, fp16, 1, st)) != PDS_OK) return rc;
+  TcConvArgs a = {};
+  a.H = Hq; a.W = Wq; a.n_slices = n; a.n0 = 0; a.n_div = 1; a.in_slices = n; a.in_C = F;
+  a.epilogue = TC_EPI_ACT; a.out_f32 = t;
   for (int r = 0; r < e->n_res; ++r) {
-    const int l1 = 2 + 2 * r, l2 = 3 + 2 * r;
-    if ((rc = tcg_conv_forward(L[l1], n, ap[0], t, st_of(l1), 1, st)) != PDS_OK) return rc;
-    if ((rc = tcg_norm_to_ap(src(l1, t), nullptr, nullptr, ap[1], n, F, 1, Hq, Wq, S, fp16, 1, st)) != PDS_OK) return rc;
-    if ((rc = tcg_conv_forward(L[l2], n, ap[1], u, st_of(l2), 1, st)) != PDS_OK) return rc;
-    float* xn = xres[r & 1];
-    if ((rc = tcg_norm_to_ap(src(l2, u), &x, nullptr, ap[0], n, F, 1, Hq, Wq, S, fp16, 1, st, xn)) != PDS_OK) return rc;
-    x = TcgNormSrc(); x.y = xn;          // materialised sum: added as is by the next block
-    x_final = xn;
+    const TcLayer& c1 = e->res[2 * r];
+    const TcLayer& c2 = e->res[2 * r + 1];
+    double* s1 = st_of(2 + 2 * r);
+    double* s2 = st_of(3 + 2 * r);
+    a.layer = &c1; a.in = ap[0]; a.stats = s1;
+    if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
+    if ((rc = tc_norm_split(t, s1, c1.gamma, c1.beta, nullptr, ap[1], n, F, Hq, Wq, S, fp16, st)) != PDS_OK) return rc;
+    a.layer = &c2; a.in = ap[1]; a.stats = s2;
+    if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
+    if ((rc = tc_norm_split(t, s2, c2.gamma, c2.beta, ap[0], ap[0], n, F, Hq, Wq, S, fp16, st)) != PDS_OK) return rc;
   }
-  if ((rc = nhwc_to_nchw(x_final, descriptor, n, F, (size_t)Hq * Wq, st)) != PDS_OK) return rc;
+  {
+    const size_t HWq = (size_t)Hq * Wq;
+    PDS_KERNEL("ap_to_nchw", st);
+    PDS_KERNEL_WORK(0, (double)n * F * HWq * (4.0 + 2.0 * S));
+    dim3 grid((unsigned)std::min<size_t>((HWq + 255) / 256, 64), (unsigned)(F / 8), (unsigned)n);
+    if (fp16) ap_to_nchw_kernel<true><<<grid, 256, 0, st>>>(ap[0], descriptor, F, HWq, S);
+    else ap_to_nchw_kernel<false><<<grid, 256, 0, st>>>(ap[0], descriptor, F, HWq, S);
+    PDS_LAUNCH_CHECK("ap_to_nchw_kernel");
+  }
   if (n_shortcut > 0) {
     // _shortcut block on the descriptor planes (embedding.py:43-44,65)
-    const int ls = n_layers - 1;
-    if ((rc = tcg_conv_forward(L[ls], n_shortcut, ap[0], t, st_of(ls), 1, st)) != PDS_OK) return rc;
-    if ((rc = instance_norm_apply(t, st_of(ls), L[ls].gamma, L[ls].beta, nullptr, nullptr, t, nullptr,
+    const int ls = n_layers - 1, ss = 2 + 2 * e->n_res;    // layer index, statistics slot
+    if ((rc = tcg_conv_forward(L[ls], n_shortcut, ap[0], t, st_of(ss), 1, st)) != PDS_OK) return rc;
+    if ((rc = instance_norm_apply(t, st_of(ss), L[ls].gamma, L[ls].beta, nullptr, nullptr, t, nullptr,
                                   n_shortcut, (size_t)Hq * Wq, (size_t)Hq * Wq, e->Fs, st)) != PDS_OK) return rc;
     if ((rc = nhwc_to_nchw(t, shortcut, n_shortcut, e->Fs, (size_t)Hq * Wq, st)) != PDS_OK) return rc;
   }

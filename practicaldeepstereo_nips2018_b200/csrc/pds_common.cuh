@@ -49,6 +49,28 @@ struct KernelScope {
 #define PDS_KERNEL(name, st) ::pds::KernelScope pds_kernel_scope__(name, st)
 #define PDS_KERNEL_WORK(flops, bytes) pds_kernel_scope__.work((double)(flops), (double)(bytes))
 
+// Programmatic dependent launch: kernels launched through launch_pdl may START (prologue: barrier
+// initialisation, TMEM allocation, loads of constant data such as weights) while the previous
+// kernel of the stream is still draining; they must call pdl_wait() before touching any global
+// memory the stream's earlier work produces or still reads, and call pdl_trigger() early so that
+// their own successor can be scheduled as their CTAs retire.  The attribute is OFF by default
+// (PDS_B200_PDL=1 enables it; measured slightly slower at C2); the device-side calls are then no-ops.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

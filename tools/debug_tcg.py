@@ -12,9 +12,14 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np  # noqa: E402
 import test_gpu_tcg as T  # noqa: E402
 
-kind, nd, cin, cout, n, spatial = T.CASES[int(sys.argv[1])]
-S = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-fp16 = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+if sys.argv[1] == 'custom':      # custom kind nd cin cout n Z Y X   (PDS_B200_TCG_TRACE=1 prints cycle stamps)
+    kind, nd, cin, cout, n = (int(a) for a in sys.argv[2:7])
+    spatial = tuple(int(a) for a in sys.argv[7:7 + 3])[3 - nd:]
+    S, fp16 = 2, 1
+else:
+    kind, nd, cin, cout, n, spatial = T.CASES[int(sys.argv[1])]
+    S = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    fp16 = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 k = {0: 3, 1: 3, 2: 4, 3: 5, 4: 4}[kind]
 g = torch.Generator(device='cpu').manual_seed(1)
 x = torch.randn((n, cin) + spatial, generator=g).cuda()
