@@ -90,6 +90,23 @@ int tc_conv3x3(const TcConvArgs& a, cudaStream_t st);
 int tc_encode_shift_maps(CUtensorMap* maps_host, const uint16_t* in2, int in_slices, int S, int C,
                          int H, int W, int D);
 
+// ---- second-level factorisation (matching_factor.cu; derivation in its header) ---------------
+// fp32 planes [n][C/4][H][W][4] -> split AP planes
+int tc_planes_to_ap(const float* y, uint16_t* out_ap, int n, int C, int H, int W, int S, int fp16, cudaStream_t st);
+// (Cout, Cin, 3, 3) fp32 -> [kx][dy][ci][co] fp32 for tc_column_ops
+int tc_transpose_weights(const float* w_oihw, float* wt, int C, cudaStream_t st);
+size_t tc_column_jobs(int D);   // J: columns per sample in `cols` ([b][J][H][C] fp32)
+int tc_column_ops(const float* Bf, const float* Q, const float* wt, float* cols, int B, int C, int H, int W, int D,
+                  cudaStream_t st);
+// t[b*D + d] = LeakyReLU(conv1(x0_d) + bias) as fp32 planes + InstanceNorm sums (stats pre-zeroed);
+// PA = conv1(A), PB = conv1(Bf) WITHOUT bias
+int tc_compose_second(const float* PA, const float* PB, const float* cols, const float* bias, float* t,
+                      double* stats, int B, int C, int H, int W, int D, cudaStream_t st);
+// out_ap[b*D + d] = IN(y) + x0_d with x0_d regenerated from A / Bf / Q
+int tc_norm_residual_first(const float* y, const double* stats, const float* gamma, const float* beta,
+                           const float* A, const float* Bf, const float* Q, uint16_t* out_ap, int B, int C, int H,
+                           int W, int D, int S, int fp16, cudaStream_t st);
+
 // InstanceNorm apply on fp32 planes y [n][C/4][H][W][4] with the sums of
 // stats[n][C][2]; the optional residual is READ FROM AP planes (sum of its
 // terms) and the result is written as AP planes (out_ap may alias res_ap).

@@ -1,0 +1,371 @@
+// Factorisation of the matching operation's first TWO convolutions (reference matching.py:53-62,
+// 97-112: conv0 on cat[left, shift_d(right)], then the first convolution of residual block 1).
+// Both are linear and the disparity only shifts the right descriptor, so per sample (not per
+// disparity slice) we compute
+//     A  = conv0_L(L) + b0          Bf = conv0_R(R)           Q = kx=2 taps of conv0_R in place
+//     PA = conv1(A) + b1            PB = conv1(Bf)
+// and a few single-column corrections; every slice then follows by shifting:
+//     x0_d = A + shift_d(B~) - [x = W-1, d >= 1] Q[W-d]
+//     conv1(x0_d) + b1 = PA + shift_d(PG~) - [x = W-1] E_d - [x = W-2] F_d          (1 <= d < W)
+// B~ is Bf extended by one column on the left (B~[-1] = Q[0]: the column next to the zero fill
+// sees R's column 0 through the right-neighbour taps); PG~ = conv1 of B~ on x' in [-2, W-1]:
+//     PG~[-2] = U2(Q[:,0])   PG~[-1] = U1(Q[:,0]) + U2(Bf[:,0])   PG~[0] = PB[0] + U0(Q[:,0])   PG~[x'] = PB[x']
+// with U_k(c)[y] = sum_{dy,ci} W1[dy][kx=k][ci] c[y+dy-1][ci] (conv1 restricted to one kernel column).
+// At the last image columns the shifted tensors would read what the reference pads with zeros:
+//     E_d = U2(Bf[:, W-d]) + U1(Q[:, W-d])      F_d = U2(Q[:, W-d])
+// (derivation in DESIGN.md 4.1).  d = 0: x0 = A + Bf, conv1 = PA + PB; d >= W: x0 = A, conv1 = PA.
+//
+// Saves, at C2, one 64->64 convolution over all 48 slices and the pass that materialised x0; x0 is
+// re-generated on the fly where the residual addition needs it.  All tensors here are fp32 planes
+// [b][C/4][H][W][4]; `cols` is [b][J][H][C] with J = 3 + 2 (D - 1).
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace pds {
+namespace {
+
+using namespace ptx;
+
+// x0 of slice d at (y, x), channels 8*c8 .. +7 (same arithmetic as tc_compose_first)
+__device__ __forceinline__ void first_x0(const float4* a4, const float4* b4, const float4* q4, size_t HW,
+                                         size_t pix, int x, int W, int d, float (&v)[8]) {
+  const size_t row = pix - x;
+  const float4 lo = __ldg(a4 + pix), hi = __ldg(a4 + HW + pix);
+  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  auto add = [&](const float4* src, size_t at, float sign) {
+    const float4 l = __ldg(src + at), h = __ldg(src + HW + at);
+    v[0] = fmaf(sign, l.x, v[0]); v[1] = fmaf(sign, l.y, v[1]); v[2] = fmaf(sign, l.z, v[2]); v[3] = fmaf(sign, l.w, v[3]);
+    v[4] = fmaf(sign, h.x, v[4]); v[5] = fmaf(sign, h.y, v[5]); v[6] = fmaf(sign, h.z, v[6]); v[7] = fmaf(sign, h.w, v[7]);
+  };
+  if (x >= d) add(b4, pix - d, 1.f);
+  else if (x == d - 1) add(q4, row, 1.f);
+  if (x == W - 1 && d >= 1 && d <= W) add(q4, row + (W - d), -1.f);
+}
+
+// fp32 planes [n][C/4][HW][4] -> split AP planes [n][S][C/8][HW][8]
+template <bool FP16, int S>
+__global__ void __launch_bounds__(256)
+planes_to_ap_kernel(const float* __restrict__ y, uint16_t* __restrict__ out_ap, int C, size_t HW) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const float4* y4 = reinterpret_cast<const float4*>(y) + ((size_t)n * (C / 4) + 2 * c8) * HW;
+  float4* o4 = reinterpret_cast<float4*>(out_ap);
+  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += (size_t)gridDim.x * blockDim.x) {
+    const float4 lo = __ldg(y4 + pix), hi = __ldg(y4 + HW + pix);
+    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint16_t t[8][3];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      float4 pk;
+      pk.x = __uint_as_float(t[0][s] | ((uint32_t)t[1][s] << 16)); pk.y = __uint_as_float(t[2][s] | ((uint32_t)t[3][s] << 16));
+      pk.z = __uint_as_float(t[4][s] | ((uint32_t)t[5][s] << 16)); pk.w = __uint_as_float(t[6][s] | ((uint32_t)t[7][s] << 16));
+      o4[((size_t)(n * S + s) * (C / 8) + c8) * HW + pix] = pk;
+    }
+  }
+}
+
+// (Cout, Cin, 3, 3) -> [kx][dy][ci][co]
+__global__ void transpose_w_kernel(const float* __restrict__ w, float* __restrict__ wt, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * C * 9) return;
+  const int co = i % C, ci = (i / C) % C, dy = (i / (C * C)) % 3, k = i / (3 * C * C);
+  wt[i] = w[((size_t)(co * C + ci) * 3 + dy) * 3 + k];
+}
+
+// Column corrections as a small tiled GEMM: one CTA per (64-row chunk, column job j, sample b)
+// computes a 64 (y) x 64 (co) tile; K = 3 (dy) x C input channels per term.  The input column
+// (with one zero row above / below) and one 64 x 64 weight slab at a time live in shared memory;
+// a thread owns 4 rows x 4 channels (one 128-bit and four scalar shared loads per 16 FMAs).
+constexpr int kColRows = 64;
+__global__ void __launch_bounds__(256)
+column_ops_kernel(const float* __restrict__ Bf, const float* __restrict__ Q, const float* __restrict__ wt,
+                  float* __restrict__ cols, int C, int H, int W, int D) {
+  extern __shared__ float xsm[];      // X [2 terms][kColRows + 2][C + 1] | W slab [C][C]
+  const int j = blockIdx.y, b = blockIdx.z, J = gridDim.y;
+  const int y0 = blockIdx.x * kColRows;
+  const float* src[2] = {nullptr, nullptr};
+  int col[2] = {0, 0}, kx[2] = {0, 0};
+  if (j == 0) { src[0] = Q; col[0] = 0; kx[0] = 0; }
+  else if (j == 1) { src[0] = Q; col[0] = 0; kx[0] = 1; src[1] = Bf; col[1] = 0; kx[1] = 2; }
+  else if (j == 2) { src[0] = Q; col[0] = 0; kx[0] = 2; }
+  else {
+    const int d = (j - 3) / 2 + 1, c = W - d;
+    if (c < 0) return;                                   // d > W: never read
+    if ((j - 3) % 2 == 0) { src[0] = Bf; col[0] = c; kx[0] = 2; src[1] = Q; col[1] = c; kx[1] = 1; }
+    else { src[0] = Q; col[0] = c; kx[0] = 2; }
+  }
+  const size_t HW = (size_t)H * W;
+  const int rows = kColRows + 2, XP = C + 1;
+  float* wsm = xsm + 2 * rows * XP;
+  for (int t = 0; t < 2; ++t) {
+    if (!src[t]) continue;
+    const float* xs = src[t] + (size_t)b * C * HW;
+    // consecutive threads walk the rows of one channel quad: 16-byte loads, stride W * 16 B
+    for (int i = threadIdx.x; i < rows * (C / 4); i += blockDim.x) {
+      const int r = i % rows, q = i / rows, yy = y0 - 1 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy >= 0 && yy < H) v = __ldg(reinterpret_cast<const float4*>(xs) + (size_t)q * HW + (size_t)yy * W + col[t]);
+      float* dst = xsm + (t * rows + r) * XP + 4 * q;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+  }
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;     // 4 channels x 4 rows per thread
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  for (int t = 0; t < 2; ++t) {
+    if (!src[t]) continue;
+    for (int dy = 0; dy < 3; ++dy) {
+      __syncthreads();                 // previous slab consumed (and, first time, X staged)
+      const float4* wsrc = reinterpret_cast<const float4*>(wt + ((size_t)(kx[t] * 3 + dy) * C) * C);
+      for (int i = threadIdx.x; i < C * C / 4; i += blockDim.x) reinterpret_cast<float4*>(wsm)[i] = __ldg(wsrc + i);
+      __syncthreads();
+      const float* xb = xsm + (t * rows + 4 * ty + dy) * XP;
+#pragma unroll 4
+      for (int ci = 0; ci < C; ++ci) {
+        const float4 w = *reinterpret_cast<const float4*>(wsm + ci * C + 4 * tx);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float a = xb[r * XP + ci];
+          acc[r][0] = fmaf(w.x, a, acc[r][0]); acc[r][1] = fmaf(w.y, a, acc[r][1]);
+          acc[r][2] = fmaf(w.z, a, acc[r][2]); acc[r][3] = fmaf(w.w, a, acc[r][3]);
+        }
+      }
+    }
+  }
+  float* out = cols + ((size_t)b * J + j) * H * C;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int y = y0 + 4 * ty + r;
+    if (y < H) *reinterpret_cast<float4*>(out + (size_t)y * C + 4 * tx) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  }
+}
+
+// t1 = LeakyReLU(conv1(x0_d) + b1) for every slice, + its InstanceNorm sums.  grid (x blocks, C/8, B*D)
+__global__ void __launch_bounds__(256, 3)
+compose_second_kernel(const float* __restrict__ PA, const float* __restrict__ PB, const float* __restrict__ cols,
+                      const float* __restrict__ bias, float* __restrict__ t, double* __restrict__ stats, int C,
+                      int H, int W, int D) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int b = n / D, d = n - b * D, J = 3 + 2 * (D - 1);
+  const size_t HW = (size_t)H * W;
+  const size_t base = ((size_t)b * (C / 4) + 2 * c8) * HW;
+  const float4* a4 = reinterpret_cast<const float4*>(PA) + base;
+  const float4* b4 = reinterpret_cast<const float4*>(PB) + base;
+  float4* o4 = reinterpret_cast<float4*>(t) + ((size_t)n * (C / 4) + 2 * c8) * HW;
+  const float* cb = cols + (size_t)b * J * H * C + 8 * c8;
+  auto colv = [&](int j, int y, float sign, float (&v)[8]) {
+    const float4* p = reinterpret_cast<const float4*>(cb + ((size_t)j * H + y) * C);
+    const float4 l = __ldg(p), h = __ldg(p + 1);
+    v[0] = fmaf(sign, l.x, v[0]); v[1] = fmaf(sign, l.y, v[1]); v[2] = fmaf(sign, l.z, v[2]); v[3] = fmaf(sign, l.w, v[3]);
+    v[4] = fmaf(sign, h.x, v[4]); v[5] = fmaf(sign, h.y, v[5]); v[6] = fmaf(sign, h.z, v[6]); v[7] = fmaf(sign, h.w, v[7]);
+  };
+  float s1[8], s2[8], b1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; b1[e] = __ldg(bias + 8 * c8 + e); }
+  const bool shifted = d < W;
+  const unsigned total = (unsigned)HW, stride = gridDim.x * blockDim.x;
+  for (unsigned p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < total; p0 += 2 * stride) {
+    float4 alo[2], ahi[2], blo[2], bhi[2];
+    int xx[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned pix = p0 + u * stride;
+      if (pix >= total) continue;
+      xx[u] = (int)(pix % (unsigned)W);
+      alo[u] = __ldg(a4 + pix); ahi[u] = __ldg(a4 + HW + pix);
+      if (shifted && xx[u] >= d) { blo[u] = __ldg(b4 + pix - d); bhi[u] = __ldg(b4 + HW + pix - d); }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned pix = p0 + u * stride;
+      if (pix >= total) continue;
+      const int x = xx[u], y = (int)(pix / (unsigned)W), xs = x - d;
+      float v[8] = {alo[u].x + b1[0], alo[u].y + b1[1], alo[u].z + b1[2], alo[u].w + b1[3],
+                    ahi[u].x + b1[4], ahi[u].y + b1[5], ahi[u].z + b1[6], ahi[u].w + b1[7]};
+      if (shifted) {
+        if (xs >= 0) {
+          v[0] += blo[u].x; v[1] += blo[u].y; v[2] += blo[u].z; v[3] += blo[u].w;
+          v[4] += bhi[u].x; v[5] += bhi[u].y; v[6] += bhi[u].z; v[7] += bhi[u].w;
+          if (xs == 0 && d >= 1) colv(0, y, 1.f, v);
+        } else if (xs == -1) colv(1, y, 1.f, v);
+        else if (xs == -2) colv(2, y, 1.f, v);
+        if (d >= 1) {
+          if (x == W - 1) colv(3 + 2 * (d - 1), y, -1.f, v);
+          else if (x == W - 2) colv(4 + 2 * (d - 1), y, -1.f, v);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[e] = v[e] > 0.f ? v[e] : 0.1f * v[e];
+        s1[e] += v[e]; s2[e] = fmaf(v[e], v[e], s2[e]);
+      }
+      stg_stream(o4 + pix, make_float4(v[0], v[1], v[2], v[3]));
+      stg_stream(o4 + HW + pix, make_float4(v[4], v[5], v[6], v[7]));
+    }
+  }
+  // block reduction of the 16 sums, then one double atomic each
+  __shared__ float red[8][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+      s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+    }
+    if (lane == 0) { red[warp][e] = s1[e]; red[warp][8 + e] = s2[e]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double acc = 0.0;
+    for (int w = 0; w < 8; ++w) acc += (double)red[w][threadIdx.x];
+    const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
+    atomicAdd(stats + ((size_t)n * C + 8 * c8 + e) * 2 + which, acc);
+  }
+}
+
+// x1 = IN(t2) + x0_d with x0 regenerated from A / Bf / Q -> split AP planes.  grid (x blocks, C/8, B*D)
+template <bool FP16, int S>
+__global__ void __launch_bounds__(256, 3)
+norm_residual_first_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                           const float* __restrict__ A, const float* __restrict__ Bf, const float* __restrict__ Q,
+                           uint16_t* __restrict__ out_ap, int C, int H, int W, int D) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int b = n / D, d = n - b * D;
+  const size_t HW = (size_t)H * W;
+  __shared__ float sc[8], sh[8];
+  if (threadIdx.x < 8) {
+    const int c = c8 * 8 + threadIdx.x;
+    const double s = stats[((size_t)n * C + c) * 2], q = stats[((size_t)n * C + c) * 2 + 1];
+    const double mean = s / (double)HW;
+    double var = q / (double)HW - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float scale = (float)(1.0 / sqrt(var + 1e-5)) * gamma[c];
+    sc[threadIdx.x] = scale;
+    sh[threadIdx.x] = beta[c] - (float)mean * scale;
+  }
+  __syncthreads();
+  const size_t base = ((size_t)b * (C / 4) + 2 * c8) * HW;
+  const float4* a4 = reinterpret_cast<const float4*>(A) + base;
+  const float4* b4 = reinterpret_cast<const float4*>(Bf) + base;
+  const float4* q4 = reinterpret_cast<const float4*>(Q) + base;
+  const float4* y4 = reinterpret_cast<const float4*>(y) + ((size_t)n * (C / 4) + 2 * c8) * HW;
+  float4* o4 = reinterpret_cast<float4*>(out_ap);
+  const unsigned total = (unsigned)HW, stride = gridDim.x * blockDim.x;
+  for (unsigned p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < total; p0 += 2 * stride) {
+    float4 lo[2], hi[2];
+    float x0[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned pix = p0 + u * stride;
+      if (pix < total) {
+        lo[u] = ldg_stream(y4 + pix); hi[u] = ldg_stream(y4 + HW + pix);
+        first_x0(a4, b4, q4, HW, pix, (int)(pix % (unsigned)W), W, d, x0[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned pix = p0 + u * stride;
+      if (pix >= total) continue;
+      const float v[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
+      uint16_t t[8][3];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_terms<FP16>(fmaf(v[e], sc[e], sh[e]) + x0[u][e], t[e]);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float4 pk;
+        pk.x = __uint_as_float(t[0][s] | ((uint32_t)t[1][s] << 16)); pk.y = __uint_as_float(t[2][s] | ((uint32_t)t[3][s] << 16));
+        pk.z = __uint_as_float(t[4][s] | ((uint32_t)t[5][s] << 16)); pk.w = __uint_as_float(t[6][s] | ((uint32_t)t[7][s] << 16));
+        stg_stream(o4 + ((size_t)(n * S + s) * (C / 8) + c8) * HW + pix, pk);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int tc_transpose_weights(const float* w_oihw, float* wt, int C, cudaStream_t st) {
+  PDS_KERNEL("tc_transpose_weights", st);
+  transpose_w_kernel<<<(unsigned)((C * C * 9 + 255) / 256), 256, 0, st>>>(w_oihw, wt, C);
+  PDS_LAUNCH_CHECK("transpose_w_kernel");
+  return PDS_OK;
+}
+
+int tc_planes_to_ap(const float* y, uint16_t* out_ap, int n, int C, int H, int W, int S, int fp16, cudaStream_t st) {
+  const size_t HW = (size_t)H * W;
+  if (n == 0 || HW == 0) return PDS_OK;
+  unsigned gx = (unsigned)((HW + 255) / 256);
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, (unsigned)(C / 8), (unsigned)n);
+  PDS_KERNEL("tc_planes_to_ap", st);
+  PDS_KERNEL_WORK(0, (double)n * C * HW * (4.0 + 2.0 * S));
+#define PDS_P2A_CASE(FF, SS) \
+  if ((fp16 != 0) == FF && S == SS) planes_to_ap_kernel<FF, SS><<<grid, 256, 0, st>>>(y, out_ap, C, HW);
+  PDS_P2A_CASE(true, 1) PDS_P2A_CASE(true, 2) PDS_P2A_CASE(true, 3)
+  PDS_P2A_CASE(false, 1) PDS_P2A_CASE(false, 2) PDS_P2A_CASE(false, 3)
+#undef PDS_P2A_CASE
+  PDS_LAUNCH_CHECK("planes_to_ap_kernel");
+  return PDS_OK;
+}
+
+size_t tc_column_jobs(int D) { return (size_t)(3 + 2 * (D > 1 ? D - 1 : 0)); }
+
+int tc_column_ops(const float* Bf, const float* Q, const float* wt, float* cols, int B, int C, int H, int W, int D,
+                  cudaStream_t st) {
+  if (B == 0) return PDS_OK;
+  if (C > 256 || C % 4 || 256 % (C / 4)) { set_error("tc_column_ops: unsupported channel count %d", C); return PDS_ERR_UNSUPPORTED; }
+  if (C != 64) { set_error("tc_column_ops: 64 channels only"); return PDS_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)((H + kColRows - 1) / kColRows), (unsigned)tc_column_jobs(D), (unsigned)B);
+  PDS_KERNEL("tc_column_ops", st);
+  PDS_KERNEL_WORK(2.0 * 3 * C * C * H * 1.5 * grid.y * B, 4.0 * grid.y * B * H * C);
+  const size_t smem = (size_t)(2 * (kColRows + 2) * (C + 1) + C * C) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    PDS_CUDA(cudaFuncSetAttribute(column_ops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  column_ops_kernel<<<grid, 256, smem, st>>>(Bf, Q, wt, cols, C, H, W, D);
+  PDS_LAUNCH_CHECK("column_ops_kernel");
+  return PDS_OK;
+}
+
+int tc_compose_second(const float* PA, const float* PB, const float* cols, const float* bias, float* t,
+                      double* stats, int B, int C, int H, int W, int D, cudaStream_t st) {
+  const size_t HW = (size_t)H * W;
+  if (B == 0 || HW == 0) return PDS_OK;
+  unsigned gx = (unsigned)((HW + 2047) / 2048);          // >= 8 pixels per thread; 16 double atomics per CTA
+  if (gx > 16) gx = 16;
+  dim3 grid(gx, (unsigned)(C / 8), (unsigned)(B * D));
+  PDS_KERNEL("tc_compose_second", st);
+  PDS_KERNEL_WORK(0, (double)B * C * HW * (8.0 + 4.0 * D));
+  compose_second_kernel<<<grid, 256, 0, st>>>(PA, PB, cols, bias, t, stats, C, H, W, D);
+  PDS_LAUNCH_CHECK("compose_second_kernel");
+  return PDS_OK;
+}
+
+int tc_norm_residual_first(const float* y, const double* stats, const float* gamma, const float* beta,
+                           const float* A, const float* Bf, const float* Q, uint16_t* out_ap, int B, int C, int H,
+                           int W, int D, int S, int fp16, cudaStream_t st) {
+  const size_t HW = (size_t)H * W;
+  if (B == 0 || HW == 0) return PDS_OK;
+  unsigned gx = (unsigned)((HW + 511) / 512);        // two pixels per thread per iteration
+  if (gx > 128) gx = 128;
+  dim3 grid(gx, (unsigned)(C / 8), (unsigned)(B * D));
+  PDS_KERNEL("tc_norm_residual_first", st);
+  PDS_KERNEL_WORK(0, (double)B * D * C * HW * (4.0 + 2.0 * S));
+#define PDS_NRF_CASE(FF, SS) \
+  if ((fp16 != 0) == FF && S == SS)  \
+    norm_residual_first_kernel<FF, SS><<<grid, 256, 0, st>>>(y, stats, gamma, beta, A, Bf, Q, out_ap, C, H, W, D);
+  PDS_NRF_CASE(true, 1) PDS_NRF_CASE(true, 2) PDS_NRF_CASE(true, 3)
+  PDS_NRF_CASE(false, 1) PDS_NRF_CASE(false, 2) PDS_NRF_CASE(false, 3)
+#undef PDS_NRF_CASE
+  PDS_LAUNCH_CHECK("norm_residual_first_kernel");
+  return PDS_OK;
+}
+
+}  // namespace pds

@@ -31,6 +31,11 @@ struct pds_matching_op {
   // right half's kx = 2 taps in place
   pds::TcLayer first[3];
   int factor = 0;
+  // second level (matching_factor.cu): block 1's first convolution without bias, its weights as
+  // [kx][dy][ci][co] fp32 for the column corrections
+  pds::TcLayer second;
+  float* wt1 = nullptr;
+  int factor2 = 0;
   void* tc_blob = nullptr;
   // tensor maps of the shifted right descriptors, cached per (buffer, shape)
   CUtensorMap* maps_dev = nullptr;
@@ -94,6 +99,13 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
       bytes += align_up(l.w_elems() * 2, 256) + align_up(l.N * 4, 256) + 2 * align_up(F * 4, 256);
     }
     op->factor = !(getenv("PDS_B200_MATCH_FACTOR") && atoi(getenv("PDS_B200_MATCH_FACTOR")) == 0);
+    op->factor2 = op->factor && n_res >= 1 && C == F &&
+                  !(getenv("PDS_B200_MATCH_FACTOR2") && atoi(getenv("PDS_B200_MATCH_FACTOR2")) == 0);
+    {
+      TcLayer& l = op->second;
+      l.Cin = F; l.Cout = F; l.N = 64; l.S = op->split; l.fp16 = op->fp16; l.wscale = op->fp16 ? 256.f : 1.f;
+      bytes += align_up(l.w_elems() * 2, 256) + align_up(l.N * 4, 256) + align_up((size_t)9 * F * F * 4, 256);
+    }
     for (int i = 0; i < 3; ++i) {
       TcLayer& l = op->first[i];
       l.Cin = C; l.Cout = F; l.N = 64; l.S = op->split; l.fp16 = op->fp16; l.wscale = op->fp16 ? 256.f : 1.f;
@@ -124,6 +136,14 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
       l.w = (uint16_t*)cur; cur += align_up(l.w_elems() * 2, 256);
       l.bias = (float*)cur; cur += align_up(l.N * 4, 256);
       rc = tc_prepare_weights(l, params[0], i == 0 ? params[1] : nullptr, st, 2 * C, i == 0 ? 0 : C, i == 2);
+    }
+    if (rc == PDS_OK && op->factor2) {
+      TcLayer& l = op->second;
+      l.w = (uint16_t*)cur; cur += align_up(l.w_elems() * 2, 256);
+      l.bias = (float*)cur; cur += align_up(l.N * 4, 256);
+      op->wt1 = (float*)cur; cur += align_up((size_t)9 * F * F * 4, 256);
+      rc = tc_prepare_weights(l, params[2], nullptr, st);
+      if (rc == PDS_OK) rc = tc_transpose_weights(params[2], op->wt1, F, st);
     }
     if (rc != PDS_OK) { cudaFree(op->tc_blob); delete op; return rc; }
     *out = op;
@@ -175,7 +195,7 @@ namespace {
 // convolution that writes them and the pass that reads them.
 struct TcPlan {
   int G;
-  size_t lap, rap, xa, t, ya, stats, first, total;
+  size_t lap, rap, xa, t, ya, stats, first, ap2, cols, total;
 };
 
 TcPlan tc_plan(const pds_matching_op* op, int B, int H, int W, int D) {
@@ -196,7 +216,9 @@ TcPlan tc_plan(const pds_matching_op* op, int B, int H, int W, int D) {
   p.t = align_up((size_t)G * op->F * hw * 4, 256);
   p.stats = align_up(n * op->F * 2 * sizeof(double) * 2 * (op->n_res > 0 ? op->n_res : 1), 256);
   p.first = align_up((size_t)B * op->F * hw * 4, 256);     // A, Bf, Q of the factorised first convolution
-  p.total = p.lap + p.rap + p.xa + p.t + p.ya + p.stats + 3 * p.first + 1024;
+  p.ap2 = align_up((size_t)2 * B * S * op->F * hw * 2, 256);                         // planes of A and Bf
+  p.cols = align_up((size_t)B * tc_column_jobs(D) * H * op->F * 4, 256);             // column corrections
+  p.total = p.lap + p.rap + p.xa + p.t + p.ya + p.stats + 5 * p.first + p.ap2 + p.cols + 1024;
   return p;
 }
 
@@ -221,9 +243,12 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
   float* t = (float*)ws.take<char>(pl.t);
   uint16_t* ya = (uint16_t*)ws.take<char>(pl.ya);
   double* stats = (double*)ws.take<char>(pl.stats);
-  float* fa = (float*)ws.take<char>(pl.first);
-  float* fb = (float*)ws.take<char>(pl.first);
+  float* fa = (float*)ws.take<char>(2 * pl.first);    // A then Bf, contiguous (one 2B-slice tensor)
+  float* fb = fa + (size_t)B * op->F * H * W;
   float* fq = (float*)ws.take<char>(pl.first);
+  float* fp = (float*)ws.take<char>(2 * pl.first);    // PA then PB
+  uint16_t* ap2 = (uint16_t*)ws.take<char>(pl.ap2);
+  float* cols = (float*)ws.take<char>(pl.cols);
   if (ws.overflow) { set_error("pds_matching_op_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
   const size_t stat_elems = (size_t)N * op->F * 2;
   PDS_CUDA(cudaMemsetAsync(stats, 0, pl.stats, st));
@@ -254,7 +279,8 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
       if ((rc = tc_conv3x3(f, st)) != PDS_OK) return rc;
       f.layer = &op->first[2]; f.out_f32 = fq;
       if ((rc = tc_conv3x3(f, st)) != PDS_OK) return rc;
-      if ((rc = tc_compose_first(fa, fb, fq, xa, B, op->F, H, W, D, S, fp16, st)) != PDS_OK) return rc;
+      if (!(op->factor2 && W >= 4))
+        if ((rc = tc_compose_first(fa, fb, fq, xa, B, op->F, H, W, D, S, fp16, st)) != PDS_OK) return rc;
     } else {
       // conv0: cat[left, shift_d(right)] gathered straight from the descriptors
       a.layer = &op->tc[0]; a.epilogue = TC_EPI_PLAIN;
@@ -263,19 +289,38 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
       if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
     }
     a.in2 = nullptr; a.in2_C = 0; a.in_slices = g; a.in_C = op->F; a.out_ap = nullptr;
+    const bool second = op->factor && pl.G == N && op->factor2 && W >= 4;
     for (int r = 0; r < op->n_res; ++r) {
       const TcLayer& c1 = op->tc[1 + 2 * r];
       const TcLayer& c2 = op->tc[2 + 2 * r];
       double* s1 = stats + stat_elems * (2 * r);
       double* s2 = stats + stat_elems * (2 * r + 1);
       const size_t soff = (size_t)n0 * op->F * 2;
-      a.layer = &c1; a.epilogue = TC_EPI_ACT; a.in = xa; a.out_f32 = t; a.stats = s1;
-      if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
+      if (r == 0 && second) {
+        // block 1's first convolution is linear too: conv1(A), conv1(Bf) over the descriptors, a few
+        // single-column corrections, and one pass that writes every slice's activation + sums
+        // (matching_factor.cu); x0 itself is never materialised
+        if ((rc = tc_planes_to_ap(fa, ap2, 2 * B, op->F, H, W, S, fp16, st)) != PDS_OK) return rc;
+        TcConvArgs f = a;
+        f.n_slices = 2 * B; f.n0 = 0; f.n_div = 1; f.epilogue = TC_EPI_F32; f.in_slices = 2 * B; f.in_C = op->F;
+        f.layer = &op->second; f.in = ap2; f.out_f32 = fp;
+        if ((rc = tc_conv3x3(f, st)) != PDS_OK) return rc;
+        if ((rc = tc_column_ops(fb, fq, op->wt1, cols, B, op->F, H, W, D, st)) != PDS_OK) return rc;
+        if ((rc = tc_compose_second(fp, fp + (size_t)B * op->F * H * W, cols, c1.bias, t, s1, B, op->F, H, W, D,
+                                    st)) != PDS_OK) return rc;
+      } else {
+        a.layer = &c1; a.epilogue = TC_EPI_ACT; a.in = xa; a.out_f32 = t; a.stats = s1;
+        if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
+      }
       if ((rc = tc_norm_split(t, s1 + soff, c1.gamma, c1.beta, nullptr, ya, g, op->F, H, W, S, fp16, st)) != PDS_OK) return rc;
-      a.layer = &c2; a.in = ya; a.stats = s2;
+      a.layer = &c2; a.epilogue = TC_EPI_ACT; a.in = ya; a.out_f32 = t; a.stats = s2;
       if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
-      // x = IN(t) + x (ResidualBlock.forward, network_blocks.py:143-144), in place on the planes
-      if ((rc = tc_norm_split(t, s2 + soff, c2.gamma, c2.beta, xa, xa, g, op->F, H, W, S, fp16, st)) != PDS_OK) return rc;
+      // x = IN(t) + x (ResidualBlock.forward, network_blocks.py:143-144)
+      if (r == 0 && second) {
+        if ((rc = tc_norm_residual_first(t, s2, c2.gamma, c2.beta, fa, fb, fq, xa, B, op->F, H, W, D, S, fp16, st)) != PDS_OK) return rc;
+      } else {   // in place on the planes
+        if ((rc = tc_norm_split(t, s2 + soff, c2.gamma, c2.beta, xa, xa, g, op->F, H, W, S, fp16, st)) != PDS_OK) return rc;
+      }
     }
     a.layer = &op->tc.back(); a.epilogue = TC_EPI_SIG; a.in = xa;
     a.out_f32 = nullptr; a.out_ap = nullptr; a.stats = nullptr; a.out_sig = signatures;
