@@ -129,6 +129,7 @@ def kernel_rooflines(report, steps, peaks):
         if flops or nbytes:
             entry['tflops'] = flops / sec / 1e12
             entry['gbs'] = nbytes / sec / 1e9
+            entry['tensor_frac'], entry['hbm_frac'] = tensor, hbm
             if tensor >= hbm:
                 entry.update(bound='tensor', unit='TFLOP/s', achieved=entry['tflops'],
                              peak=peaks['bf16_tflops_sustained'], frac=tensor)
@@ -283,16 +284,16 @@ def main():
         launches = _capi.launch_count() - launches0
 
         # ---- e2e: public API with HOST buffers, H2D + D2H inside the timed region ------
-        d2h = torch.empty((args.batch, H, W), dtype=torch.float32).pin_memory()
-        for i in range(2):
-            l, r = host_pairs[i % len(host_pairs)]
-            d2h.copy_(net(l.to(dev, non_blocking=True), r.to(dev, non_blocking=True)))
+        # pipeline.HostPipeline is the package's serving call: per pair, upload of both images from
+        # pinned memory (copy stream, overlapped with the previous pair's forward), forward,
+        # download of the disparity map
+        from practicaldeepstereo_nips2018_b200.pipeline import HostPipeline
+        pipe = HostPipeline(net, dev)
+        d2h = [torch.empty((args.batch, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+        pipe.run([host_pairs[i % len(host_pairs)] for i in range(2)], out=d2h)
         barrier()
         start.record()
-        for i in range(args.steps):
-            l, r = host_pairs[i % len(host_pairs)]
-            d2h.copy_(net(l.to(dev, non_blocking=True), r.to(dev, non_blocking=True)),
-                      non_blocking=True)
+        pipe.run((host_pairs[i % len(host_pairs)] for i in range(args.steps)), out=d2h)
         stop.record()
         barrier()
         e2e_ms = max_over_ranks(start.elapsed_time(stop))
@@ -324,7 +325,9 @@ def main():
         if dominant:
             roofline = {'bound': dominant['bound'], 'achieved': dominant['achieved'],
                         'peak': dominant['peak'], 'unit': dominant['unit'],
-                        'frac': dominant['frac'], 'traffic': traffic.get(dominant['kernel']),
+                        'frac': dominant['frac'], 'tensor_frac': dominant['tensor_frac'],
+                        'hbm_frac': dominant['hbm_frac'], 'tflops': dominant['tflops'], 'gbs': dominant['gbs'],
+                        'traffic': traffic.get(dominant['kernel']),
                         'traffic_source': traffic.get('_source') if dominant['kernel'] in traffic else None,
                         'kernel': dominant['kernel'],
                         'peak_source': peaks['source'],

@@ -743,10 +743,11 @@ int launch_tc(TcKernelParams& p, cudaStream_t st) {
   // PDS_B200_PROFILE_DETAIL=1: one profiler class per epilogue variant and slice count
   static const bool detail = getenv("PDS_B200_PROFILE_DETAIL") && atoi(getenv("PDS_B200_PROFILE_DETAIL"));
   static std::string names[8][2];
-  std::string& nm = names[p.epilogue & 7][p.n_slices > 8 ? 1 : 0];
+  const bool per_sample = p.n_div == 1 && !p.in_global;     // descriptor-level launch (not one slice per disparity)
+  std::string& nm = names[p.epilogue & 7][per_sample ? 0 : 1];
   if (nm.empty())
-    nm = detail ? base + "[epi " + std::to_string(p.epilogue) + (p.n_slices > 8 ? ", all slices]" : ", descriptors]")
-                : base;
+    nm = base + (detail ? "[epi " + std::to_string(p.epilogue) + (per_sample ? ", per sample]" : ", all slices]")
+                        : (per_sample ? "[per sample]" : ""));
   PDS_KERNEL(nm.c_str(), st);
   {
     // reference FLOPs of the layer (real Cout, all Cin); bytes: AP terms in (both inputs), output as written

@@ -1,0 +1,60 @@
+"""Host-buffer inference pipeline: the call a serving loop makes.
+
+The reference moves every example to the GPU and runs the network back to back
+(trainer.py:241-244: ``_move_tensors_to_cuda`` then ``network(left, right)``), so the
+upload of a pair is serialised with its forward.  ``HostPipeline`` keeps the same
+per-pair work -- upload of both images from pinned host memory, ``PdsNetwork.forward``,
+download of the disparity map -- but issues the upload of pair i+1 on a copy stream while
+pair i computes; results land in pinned host buffers.
+"""
+import torch
+
+
+class HostPipeline(object):
+    def __init__(self, network, device=None, depth=2):
+        self._network = network
+        self._device = device if device is not None else next(network.parameters()).device
+        self._copy_stream = torch.cuda.Stream(self._device)
+        self._depth = max(1, depth)
+
+    def _upload(self, pair):
+        """H2D of one (left, right) pair on the copy stream; returns tensors + ready event."""
+        with torch.cuda.stream(self._copy_stream):
+            left = pair[0].to(self._device, non_blocking=True)
+            right = pair[1].to(self._device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        return left, right, ready
+
+    def run(self, host_pairs, out=None):
+        """host_pairs: iterable of (left, right) pinned CPU tensors [B, 3, H, W].
+        out: optional list of pinned CPU tensors [B, H, W] (reused round-robin).
+        Returns the list of host disparity tensors, one per pair (valid after
+        ``torch.cuda.current_stream().synchronize()``)."""
+        compute = torch.cuda.current_stream(self._device)
+        pairs = iter(host_pairs)
+        inflight, results, k = [], [], 0
+        with torch.no_grad():
+            for pair in pairs:
+                inflight.append(self._upload(pair))
+                if len(inflight) < self._depth:
+                    continue
+                k = self._step(inflight.pop(0), compute, out, results, k)
+            while inflight:
+                k = self._step(inflight.pop(0), compute, out, results, k)
+        return results
+
+    def _step(self, item, compute, out, results, k):
+        left, right, ready = item
+        compute.wait_event(ready)
+        disparity = self._network(left, right)
+        # the device copies of the inputs are released only once the forward has consumed them
+        left.record_stream(compute)
+        right.record_stream(compute)
+        if out is not None:
+            host = out[k % len(out)]
+        else:
+            host = torch.empty(disparity.shape, dtype=disparity.dtype).pin_memory()
+        host.copy_(disparity, non_blocking=True)
+        results.append(host)
+        return k + 1

@@ -96,3 +96,25 @@ def test_network_vs_torch_port_kitti_like():
                                     st['disparity'].cpu().numpy(), st['cost'].cpu().numpy(),
                                     (28, 10), cost_err)
     assert safe > 0.9 and flips < 1e-2 and err <= 1e-3 + 50 * cost_err
+
+
+def test_host_pipeline_matches_direct_calls():
+    """pipeline.HostPipeline (uploads overlapped with the previous forward) returns exactly what
+    PdsNetwork.forward returns for every pair, in order."""
+    from practicaldeepstereo_nips2018_b200.pipeline import HostPipeline
+    torch.manual_seed(3)
+    net = PdsNetwork.default(63, precision='fp16x2').cuda().eval()
+    pairs = [(torch.rand(1, 3, 64, 128).mul(255).pin_memory(), torch.rand(1, 3, 64, 128).mul(255).pin_memory())
+             for _ in range(5)]
+    with torch.no_grad():
+        direct = [net(l.cuda(), r.cuda()).cpu() for l, r in pairs]
+    out = HostPipeline(net).run(pairs)
+    torch.cuda.synchronize()
+    assert len(out) == len(pairs)
+    for a, b in zip(out, direct):
+        assert torch.equal(a, b)
+    # reused output buffers (round-robin of 2): the last two results are still intact
+    bufs = [torch.empty(1, 64, 128).pin_memory() for _ in range(2)]
+    out2 = HostPipeline(net).run(pairs, out=bufs)
+    torch.cuda.synchronize()
+    assert torch.equal(out2[-1], direct[-1]) and torch.equal(out2[-2], direct[-2])
