@@ -118,3 +118,47 @@ def test_host_pipeline_matches_direct_calls():
     out2 = HostPipeline(net).run(pairs, out=bufs)
     torch.cuda.synchronize()
     assert torch.equal(out2[-1], direct[-1]) and torch.equal(out2[-2], direct[-2])
+
+
+@pytest.mark.parametrize('name,H,W,md,precision', [
+    ('C2', 540, 960, 191, 'fp16x2'),
+    ('C4', 375, 1242, 191, 'fp16x2'),
+    ('C3', 540, 960, 255, 'fp16x2'),
+    ('C3-bf16', 540, 960, 255, 'bf16'),
+])
+def test_full_size_configs_vs_torch_port(name, H, W, md, precision):
+    """BASELINE.json's full-size configurations against the ATen composition of the same
+    operators on the same device (fp32, TF32 off): margin-aware parity for the fp32-grade
+    precision, MAE / 3-pixel error (errors.py:9-74 semantics) for plain bf16 operands."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    params = synth.make_params(synth.network_specs(), 81)
+    net = load_module(PdsNetwork.default(md, precision=precision), params)
+    g = torch.Generator().manual_seed(82)
+    left = (torch.rand(1, 3, H, W, generator=g) * 255).cuda()
+    right = (torch.rand(1, 3, H, W, generator=g) * 255).cuda()
+    right[..., :-17] = 0.8 * left[..., 17:] + 0.2 * right[..., :-17]
+    ph, pw = -H % 64, -W % 64
+    with torch.no_grad():
+        disp = net(left, right)
+        cost = net.pass_through_network(net._size_adapter.pad(left), net._size_adapter.pad(right))[0]
+        _, idx = net._estimator(cost, crop_top=ph, crop_left=pw, return_argmax=True)
+        st = torch_port.network_stages(left, right, tdict(params), md)
+    assert disp.shape == (1, H, W) and cost.shape == (1, (md + 1) // 2, H + ph, W + pw)
+    assert torch.isfinite(disp).all()
+    ref = st['disparity']
+    mae = float((disp - ref).abs().mean())
+    bad3 = float(((disp - ref).abs() > 3).float().mean())
+    if precision == 'bf16':
+        # single-term operands: not an fp32-grade mode; judged on the reference's own metrics.  With
+        # random weights the cost volume is nearly flat along the disparity axis, so every arg-max
+        # flip moves the disparity by tens of pixels (SURVEY.md 0: the reference's own bf16 run
+        # differs from its fp32 run by up to 55 px); measured here: MAE 3.8 px, 3PE 5.1 %
+        assert mae < 6.0 and bad3 < 0.08, (mae, bad3)
+        return
+    cost_err = max_abs(cost, st['cost'])
+    assert cost_err <= 2e-3, cost_err
+    flips, err, safe = margin_aware(disp.cpu().numpy(), idx.cpu().numpy(), ref.cpu().numpy(),
+                                    st['cost'].cpu().numpy(), (ph, pw), cost_err)
+    assert safe > 0.9 and flips < 1e-2 and err <= 1e-3 + 50 * cost_err, (safe, flips, err)
+    assert mae < 0.05 and bad3 < 5e-3, (mae, bad3)
