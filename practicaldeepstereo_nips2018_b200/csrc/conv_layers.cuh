@@ -120,7 +120,10 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
                            const float* beta_host, const float* w_host, float bias, int B, int D,
                            int H, int W, cudaStream_t st, float* disparity = nullptr,
                            int64_t* argmax = nullptr, int R = 0, int step = 1, int crop_top = 0,
-                           int crop_left = 0);
+                           int crop_left = 0, float* state = nullptr);
+// Scratch for the fused form (partial SubpixelMap states of the disparity-axis segments); with it
+// the fused kernel keeps the segmentation of the plain one and a merge kernel finishes.
+size_t hourglass_tail_state_bytes(int B, int D, int H, int W);
 
 // [N][C][S] <-> [N][S][C]
 int nchw_to_nhwc(const float* in, float* out, int N, int C, size_t S, cudaStream_t st);

@@ -52,13 +52,17 @@ struct MapState {
 #pragma unroll
     for (int r = 0; r < R; ++r) { before[r] = 0.f; after[r] = 0.f; hist[r] = 0.f; }
   }
-  __device__ __forceinline__ void push(float x, int d) {
-    if (d == 0) {
-      best = x; idx = 0; hist[0] = x;
-      return;
-    }
+  // A scan may cover only a SEGMENT [z0, z1) of the disparity axis (segments are merged by
+  // subpixel_merge_kernel): values just before the segment only warm the history up, values just
+  // after it are only captured into the window of a maximum near the segment's end.
+  __device__ __forceinline__ void warm(float x) {
+#pragma unroll
+    for (int r = R - 1; r > 0; --r) hist[r] = hist[r - 1];
+    hist[0] = x;
+  }
+  __device__ __forceinline__ void push(float x, int d, bool first) {
     const int off = d - idx;
-    if (takes_over(x, best)) {
+    if (first || takes_over(x, best)) {
       best = x; idx = d;
 #pragma unroll
       for (int r = 0; r < R; ++r) before[r] = hist[r];
@@ -66,9 +70,12 @@ struct MapState {
 #pragma unroll
       for (int r = 0; r < R; ++r) if (off == r + 1) after[r] = x;
     }
+    warm(x);
+  }
+  __device__ __forceinline__ void tail(float x, int d) {
+    const int off = d - idx;
 #pragma unroll
-    for (int r = R - 1; r > 0; --r) hist[r] = hist[r - 1];
-    hist[0] = x;
+    for (int r = 0; r < R; ++r) if (off == r + 1) after[r] = x;
   }
   // softmax over the window, max-subtracted, summation in shift order (estimator.py:66-90)
   __device__ __forceinline__ float disparity(int D, int step) const {
@@ -96,13 +103,14 @@ struct FusedParams {
   float* disparity;      // (B, 2H - crop_top, 2W - crop_left)
   int64_t* argmax;       // same shape or null
   int step, crop_top, crop_left;
+  float* state;          // [segment][2 + 2R fields][B][2H][2W]: partial SubpixelMap states
 };
 
 // R == 0: writes the cost volume (B, D, 2H, 2W).  R >= 1: the volume is never written -- every
 // thread feeds the four output pixels it owns into the SubpixelMap state (window radius R) and
 // stores their disparities, cropped (SizeAdapter.unpad), at the end of its march along z.
 template <int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, R > 0 ? 2 : 1)   // fused: two CTAs per SM despite the estimator state
 hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f) {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   const int b = blockIdx.z / p.nseg, seg = blockIdx.z - b * p.nseg;
@@ -144,7 +152,9 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
     for (int c = 0; c < 4; ++c) state[c].init();
   }
 
-  for (int zi = z0 - 1; zi <= z1; ++zi) {
+  // fused: the scan of a segment extends R outputs to either side (history warm-up / window capture)
+  const int zs = R > 0 ? max(0, z0 - R) : z0, ze = R > 0 ? min(p.D, z1 + R) : z1;
+  for (int zi = zs - 1; zi <= ze; ++zi) {
     if (zi >= 0 && zi < p.D) {
       float4 v[3][3];
       const float4* pl = base + (size_t)zi * plane + (size_t)y * p.W + x;
@@ -178,20 +188,43 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
       }
     }
     const int zo = zi - 1;
-    if (zo >= z0 && zo < z1) {
+    if (zo >= zs && zo < ze) {
       if (R == 0) {
         float* o = obase + (size_t)zo * oplane;
         *reinterpret_cast<float2*>(o) = make_float2(acc[0][0] + p.bias, acc[0][1] + p.bias);
         *reinterpret_cast<float2*>(o + OW) = make_float2(acc[0][2] + p.bias, acc[0][3] + p.bias);
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) state[c].push(acc[0][c] + p.bias, zo);
+        for (int c = 0; c < 4; ++c) {
+          const float val = acc[0][c] + p.bias;
+          if (zo < z0) state[c].warm(val);
+          else if (zo < z1) state[c].push(val, zo, zo == z0);
+          else state[c].tail(val, zo);
+        }
       }
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) { acc[0][c] = acc[1][c]; acc[1][c] = acc[2][c]; acc[2][c] = 0.f; }
   }
   if (R > 0) {
+    if (f.state) {
+      // partial state of this segment for the four pixels: fields best, idx, before[R], after[R]
+      const int OH = 2 * p.H;
+      const size_t fplane = (size_t)p.B * OH * OW;
+      float* sp = f.state + (size_t)seg * (2 + 2 * R) * fplane + ((size_t)b * OH + 2 * y) * OW + 2 * x;
+      constexpr int RR = R > 0 ? R : 1;
+#pragma unroll
+      for (int k = 0; k < 2 + 2 * RR; ++k) {
+        float q[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          q[c] = k == 0 ? state[c].best : (k == 1 ? __int_as_float(state[c].idx)
+                        : (k < 2 + RR ? state[c].before[k - 2] : state[c].after[k - 2 - RR]));
+        *reinterpret_cast<float2*>(sp + (size_t)k * fplane) = make_float2(q[0], q[1]);
+        *reinterpret_cast<float2*>(sp + (size_t)k * fplane + OW) = make_float2(q[2], q[3]);
+      }
+      return;
+    }
     const int Hc = 2 * p.H - f.crop_top, Wc = OW - f.crop_left;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -204,21 +237,57 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
   }
 }
 
+// Merges the per-segment SubpixelMap states (lowest index wins ties, the first NaN wins) and
+// writes the cropped disparity.  One thread per output pixel.
+template <int R>
+__global__ void __launch_bounds__(256)
+subpixel_merge_kernel(const float* __restrict__ state, float* __restrict__ disparity, int64_t* __restrict__ argmax,
+                      int B, int OH, int OW, int D, int nseg, int step, int crop_top, int crop_left) {
+  const int Hc = OH - crop_top, Wc = OW - crop_left;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * Hc * Wc) return;
+  const int ox = (int)(i % Wc), oy = (int)((i / Wc) % Hc), b = (int)(i / ((size_t)Wc * Hc));
+  const size_t fplane = (size_t)B * OH * OW;
+  const size_t at = ((size_t)b * OH + oy + crop_top) * OW + ox + crop_left;
+  int win = 0;
+  float best = state[at];
+  for (int s = 1; s < nseg; ++s) {
+    const float v = state[(size_t)s * (2 + 2 * R) * fplane + at];
+    if (takes_over(v, best)) { best = v; win = s; }
+  }
+  MapState<R> m;
+  const float* sp = state + (size_t)win * (2 + 2 * R) * fplane + at;
+  m.best = best;
+  m.idx = __float_as_int(sp[fplane]);
+#pragma unroll
+  for (int r = 0; r < R; ++r) { m.before[r] = sp[(size_t)(2 + r) * fplane]; m.after[r] = sp[(size_t)(2 + R + r) * fplane]; }
+  disparity[i] = m.disparity(D, step);
+  if (argmax) argmax[i] = m.idx;
+}
+
 }  // namespace
 
 // w_host: the layer's weight in PyTorch layout (Cin = 4, Cout = 1, 3, 4, 4), on the HOST.
 // disparity != null: fused with SubpixelMap (window radius R = half_support_window / step in
 // 1..4) and the SizeAdapter crop; `out` is not written.
+size_t hourglass_tail_state_bytes(int B, int D, int H, int W) {
+  const int nseg = (D + 47) / 48;
+  return align_up((size_t)nseg * (2 + 2 * 4) * B * (2 * H) * (2 * W) * sizeof(float), 256);
+}
+
 int hourglass_tail_forward(const float* in, float* out, const double* stats, const float* gamma_host,
                            const float* beta_host, const float* w_host, float bias, int B, int D,
                            int H, int W, cudaStream_t st, float* disparity, int64_t* argmax, int R,
-                           int step, int crop_top, int crop_left) {
+                           int step, int crop_top, int crop_left, float* state) {
   if (B == 0 || D == 0 || H == 0 || W == 0) return PDS_OK;
   TailParams p;
   p.in = reinterpret_cast<const float4*>(in); p.out = out; p.stats = stats;
   p.B = B; p.D = D; p.H = H; p.W = W;
   const bool fused = disparity != nullptr;
-  p.zseg = fused ? D : (D > 48 ? 48 : D);
+  // fused with a state buffer: the disparity axis stays segmented (parallelism), every segment
+  // leaves a partial SubpixelMap state and subpixel_merge_kernel finishes; without one a thread
+  // scans the whole axis
+  p.zseg = (fused && !state) ? D : (D > 48 ? 48 : D);
   p.nseg = (D + p.zseg - 1) / p.zseg;
   for (int c = 0; c < 4; ++c) { p.gamma[c] = gamma_host ? gamma_host[c] : 1.f; p.beta[c] = beta_host ? beta_host[c] : 0.f; }
   for (int ci = 0; ci < 4; ++ci)
@@ -228,6 +297,7 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
   p.bias = bias;
   FusedParams f;
   f.disparity = disparity; f.argmax = argmax; f.step = step; f.crop_top = crop_top; f.crop_left = crop_left;
+  f.state = (fused && p.nseg > 1) ? state : nullptr;
   dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8), (unsigned)(B * p.nseg));
   if (grid.z > 65535) { set_error("hourglass_tail: batch too large"); return PDS_ERR_UNSUPPORTED; }
   if (fused && (R < 1 || R > 4 || crop_top < 0 || crop_left < 0 || crop_top > 2 * H || crop_left > 2 * W)) {
@@ -246,6 +316,20 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
     default: hourglass_tail_kernel<4><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
   }
   PDS_LAUNCH_CHECK("hourglass_tail_kernel");
+  if (f.state) {
+    const int OH = 2 * H, OW = 2 * W;
+    const size_t n = (size_t)B * (OH - crop_top) * (OW - crop_left);
+    PDS_KERNEL("subpixel_merge", st);
+    PDS_KERNEL_WORK(0, (double)n * (4.0 * p.nseg + 4.0 * (2 + 2 * R)));
+    const unsigned g = (unsigned)((n + 255) / 256);
+    switch (R) {
+      case 1: subpixel_merge_kernel<1><<<g, 256, 0, st>>>(state, disparity, argmax, B, OH, OW, D, p.nseg, step, crop_top, crop_left); break;
+      case 2: subpixel_merge_kernel<2><<<g, 256, 0, st>>>(state, disparity, argmax, B, OH, OW, D, p.nseg, step, crop_top, crop_left); break;
+      case 3: subpixel_merge_kernel<3><<<g, 256, 0, st>>>(state, disparity, argmax, B, OH, OW, D, p.nseg, step, crop_top, crop_left); break;
+      default: subpixel_merge_kernel<4><<<g, 256, 0, st>>>(state, disparity, argmax, B, OH, OW, D, p.nseg, step, crop_top, crop_left); break;
+    }
+    PDS_LAUNCH_CHECK("subpixel_merge_kernel");
+  }
   return PDS_OK;
 }
 

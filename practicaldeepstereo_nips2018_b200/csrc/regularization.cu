@@ -191,10 +191,11 @@ struct TailFusion {
   float* disparity = nullptr;
   int64_t* argmax = nullptr;
   int R = 0, step = 1, crop_top = 0, crop_left = 0;
+  float* state = nullptr;      // workspace for the segment states (taken by the forward functions)
 };
 
 struct TcgBuffers {
-  size_t sc_cl, ap, y_l0, y_d[4], y_s[4], y_u[4], y_e[4], y_half, stats, total;
+  size_t sc_cl, ap, y_l0, y_d[4], y_s[4], y_u[4], y_e[4], y_half, stats, tail_state, total;
 };
 
 TcgBuffers tcg_buffers(const pds_regularization* reg, int B, int D, int H, int W) {
@@ -209,7 +210,8 @@ TcgBuffers tcg_buffers(const pds_regularization* reg, int B, int D, int H, int W
   for (int k = 0; k < 4; ++k) { c /= 2; v *= 8; b.y_u[k] = b.y_e[k] = buf(B * v * c * 4); }
   b.y_half = buf(B * vox * 8 * (F / 2) * 4);
   b.stats = buf((size_t)18 * B * 16 * F * 2 * sizeof(double));
-  b.total = b.sc_cl + 2 * b.ap + b.y_l0 + b.y_half + b.stats + 1024;
+  b.tail_state = hourglass_tail_state_bytes(B, 2 * D, 2 * H, 2 * W);
+  b.total = b.sc_cl + 2 * b.ap + b.y_l0 + b.y_half + b.stats + b.tail_state + 1024;
   for (int k = 0; k < 4; ++k) b.total += b.y_d[k] + b.y_s[k] + b.y_u[k] + b.y_e[k];
   return b;
 }
@@ -235,6 +237,7 @@ int tcg_forward(pds_regularization* reg, const float* signatures, const float* s
   for (int k = 0; k < 4; ++k) { y_u[k] = (float*)ws.take<char>(bs.y_u[k]); y_e[k] = (float*)ws.take<char>(bs.y_e[k]); }
   float* y_half = (float*)ws.take<char>(bs.y_half);
   double* stats = (double*)ws.take<char>(bs.stats);
+  float* tail_state = (float*)ws.take<char>(bs.tail_state);
   if (ws.overflow) { set_error("pds_regularization_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
   PDS_CUDA(cudaMemsetAsync(stats, 0, bs.stats, st));
   const size_t stat_stride = (size_t)B * 16 * F * 2;
@@ -281,7 +284,7 @@ int tcg_forward(pds_regularization* reg, const float* signatures, const float* s
   if ((rc = tcg_conv_forward(L[li], B, ap[1], y_half, st_of(li), 1, st)) != PDS_OK) return rc;
   return hourglass_tail_forward(y_half, cost, st_of(li), reg->tail_gamma, reg->tail_beta, reg->tail_w,
                                 reg->tail_bias, B, 2 * D, 2 * H, 2 * W, st, tf.disparity, tf.argmax, tf.R,
-                                tf.step, tf.crop_top, tf.crop_left);
+                                tf.step, tf.crop_top, tf.crop_left, tail_state);
 }
 
 }  // namespace
@@ -359,6 +362,7 @@ extern "C" size_t pds_regularization_workspace_bytes(const pds_regularization* r
   }
   bytes += buf(B * vox * 8 * (F / 2));                               // half-size volume
   bytes += align_up((size_t)B * 16 * F * 2 * sizeof(double), 256);   // stats (largest layer)
+  bytes += hourglass_tail_state_bytes(B, 2 * D, 2 * H, 2 * W);       // fused tail + estimator
   return bytes + 1024;
 }
 
@@ -395,6 +399,7 @@ int regularization_forward(pds_regularization* reg, const float* signatures, con
   // remaining buffers are taken as the pipeline advances; stats last would break the
   // accounting, so reserve it now
   stats = ws.take<double>((size_t)B * 16 * F * 2);
+  float* tail_state = (float*)ws.take<char>(hourglass_tail_state_bytes(B, 2 * D, 2 * H, 2 * W));
   if (ws.overflow) { set_error("pds_regularization_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
 
   int rc;
@@ -445,7 +450,7 @@ int regularization_forward(pds_regularization* reg, const float* signatures, con
     g.D *= 2; g.H *= 2; g.W *= 2;
     return hourglass_tail_forward(half, cost, stats, reg->tail_gamma, reg->tail_beta, reg->tail_w,
                                   reg->tail_bias, B, g.D, g.H, g.W, st, tf.disparity, tf.argmax, tf.R,
-                                  tf.step, tf.crop_top, tf.crop_left);
+                                  tf.step, tf.crop_top, tf.crop_left, tail_state);
   }
   if ((rc = conv_block(L[li++], g, out, half, stats, nullptr, nullptr, half, nullptr, 0, st)) != PDS_OK) return rc;
   g.D *= 2; g.H *= 2; g.W *= 2;

@@ -8,9 +8,11 @@ from torch import nn
 from . import embedding, estimator, matching, regularization, size_adapter
 
 
-# Regularization.forward_disparity (hourglass tail + estimator + crop in one kernel, bit-identical)
-# is built and tested but, with its serial scan along the full disparity axis, currently slower
-# than the two separate kernels at C2 (0.70 ms vs 0.28 + 0.11 ms): off unless asked for.
+# Regularization.forward_disparity: hourglass tail + estimator + crop as one pipeline whose cost
+# volume is never written (bit-identical to the separate calls: per-segment SubpixelMap states +
+# a merge kernel).  Built and tested, but carrying the estimator state through the transposed
+# convolution costs more than the 424 MB round trip it saves at C2 (0.52 + 0.01 ms vs 0.28 +
+# 0.11 ms): off unless PDS_B200_FUSE_TAIL=1.
 FUSE_TAIL_AND_ESTIMATOR = os.environ.get('PDS_B200_FUSE_TAIL', '0') == '1'
 
 
