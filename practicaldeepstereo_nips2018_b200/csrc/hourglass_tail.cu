@@ -16,6 +16,8 @@
 // the current input plane is read through L1 (neighbouring threads share it).
 // The 192 weights live in the kernel parameter (constant bank): every FFMA takes
 // its weight as a constant operand, no shared-memory or register traffic.
+#include <stdlib.h>
+
 #include "conv_layers.cuh"
 
 namespace pds {
@@ -110,9 +112,9 @@ struct FusedParams {
 // thread feeds the four output pixels it owns into the SubpixelMap state (window radius R) and
 // stores their disparities, cropped (SizeAdapter.unpad), at the end of its march along z.
 template <int R>
-__global__ void __launch_bounds__(256, R > 0 ? 2 : 1)   // fused: two CTAs per SM despite the estimator state
+__global__ void __launch_bounds__(256, R > 0 ? 2 : 0)   // fused: two CTAs per SM despite the estimator state
 hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f) {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   const int b = blockIdx.z / p.nseg, seg = blockIdx.z - b * p.nseg;
   const int z0 = seg * p.zseg, z1 = min(p.D, z0 + p.zseg);
   if (x >= p.W || y >= p.H) return;
@@ -271,7 +273,7 @@ subpixel_merge_kernel(const float* __restrict__ state, float* __restrict__ dispa
 // disparity != null: fused with SubpixelMap (window radius R = half_support_window / step in
 // 1..4) and the SizeAdapter crop; `out` is not written.
 size_t hourglass_tail_state_bytes(int B, int D, int H, int W) {
-  const int nseg = (D + 47) / 48;
+  const int nseg = (D + 11) / 12;      // upper bound over the segment lengths in use
   return align_up((size_t)nseg * (2 + 2 * 4) * B * (2 * H) * (2 * W) * sizeof(float), 256);
 }
 
@@ -287,7 +289,9 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
   // fused with a state buffer: the disparity axis stays segmented (parallelism), every segment
   // leaves a partial SubpixelMap state and subpixel_merge_kernel finishes; without one a thread
   // scans the whole axis
-  p.zseg = (fused && !state) ? D : (D > 48 ? 48 : D);
+  const int zseg_env = getenv("PDS_B200_TAIL_ZSEG") ? atoi(getenv("PDS_B200_TAIL_ZSEG")) : 48;
+  const int by = getenv("PDS_B200_TAIL_BY") ? atoi(getenv("PDS_B200_TAIL_BY")) : 8;
+  p.zseg = (fused && !state) ? D : (D > zseg_env ? zseg_env : D);
   p.nseg = (D + p.zseg - 1) / p.zseg;
   for (int c = 0; c < 4; ++c) { p.gamma[c] = gamma_host ? gamma_host[c] : 1.f; p.beta[c] = beta_host ? beta_host[c] : 0.f; }
   for (int ci = 0; ci < 4; ++ci)
@@ -298,7 +302,7 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
   FusedParams f;
   f.disparity = disparity; f.argmax = argmax; f.step = step; f.crop_top = crop_top; f.crop_left = crop_left;
   f.state = (fused && p.nseg > 1) ? state : nullptr;
-  dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + 7) / 8), (unsigned)(B * p.nseg));
+  dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + by - 1) / by), (unsigned)(B * p.nseg));
   if (grid.z > 65535) { set_error("hourglass_tail: batch too large"); return PDS_ERR_UNSUPPORTED; }
   if (fused && (R < 1 || R > 4 || crop_top < 0 || crop_left < 0 || crop_top > 2 * H || crop_left > 2 * W)) {
     set_error("hourglass_tail: fused estimator needs a window radius in 1..4 and a crop inside the image");
@@ -309,11 +313,11 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
                   (double)B * D * H * W * 16 + (fused ? 4.0 * B * (2 * H - crop_top) * (2 * W - crop_left)
                                                        : (double)B * D * H * W * 16));
   switch (fused ? R : 0) {
-    case 0: hourglass_tail_kernel<0><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
-    case 1: hourglass_tail_kernel<1><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
-    case 2: hourglass_tail_kernel<2><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
-    case 3: hourglass_tail_kernel<3><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
-    default: hourglass_tail_kernel<4><<<grid, dim3(32, 8), 0, st>>>(p, f); break;
+    case 0: hourglass_tail_kernel<0><<<grid, dim3(32, by), 0, st>>>(p, f); break;
+    case 1: hourglass_tail_kernel<1><<<grid, dim3(32, by), 0, st>>>(p, f); break;
+    case 2: hourglass_tail_kernel<2><<<grid, dim3(32, by), 0, st>>>(p, f); break;
+    case 3: hourglass_tail_kernel<3><<<grid, dim3(32, by), 0, st>>>(p, f); break;
+    default: hourglass_tail_kernel<4><<<grid, dim3(32, by), 0, st>>>(p, f); break;
   }
   PDS_LAUNCH_CHECK("hourglass_tail_kernel");
   if (f.state) {
