@@ -215,6 +215,8 @@ def main():
     ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=1, help='stereo pairs per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--streams', type=int, default=1,
+                    help='compute streams of the e2e serving pipeline (pairs dealt round-robin)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     H, W, md, desc = WORKLOADS[args.workload]
@@ -288,7 +290,7 @@ def main():
         # pinned memory (copy stream, overlapped with the previous pair's forward), forward,
         # download of the disparity map
         from practicaldeepstereo_nips2018_b200.pipeline import HostPipeline
-        pipe = HostPipeline(net, dev)
+        pipe = HostPipeline(net, dev, streams=args.streams)
         d2h = [torch.empty((args.batch, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
         pipe.run([host_pairs[i % len(host_pairs)] for i in range(2)], out=d2h)
         barrier()

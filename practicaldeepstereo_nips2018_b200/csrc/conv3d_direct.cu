@@ -194,12 +194,7 @@ int launch_k3s1(const ConvLayer& l, const ConvGeom& g, const float* in, float* o
   p.zseg = zseg;
   p.nseg = (g.D + zseg - 1) / zseg;
   const size_t smem = (size_t)(4 * (CIN / 4) * (TY + 2) * 34 + 27 * CIN * (COUT / 4)) * sizeof(float4);
-  static bool configured = false;
-  if (!configured) {
-    PDS_CUDA(cudaFuncSetAttribute(conv3d_k3s1_direct_kernel<CIN, COUT, PX>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  PDS_CUDA(allow_dynamic_smem(conv3d_k3s1_direct_kernel<CIN, COUT, PX>, (int)smem));
   dim3 grid((unsigned)((g.W + 31) / 32), (unsigned)((g.H + TY - 1) / TY), (unsigned)(g.N * p.nseg));
   if (grid.z > 65535) { set_error("conv3d_direct: grid too large"); return PDS_ERR_UNSUPPORTED; }
   static const std::string name = "conv3d_k3s1_direct<" + std::to_string(CIN) + "," + std::to_string(COUT) + ">";

@@ -730,12 +730,7 @@ int launch_tc(TcKernelParams& p, cudaStream_t st) {
   }
   p.stages = stages;
   const size_t smem = p.wres_bytes + (size_t)stages * p.stage_bytes + kTailBytes;
-  static bool configured = false;
-  if (!configured) {
-    PDS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<S, NT, N, WRES>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  PDS_CUDA(allow_dynamic_smem(conv3x3_tc_kernel<S, NT, N, WRES>, 227 * 1024));
   const int total = p.tiles_x * p.tiles_y * p.n_slices;
   const int grid = total < num_sms() ? total : num_sms();
   static const std::string base = "conv3x3_tc<S=" + std::to_string(S) + ",NT=" + std::to_string(NT) +

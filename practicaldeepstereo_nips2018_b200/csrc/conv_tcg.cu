@@ -565,11 +565,7 @@ const char* tcg_name(int S, int N, const TcgPlan& pl) {
 template <int S, int N>
 int launch_tcg(const TcgParams& p, const TcgPlan& pl, size_t smem, int grid, cudaStream_t st, double flops,
                double bytes) {
-  static bool configured = false;
-  if (!configured) {
-    PDS_CUDA(cudaFuncSetAttribute(conv_tcg_kernel<S, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  PDS_CUDA(allow_dynamic_smem(conv_tcg_kernel<S, N>, 227 * 1024));
   PDS_KERNEL(tcg_name(S, N, pl), st);
   PDS_KERNEL_WORK(flops, bytes);
   PDS_CUDA(launch_pdl(conv_tcg_kernel<S, N>, dim3(grid), dim3(kThreads), smem, st, p));

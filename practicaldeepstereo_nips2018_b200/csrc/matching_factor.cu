@@ -324,11 +324,7 @@ int tc_column_ops(const float* Bf, const float* Q, const float* wt, float* cols,
   PDS_KERNEL("tc_column_ops", st);
   PDS_KERNEL_WORK(2.0 * 3 * C * C * H * 1.5 * grid.y * B, 4.0 * grid.y * B * H * C);
   const size_t smem = (size_t)(2 * (kColRows + 2) * (C + 1) + C * C) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    PDS_CUDA(cudaFuncSetAttribute(column_ops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  PDS_CUDA(allow_dynamic_smem(column_ops_kernel, (int)smem));
   column_ops_kernel<<<grid, 256, smem, st>>>(Bf, Q, wt, cols, C, H, W, D);
   PDS_LAUNCH_CHECK("column_ops_kernel");
   return PDS_OK;

@@ -256,8 +256,10 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
   if ((rc = tc_pack_nchw(left, lap, B, op->C, H, W, S, fp16, st)) != PDS_OK) return rc;
   if ((rc = tc_pack_nchw(right, rap, B, op->C, H, W, S, fp16, st)) != PDS_OK) return rc;
   // shifted-read tensor maps of the right descriptors: re-encoded only when the buffer or shape changes
-  if (op->maps_key_ptr != rap || op->maps_key[0] != B || op->maps_key[1] != H || op->maps_key[2] != W ||
-      op->maps_key[3] != D) {
+  // (only the un-factorised first convolution reads them)
+  const bool need_maps = !(op->factor && pl.G == N);
+  if (need_maps && (op->maps_key_ptr != rap || op->maps_key[0] != B || op->maps_key[1] != H ||
+                    op->maps_key[2] != W || op->maps_key[3] != D)) {
     if ((rc = tc_encode_shift_maps(op->maps_host, rap, B, S, op->C, H, W, D)) != PDS_OK) return rc;
     PDS_CUDA(cudaMemcpyAsync(op->maps_dev, op->maps_host, D * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
     op->maps_key_ptr = rap; op->maps_key[0] = B; op->maps_key[1] = H; op->maps_key[2] = W; op->maps_key[3] = D;

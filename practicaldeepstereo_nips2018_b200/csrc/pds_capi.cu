@@ -66,6 +66,19 @@ KernelScope::~KernelScope() {
   g_pending.push_back({name_, start_, stop, flops_, bytes_});
 }
 
+cudaError_t allow_dynamic_smem_impl(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;     // (kernel, device) -> bytes allowed
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find({kernel, dev});
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[{kernel, dev}] = bytes;
+  return e;
+}
+
 bool pdl_enabled() {
   // measured at C2: 4.50 ms/step with the attribute, 4.39 ms without (the step is GPU-bound and the
   // kernels' tails are short) -> off unless PDS_B200_PDL=1

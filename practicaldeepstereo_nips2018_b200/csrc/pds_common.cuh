@@ -84,6 +84,14 @@ inline int num_sms() {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: set once per (kernel,
+// device), so that one process may drive several GPUs.
+cudaError_t allow_dynamic_smem_impl(const void* kernel, int bytes);
+template <typename F>
+inline cudaError_t allow_dynamic_smem(F kernel, int bytes) {
+  return allow_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 // Streaming 128-bit accesses that do not pollute L1 (data touched once).
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 r;

@@ -55,10 +55,15 @@ class _KernelHandle(object):
         return self._handle
 
     def workspace(self, nbytes, device):
-        ws = self._workspace
-        if ws is None or ws.numel() < nbytes or ws.device != device:
-            self._workspace = ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8,
-                                               device=device)
+        """Scratch buffer for the calling stream (one per CUDA stream, so that pipelines which
+        keep several pairs in flight on different streams do not share scratch memory)."""
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+        if self._workspace is None:
+            self._workspace = {}
+        ws = self._workspace.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._workspace[key] = ws
         return ws
 
     def release(self):

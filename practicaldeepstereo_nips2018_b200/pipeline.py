@@ -11,11 +11,16 @@ import torch
 
 
 class HostPipeline(object):
-    def __init__(self, network, device=None, depth=2):
+    def __init__(self, network, device=None, depth=2, streams=1):
+        """depth: uploads issued ahead of the forward that consumes them.  streams > 1: pairs are
+        dealt round-robin to that many compute streams, so that the latency-bound layers of one
+        pair (the deep hourglass levels occupy a few dozen SMs) overlap the other pair's work;
+        every stream has its own scratch memory (matching._KernelHandle.workspace)."""
         self._network = network
         self._device = device if device is not None else next(network.parameters()).device
         self._copy_stream = torch.cuda.Stream(self._device)
-        self._depth = max(1, depth)
+        self._streams = [torch.cuda.Stream(self._device) for _ in range(streams)] if streams > 1 else []
+        self._depth = max(1, depth, streams)
 
     def _upload(self, pair):
         """H2D of one (left, right) pair on the copy stream; returns tensors + ready event."""
@@ -31,7 +36,9 @@ class HostPipeline(object):
         out: optional list of pinned CPU tensors [B, H, W] (reused round-robin).
         Returns the list of host disparity tensors, one per pair (valid after
         ``torch.cuda.current_stream().synchronize()``)."""
-        compute = torch.cuda.current_stream(self._device)
+        caller = torch.cuda.current_stream(self._device)
+        for s in self._streams:                    # work queued by the caller comes first
+            s.wait_stream(caller)
         pairs = iter(host_pairs)
         inflight, results, k = [], [], 0
         with torch.no_grad():
@@ -39,10 +46,19 @@ class HostPipeline(object):
                 inflight.append(self._upload(pair))
                 if len(inflight) < self._depth:
                     continue
-                k = self._step(inflight.pop(0), compute, out, results, k)
+                k = self._dispatch(inflight.pop(0), caller, out, results, k)
             while inflight:
-                k = self._step(inflight.pop(0), compute, out, results, k)
+                k = self._dispatch(inflight.pop(0), caller, out, results, k)
+        for s in self._streams:                    # the caller's stream sees every result
+            caller.wait_stream(s)
         return results
+
+    def _dispatch(self, item, caller, out, results, k):
+        if not self._streams:
+            return self._step(item, caller, out, results, k)
+        stream = self._streams[k % len(self._streams)]
+        with torch.cuda.stream(stream):
+            return self._step(item, stream, out, results, k)
 
     def _step(self, item, compute, out, results, k):
         left, right, ready = item

@@ -118,6 +118,12 @@ def test_host_pipeline_matches_direct_calls():
     out2 = HostPipeline(net).run(pairs, out=bufs)
     torch.cuda.synchronize()
     assert torch.equal(out2[-1], direct[-1]) and torch.equal(out2[-2], direct[-2])
+    # two compute streams (pairs dealt round-robin, one scratch buffer per stream): same results
+    for _ in range(3):
+        out3 = HostPipeline(net, streams=2).run(pairs)
+        torch.cuda.synchronize()
+        for a, b in zip(out3, direct):
+            assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize('name,H,W,md,precision', [
