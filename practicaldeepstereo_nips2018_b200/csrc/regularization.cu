@@ -98,7 +98,8 @@ int conv_block(const ConvLayer& l, const ConvGeom& g, const float* in, float* y,
                cudaStream_t st) {
   const size_t S = (size_t)l.dim[0].out_size(g.D) * l.dim[1].out_size(g.H) * l.dim[2].out_size(g.W);
   PDS_CUDA(cudaMemsetAsync(stats, 0, (size_t)g.N * l.Cout * 2 * sizeof(double), st));
-  static const bool direct = getenv("PDS_B200_DIRECT3D") && atoi(getenv("PDS_B200_DIRECT3D"));
+  // direct FFMA kernels for the 8 / 16-channel 3x3x3 layers (4.64 -> 4.06 ms for the fp32 hourglass at C2)
+  static const bool direct = !(getenv("PDS_B200_DIRECT3D") && atoi(getenv("PDS_B200_DIRECT3D")) == 0);
   bool handled = false;
   int rc = PDS_OK;
   if (direct) rc = conv_forward_direct(l, g, in, y, stats, st, &handled);

@@ -21,9 +21,13 @@ class HostPipeline(object):
         self._copy_stream = torch.cuda.Stream(self._device)
         self._streams = [torch.cuda.Stream(self._device) for _ in range(streams)] if streams > 1 else []
         self._depth = max(1, depth, streams)
+        self._download = True
 
     def _upload(self, pair):
-        """H2D of one (left, right) pair on the copy stream; returns tensors + ready event."""
+        """H2D of one (left, right) pair on the copy stream; returns tensors + ready event
+        (device-resident pairs are passed through)."""
+        if pair[0].is_cuda and pair[1].is_cuda:
+            return pair[0], pair[1], None
         with torch.cuda.stream(self._copy_stream):
             left = pair[0].to(self._device, non_blocking=True)
             right = pair[1].to(self._device, non_blocking=True)
@@ -31,11 +35,13 @@ class HostPipeline(object):
             ready.record(self._copy_stream)
         return left, right, ready
 
-    def run(self, host_pairs, out=None):
-        """host_pairs: iterable of (left, right) pinned CPU tensors [B, 3, H, W].
-        out: optional list of pinned CPU tensors [B, H, W] (reused round-robin).
-        Returns the list of host disparity tensors, one per pair (valid after
-        ``torch.cuda.current_stream().synchronize()``)."""
+    def run(self, host_pairs, out=None, download=True):
+        """host_pairs: iterable of (left, right) pinned CPU tensors [B, 3, H, W] (CUDA tensors
+        are taken as they are).  out: optional list of pinned CPU tensors [B, H, W] (reused
+        round-robin).  Returns the list of disparity tensors, one per pair -- on the host
+        (valid after ``torch.cuda.current_stream().synchronize()``), or on the device when
+        ``download=False``."""
+        self._download = download
         caller = torch.cuda.current_stream(self._device)
         for s in self._streams:                    # work queued by the caller comes first
             s.wait_stream(caller)
@@ -62,11 +68,16 @@ class HostPipeline(object):
 
     def _step(self, item, compute, out, results, k):
         left, right, ready = item
-        compute.wait_event(ready)
+        if ready is not None:
+            compute.wait_event(ready)
         disparity = self._network(left, right)
         # the device copies of the inputs are released only once the forward has consumed them
         left.record_stream(compute)
         right.record_stream(compute)
+        if not self._download:
+            disparity.record_stream(torch.cuda.current_stream(self._device))
+            results.append(disparity)
+            return k + 1
         if out is not None:
             host = out[k % len(out)]
         else:
