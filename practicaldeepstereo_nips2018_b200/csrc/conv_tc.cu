@@ -723,6 +723,8 @@ int launch_tc(TcKernelParams& p, cudaStream_t st) {
   const size_t budget = 227 * 1024 - kTailBytes - p.wres_bytes;
   int stages = (int)(budget / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  static const int stage_cap = getenv("PDS_B200_TC_STAGES") ? atoi(getenv("PDS_B200_TC_STAGES")) : 0;
+  if (stage_cap >= 2 && stages > stage_cap) stages = stage_cap;   // leaves shared memory for co-resident CTAs
   if (stages < 2) {
     set_error("conv3x3_tc: stage of %u bytes (+ %u resident) does not fit twice in shared memory",
               p.stage_bytes, p.wres_bytes);

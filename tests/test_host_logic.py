@@ -120,3 +120,39 @@ def test_network_train_mode_matches_golden(golden):
     cost = net(torch.from_numpy(li), torch.from_numpy(ri))
     assert cost.shape == (1, 32, 62, 100)
     assert torch.allclose(cost.detach(), torch.from_numpy(g['cost_unpadded']), atol=1e-4)
+
+
+def test_precision_does_not_change_the_state_dict():
+    """Every precision builds the reference's 122-key state_dict (checkpoints load unchanged)."""
+    ref = list(PdsNetwork.default(191).state_dict().keys())
+    for precision in _capi.PRECISIONS:
+        assert list(PdsNetwork.default(191, precision=precision).state_dict().keys()) == ref
+    with pytest.raises(ValueError):
+        embedding.Embedding(precision='int8')
+    with pytest.raises(ValueError):
+        regularization.Regularization(precision='int8')
+
+
+def test_kernel_paths_refuse_cpu_tensors_and_keep_autograd():
+    """No CPU fallback on the product path: eval / no-grad calls on CPU tensors raise; calls that
+    need gradients run the ATen composition (training keeps working)."""
+    torch.manual_seed(0)
+    net = PdsNetwork.default(63, precision='fp16x2').eval()
+    left, right = torch.rand(1, 3, 64, 128), torch.rand(1, 3, 64, 128)   # smallest legal size (SURVEY 4)
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        net(left, right)
+    emb = embedding.Embedding(precision='fp16x2')
+    assert not emb.uses_kernels(left)                       # CPU tensor: module composition
+    with torch.no_grad():
+        d, s = emb(left)
+    assert d.shape == (1, 64, 16, 32) and s.shape == (1, 8, 16, 32)
+    net.train()
+    cost = net(left, right)                                 # autograd path
+    assert cost.shape == (1, 32, 64, 128) and cost.requires_grad
+    cost.mean().backward()
+    assert all(p.grad is not None for p in net.parameters())
+
+
+def test_host_pipeline_is_importable_without_a_gpu():
+    from practicaldeepstereo_nips2018_b200 import pipeline
+    assert callable(pipeline.HostPipeline)
