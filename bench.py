@@ -279,7 +279,7 @@ def main():
         # layers of one pair overlap the other pairs' work); --streams 1 = plain back-to-back calls
         from practicaldeepstereo_nips2018_b200.pipeline import HostPipeline
         pipe = HostPipeline(net, dev, streams=args.streams)
-        pipe.run([pairs[i % len(pairs)] for i in range(max(2, args.streams))], download=False)
+        pipe.run([pairs[i % len(pairs)] for i in range(2 * max(2, args.streams))], download=False)
         barrier()
         launches0 = _capi.launch_count()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -296,7 +296,7 @@ def main():
         # pinned memory (copy stream, overlapped with the previous pair's forward), forward,
         # download of the disparity map
         d2h = [torch.empty((args.batch, H, W), dtype=torch.float32).pin_memory() for _ in range(2 * max(1, args.streams))]
-        pipe.run([host_pairs[i % len(host_pairs)] for i in range(max(2, args.streams))], out=d2h)
+        pipe.run([host_pairs[i % len(host_pairs)] for i in range(2 * max(2, args.streams))], out=d2h)
         barrier()
         start.record()
         pipe.run((host_pairs[i % len(host_pairs)] for i in range(args.steps)), out=d2h)

@@ -22,18 +22,32 @@ class HostPipeline(object):
         self._streams = [torch.cuda.Stream(self._device) for _ in range(streams)] if streams > 1 else []
         self._depth = max(1, depth, streams)
         self._download = True
+        # staging slots: uploads in flight + pairs being computed
+        self._slots = [{'left': None, 'right': None, 'consumed': None}
+                       for _ in range(self._depth + max(1, streams) + 1)]
+        self._next_slot = 0
 
     def _upload(self, pair):
-        """H2D of one (left, right) pair on the copy stream; returns tensors + ready event
-        (device-resident pairs are passed through)."""
+        """H2D of one (left, right) pair on the copy stream into a preallocated staging slot
+        (no allocation per pair: the caching allocator would otherwise fall back to cudaMalloc
+        whenever a block shared between streams is not yet reusable); returns tensors, the event
+        that marks the upload complete and the slot (device-resident pairs are passed through)."""
         if pair[0].is_cuda and pair[1].is_cuda:
-            return pair[0], pair[1], None
+            return pair[0], pair[1], None, None
+        slot = self._slots[self._next_slot % len(self._slots)]
+        self._next_slot += 1
+        if slot['left'] is None or slot['left'].shape != pair[0].shape or slot['right'].shape != pair[1].shape:
+            slot['left'] = torch.empty(pair[0].shape, dtype=pair[0].dtype, device=self._device)
+            slot['right'] = torch.empty(pair[1].shape, dtype=pair[1].dtype, device=self._device)
+            slot['consumed'] = None
         with torch.cuda.stream(self._copy_stream):
-            left = pair[0].to(self._device, non_blocking=True)
-            right = pair[1].to(self._device, non_blocking=True)
+            if slot['consumed'] is not None:          # the forward that last read this slot is done
+                self._copy_stream.wait_event(slot['consumed'])
+            slot['left'].copy_(pair[0], non_blocking=True)
+            slot['right'].copy_(pair[1], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self._copy_stream)
-        return left, right, ready
+        return slot['left'], slot['right'], ready, slot
 
     def run(self, host_pairs, out=None, download=True):
         """host_pairs: iterable of (left, right) pinned CPU tensors [B, 3, H, W] (CUDA tensors
@@ -67,13 +81,13 @@ class HostPipeline(object):
             return self._step(item, stream, out, results, k)
 
     def _step(self, item, compute, out, results, k):
-        left, right, ready = item
+        left, right, ready, slot = item
         if ready is not None:
             compute.wait_event(ready)
         disparity = self._network(left, right)
-        # the device copies of the inputs are released only once the forward has consumed them
-        left.record_stream(compute)
-        right.record_stream(compute)
+        if slot is not None:
+            slot['consumed'] = torch.cuda.Event()
+            slot['consumed'].record(compute)
         if not self._download:
             disparity.record_stream(torch.cuda.current_stream(self._device))
             results.append(disparity)
