@@ -208,7 +208,7 @@ def run_reference(args, H, W, md, desc):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=60)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('PDS_B200_PRECISION', 'fp16x2'))
@@ -362,7 +362,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            times = cpu_forward_seconds(H, W, md, reps=2, threads=cores)
+            times = cpu_forward_seconds(H, W, md, reps=10, threads=cores)    # ~10 s of CPU work
             line['cpu_baseline'] = {'value': 1.0 / statistics.median(times), 'unit': 'pairs/s',
                                     'cores': cores, 'kind': 'port',
                                     'sample': f'{len(times)} x one full {W}x{H} pair, torch port of '
