@@ -15,6 +15,8 @@
 // loaded.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "pds_common.cuh"
 
 namespace pds {
@@ -77,65 +79,73 @@ subpixel_map_kernel(const T* __restrict__ cost, float* __restrict__ disparity,
   const size_t plane = (size_t)H * W;
   const T* p = cost + (size_t)b * D * plane + (size_t)y * W + x0;
 
-  float best[V], before[V][R], after[V][R], hist[V][R];
+  float best[V], before[V][R], after[V][R], prev[V][R];
   int idx[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    idx[i] = 0;
+    idx[i] = 0; best[i] = 0.f;
 #pragma unroll
-    for (int r = 0; r < R; ++r) { before[i][r] = 0.f; after[i][r] = 0.f; hist[i][r] = 0.f; }
+    for (int r = 0; r < R; ++r) { before[i][r] = 0.f; after[i][r] = 0.f; prev[i][r] = 0.f; }
   }
-  {
-    float v[V];
-    Vec<T, V>::load(p, v);
+  // The scan works on chunks of planes held in registers; per element it only runs the
+  // chunk-local first-maximum (compare + two selects).  The window around the maximum is
+  // captured once per chunk with compile-time register indices (select chains on the local
+  // arg-max j): prev[] carries the last R values of the previous chunk, after-values that lie
+  // beyond the chunk are filled in at the start of the next one.  The final state equals the
+  // element-by-element scan of the reference semantics (lowest index on ties, first NaN wins).
+  auto process = [&](auto uc, int d0, const float (&v)[decltype(uc)::value][V]) {
+    constexpr int U = decltype(uc)::value;
 #pragma unroll
-    for (int i = 0; i < V; ++i) { best[i] = v[i]; hist[i][0] = v[i]; }
-  }
-  // hist[i][r] holds the value at (d - 1 - r) when element d is processed.
-  int d = 1;
+    for (int i = 0; i < V; ++i) {
+      // (1) after-values of the current maximum that fall into this chunk
+      const int off0 = d0 - idx[i];                      // >= 1 (ignored in the first chunk)
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int u = 0; u <= r && u < U; ++u)
+          if (off0 == r + 1 - u) after[i][r] = v[u][i];
+      // (2) first maximum of the chunk
+      float m = v[0][i];
+      int j = 0;
+#pragma unroll
+      for (int u = 1; u < U; ++u) {
+        const bool t = takes_over(v[u][i], m);
+        m = t ? v[u][i] : m;
+        j = t ? u : j;
+      }
+      // (3) does it take over?  (4) capture its window
+      if (d0 == 0 || takes_over(m, best[i])) {
+        best[i] = m; idx[i] = d0 + j;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (j == u) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              // x_{j-1-r}: inside the chunk or from the previous chunk's tail
+              before[i][r] = (u - 1 - r >= 0) ? v[(u - 1 - r >= 0) ? u - 1 - r : 0][i]
+                                              : prev[i][(r - u >= 0 && r - u < R) ? r - u : 0];
+              if (u + 1 + r < U) after[i][r] = v[(u + 1 + r < U) ? u + 1 + r : 0][i];
+            }
+          }
+        }
+      }
+      // (5) tail of this chunk for the next one
+#pragma unroll
+      for (int r = R - 1; r >= 0; --r)      // descending: a chunk shorter than R shifts the old tail up
+        prev[i][r] = (U - 1 - r >= 0) ? v[(U - 1 - r >= 0) ? U - 1 - r : 0][i] : prev[i][(r - U >= 0) ? r - U : 0];
+    }
+  };
+  int d = 0;
   for (; d + UNROLL <= D; d += UNROLL) {
     float v[UNROLL][V];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) Vec<T, V>::load(p + (size_t)(d + u) * plane, v[u]);
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float x = v[u][i];
-        const int off = (d + u) - idx[i];        // >= 1
-        if (takes_over(x, best[i])) {
-          best[i] = x; idx[i] = d + u;
-#pragma unroll
-          for (int r = 0; r < R; ++r) before[i][r] = hist[i][r];
-        } else {
-#pragma unroll
-          for (int r = 0; r < R; ++r) if (off == r + 1) after[i][r] = x;
-        }
-#pragma unroll
-        for (int r = R - 1; r > 0; --r) hist[i][r] = hist[i][r - 1];
-        hist[i][0] = x;
-      }
-    }
+    process(std::integral_constant<int, UNROLL>(), d, v);
   }
   for (; d < D; ++d) {
-    float v[V];
-    Vec<T, V>::load(p + (size_t)d * plane, v);
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float x = v[i];
-      const int off = d - idx[i];
-      if (takes_over(x, best[i])) {
-        best[i] = x; idx[i] = d;
-#pragma unroll
-        for (int r = 0; r < R; ++r) before[i][r] = hist[i][r];
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) if (off == r + 1) after[i][r] = x;
-      }
-#pragma unroll
-      for (int r = R - 1; r > 0; --r) hist[i][r] = hist[i][r - 1];
-      hist[i][0] = x;
-    }
+    float v[1][V];
+    Vec<T, V>::load(p + (size_t)d * plane, v[0]);
+    process(std::integral_constant<int, 1>(), d, v);
   }
 
   const int Wc = W - crop_left;
@@ -215,11 +225,11 @@ int launch(const T* cost, float* disparity, int64_t* argmax, int B, int D, int H
   PDS_KERNEL("subpixel_map", st);
   // rows above crop_top are never loaded; every other cost element is read once
   PDS_KERNEL_WORK(0, (double)B * Hc * ((double)D * W * sizeof(T) + (double)(W - crop_left) * 4));
-  // 128 threads, 4 planes in flight per thread: measured best at C2 (77 us; 64 threads x 8 planes:
-  // 112 us, 256 x 4: 121 us, 2 pixels per thread: 81-86 us) -- fewer registers, more resident warps
+  // 128 threads, chunks of 6 planes: measured best at C2 (50 us = 4.0 TB/s; chunks of 4 / 8 / 12 /
+  // 16: 57 / 71 / 63 / 61 us; the element-by-element scan was instruction-bound at 77-112 us)
   dim3 grid((unsigned)(((size_t)quads * Hc + 127) / 128), (unsigned)B);
 #define PDS_EST(RR)                                                                  \
-  subpixel_map_kernel<T, V, RR, 4, 128><<<grid, 128, 0, st>>>(cost, disparity, argmax, D, H, W, \
+  subpixel_map_kernel<T, V, RR, 6, 128><<<grid, 128, 0, st>>>(cost, disparity, argmax, D, H, W, \
                                                               step, crop_top, crop_left, quads)
   switch (R) {
     case 1: PDS_EST(1); break;
