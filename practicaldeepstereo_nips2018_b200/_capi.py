@@ -12,6 +12,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libpds_b200.so')
+if os.environ.get('PDS_B200_LIB'):          # experiments: an alternative build of the same library
+    LIB_PATH = os.environ['PDS_B200_LIB']
 
 PDS_OK, PDS_ERR_INVALID_ARGUMENT, PDS_ERR_CUDA, PDS_ERR_WORKSPACE, PDS_ERR_UNSUPPORTED = range(5)
 PDS_F32, PDS_BF16 = 0, 1
