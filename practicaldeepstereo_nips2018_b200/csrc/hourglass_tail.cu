@@ -33,8 +33,35 @@ struct TailParams {
   float bias;
 };
 
-__device__ __forceinline__ float dot4(const float4& v, const float* w) {
-  return fmaf(v.x, w[0], fmaf(v.y, w[1], fmaf(v.z, w[2], v.w * w[3])));
+// Row DY (0..2 <-> input y - 1..y + 1) of the 3 x 3 input neighbourhoods of NP pixels of plane zi
+// -> every accumulator that row feeds: out z = zi - tz + 1 uses kd = 2 - tz (slot 2 - tz: 0 is
+// out zi-1, 2 is out zi+1); out row class cy takes kernel row 1 - cy + 2*ty from input row
+// 1 + cy - ty.  One fused multiply-add chain per accumulator, the same order in every kernel of
+// this file (the fused and the plain paths agree bit for bit); the pixel loop is innermost so the
+// NP pixels share each weight fetch.
+template <int DY, int NP>
+__device__ __forceinline__ void tail_accumulate_row(float (&acc)[NP][3][4], const float4 (&v)[NP][3],
+                                                    const float (&w)[3][4][4][4]) {
+#pragma unroll
+  for (int cy = 0; cy < 2; ++cy) {
+    const int ty = 1 + cy - DY;
+    if (ty < 0 || ty > 1) continue;
+#pragma unroll
+    for (int tz = 0; tz < 3; ++tz)
+#pragma unroll
+      for (int cx = 0; cx < 2; ++cx)
+#pragma unroll
+        for (int tx = 0; tx < 2; ++tx) {
+          const float* ww = w[2 - tz][1 - cy + 2 * ty][1 - cx + 2 * tx];
+#pragma unroll
+          for (int px = 0; px < NP; ++px) {
+            const float4& q = v[px][1 + cx - tx];
+            float a = acc[px][2 - tz][cy * 2 + cx];
+            a = fmaf(q.x, ww[0], a); a = fmaf(q.y, ww[1], a); a = fmaf(q.z, ww[2], a); a = fmaf(q.w, ww[3], a);
+            acc[px][2 - tz][cy * 2 + cx] = a;
+          }
+        }
+  }
 }
 
 // th.max semantics (estimator.cu): strictly greater keeps the lowest index; the first NaN wins.
@@ -143,11 +170,11 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
 #pragma unroll
   for (int d = 0; d < 3; ++d) { okx[d] = x + d - 1 >= 0 && x + d - 1 < p.W; oky[d] = y + d - 1 >= 0 && y + d - 1 < p.H; }
 
-  float acc[3][4];   // [out z - zi + 1][cy*2+cx]
+  float acc[1][3][4];   // [pixel][out z - zi + 1][cy*2+cx]
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[k][c] = 0.f;
+    for (int c = 0; c < 4; ++c) acc[0][k][c] = 0.f;
   MapState<(R > 0 ? R : 1)> state[4];
   if (R > 0) {
 #pragma unroll
@@ -158,7 +185,7 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
   const int zs = R > 0 ? max(0, z0 - R) : z0, ze = R > 0 ? min(p.D, z1 + R) : z1;
   for (int zi = zs - 1; zi <= ze; ++zi) {
     if (zi >= 0 && zi < p.D) {
-      float4 v[3][3];
+      float4 v[3][1][3];
       const float4* pl = base + (size_t)zi * plane + (size_t)y * p.W + x;
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
@@ -168,37 +195,25 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
             float4 t = __ldg(pl + (dy - 1) * p.W + (dx - 1));
             t.x = fmaf(t.x, sc[0], sh[0]); t.y = fmaf(t.y, sc[1], sh[1]);
             t.z = fmaf(t.z, sc[2], sh[2]); t.w = fmaf(t.w, sc[3], sh[3]);
-            v[dy][dx] = t;
+            v[dy][0][dx] = t;
           } else {
-            v[dy][dx] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero padding of the NORMALISED tensor
+            v[dy][0][dx] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero padding of the NORMALISED tensor
           }
         }
-      // input plane zi feeds out z = zi - tz + 1 with kd = 2 - tz
-#pragma unroll
-      for (int tz = 0; tz < 3; ++tz) {
-        const int kd = 2 - tz, slot = 2 - tz;   // slot 0: out zi-1, 1: out zi, 2: out zi+1
-#pragma unroll
-        for (int cy = 0; cy < 2; ++cy)
-#pragma unroll
-          for (int cx = 0; cx < 2; ++cx)
-#pragma unroll
-            for (int ty = 0; ty < 2; ++ty)
-#pragma unroll
-              for (int tx = 0; tx < 2; ++tx)
-                acc[slot][cy * 2 + cx] +=
-                    dot4(v[1 + cy - ty][1 + cx - tx], p.w[kd][1 - cy + 2 * ty][1 - cx + 2 * tx]);
-      }
+      tail_accumulate_row<0, 1>(acc, v[0], p.w);
+      tail_accumulate_row<1, 1>(acc, v[1], p.w);
+      tail_accumulate_row<2, 1>(acc, v[2], p.w);
     }
     const int zo = zi - 1;
     if (zo >= zs && zo < ze) {
       if (R == 0) {
         float* o = obase + (size_t)zo * oplane;
-        *reinterpret_cast<float2*>(o) = make_float2(acc[0][0] + p.bias, acc[0][1] + p.bias);
-        *reinterpret_cast<float2*>(o + OW) = make_float2(acc[0][2] + p.bias, acc[0][3] + p.bias);
+        *reinterpret_cast<float2*>(o) = make_float2(acc[0][0][0] + p.bias, acc[0][0][1] + p.bias);
+        *reinterpret_cast<float2*>(o + OW) = make_float2(acc[0][0][2] + p.bias, acc[0][0][3] + p.bias);
       } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float val = acc[0][c] + p.bias;
+          const float val = acc[0][0][c] + p.bias;
           if (zo < z0) state[c].warm(val);
           else if (zo < z1) state[c].push(val, zo, zo == z0);
           else state[c].tail(val, zo);
@@ -206,7 +221,7 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
       }
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { acc[0][c] = acc[1][c]; acc[1][c] = acc[2][c]; acc[2][c] = 0.f; }
+    for (int c = 0; c < 4; ++c) { acc[0][0][c] = acc[0][1][c]; acc[0][1][c] = acc[0][2][c]; acc[0][2][c] = 0.f; }
   }
   if (R > 0) {
     if (f.state) {
@@ -236,6 +251,118 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
       f.disparity[o] = state[c].disparity(p.D, f.step);
       if (f.argmax) f.argmax[o] = state[c].idx;
     }
+  }
+}
+
+// Shared-memory tiled form of the plain (cost-volume writing) kernel.  The per-thread kernel above
+// is instruction-issue bound: ~470 instructions per thread and plane for 192 useful FFMAs (border
+// predicates, 9x redundant normalisation, and -- sm_100 stages constant operands through uniform
+// registers -- one LDCU.128 per four weights).  Here a CTA of 32 x 8 threads covers 64 x 8 input
+// columns: each input plane is staged ONCE (66 x 10 voxels with the halo, normalised on the way in,
+// zeros outside the volume), every thread owns the two columns tx and tx + 32 (conflict-free
+// LDS.128, coalesced stores) and the two pixels share every weight fetch.  The next plane's global
+// loads are in flight while the current one is consumed; one __syncthreads per plane.
+constexpr int kTileW = 66, kTileH = 10, kTileN = kTileW * kTileH, kTilePer = (kTileN + 255) / 256;
+
+__global__ void __launch_bounds__(256, 2)
+hourglass_tail_tiled_kernel(const __grid_constant__ TailParams p) {
+  __shared__ float4 tile[2][kTileH][kTileW];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 8, y = y0 + ty;
+  const int b = blockIdx.z / p.nseg, seg = blockIdx.z - b * p.nseg;
+  const int z0 = seg * p.zseg, z1 = min(p.D, z0 + p.zseg);
+  float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.stats) {
+    const double n = (double)p.D * p.H * p.W;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double s = p.stats[(b * 4 + c) * 2], q = p.stats[(b * 4 + c) * 2 + 1];
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+      sc[c] = rstd * p.gamma[c];
+      sh[c] = p.beta[c] - (float)mean * sc[c];
+    }
+  }
+  const size_t plane = (size_t)p.H * p.W;
+  const float4* base = p.in + (size_t)b * p.D * plane;
+  // the (up to) kTilePer tile elements this thread stages per plane
+  int soff[kTilePer];        // offset inside a plane; -1: outside the image (zero), -2: no element
+  int sidx[kTilePer];        // float4 index inside one tile buffer
+#pragma unroll
+  for (int k = 0; k < kTilePer; ++k) {
+    const int e = tid + 256 * k;
+    const int ly = e / kTileW, lx = e - ly * kTileW, gy = y0 + ly - 1, gx = x0 + lx - 1;
+    const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+    soff[k] = e < kTileN ? (ok ? gy * p.W + gx : -1) : -2;
+    sidx[k] = e < kTileN ? e : 0;
+  }
+  auto fetch = [&](int zi, float4 (&r)[kTilePer]) {
+    const bool zok = zi >= 0 && zi < p.D;
+#pragma unroll
+    for (int k = 0; k < kTilePer; ++k) {
+      r[k] = make_float4(0.f, 0.f, 0.f, 0.f);              // zero padding of the NORMALISED tensor
+      if (zok && soff[k] >= 0) {
+        const float4 t = __ldg(base + (size_t)zi * plane + soff[k]);
+        r[k] = make_float4(fmaf(t.x, sc[0], sh[0]), fmaf(t.y, sc[1], sh[1]), fmaf(t.z, sc[2], sh[2]), fmaf(t.w, sc[3], sh[3]));
+      }
+    }
+  };
+  auto stash = [&](int buf, const float4 (&r)[kTilePer]) {
+    float4* t = &tile[buf][0][0];
+#pragma unroll
+    for (int k = 0; k < kTilePer; ++k) if (soff[k] > -2) t[sidx[k]] = r[k];
+  };
+  const int OW = 2 * p.W;
+  const size_t oplane = (size_t)4 * plane;
+  float* obase = p.out + (size_t)b * p.D * oplane + (size_t)(2 * y) * OW + 2 * (x0 + tx);
+  const bool in0 = y < p.H && x0 + tx < p.W, in1 = y < p.H && x0 + 32 + tx < p.W;
+  float acc[2][3][4];
+#pragma unroll
+  for (int px = 0; px < 2; ++px)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[px][k][c] = 0.f;
+
+  float4 r[kTilePer];
+  fetch(z0 - 1, r);
+  stash(0, r);
+  __syncthreads();
+  int cur = 0;
+  for (int zi = z0 - 1; zi <= z1; ++zi) {
+    if (zi < z1) fetch(zi + 1, r);                         // in flight while plane zi is consumed
+    if (zi >= 0 && zi < p.D) {
+      float4 v[2][3];
+#define PDS_TAIL_ROW(DY)                                                                      \
+      _Pragma("unroll") for (int px = 0; px < 2; ++px)                                         \
+      _Pragma("unroll") for (int dx = 0; dx < 3; ++dx) v[px][dx] = tile[cur][ty + DY][tx + 32 * px + dx]; \
+      tail_accumulate_row<DY, 2>(acc, v, p.w);
+      PDS_TAIL_ROW(0)
+      PDS_TAIL_ROW(1)
+      PDS_TAIL_ROW(2)
+#undef PDS_TAIL_ROW
+    }
+    const int zo = zi - 1;
+    if (zo >= z0 && zo < z1) {
+      float* o = obase + (size_t)zo * oplane;
+      if (in0) {
+        *reinterpret_cast<float2*>(o) = make_float2(acc[0][0][0] + p.bias, acc[0][0][1] + p.bias);
+        *reinterpret_cast<float2*>(o + OW) = make_float2(acc[0][0][2] + p.bias, acc[0][0][3] + p.bias);
+      }
+      if (in1) {
+        *reinterpret_cast<float2*>(o + 64) = make_float2(acc[1][0][0] + p.bias, acc[1][0][1] + p.bias);
+        *reinterpret_cast<float2*>(o + 64 + OW) = make_float2(acc[1][0][2] + p.bias, acc[1][0][3] + p.bias);
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < 2; ++px)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { acc[px][0][c] = acc[px][1][c]; acc[px][1][c] = acc[px][2][c]; acc[px][2][c] = 0.f; }
+    if (zi < z1) stash(cur ^ 1, r);
+    __syncthreads();
+    cur ^= 1;
   }
 }
 
@@ -312,8 +439,12 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
   PDS_KERNEL_WORK(2.0 * 192 * B * D * H * W,
                   (double)B * D * H * W * 16 + (fused ? 4.0 * B * (2 * H - crop_top) * (2 * W - crop_left)
                                                        : (double)B * D * H * W * 16));
+  static const bool tiled = !(getenv("PDS_B200_TAIL_TILED") && atoi(getenv("PDS_B200_TAIL_TILED")) == 0);
   switch (fused ? R : 0) {
-    case 0: hourglass_tail_kernel<0><<<grid, dim3(32, by), 0, st>>>(p, f); break;
+    case 0:
+      if (tiled) hourglass_tail_tiled_kernel<<<dim3((unsigned)((W + 63) / 64), (unsigned)((H + 7) / 8), grid.z), dim3(32, 8), 0, st>>>(p);
+      else hourglass_tail_kernel<0><<<grid, dim3(32, by), 0, st>>>(p, f);
+      break;
     case 1: hourglass_tail_kernel<1><<<grid, dim3(32, by), 0, st>>>(p, f); break;
     case 2: hourglass_tail_kernel<2><<<grid, dim3(32, by), 0, st>>>(p, f); break;
     case 3: hourglass_tail_kernel<3><<<grid, dim3(32, by), 0, st>>>(p, f); break;
