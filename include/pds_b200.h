@@ -197,6 +197,30 @@ int pds_embedding_forward(pds_embedding* emb, const float* images,
                           int n_shortcut, int H, int W, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* ---- f3: the input path in front of the embedding ---------------------------
+ * The images as the caller holds them, UN-padded: dataset.py:67-72 decodes to
+ * interleaved uint8 (cv2) and converts to float CHW on the host; this entry
+ * takes either form.  SizeAdapter.pad (size_adapter.py:29-43: pad_top rows and
+ * pad_left columns of zeros, padded extent (h + pad_top) x (w + pad_left), both
+ * multiples of 4) and the first InstanceNorm2d (embedding.py:32, statistics
+ * over the padded image) are fused into the kernel that writes the first
+ * convolution's operands.  The batch is images_a (n_a samples) followed by
+ * images_b (n_b samples; may be NULL with n_b == 0): left and right images
+ * without a concatenation copy.  Outputs and workspace as pds_embedding_forward
+ * with n = n_a + n_b and the PADDED extent.                                   */
+enum pds_image_layout {
+  PDS_IMAGE_F32_NCHW = 0, /* float32 (n, C, h, w)                     */
+  PDS_IMAGE_U8_NCHW = 1,  /* uint8   (n, C, h, w)                     */
+  PDS_IMAGE_U8_NHWC = 2   /* uint8   (n, h, w, C): cv2 / decoder order */
+};
+int pds_embedding_forward_images(pds_embedding* emb, const void* images_a,
+                                 int n_a, const void* images_b, int n_b,
+                                 int layout, int h, int w, int pad_top,
+                                 int pad_left, float* descriptor,
+                                 float* shortcut, int n_shortcut,
+                                 void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
 /* ---- a4: SubpixelMap.__call__ (estimator.py:45-91) -----------------------
  * cost (B, D, H, W) of `dtype` -> disparity (B, H-crop_top, W-crop_left)
  * float32; the crop is SizeAdapter.unpad (size_adapter.py:51-52) fused into

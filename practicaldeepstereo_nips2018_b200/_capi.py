@@ -18,6 +18,7 @@ if os.environ.get('PDS_B200_LIB'):          # experiments: an alternative build 
 PDS_OK, PDS_ERR_INVALID_ARGUMENT, PDS_ERR_CUDA, PDS_ERR_WORKSPACE, PDS_ERR_UNSUPPORTED = range(5)
 PDS_F32, PDS_BF16 = 0, 1
 PRECISIONS = {'fp32': 0, 'bf16x3': 1, 'bf16x2': 2, 'bf16': 3, 'fp16x2': 4, 'fp16': 5}
+IMAGE_LAYOUTS = {'f32_nchw': 0, 'u8_nchw': 1, 'u8_nhwc': 2}   # enum pds_image_layout
 
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
 
@@ -52,6 +53,8 @@ SIGNATURES = {
     'pds_embedding_destroy': (None, [_vp]),
     'pds_embedding_workspace_bytes': (_sz, [_vp, _i, _i, _i]),
     'pds_embedding_forward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    'pds_embedding_forward_images': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _sz,
+                                          _vp]),
     'pds_subpixel_map': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

@@ -416,7 +416,7 @@ struct NormParams {
 };
 
 template <bool FP16, int S>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 tcg_norm_to_ap_kernel(const NormParams p) {
   extern __shared__ float sm[];          // scale_a[C], shift_a[C], scale_b[C], shift_b[C]
   const int n = blockIdx.y;
@@ -448,64 +448,80 @@ tcg_norm_to_ap_kernel(const NormParams p) {
     sm[2 * p.C + c] = sc; sm[3 * p.C + c] = sh;
   }
   __syncthreads();
-  // one CTA per image row (z, y) (grid-stride over rows); threads walk the row's (x, channel
-  // group) items -- no per-item division: G is a power of two
+  // work unit = 256 consecutive (x, channel group) items of one image row (z, y); the CTAs walk
+  // the units grid-stride, two at a time with both units' loads issued before the first store (the
+  // per-CTA prologue above -- double-precision statistics -- is amortised over many units, and
+  // enough bytes are in flight per SM).  No per-item division: G is a power of two.
   const int G = p.C / 8, gshift = 31 - __clz(G);
   const int sep = p.phases > 1;
   const int sepz = p.phases == 8;
   const int IZ = sepz ? p.Z / 2 : p.Z, IY = sep ? p.Y / 2 : p.Y, IX = sep ? p.X / 2 : p.X;
   const size_t plane = (size_t)IZ * IY * IX;
   const int rows = p.Z * p.Y, items = p.X * G;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int z = row / p.Y, y = row - z * p.Y;
-    const size_t vox0 = (size_t)row * p.X;
-    const int zz = sepz ? z >> 1 : z, yy = sep ? y >> 1 : y;
-    const int ph_zy = sep ? ((sepz ? (z & 1) * 4 : 0) + (y & 1) * 2) : 0;
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-      const int g = i & (G - 1), x = i >> gshift;
-      const size_t off = ((size_t)n * V + vox0 + x) * p.C + 8 * g;
-      const float4* pa = reinterpret_cast<const float4*>(p.ya + off);
-      const float4 a0 = ldg_stream(pa), a1 = ldg_stream(pa + 1);
-      float4 b0, b1, c0, c1;
-      if (p.yb) {
-        const float4* pb = reinterpret_cast<const float4*>(p.yb + off);
-        b0 = ldg_stream(pb); b1 = ldg_stream(pb + 1);
-      }
-      if (p.bcast) {
-        const float4* pc = reinterpret_cast<const float4*>(p.bcast + (((size_t)n * p.Y + y) * p.X + x) * p.C + 8 * g);
-        c0 = __ldg(pc); c1 = __ldg(pc + 1);
-      }
-      float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float* sa = sm + 8 * g;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sa[e], sa[p.C + e]);
-      if (p.yb) {
-        const float w[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += fmaf(w[e], sa[2 * p.C + e], sa[3 * p.C + e]);
-      }
-      if (p.bcast) {
-        v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w;
-        v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
-      }
-      if (p.out_f32) {
-        float4* po = reinterpret_cast<float4*>(p.out_f32 + off);
-        po[0] = make_float4(v[0], v[1], v[2], v[3]);
-        po[1] = make_float4(v[4], v[5], v[6], v[7]);
-      }
-      uint16_t t[8][3];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
-      const int ph = ph_zy + (sep ? (x & 1) : 0);
-      const size_t pos = ((size_t)zz * IY + yy) * IX + (sep ? x >> 1 : x);
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        float4 pk;
-        pk.x = __uint_as_float(t[0][s] | ((uint32_t)t[1][s] << 16)); pk.y = __uint_as_float(t[2][s] | ((uint32_t)t[3][s] << 16));
-        pk.z = __uint_as_float(t[4][s] | ((uint32_t)t[5][s] << 16)); pk.w = __uint_as_float(t[6][s] | ((uint32_t)t[7][s] << 16));
-        stg_stream(reinterpret_cast<float4*>(p.out) + ((((size_t)n * S + s) * p.phases + ph) * G + g) * plane + pos, pk);
-      }
+  const int chunks = (items + 255) >> 8, units = rows * chunks;
+  struct Unit { int row, y, x, g; bool live; size_t off; float4 a0, a1, b0, b1, c0, c1; };
+  auto load = [&](int u, Unit& w) {
+    w.live = u < units;
+    if (!w.live) return;
+    w.row = u / chunks;
+    const int i = ((u - w.row * chunks) << 8) + (int)threadIdx.x;
+    w.live = i < items;
+    if (!w.live) return;
+    w.g = i & (G - 1); w.x = i >> gshift;
+    w.y = w.row % p.Y;
+    w.off = ((size_t)n * V + (size_t)w.row * p.X + w.x) * p.C + 8 * w.g;
+    const float4* pa = reinterpret_cast<const float4*>(p.ya + w.off);
+    w.a0 = ldg_stream(pa); w.a1 = ldg_stream(pa + 1);
+    if (p.yb) {
+      const float4* pb = reinterpret_cast<const float4*>(p.yb + w.off);
+      w.b0 = ldg_stream(pb); w.b1 = ldg_stream(pb + 1);
     }
+    if (p.bcast) {
+      const float4* pc = reinterpret_cast<const float4*>(p.bcast + (((size_t)n * p.Y + w.y) * p.X + w.x) * p.C + 8 * w.g);
+      w.c0 = __ldg(pc); w.c1 = __ldg(pc + 1);
+    }
+  };
+  auto finish = [&](const Unit& w) {
+    if (!w.live) return;
+    const int z = w.row / p.Y, y = w.y, x = w.x, g = w.g;
+    float v[8] = {w.a0.x, w.a0.y, w.a0.z, w.a0.w, w.a1.x, w.a1.y, w.a1.z, w.a1.w};
+    const float* sa = sm + 8 * g;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sa[e], sa[p.C + e]);
+    if (p.yb) {
+      const float q[8] = {w.b0.x, w.b0.y, w.b0.z, w.b0.w, w.b1.x, w.b1.y, w.b1.z, w.b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += fmaf(q[e], sa[2 * p.C + e], sa[3 * p.C + e]);
+    }
+    if (p.bcast) {
+      v[0] += w.c0.x; v[1] += w.c0.y; v[2] += w.c0.z; v[3] += w.c0.w;
+      v[4] += w.c1.x; v[5] += w.c1.y; v[6] += w.c1.z; v[7] += w.c1.w;
+    }
+    if (p.out_f32) {
+      float4* po = reinterpret_cast<float4*>(p.out_f32 + w.off);
+      po[0] = make_float4(v[0], v[1], v[2], v[3]);
+      po[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    uint16_t t[8][3];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
+    const int zz = sepz ? z >> 1 : z, yy = sep ? y >> 1 : y;
+    const int ph = (sep ? ((sepz ? (z & 1) * 4 : 0) + (y & 1) * 2) : 0) + (sep ? (x & 1) : 0);
+    const size_t pos = ((size_t)zz * IY + yy) * IX + (sep ? x >> 1 : x);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      float4 pk;
+      pk.x = __uint_as_float(t[0][s] | ((uint32_t)t[1][s] << 16)); pk.y = __uint_as_float(t[2][s] | ((uint32_t)t[3][s] << 16));
+      pk.z = __uint_as_float(t[4][s] | ((uint32_t)t[5][s] << 16)); pk.w = __uint_as_float(t[6][s] | ((uint32_t)t[7][s] << 16));
+      stg_stream(reinterpret_cast<float4*>(p.out) + ((((size_t)n * S + s) * p.phases + ph) * G + g) * plane + pos, pk);
+    }
+  };
+  for (int u = blockIdx.x; u < units; u += 2 * gridDim.x) {
+    Unit w0, w1;
+    load(u, w0);
+    load(u + gridDim.x, w1);
+    finish(w0);
+    finish(w1);
   }
 }
 
@@ -714,11 +730,24 @@ int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast,
   p.bcast = bcast; p.out = out_ap; p.out_f32 = out_f32;
   p.C = C; p.Z = Z; p.Y = Y; p.X = X; p.S = S; p.phases = phases;
   if (C & (C - 1)) { set_error("tcg_norm_to_ap: channel count must be a power of two"); return PDS_ERR_UNSUPPORTED; }
-  unsigned gx = (unsigned)(Z * Y);                   // one CTA per row, grid-stride beyond the cap
-  const unsigned cap = (unsigned)(num_sms() * 32);
+  // units of 256 items, two per CTA iteration; at most two waves of the resident CTAs
+  const unsigned units = (unsigned)(Z * Y) * (unsigned)((X * (C / 8) + 255) / 256);
+  unsigned gx = (units + 1) / 2;
+  const unsigned cap = (unsigned)(num_sms() * 4);
   if (gx > cap) gx = cap;
   dim3 grid(gx, (unsigned)n);
-  PDS_KERNEL(b ? "tcg_norm2_to_ap" : "tcg_norm_to_ap", st);
+  static const bool detail = getenv("PDS_B200_PROFILE_DETAIL") && atoi(getenv("PDS_B200_PROFILE_DETAIL"));
+  const char* name = b ? "tcg_norm2_to_ap" : "tcg_norm_to_ap";
+  if (detail) {
+    static std::mutex mu;
+    static std::set<std::string> names;
+    std::string nm = std::string(name) + "[" + std::to_string(C) + "ch " + std::to_string(Z) + "x" + std::to_string(Y) +
+                     "x" + std::to_string(X) + " ph" + std::to_string(phases) + (bcast ? " +bcast" : "") +
+                     (out_f32 ? " +f32" : "") + "]";
+    std::lock_guard<std::mutex> lock(mu);
+    name = names.insert(nm).first->c_str();
+  }
+  PDS_KERNEL(name, st);
   PDS_KERNEL_WORK(0, (double)n * Z * Y * X * C * (4.0 + 2.0 * S + (b ? 4.0 : 0.0) + (out_f32 ? 4.0 : 0.0)));
   const size_t smem = (size_t)4 * C * sizeof(float);
 #define PDS_TCG_NORM_CASE(FF, SS) \

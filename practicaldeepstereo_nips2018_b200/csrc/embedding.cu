@@ -36,19 +36,45 @@ namespace {
 
 using namespace ptx;
 
-// sum / sum of squares of every (sample, channel) plane of an NCHW image
+// f3 -- the input path: the images as the caller holds them (dataset.py:67-72: cv2's interleaved
+// uint8, converted to float and permuted on the host by the reference; or float / uint8 planar
+// tensors), un-padded.  SizeAdapter.pad (size_adapter.py:29-43: zeros on top / left up to the
+// padded extent H x W) and the first InstanceNorm2d (embedding.py:32) happen while the operand
+// planes are written; the left and the right batch are two pointers (no torch.cat).
+struct ImageSrc {
+  const void* a; const void* b;   // samples 0 .. n_a-1 from a, the rest from b
+  int n_a, layout, C, h, w, pad_top, pad_left;
+};
+
+template <int LAYOUT>
+__device__ __forceinline__ float image_at(const ImageSrc& s, int n, int c, int y, int x) {
+  const bool first = n < s.n_a;
+  const void* base = first ? s.a : s.b;
+  const size_t m = (size_t)(first ? n : n - s.n_a) * s.C * s.h * s.w;
+  if (LAYOUT == PDS_IMAGE_F32_NCHW) return __ldg((const float*)base + m + ((size_t)c * s.h + y) * s.w + x);
+  if (LAYOUT == PDS_IMAGE_U8_NCHW) return (float)__ldg((const unsigned char*)base + m + ((size_t)c * s.h + y) * s.w + x);
+  return (float)__ldg((const unsigned char*)base + m + ((size_t)y * s.w + x) * s.C + c);
+}
+
+// sum / sum of squares of every (sample, channel) plane (the padding contributes zeros)
+template <int LAYOUT>
 __global__ void __launch_bounds__(256)
-image_stats_kernel(const float* __restrict__ img, double* __restrict__ stats, size_t HW) {
-  const int plane = blockIdx.y;
-  const float* p = img + (size_t)plane * HW;
+image_stats_kernel(const ImageSrc src, double* __restrict__ stats) {
+  const int n = blockIdx.y / src.C, c = blockIdx.y - n * src.C;
+  const size_t hw = (size_t)src.h * src.w;
   double s = 0.0, q = 0.0;
-  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < HW; i += (size_t)gridDim.x * blockDim.x * 4) {
-    if (i + 3 < HW) {
-      const float4 v = *reinterpret_cast<const float4*>(p + i);
+  if (LAYOUT == PDS_IMAGE_F32_NCHW && hw % 4 == 0) {
+    const bool first = n < src.n_a;
+    const float* p = (const float*)(first ? src.a : src.b) + ((size_t)(first ? n : n - src.n_a) * src.C + c) * hw;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hw; i += (size_t)gridDim.x * blockDim.x * 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p + i));
       s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
       q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
-    } else {
-      for (size_t j = i; j < HW; ++j) { s += p[j]; q += (double)p[j] * p[j]; }
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+      const float v = image_at<LAYOUT>(src, n, c, (int)(i / src.w), (int)(i % src.w));
+      s += v; q += (double)v * v;
     }
   }
   __shared__ double rs[8], rq[8];
@@ -58,18 +84,19 @@ image_stats_kernel(const float* __restrict__ img, double* __restrict__ stats, si
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w) { s += rs[w]; q += rq[w]; }
-    atomicAdd(stats + 2 * plane, s);
-    atomicAdd(stats + 2 * plane + 1, q);
+    atomicAdd(stats + 2 * blockIdx.y, s);
+    atomicAdd(stats + 2 * blockIdx.y + 1, q);
   }
 }
 
-// InstanceNorm2d(C <= 8, affine=False, eps 1e-5) of an NCHW image -> phase-separated AP planes
+// InstanceNorm2d(C <= 8, affine=False, eps 1e-5) of the PADDED image (statistics over H x W, the
+// pad region normalises to -mean * rstd) -> phase-separated AP planes
 // [n][S][4 phases][1 plane][H/2][W/2][8] with channels C..7 zero.  One thread = one pixel.
-template <bool FP16>
+template <bool FP16, int LAYOUT>
 __global__ void __launch_bounds__(256)
-image_norm_to_ap_kernel(const float* __restrict__ img, const double* __restrict__ stats,
-                        uint16_t* __restrict__ out, int C, int H, int W, int S) {
-  const int n = blockIdx.y;
+image_norm_to_ap_kernel(const ImageSrc src, const double* __restrict__ stats,
+                        uint16_t* __restrict__ out, int H, int W, int S) {
+  const int n = blockIdx.y, C = src.C;
   const size_t HW = (size_t)H * W;
   __shared__ float sc[8], sh[8];
   if (threadIdx.x < 8) {
@@ -89,10 +116,12 @@ image_norm_to_ap_kernel(const float* __restrict__ img, const double* __restrict_
   const size_t plane = (size_t)IY * IX;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (size_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % W), y = (int)(i / W);
+    const int sy = y - src.pad_top, sx = x - src.pad_left;
+    const bool inside = sy >= 0 && sx >= 0;
     uint16_t t[8][3];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const float v = c < C ? fmaf(img[((size_t)n * C + c) * HW + i], sc[c], sh[c]) : 0.f;
+      const float v = c < C ? fmaf(inside ? image_at<LAYOUT>(src, n, c, sy, sx) : 0.f, sc[c], sh[c]) : 0.f;
       split_terms<FP16>(v, t[c]);
     }
     const int ph = (y & 1) * 2 + (x & 1);
@@ -271,15 +300,45 @@ extern "C" size_t pds_embedding_workspace_bytes(const pds_embedding* e, int n, i
   return pds::buffers(e, n, H, W).total;
 }
 
+namespace pds {
+namespace {
+int embedding_forward(pds_embedding* e, const ImageSrc& img, float* descriptor, float* shortcut, int n,
+                      int n_shortcut, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+}
+}  // namespace pds
+
 extern "C" int pds_embedding_forward(pds_embedding* e, const float* images, float* descriptor,
                                      float* shortcut, int n, int n_shortcut, int H, int W,
                                      void* workspace, size_t workspace_bytes, void* stream) {
-  using namespace pds;
   PDS_CHECK_ARG(e && images && descriptor, "pds_embedding_forward: null pointer");
+  pds::ImageSrc img = {images, nullptr, n, PDS_IMAGE_F32_NCHW, e->Cin, H, W, 0, 0};
+  return pds::embedding_forward(e, img, descriptor, shortcut, n, n_shortcut, H, W, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pds_embedding_forward_images(pds_embedding* e, const void* images_a, int n_a,
+                                            const void* images_b, int n_b, int layout, int h, int w,
+                                            int pad_top, int pad_left, float* descriptor, float* shortcut,
+                                            int n_shortcut, void* workspace, size_t workspace_bytes,
+                                            void* stream) {
+  PDS_CHECK_ARG(e && descriptor && n_a >= 0 && n_b >= 0 && (images_a || n_a == 0) && (images_b || n_b == 0),
+                "pds_embedding_forward_images: null pointer");
+  PDS_CHECK_ARG(layout == PDS_IMAGE_F32_NCHW || layout == PDS_IMAGE_U8_NCHW || layout == PDS_IMAGE_U8_NHWC,
+                "pds_embedding_forward_images: unknown image layout");
+  PDS_CHECK_ARG(h >= 1 && w >= 1 && pad_top >= 0 && pad_left >= 0,
+                "pds_embedding_forward_images: bad image extent or padding");
+  pds::ImageSrc img = {images_a, images_b, n_a, layout, e->Cin, h, w, pad_top, pad_left};
+  return pds::embedding_forward(e, img, descriptor, shortcut, n_a + n_b, n_shortcut, h + pad_top, w + pad_left,
+                                workspace, workspace_bytes, stream);
+}
+
+namespace pds {
+namespace {
+int embedding_forward(pds_embedding* e, const ImageSrc& img, float* descriptor, float* shortcut, int n,
+                      int n_shortcut, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
   PDS_CHECK_ARG(n >= 0 && n_shortcut >= 0 && n_shortcut <= n && (shortcut || n_shortcut == 0),
                 "pds_embedding_forward: bad sample counts");
   PDS_CHECK_ARG(H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0,
-                "pds_embedding_forward: height and width must be multiples of 4");
+                "pds_embedding_forward: (padded) height and width must be multiples of 4");
   if (n == 0) return PDS_OK;
   if (!workspace || workspace_bytes < pds_embedding_workspace_bytes(e, n, H, W) || ((uintptr_t)workspace & 255)) {
     set_error("pds_embedding_forward: workspace too small or not 256-byte aligned");
@@ -308,21 +367,29 @@ extern "C" int pds_embedding_forward(pds_embedding* e, const float* images, floa
   const int n_layers = (int)L.size();
   double* img_stats = st_of(3 + 2 * e->n_res);   // slot after the layers'
 
-  // InstanceNorm2d of the image -> phase-separated planes (embedding.py:32)
+  // pad + InstanceNorm2d of the image -> phase-separated planes (size_adapter.py:42, embedding.py:32)
   {
-    const size_t HW = (size_t)H * W;
+    const size_t HW = (size_t)H * W, hw = (size_t)img.h * img.w;
+    const double in_bytes = (double)n * e->Cin * hw * (img.layout == PDS_IMAGE_F32_NCHW ? 4.0 : 1.0);
+    dim3 sgrid((unsigned)std::min<size_t>((hw / 4 + 255) / 256, 64), (unsigned)(n * e->Cin));
+    dim3 grid((unsigned)std::min<size_t>((HW + 255) / 256, (size_t)num_sms() * 8), (unsigned)n);
     {
       PDS_KERNEL("image_stats", st);
-      PDS_KERNEL_WORK(0, 4.0 * n * e->Cin * HW);
-      dim3 grid((unsigned)std::min<size_t>((HW / 4 + 255) / 256, 64), (unsigned)(n * e->Cin));
-      image_stats_kernel<<<grid, 256, 0, st>>>(images, img_stats, HW);
+      PDS_KERNEL_WORK(0, in_bytes);
+      switch (img.layout) {
+        case PDS_IMAGE_F32_NCHW: image_stats_kernel<PDS_IMAGE_F32_NCHW><<<sgrid, 256, 0, st>>>(img, img_stats); break;
+        case PDS_IMAGE_U8_NCHW: image_stats_kernel<PDS_IMAGE_U8_NCHW><<<sgrid, 256, 0, st>>>(img, img_stats); break;
+        default: image_stats_kernel<PDS_IMAGE_U8_NHWC><<<sgrid, 256, 0, st>>>(img, img_stats); break;
+      }
       PDS_LAUNCH_CHECK("image_stats_kernel");
     }
     PDS_KERNEL("image_norm_to_ap", st);
-    PDS_KERNEL_WORK(0, (double)n * HW * (4.0 * e->Cin + 16.0 * S));
-    dim3 grid((unsigned)std::min<size_t>((HW + 255) / 256, (size_t)num_sms() * 8), (unsigned)n);
-    if (fp16) image_norm_to_ap_kernel<true><<<grid, 256, 0, st>>>(images, img_stats, ap[0], e->Cin, H, W, S);
-    else image_norm_to_ap_kernel<false><<<grid, 256, 0, st>>>(images, img_stats, ap[0], e->Cin, H, W, S);
+    PDS_KERNEL_WORK(0, in_bytes + (double)n * HW * 16.0 * S);
+#define PDS_IMG_CASE(FF, LL) \
+    if ((fp16 != 0) == FF && img.layout == LL) image_norm_to_ap_kernel<FF, LL><<<grid, 256, 0, st>>>(img, img_stats, ap[0], H, W, S);
+    PDS_IMG_CASE(true, PDS_IMAGE_F32_NCHW) PDS_IMG_CASE(true, PDS_IMAGE_U8_NCHW) PDS_IMG_CASE(true, PDS_IMAGE_U8_NHWC)
+    PDS_IMG_CASE(false, PDS_IMAGE_F32_NCHW) PDS_IMG_CASE(false, PDS_IMAGE_U8_NCHW) PDS_IMG_CASE(false, PDS_IMAGE_U8_NHWC)
+#undef PDS_IMG_CASE
     PDS_LAUNCH_CHECK("image_norm_to_ap_kernel");
   }
   // two stride-2 5x5 blocks
@@ -366,3 +433,5 @@ extern "C" int pds_embedding_forward(pds_embedding* e, const float* images, floa
   }
   return PDS_OK;
 }
+}  // namespace
+}  // namespace pds

@@ -70,6 +70,56 @@ class Embedding(nn.Module):
                 H, W, _capi.ptr(ws), ws.numel(), _capi.stream_ptr(images.device)))
         return descriptor, shortcut
 
+    # -- f3: un-padded float / uint8 images straight into the first operand planes ----------
+    def image_geometry(self, image):
+        """(layout, h, w) of a batch of images the fused input path accepts: float32
+        (B,C,h,w), uint8 (B,C,h,w) or uint8 (B,h,w,C) (decoder order, dataset.py:67-72);
+        None for anything else."""
+        cin = self._shape[0]
+        if not torch.is_tensor(image) or image.dim() != 4:
+            return None
+        if image.dtype == torch.float32 and image.size(1) == cin:
+            return _capi.IMAGE_LAYOUTS['f32_nchw'], image.size(2), image.size(3)
+        if image.dtype == torch.uint8 and image.size(1) == cin:
+            return _capi.IMAGE_LAYOUTS['u8_nchw'], image.size(2), image.size(3)
+        if image.dtype == torch.uint8 and image.size(3) == cin:
+            return _capi.IMAGE_LAYOUTS['u8_nhwc'], image.size(1), image.size(2)
+        return None
+
+    def can_embed_images(self, left_images, right_images):
+        cin, f, fs, _ = self._shape
+        return (self.precision != 'fp32' and self.image_geometry(left_images) is not None
+                and left_images.is_cuda and left_images.shape == right_images.shape
+                and left_images.dtype == right_images.dtype
+                and left_images.device == right_images.device
+                and not _needs_autograd(left_images, right_images, self)
+                and cin <= 8 and f == 64 and fs in (4, 8, 12, 16))
+
+    def embed_images(self, left_images, right_images, pad_top, pad_left):
+        """SizeAdapter.pad + Embedding of both batches in one pipeline
+        (pds_embedding_forward_images): returns the left descriptors, the right
+        descriptors and the shortcut of the left images, all at the PADDED extent / 4."""
+        cin, f, fs, _ = self._shape
+        layout, h, w = self.image_geometry(left_images)
+        H, W = h + pad_top, w + pad_left
+        if H % 4 or W % 4:
+            raise ValueError('padded height and width should be multiples of 4')
+        left_images, right_images = left_images.detach().contiguous(), right_images.detach().contiguous()
+        batch = left_images.size(0)
+        device = left_images.device
+        lib = _capi.lib()
+        handle = self._kernel.get(list(self.parameters()), self.precision, device)
+        descriptor = torch.empty((2 * batch, f, H // 4, W // 4), dtype=torch.float32, device=device)
+        shortcut = torch.empty((batch, fs, H // 4, W // 4), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            nbytes = lib.pds_embedding_workspace_bytes(handle, 2 * batch, H, W)
+            ws = self._kernel.workspace(nbytes, device)
+            _capi.check(lib.pds_embedding_forward_images(
+                handle, _capi.ptr(left_images), batch, _capi.ptr(right_images), batch, layout, h, w,
+                pad_top, pad_left, _capi.ptr(descriptor), _capi.ptr(shortcut), batch,
+                _capi.ptr(ws), ws.numel(), _capi.stream_ptr(device)))
+        return descriptor[:batch], descriptor[batch:], shortcut
+
     def forward(self, image, with_shortcut=True):
         """image (B,3,H,W) -> descriptor (B,64,H/4,W/4), shortcut (B,8,H/4,W/4).
 

@@ -65,27 +65,56 @@ class PdsNetwork(nn.Module):
         signatures = self._matching(left_descriptor, right_descriptor)
         return self._regularization(signatures, shortcut_from_left), shortcut_from_left
 
+    def _embed_unpadded(self, left_image, right_image):
+        """f3 -- the input path: un-padded float32 or uint8 images (planar, or interleaved
+        as the decoder leaves them, dataset.py:67-72) go straight into the kernel that
+        pads (size_adapter.py:29-43), normalises (embedding.py:32) and writes the first
+        convolution's operands.  Returns None when that path does not apply."""
+        emb, adapter = self._embedding, self._size_adapter
+        if not (isinstance(emb, embedding.Embedding) and isinstance(adapter, size_adapter.SizeAdapter)
+                and emb.can_embed_images(left_image, right_image)):
+            return None
+        _, height, width = emb.image_geometry(left_image)
+        pad_top, pad_left = adapter.padding_for(height, width)
+        adapter._pixels_pad_to_height, adapter._pixels_pad_to_width = pad_top, pad_left
+        return emb.embed_images(left_image, right_image, pad_top, pad_left)
+
+    @staticmethod
+    def _as_float_planes(image):
+        """uint8 images (planar or interleaved) as the float (B,3,H,W) tensor the reference's
+        data loader produces (dataset.py:67-72)."""
+        if torch.is_tensor(image) and image.dtype == torch.uint8:
+            if image.dim() == 4 and image.size(1) != 3 and image.size(3) == 3:
+                image = image.permute(0, 3, 1, 2)
+            return image.float()
+        return image
+
     def forward(self, left_image, right_image):
         """Sub-pixel disparity [B, H, W] in eval mode, matching cost
-        [B, (md + 1) / 2, H, W] in training mode."""
-        left, right = self._size_adapter.pad(left_image), self._size_adapter.pad(right_image)
+        [B, (md + 1) / 2, H, W] in training mode.  Besides the reference's float
+        (B,3,H,W) images, uint8 images (B,3,H,W) or (B,H,W,3) are accepted."""
         reg, est = self._regularization, self._estimator
-        if (FUSE_TAIL_AND_ESTIMATOR and not self.training and left.is_cuda
-                and isinstance(est, estimator.SubpixelMap)
+        embedded = self._embed_unpadded(left_image, right_image)
+        if embedded is None:
+            left_image, right_image = self._as_float_planes(left_image), self._as_float_planes(right_image)
+            left, right = self._size_adapter.pad(left_image), self._size_adapter.pad(right_image)
+            embedded = self._embed(left, right)
+        left_descriptor, right_descriptor, shortcut = embedded
+        signatures = self._matching(left_descriptor, right_descriptor)
+        on_kernels = signatures.is_cuda and isinstance(est, estimator.SubpixelMap)
+        if (FUSE_TAIL_AND_ESTIMATOR and not self.training and on_kernels
                 and isinstance(reg, regularization.Regularization) and reg.can_fuse_estimator(est)
-                and not matching._needs_autograd(left, right, self)):
+                and not matching._needs_autograd(signatures, shortcut, self)):
             # hourglass tail, estimator and SizeAdapter.unpad as one pipeline: the cost volume
             # (212 MB at 960x540) is never written (bit-identical to the separate calls below)
-            left_descriptor, right_descriptor, shortcut = self._embed(left, right)
-            signatures = self._matching(left_descriptor, right_descriptor)
             return reg.forward_disparity(signatures, shortcut, est._half_support_window,
                                          est._disparity_step,
                                          crop_top=self._size_adapter._pixels_pad_to_height,
                                          crop_left=self._size_adapter._pixels_pad_to_width)
-        cost = self.pass_through_network(left, right)[0]
+        cost = reg(signatures, shortcut)
         if self.training:
             return self._size_adapter.unpad(cost)
-        if isinstance(est, estimator.SubpixelMap) and cost.is_cuda:
+        if on_kernels:
             # SizeAdapter.unpad fused into the estimator's store
             return est(cost, crop_top=self._size_adapter._pixels_pad_to_height,
                        crop_left=self._size_adapter._pixels_pad_to_width)

@@ -36,11 +36,14 @@ class HostPipeline(object):
             return pair[0], pair[1], None, None
         slot = self._slots[self._next_slot % len(self._slots)]
         self._next_slot += 1
-        if slot['left'] is None or slot['left'].shape != pair[0].shape or slot['right'].shape != pair[1].shape:
-            slot['left'] = torch.empty(pair[0].shape, dtype=pair[0].dtype, device=self._device)
-            slot['right'] = torch.empty(pair[1].shape, dtype=pair[1].dtype, device=self._device)
-            slot['consumed'] = None
         with torch.cuda.stream(self._copy_stream):
+            if (slot['left'] is None or slot['left'].shape != pair[0].shape or slot['right'].shape != pair[1].shape
+                    or slot['left'].dtype != pair[0].dtype or slot['right'].dtype != pair[1].dtype):
+                # allocated ON the copy stream: a block the caching allocator hands out here was last
+                # used on this stream, not by a forward that is still in flight on a compute stream
+                slot['left'] = torch.empty(pair[0].shape, dtype=pair[0].dtype, device=self._device)
+                slot['right'] = torch.empty(pair[1].shape, dtype=pair[1].dtype, device=self._device)
+                slot['consumed'] = None
             if slot['consumed'] is not None:          # the forward that last read this slot is done
                 self._copy_stream.wait_event(slot['consumed'])
             slot['left'].copy_(pair[0], non_blocking=True)
@@ -50,7 +53,8 @@ class HostPipeline(object):
         return slot['left'], slot['right'], ready, slot
 
     def run(self, host_pairs, out=None, download=True):
-        """host_pairs: iterable of (left, right) pinned CPU tensors [B, 3, H, W] (CUDA tensors
+        """host_pairs: iterable of (left, right) pinned CPU tensors [B, 3, H, W] float32 -- or uint8
+        [B, 3, H, W] / [B, H, W, 3], a quarter of the upload (PdsNetwork.forward) -- (CUDA tensors
         are taken as they are).  out: optional list of pinned CPU tensors [B, H, W] (reused
         round-robin).  Returns the list of disparity tensors, one per pair -- on the host
         (valid after ``torch.cuda.current_stream().synchronize()``), or on the device when
@@ -86,6 +90,8 @@ class HostPipeline(object):
             compute.wait_event(ready)
         disparity = self._network(left, right)
         if slot is not None:
+            left.record_stream(compute)            # staging memory is not recycled under the forward
+            right.record_stream(compute)
             slot['consumed'] = torch.cuda.Event()
             slot['consumed'].record(compute)
         if not self._download:

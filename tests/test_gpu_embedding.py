@@ -79,3 +79,54 @@ def test_network_fp16x2_vs_torch_port():
                                     st['disparity'].float().cpu().numpy(),
                                     st['cost'].float().cpu().numpy(), (28, 10), cost_err)
     assert safe > 0.9 and flips < 1e-2 and err <= 1e-3 + 50 * cost_err
+
+
+def test_input_path_pad_and_uint8_are_bit_identical():
+    """f3: pds_embedding_forward_images (un-padded images, SizeAdapter.pad + the first
+    InstanceNorm2d fused, left / right as two pointers, float32 or uint8 planar or uint8
+    interleaved as cv2 decodes them, dataset.py:67-72) == pad + cat + embed, bit for bit."""
+    params = synth.make_params(synth.embedding_specs(), 55)
+    emb = load_module(embedding.Embedding(precision='fp16x2'), params)
+    g = torch.Generator().manual_seed(56)
+    left8 = torch.randint(0, 256, (2, 3, 62, 100), dtype=torch.uint8, generator=g).cuda()
+    right8 = torch.randint(0, 256, (2, 3, 62, 100), dtype=torch.uint8, generator=g).cuda()
+    pad_top, pad_left = 2, 28                                    # SizeAdapter: 62 x 100 -> 64 x 128
+    with torch.no_grad():
+        padded = torch.nn.functional.pad(torch.cat([left8, right8]).float(), (pad_left, 0, pad_top, 0))
+        d_ref, s_ref = emb.embed(padded, 2)
+        for l, r in ((left8.float(), right8.float()), (left8, right8),
+                     (left8.permute(0, 2, 3, 1).contiguous(), right8.permute(0, 2, 3, 1).contiguous())):
+            assert emb.can_embed_images(l, r)
+            dl, dr, s = emb.embed_images(l, r, pad_top, pad_left)
+            assert dl.shape == (2, 64, 16, 32) and s.shape == (2, 8, 16, 32)
+            assert torch.equal(torch.cat([dl, dr]), d_ref) and torch.equal(s, s_ref)
+        # float images whose plane size is not a multiple of 4 (scalar statistics path)
+        lo, ro = left8[..., :61, :99].float().contiguous(), right8[..., :61, :99].float().contiguous()
+        padded = torch.nn.functional.pad(torch.cat([lo, ro]), (29, 0, 3, 0))
+        d_ref, s_ref = emb.embed(padded, 2)
+        dl, dr, s = emb.embed_images(lo, ro, 3, 29)
+        assert torch.equal(torch.cat([dl, dr]), d_ref) and torch.equal(s, s_ref)
+    with pytest.raises(ValueError):
+        emb.embed_images(left8, right8, 1, 0)                    # padded extent not a multiple of 4
+    assert not emb.can_embed_images(left8, right8[:1])
+    assert not emb.can_embed_images(left8.double(), right8.double())
+
+
+def test_network_accepts_uint8_images():
+    """PdsNetwork.forward on uint8 images (planar and interleaved) == on their float copies."""
+    params = synth.make_params(synth.network_specs(), 57)
+    net = load_module(PdsNetwork.default(63, precision='fp16x2'), params)
+    g = torch.Generator().manual_seed(58)
+    left8 = torch.randint(0, 256, (1, 62, 100, 3), dtype=torch.uint8, generator=g).cuda()
+    right8 = torch.randint(0, 256, (1, 62, 100, 3), dtype=torch.uint8, generator=g).cuda()
+    left, right = left8.permute(0, 3, 1, 2).float().contiguous(), right8.permute(0, 3, 1, 2).float().contiguous()
+    with torch.no_grad():
+        ref = net(left, right)
+        cost = net.pass_through_network(net._size_adapter.pad(left), net._size_adapter.pad(right))[0]
+        ref2 = net._estimator(cost, crop_top=2, crop_left=28)    # the padded-float path of earlier rounds
+        assert ref.shape == (1, 62, 100) and torch.equal(ref, ref2)
+        assert torch.equal(net(left8, right8), ref)
+        assert torch.equal(net(left8.permute(0, 3, 1, 2).contiguous(), right8.permute(0, 3, 1, 2).contiguous()), ref)
+    fp32 = load_module(PdsNetwork.default(63, precision='fp32'), params)   # no fused input path: converted
+    with torch.no_grad():
+        assert torch.equal(fp32(left8, right8), fp32(left, right))
