@@ -85,8 +85,11 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def synthetic_pairs(n, batch, H, W, device, seed=0, pinned=False):
-    """`n` distinct seeded stereo pairs: right = left shifted by a few px + noise, 0..255."""
+def synthetic_pairs(n, batch, H, W, device, seed=0, pinned=False, images='f32'):
+    """`n` distinct seeded stereo pairs: right = left shifted by a few px + noise, 0..255.
+    images: 'f32' = float (B,3,H,W) as the reference's data loader delivers them
+    (dataset.py:67-72); 'u8' = the same images rounded, interleaved uint8 (B,H,W,3) as the decoder
+    leaves them (the input path of INTEGRATION.md, a quarter of the upload)."""
     g = torch.Generator().manual_seed(seed)
     pairs = []
     for i in range(n):
@@ -94,6 +97,9 @@ def synthetic_pairs(n, batch, H, W, device, seed=0, pinned=False):
         right = torch.rand(batch, 3, H, W, generator=g) * 255
         s = 4 + 3 * i
         right[..., :-s] = 0.8 * left[..., s:] + 0.2 * right[..., :-s]
+        if images == 'u8':
+            left = left.round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+            right = right.round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
         if pinned:
             pairs.append((left.pin_memory(), right.pin_memory()))
         else:
@@ -215,6 +221,9 @@ def main():
     ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=1, help='stereo pairs per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--images', default='f32', choices=['f32', 'u8'],
+                    help="host images: float (B,3,H,W) as the reference's loader yields (default) or "
+                         "interleaved uint8 (B,H,W,3)")
     ap.add_argument('--streams', type=int, default=3,
                     help='compute streams of the e2e serving pipeline (pairs dealt round-robin)')
     args = ap.parse_args()
@@ -247,7 +256,7 @@ def main():
 
     Hp, Wp = H + (-H) % 64, W + (-W) % 64
     pairs = synthetic_pairs(4, args.batch, H, W, dev, seed=1000 + rank)
-    host_pairs = synthetic_pairs(4, args.batch, H, W, dev, seed=2000 + rank, pinned=True)
+    host_pairs = synthetic_pairs(4, args.batch, H, W, dev, seed=2000 + rank, pinned=True, images=args.images)
 
     def barrier():
         torch.cuda.synchronize()
@@ -348,12 +357,12 @@ def main():
             'data': 'synthetic',
             'config': {'workload': desc, 'batch_per_gpu': args.batch, 'maximum_disparity': md,
                        'precision': args.precision, 'parallelism': f'replicas x{world}',
-                       'streams_per_gpu': args.streams,
+                       'streams_per_gpu': args.streams, 'host_images': args.images,
                        'l2': 'per-step working set > 1 GB (>> 126 MB L2); 4 rotating input pairs',
                        'embedding': ('own tcgen05 kernels' if args.precision != 'fp32'
                                      else 'ATen/cuDNN fp32 (TF32 off)')},
             'e2e': {'value': total_pairs / (e2e_ms / 1e3), 'unit': 'pairs/s',
-                    'h2d_bytes_per_step': 2 * args.batch * 3 * H * W * 4,
+                    'h2d_bytes_per_step': 2 * args.batch * 3 * H * W * (4 if args.images == 'f32' else 1),
                     'd2h_bytes_per_step': args.batch * H * W * 4},
             'gpu_launches': launches,
             'clocks': sampler.summary() if sampler else None,

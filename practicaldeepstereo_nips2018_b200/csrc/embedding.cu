@@ -71,11 +71,26 @@ image_stats_kernel(const ImageSrc src, double* __restrict__ stats) {
       s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
       q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
     }
-  } else {
+  } else if (LAYOUT == PDS_IMAGE_F32_NCHW) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
       const float v = image_at<LAYOUT>(src, n, c, (int)(i / src.w), (int)(i % src.w));
       s += v; q += (double)v * v;
     }
+  } else {
+    // uint8: integer sums are exact (and equal to the double sums of the float path); a thread's
+    // share stays far below 2^32 / 255^2 elements, the totals are carried in 64 bits
+    const bool first = n < src.n_a;
+    const unsigned char* p = (const unsigned char*)(first ? src.a : src.b) + (size_t)(first ? n : n - src.n_a) * src.C * hw;
+    const size_t stride = LAYOUT == PDS_IMAGE_U8_NHWC ? (size_t)src.C : 1;
+    p += LAYOUT == PDS_IMAGE_U8_NHWC ? (size_t)c : (size_t)c * hw;
+    unsigned long long ts = 0, tq = 0;
+    unsigned int us = 0, uq = 0, cnt = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) {
+      const unsigned int v = __ldg(p + i * stride);
+      us += v; uq += v * v;
+      if (++cnt == 32768) { ts += us; tq += uq; us = uq = cnt = 0; }
+    }
+    s = (double)(ts + us); q = (double)(tq + uq);
   }
   __shared__ double rs[8], rq[8];
 #pragma unroll
@@ -371,7 +386,8 @@ int embedding_forward(pds_embedding* e, const ImageSrc& img, float* descriptor, 
   {
     const size_t HW = (size_t)H * W, hw = (size_t)img.h * img.w;
     const double in_bytes = (double)n * e->Cin * hw * (img.layout == PDS_IMAGE_F32_NCHW ? 4.0 : 1.0);
-    dim3 sgrid((unsigned)std::min<size_t>((hw / 4 + 255) / 256, 64), (unsigned)(n * e->Cin));
+    dim3 sgrid((unsigned)std::min<size_t>((hw / 4 + 255) / 256, img.layout == PDS_IMAGE_F32_NCHW ? 64 : 128),
+               (unsigned)(n * e->Cin));
     dim3 grid((unsigned)std::min<size_t>((HW + 255) / 256, (size_t)num_sms() * 8), (unsigned)n);
     {
       PDS_KERNEL("image_stats", st);
