@@ -298,21 +298,26 @@ hourglass_tail_tiled_kernel(const __grid_constant__ TailParams p) {
     soff[k] = e < kTileN ? (ok ? gy * p.W + gx : -1) : -2;
     sidx[k] = e < kTileN ? e : 0;
   }
-  auto fetch = [&](int zi, float4 (&r)[kTilePer]) {
-    const bool zok = zi >= 0 && zi < p.D;
+  // fetch only issues the loads (raw values); the normalisation happens in stash, after the
+  // current plane has been consumed, so nothing waits on the loads in between
+  auto fetch = [&](int zi, float4 (&r)[kTilePer], bool& zok) {
+    zok = zi >= 0 && zi < p.D;
 #pragma unroll
     for (int k = 0; k < kTilePer; ++k) {
-      r[k] = make_float4(0.f, 0.f, 0.f, 0.f);              // zero padding of the NORMALISED tensor
-      if (zok && soff[k] >= 0) {
-        const float4 t = __ldg(base + (size_t)zi * plane + soff[k]);
-        r[k] = make_float4(fmaf(t.x, sc[0], sh[0]), fmaf(t.y, sc[1], sh[1]), fmaf(t.z, sc[2], sh[2]), fmaf(t.w, sc[3], sh[3]));
-      }
+      r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (zok && soff[k] >= 0) r[k] = __ldg(base + (size_t)zi * plane + soff[k]);
     }
   };
-  auto stash = [&](int buf, const float4 (&r)[kTilePer]) {
+  auto stash = [&](int buf, const float4 (&r)[kTilePer], bool zok) {
     float4* t = &tile[buf][0][0];
 #pragma unroll
-    for (int k = 0; k < kTilePer; ++k) if (soff[k] > -2) t[sidx[k]] = r[k];
+    for (int k = 0; k < kTilePer; ++k)
+      if (soff[k] > -2) {
+        const bool live = zok && soff[k] >= 0;              // else: zero padding of the NORMALISED tensor
+        t[sidx[k]] = live ? make_float4(fmaf(r[k].x, sc[0], sh[0]), fmaf(r[k].y, sc[1], sh[1]),
+                                        fmaf(r[k].z, sc[2], sh[2]), fmaf(r[k].w, sc[3], sh[3]))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
   };
   const int OW = 2 * p.W;
   const size_t oplane = (size_t)4 * plane;
@@ -327,12 +332,13 @@ hourglass_tail_tiled_kernel(const __grid_constant__ TailParams p) {
       for (int c = 0; c < 4; ++c) acc[px][k][c] = 0.f;
 
   float4 r[kTilePer];
-  fetch(z0 - 1, r);
-  stash(0, r);
+  bool rz;
+  fetch(z0 - 1, r, rz);
+  stash(0, r, rz);
   __syncthreads();
   int cur = 0;
   for (int zi = z0 - 1; zi <= z1; ++zi) {
-    if (zi < z1) fetch(zi + 1, r);                         // in flight while plane zi is consumed
+    if (zi < z1) fetch(zi + 1, r, rz);                     // in flight while plane zi is consumed
     if (zi >= 0 && zi < p.D) {
       float4 v[2][3];
 #define PDS_TAIL_ROW(DY)                                                                      \
@@ -360,7 +366,7 @@ hourglass_tail_tiled_kernel(const __grid_constant__ TailParams p) {
     for (int px = 0; px < 2; ++px)
 #pragma unroll
       for (int c = 0; c < 4; ++c) { acc[px][0][c] = acc[px][1][c]; acc[px][1][c] = acc[px][2][c]; acc[px][2][c] = 0.f; }
-    if (zi < z1) stash(cur ^ 1, r);
+    if (zi < z1) stash(cur ^ 1, r, rz);
     __syncthreads();
     cur ^= 1;
   }
