@@ -118,12 +118,20 @@ def load_peaks():
             'source': 'fallback'}
 
 
-def kernel_rooflines(report, steps, peaks):
+# 16-bit tensor-core products issued per reference (fp32) multiply-add by the split-operand
+# precisions: the tensor pipe is busy `products` times the algorithmic FLOPs
+PRODUCTS_PER_MAC = {'fp16x2': 3, 'bf16x2': 3, 'bf16x3': 6, 'bf16': 1, 'fp16': 1}
+
+
+def kernel_rooflines(report, steps, peaks, precision='fp16x2'):
     """Per-kernel-class roofline from the live CUDA-event profile of `steps` steps.
     Algorithmic FLOPs / bytes per launch come from the library's own accounting
     (pds_profiler_read_work: reference FLOP count of the layer, minimum HBM bytes;
-    DESIGN.md section 4); a class is graded on the roof it is closer to."""
+    DESIGN.md section 4).  `achieved`, `peak`, `frac` are always ALGORITHMIC work over the
+    measured peak; a class is bound by the roof it is closer to, where the tensor roof counts
+    the products actually issued (`executed_frac` = tensor_frac x products per reference MAC)."""
     out = []
+    products = PRODUCTS_PER_MAC.get(precision, 1)
     for name, (launches, ms, flops, nbytes) in sorted(report.items(), key=lambda kv: -kv[1][1]):
         if launches == 0 or ms <= 0:
             continue
@@ -136,7 +144,12 @@ def kernel_rooflines(report, steps, peaks):
             entry['tflops'] = flops / sec / 1e12
             entry['gbs'] = nbytes / sec / 1e9
             entry['tensor_frac'], entry['hbm_frac'] = tensor, hbm
-            if tensor >= hbm:
+            on_tensor_cores = name.startswith('conv3x3_tc') or name.startswith('conv_tcg')
+            executed = tensor * (products if on_tensor_cores else 1)
+            if on_tensor_cores:
+                entry['products_per_reference_mac'] = products
+                entry['executed_frac'] = executed
+            if executed >= hbm:
                 entry.update(bound='tensor', unit='TFLOP/s', achieved=entry['tflops'],
                              peak=peaks['bf16_tflops_sustained'], frac=tensor)
             else:
@@ -330,7 +343,7 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         total_pairs = args.steps * args.batch * world
-        kernels = kernel_rooflines(report, args.steps, peaks)
+        kernels = kernel_rooflines(report, args.steps, peaks, args.precision)
         dominant = next((k for k in kernels if 'achieved' in k), None)
         roofline = None
         traffic = {}
@@ -341,6 +354,13 @@ def main():
             roofline = {'bound': dominant['bound'], 'achieved': dominant['achieved'],
                         'peak': dominant['peak'], 'unit': dominant['unit'],
                         'frac': dominant['frac'], 'tensor_frac': dominant['tensor_frac'],
+                        'executed_frac': dominant.get('executed_frac'),
+                        'products_per_reference_mac': dominant.get('products_per_reference_mac'),
+                        'note': 'achieved/frac count the reference (fp32) FLOPs of the layer; the fp32-grade '
+                                'split-operand precision issues products_per_reference_mac 16-bit tensor-core '
+                                'products per reference multiply-add, executed_frac is the share of the '
+                                'measured bf16 peak those occupy',
+
                         'hbm_frac': dominant['hbm_frac'], 'tflops': dominant['tflops'], 'gbs': dominant['gbs'],
                         'traffic': traffic.get(dominant['kernel']),
                         'traffic_source': traffic.get('_source') if dominant['kernel'] in traffic else None,
