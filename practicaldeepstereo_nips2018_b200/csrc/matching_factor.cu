@@ -144,87 +144,104 @@ column_ops_kernel(const float* __restrict__ Bf, const float* __restrict__ Q, con
   }
 }
 
-// t1 = LeakyReLU(conv1(x0_d) + b1) for every slice, + its InstanceNorm sums.  grid (x blocks, C/8, B*D)
-__global__ void __launch_bounds__(256, 3)
+// t1 = LeakyReLU(conv1(x0_d) + b1) for every slice, + its InstanceNorm sums.
+// grid (row blocks, C/8, B).  A CTA stages R rows of eight channels of the two per-sample terms
+// in shared memory ONCE and produces those rows of ALL D disparity slices from them: a thread
+// owns one image column (its left-term values stay in registers), walks d = 0 .. D-1 reading the
+// right term at x - d from shared memory, and the kernel is a pure 4 B/element store stream (the
+// first version re-read both terms from L2 for every slice and ran at half the store bandwidth).
+// InstanceNorm sums: per thread over the R rows, butterfly over the warp (16 shuffles for the 16
+// sums), double atomics in shared memory, one global double atomic per (slice, channel) and CTA.
+template <int R>
+__global__ void __launch_bounds__(256, 2)
 compose_second_kernel(const float* __restrict__ PA, const float* __restrict__ PB, const float* __restrict__ cols,
                       const float* __restrict__ bias, float* __restrict__ t, double* __restrict__ stats, int C,
                       int H, int W, int D) {
-  const int c8 = blockIdx.y, n = blockIdx.z;
-  const int b = n / D, d = n - b * D, J = 3 + 2 * (D - 1);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* sA = reinterpret_cast<float4*>(smem_raw);          // [2][R][W]: channels 0-3 | 4-7
+  float4* sB = sA + 2 * R * W;                               // [2][R][W]
+  double* sstat = reinterpret_cast<double*>(sB + 2 * R * W); // [D][16]
+  float4* sC = reinterpret_cast<float4*>(sstat + D * 16);    // [J][R][2]: border-correction columns
+  const int c8 = blockIdx.y, b = blockIdx.z, y0 = blockIdx.x * R, nr = min(R, H - y0), J = 3 + 2 * (D - 1);
+  const int tid = threadIdx.x, lane = tid & 31;
   const size_t HW = (size_t)H * W;
-  const size_t base = ((size_t)b * (C / 4) + 2 * c8) * HW;
-  const float4* a4 = reinterpret_cast<const float4*>(PA) + base;
-  const float4* b4 = reinterpret_cast<const float4*>(PB) + base;
-  float4* o4 = reinterpret_cast<float4*>(t) + ((size_t)n * (C / 4) + 2 * c8) * HW;
-  const float* cb = cols + (size_t)b * J * H * C + 8 * c8;
-  auto colv = [&](int j, int y, float sign, float (&v)[8]) {
-    const float4* p = reinterpret_cast<const float4*>(cb + ((size_t)j * H + y) * C);
-    const float4 l = __ldg(p), h = __ldg(p + 1);
-    v[0] = fmaf(sign, l.x, v[0]); v[1] = fmaf(sign, l.y, v[1]); v[2] = fmaf(sign, l.z, v[2]); v[3] = fmaf(sign, l.w, v[3]);
-    v[4] = fmaf(sign, h.x, v[4]); v[5] = fmaf(sign, h.y, v[5]); v[6] = fmaf(sign, h.z, v[6]); v[7] = fmaf(sign, h.w, v[7]);
-  };
-  float s1[8], s2[8], b1[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; b1[e] = __ldg(bias + 8 * c8 + e); }
-  const bool shifted = d < W;
-  const unsigned total = (unsigned)HW, stride = gridDim.x * blockDim.x;
-  for (unsigned p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < total; p0 += 2 * stride) {
-    float4 alo[2], ahi[2], blo[2], bhi[2];
-    int xx[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const unsigned pix = p0 + u * stride;
-      if (pix >= total) continue;
-      xx[u] = (int)(pix % (unsigned)W);
-      alo[u] = __ldg(a4 + pix); ahi[u] = __ldg(a4 + HW + pix);
-      if (shifted && xx[u] >= d) { blo[u] = __ldg(b4 + pix - d); bhi[u] = __ldg(b4 + HW + pix - d); }
+  {
+    const float4* a4 = reinterpret_cast<const float4*>(PA) + ((size_t)b * (C / 4) + 2 * c8) * HW + (size_t)y0 * W;
+    const float4* b4 = reinterpret_cast<const float4*>(PB) + ((size_t)b * (C / 4) + 2 * c8) * HW + (size_t)y0 * W;
+    for (int i = tid; i < nr * W; i += 256) {
+      sA[i] = __ldg(a4 + i); sA[R * W + i] = __ldg(a4 + HW + i);
+      sB[i] = __ldg(b4 + i); sB[R * W + i] = __ldg(b4 + HW + i);
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const unsigned pix = p0 + u * stride;
-      if (pix >= total) continue;
-      const int x = xx[u], y = (int)(pix / (unsigned)W), xs = x - d;
-      float v[8] = {alo[u].x + b1[0], alo[u].y + b1[1], alo[u].z + b1[2], alo[u].w + b1[3],
-                    ahi[u].x + b1[4], ahi[u].y + b1[5], ahi[u].z + b1[6], ahi[u].w + b1[7]};
-      if (shifted) {
-        if (xs >= 0) {
-          v[0] += blo[u].x; v[1] += blo[u].y; v[2] += blo[u].z; v[3] += blo[u].w;
-          v[4] += bhi[u].x; v[5] += bhi[u].y; v[6] += bhi[u].z; v[7] += bhi[u].w;
-          if (xs == 0 && d >= 1) colv(0, y, 1.f, v);
-        } else if (xs == -1) colv(1, y, 1.f, v);
-        else if (xs == -2) colv(2, y, 1.f, v);
-        if (d >= 1) {
-          if (x == W - 1) colv(3 + 2 * (d - 1), y, -1.f, v);
-          else if (x == W - 2) colv(4 + 2 * (d - 1), y, -1.f, v);
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        v[e] = v[e] > 0.f ? v[e] : 0.1f * v[e];
-        s1[e] += v[e]; s2[e] = fmaf(v[e], v[e], s2[e]);
-      }
-      stg_stream(o4 + pix, make_float4(v[0], v[1], v[2], v[3]));
-      stg_stream(o4 + HW + pix, make_float4(v[4], v[5], v[6], v[7]));
+    for (int i = tid; i < D * 16; i += 256) sstat[i] = 0.0;
+    const float* cb = cols + (size_t)b * J * H * C + 8 * c8;
+    for (int i = tid; i < J * R * 2; i += 256) {
+      const int h = i & 1, r = (i >> 1) % R, j = (i >> 1) / R;
+      if (r < nr) sC[i] = __ldg(reinterpret_cast<const float4*>(cb + ((size_t)j * H + y0 + r) * C) + h);
     }
-  }
-  // block reduction of the 16 sums, then one double atomic each
-  __shared__ float red[8][16];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
-      s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
-    }
-    if (lane == 0) { red[warp][e] = s1[e]; red[warp][8 + e] = s2[e]; }
   }
   __syncthreads();
-  if (threadIdx.x < 16) {
-    double acc = 0.0;
-    for (int w = 0; w < 8; ++w) acc += (double)red[w][threadIdx.x];
-    const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
-    atomicAdd(stats + ((size_t)n * C + 8 * c8 + e) * 2 + which, acc);
+  float b1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) b1[e] = __ldg(bias + 8 * c8 + e);
+  float4* tb = reinterpret_cast<float4*>(t) + ((size_t)b * D * (C / 4) + 2 * c8) * HW + (size_t)y0 * W;
+  for (int x0 = 0; x0 < W; x0 += 256) {
+    const int x = x0 + tid;
+    const bool valid = x < W;
+    float4 alo[R], ahi[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      alo[r] = make_float4(b1[0], b1[1], b1[2], b1[3]); ahi[r] = make_float4(b1[4], b1[5], b1[6], b1[7]);
+      if (valid && r < nr) {
+        const float4 l = sA[r * W + x], h = sA[(R + r) * W + x];
+        alo[r].x += l.x; alo[r].y += l.y; alo[r].z += l.z; alo[r].w += l.w;
+        ahi[r].x += h.x; ahi[r].y += h.y; ahi[r].z += h.z; ahi[r].w += h.w;
+      }
+    }
+    for (int d = 0; d < D; ++d) {
+      const int xs = x - d;
+      const bool shifted = d < W, has_b = valid && shifted && xs >= 0;
+      const int jp = !(valid && shifted) ? -1 : (xs == 0 && d >= 1) ? 0 : xs == -1 ? 1 : xs == -2 ? 2 : -1;
+      const int jm = !(valid && shifted && d >= 1) ? -1 : x == W - 1 ? 3 + 2 * (d - 1) : x == W - 2 ? 4 + 2 * (d - 1) : -1;
+      float4* o4 = tb + (size_t)d * (C / 4) * HW + x;
+      float sum[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) sum[e] = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!(valid && r < nr)) continue;
+        float v[8] = {alo[r].x, alo[r].y, alo[r].z, alo[r].w, ahi[r].x, ahi[r].y, ahi[r].z, ahi[r].w};
+        if (has_b) {
+          const float4 l = sB[r * W + xs], h = sB[(R + r) * W + xs];
+          v[0] += l.x; v[1] += l.y; v[2] += l.z; v[3] += l.w;
+          v[4] += h.x; v[5] += h.y; v[6] += h.z; v[7] += h.w;
+        }
+        if (jp >= 0 || jm >= 0) {                // border columns only
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int j = k == 0 ? jp : jm;
+            if (j < 0) continue;
+            const float sign = k == 0 ? 1.f : -1.f;
+            const float4 l = sC[(j * R + r) * 2], h = sC[(j * R + r) * 2 + 1];
+            v[0] = fmaf(sign, l.x, v[0]); v[1] = fmaf(sign, l.y, v[1]); v[2] = fmaf(sign, l.z, v[2]); v[3] = fmaf(sign, l.w, v[3]);
+            v[4] = fmaf(sign, h.x, v[4]); v[5] = fmaf(sign, h.y, v[5]); v[6] = fmaf(sign, h.z, v[6]); v[7] = fmaf(sign, h.w, v[7]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[e] = fmaxf(v[e], 0.1f * v[e]);       // LeakyReLU(0.1)
+          sum[e] += v[e]; sum[8 + e] = fmaf(v[e], v[e], sum[8 + e]);
+        }
+        stg_stream(o4 + r * W, make_float4(v[0], v[1], v[2], v[3]));
+        stg_stream(o4 + HW + r * W, make_float4(v[4], v[5], v[6], v[7]));
+      }
+      const float total = ptx::warp_transpose_reduce<16>(sum, lane);     // lane k (and k + 16): sum k
+      if (lane < 16) atomicAdd(&sstat[d * 16 + lane], (double)total);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < D * 16; i += 256) {
+    const int d = i >> 4, k = i & 15, e = k & 7, which = k >> 3;
+    atomicAdd(stats + ((size_t)(b * D + d) * C + 8 * c8 + e) * 2 + which, sstat[i]);
   }
 }
 
@@ -334,12 +351,15 @@ int tc_compose_second(const float* PA, const float* PB, const float* cols, const
                       double* stats, int B, int C, int H, int W, int D, cudaStream_t st) {
   const size_t HW = (size_t)H * W;
   if (B == 0 || HW == 0) return PDS_OK;
-  unsigned gx = (unsigned)((HW + 2047) / 2048);          // >= 8 pixels per thread; 16 double atomics per CTA
-  if (gx > 16) gx = 16;
-  dim3 grid(gx, (unsigned)(C / 8), (unsigned)(B * D));
+  constexpr int R = 4;
+  const size_t smem = (size_t)4 * R * W * sizeof(float4) + (size_t)D * 16 * sizeof(double) +
+                      (size_t)(3 + 2 * (D - 1)) * R * 2 * sizeof(float4);
+  if (smem > 200 * 1024) { set_error("tc_compose_second: image too wide (%d)", W); return PDS_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)((H + R - 1) / R), (unsigned)(C / 8), (unsigned)B);
+  PDS_CUDA(allow_dynamic_smem(compose_second_kernel<R>, (int)smem));
   PDS_KERNEL("tc_compose_second", st);
   PDS_KERNEL_WORK(0, (double)B * C * HW * (8.0 + 4.0 * D));
-  compose_second_kernel<<<grid, 256, 0, st>>>(PA, PB, cols, bias, t, stats, C, H, W, D);
+  compose_second_kernel<R><<<grid, 256, smem, st>>>(PA, PB, cols, bias, t, stats, C, H, W, D);
   PDS_LAUNCH_CHECK("compose_second_kernel");
   return PDS_OK;
 }
