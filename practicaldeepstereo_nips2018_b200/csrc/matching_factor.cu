@@ -245,60 +245,95 @@ compose_second_kernel(const float* __restrict__ PA, const float* __restrict__ PB
   }
 }
 
-// x1 = IN(t2) + x0_d with x0 regenerated from A / Bf / Q -> split AP planes.  grid (x blocks, C/8, B*D)
-template <bool FP16, int S>
-__global__ void __launch_bounds__(256, 3)
+// x1 = IN(t2) + x0_d with x0 regenerated from A / Bf / Q -> split AP planes.
+// grid (row blocks, C/8, B): like compose_second_kernel, a CTA stages R rows of eight channels of
+// the three per-sample terms in shared memory once and walks all D slices of those rows; per
+// slice it streams t2 (fp32) in and the operand planes out -- the only DRAM traffic left.  The
+// InstanceNorm scale / shift of every slice are computed once per CTA.
+template <bool FP16, int S, int R>
+__global__ void __launch_bounds__(256, 2)
 norm_residual_first_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                            const float* __restrict__ gamma, const float* __restrict__ beta,
                            const float* __restrict__ A, const float* __restrict__ Bf, const float* __restrict__ Q,
                            uint16_t* __restrict__ out_ap, int C, int H, int W, int D) {
-  const int c8 = blockIdx.y, n = blockIdx.z;
-  const int b = n / D, d = n - b * D;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* sA = reinterpret_cast<float4*>(smem_raw);          // [2][R][W]: channels 0-3 | 4-7
+  float4* sB = sA + 2 * R * W;
+  float4* sQ = sB + 2 * R * W;
+  float4* snorm = sQ + 2 * R * W;                            // [D][4]: scale 0-3, scale 4-7, shift 0-3, shift 4-7
+  const int c8 = blockIdx.y, b = blockIdx.z, y0 = blockIdx.x * R, nr = min(R, H - y0);
+  const int tid = threadIdx.x;
   const size_t HW = (size_t)H * W;
-  __shared__ float sc[8], sh[8];
-  if (threadIdx.x < 8) {
-    const int c = c8 * 8 + threadIdx.x;
-    const double s = stats[((size_t)n * C + c) * 2], q = stats[((size_t)n * C + c) * 2 + 1];
-    const double mean = s / (double)HW;
-    double var = q / (double)HW - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float scale = (float)(1.0 / sqrt(var + 1e-5)) * gamma[c];
-    sc[threadIdx.x] = scale;
-    sh[threadIdx.x] = beta[c] - (float)mean * scale;
+  {
+    const size_t base = ((size_t)b * (C / 4) + 2 * c8) * HW + (size_t)y0 * W;
+    const float4* a4 = reinterpret_cast<const float4*>(A) + base;
+    const float4* b4 = reinterpret_cast<const float4*>(Bf) + base;
+    const float4* q4 = reinterpret_cast<const float4*>(Q) + base;
+    for (int i = tid; i < nr * W; i += 256) {
+      sA[i] = __ldg(a4 + i); sA[R * W + i] = __ldg(a4 + HW + i);
+      sB[i] = __ldg(b4 + i); sB[R * W + i] = __ldg(b4 + HW + i);
+      sQ[i] = __ldg(q4 + i); sQ[R * W + i] = __ldg(q4 + HW + i);
+    }
+    float* sn = reinterpret_cast<float*>(snorm);
+    for (int i = tid; i < D * 8; i += 256) {
+      const int d = i >> 3, e = i & 7, c = c8 * 8 + e;
+      const double s = stats[((size_t)(b * D + d) * C + c) * 2], q = stats[((size_t)(b * D + d) * C + c) * 2 + 1];
+      const double mean = s / (double)HW;
+      double var = q / (double)HW - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float scale = (float)(1.0 / sqrt(var + 1e-5)) * gamma[c];
+      sn[d * 16 + e] = scale;
+      sn[d * 16 + 8 + e] = beta[c] - (float)mean * scale;
+    }
   }
   __syncthreads();
-  const size_t base = ((size_t)b * (C / 4) + 2 * c8) * HW;
-  const float4* a4 = reinterpret_cast<const float4*>(A) + base;
-  const float4* b4 = reinterpret_cast<const float4*>(Bf) + base;
-  const float4* q4 = reinterpret_cast<const float4*>(Q) + base;
-  const float4* y4 = reinterpret_cast<const float4*>(y) + ((size_t)n * (C / 4) + 2 * c8) * HW;
   float4* o4 = reinterpret_cast<float4*>(out_ap);
-  const unsigned total = (unsigned)HW, stride = gridDim.x * blockDim.x;
-  for (unsigned p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < total; p0 += 2 * stride) {
-    float4 lo[2], hi[2];
-    float x0[2][8];
+  for (int x0 = 0; x0 < W; x0 += 256) {
+    const int x = x0 + tid;
+    if (x >= W) continue;
+    float4 alo[R], ahi[R];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const unsigned pix = p0 + u * stride;
-      if (pix < total) {
-        lo[u] = ldg_stream(y4 + pix); hi[u] = ldg_stream(y4 + HW + pix);
-        first_x0(a4, b4, q4, HW, pix, (int)(pix % (unsigned)W), W, d, x0[u]);
-      }
-    }
+    for (int r = 0; r < R; ++r)
+      if (r < nr) { alo[r] = sA[r * W + x]; ahi[r] = sA[(R + r) * W + x]; }
+    for (int d = 0; d < D; ++d) {
+      const int n = b * D + d;
+      const float4* y4 = reinterpret_cast<const float4*>(y) + ((size_t)n * (C / 4) + 2 * c8) * HW + (size_t)y0 * W + x;
+      float4 lo[R], hi[R];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const unsigned pix = p0 + u * stride;
-      if (pix >= total) continue;
-      const float v[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
-      uint16_t t[8][3];
+      for (int r = 0; r < R; ++r)
+        if (r < nr) { lo[r] = ldg_stream(y4 + r * W); hi[r] = ldg_stream(y4 + HW + r * W); }
+      const float4 sc0 = snorm[d * 4], sc1 = snorm[d * 4 + 1], sh0 = snorm[d * 4 + 2], sh1 = snorm[d * 4 + 3];
+      const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+      const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+      // x0 of slice d (same arithmetic as tc_compose_first): A + shifted Bf, Q at the two borders
+      const int plus = x >= d ? x - d : (x == d - 1 ? 0 : -1);
+      const float4* psrc = x >= d ? sB : sQ;
+      const int minus = (x == W - 1 && d >= 1 && d <= W) ? W - d : -1;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) split_terms<FP16>(fmaf(v[e], sc[e], sh[e]) + x0[u][e], t[e]);
+      for (int r = 0; r < R; ++r) {
+        if (r >= nr) continue;
+        float x0v[8] = {alo[r].x, alo[r].y, alo[r].z, alo[r].w, ahi[r].x, ahi[r].y, ahi[r].z, ahi[r].w};
+        if (plus >= 0) {
+          const float4 l = psrc[r * W + plus], h = psrc[(R + r) * W + plus];
+          x0v[0] += l.x; x0v[1] += l.y; x0v[2] += l.z; x0v[3] += l.w;
+          x0v[4] += h.x; x0v[5] += h.y; x0v[6] += h.z; x0v[7] += h.w;
+        }
+        if (minus >= 0) {
+          const float4 l = sQ[r * W + minus], h = sQ[(R + r) * W + minus];
+          x0v[0] -= l.x; x0v[1] -= l.y; x0v[2] -= l.z; x0v[3] -= l.w;
+          x0v[4] -= h.x; x0v[5] -= h.y; x0v[6] -= h.z; x0v[7] -= h.w;
+        }
+        const float v[8] = {lo[r].x, lo[r].y, lo[r].z, lo[r].w, hi[r].x, hi[r].y, hi[r].z, hi[r].w};
+        uint16_t t[8][3];
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        float4 pk;
-        pk.x = __uint_as_float(t[0][s] | ((uint32_t)t[1][s] << 16)); pk.y = __uint_as_float(t[2][s] | ((uint32_t)t[3][s] << 16));
-        pk.z = __uint_as_float(t[4][s] | ((uint32_t)t[5][s] << 16)); pk.w = __uint_as_float(t[6][s] | ((uint32_t)t[7][s] << 16));
-        stg_stream(o4 + ((size_t)(n * S + s) * (C / 8) + c8) * HW + pix, pk);
+        for (int e = 0; e < 8; ++e) split_terms<FP16>(fmaf(v[e], sc[e], sh[e]) + x0v[e], t[e]);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          float4 pk;
+          pk.x = __uint_as_float(t[0][s] | ((uint32_t)t[1][s] << 16)); pk.y = __uint_as_float(t[2][s] | ((uint32_t)t[3][s] << 16));
+          pk.z = __uint_as_float(t[4][s] | ((uint32_t)t[5][s] << 16)); pk.w = __uint_as_float(t[6][s] | ((uint32_t)t[7][s] << 16));
+          stg_stream(o4 + ((size_t)(n * S + s) * (C / 8) + c8) * HW + (size_t)(y0 + r) * W + x, pk);
+        }
       }
     }
   }
@@ -369,14 +404,17 @@ int tc_norm_residual_first(const float* y, const double* stats, const float* gam
                            int W, int D, int S, int fp16, cudaStream_t st) {
   const size_t HW = (size_t)H * W;
   if (B == 0 || HW == 0) return PDS_OK;
-  unsigned gx = (unsigned)((HW + 511) / 512);        // two pixels per thread per iteration
-  if (gx > 128) gx = 128;
-  dim3 grid(gx, (unsigned)(C / 8), (unsigned)(B * D));
+  constexpr int R = 4;
+  const size_t smem = (size_t)6 * R * W * sizeof(float4) + (size_t)D * 4 * sizeof(float4);
+  if (smem > 200 * 1024) { set_error("tc_norm_residual_first: image too wide (%d)", W); return PDS_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)((H + R - 1) / R), (unsigned)(C / 8), (unsigned)B);
   PDS_KERNEL("tc_norm_residual_first", st);
   PDS_KERNEL_WORK(0, (double)B * D * C * HW * (4.0 + 2.0 * S));
 #define PDS_NRF_CASE(FF, SS) \
-  if ((fp16 != 0) == FF && S == SS)  \
-    norm_residual_first_kernel<FF, SS><<<grid, 256, 0, st>>>(y, stats, gamma, beta, A, Bf, Q, out_ap, C, H, W, D);
+  if ((fp16 != 0) == FF && S == SS) {  \
+    PDS_CUDA(allow_dynamic_smem(norm_residual_first_kernel<FF, SS, R>, (int)smem));  \
+    norm_residual_first_kernel<FF, SS, R><<<grid, 256, smem, st>>>(y, stats, gamma, beta, A, Bf, Q, out_ap, C, H, W, D);  \
+  }
   PDS_NRF_CASE(true, 1) PDS_NRF_CASE(true, 2) PDS_NRF_CASE(true, 3)
   PDS_NRF_CASE(false, 1) PDS_NRF_CASE(false, 2) PDS_NRF_CASE(false, 3)
 #undef PDS_NRF_CASE
