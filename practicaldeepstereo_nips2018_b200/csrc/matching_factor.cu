@@ -386,15 +386,24 @@ int tc_compose_second(const float* PA, const float* PB, const float* cols, const
                       double* stats, int B, int C, int H, int W, int D, cudaStream_t st) {
   const size_t HW = (size_t)H * W;
   if (B == 0 || HW == 0) return PDS_OK;
-  constexpr int R = 4;
-  const size_t smem = (size_t)4 * R * W * sizeof(float4) + (size_t)D * 16 * sizeof(double) +
-                      (size_t)(3 + 2 * (D - 1)) * R * 2 * sizeof(float4);
+  // rows per CTA: as many as leave two CTAs per SM (wide images fall back to fewer rows)
+  auto smem_for = [&](int R) {
+    return (size_t)4 * R * W * sizeof(float4) + (size_t)D * 16 * sizeof(double) +
+           (size_t)(3 + 2 * (D - 1)) * R * 2 * sizeof(float4);
+  };
+  const int R = smem_for(4) <= 100 * 1024 ? 4 : (smem_for(2) <= 100 * 1024 ? 2 : 1);
+  const size_t smem = smem_for(R);
   if (smem > 200 * 1024) { set_error("tc_compose_second: image too wide (%d)", W); return PDS_ERR_UNSUPPORTED; }
   dim3 grid((unsigned)((H + R - 1) / R), (unsigned)(C / 8), (unsigned)B);
-  PDS_CUDA(allow_dynamic_smem(compose_second_kernel<R>, (int)smem));
   PDS_KERNEL("tc_compose_second", st);
   PDS_KERNEL_WORK(0, (double)B * C * HW * (8.0 + 4.0 * D));
-  compose_second_kernel<R><<<grid, 256, smem, st>>>(PA, PB, cols, bias, t, stats, C, H, W, D);
+#define PDS_COMPOSE_CASE(RR) \
+  if (R == RR) {  \
+    PDS_CUDA(allow_dynamic_smem(compose_second_kernel<RR>, (int)smem));  \
+    compose_second_kernel<RR><<<grid, 256, smem, st>>>(PA, PB, cols, bias, t, stats, C, H, W, D);  \
+  }
+  PDS_COMPOSE_CASE(4) PDS_COMPOSE_CASE(2) PDS_COMPOSE_CASE(1)
+#undef PDS_COMPOSE_CASE
   PDS_LAUNCH_CHECK("compose_second_kernel");
   return PDS_OK;
 }
@@ -404,19 +413,22 @@ int tc_norm_residual_first(const float* y, const double* stats, const float* gam
                            int W, int D, int S, int fp16, cudaStream_t st) {
   const size_t HW = (size_t)H * W;
   if (B == 0 || HW == 0) return PDS_OK;
-  constexpr int R = 4;
-  const size_t smem = (size_t)6 * R * W * sizeof(float4) + (size_t)D * 4 * sizeof(float4);
+  auto smem_for = [&](int R) { return (size_t)6 * R * W * sizeof(float4) + (size_t)D * 4 * sizeof(float4); };
+  const int R = smem_for(4) <= 100 * 1024 ? 4 : (smem_for(2) <= 100 * 1024 ? 2 : 1);
+  const size_t smem = smem_for(R);
   if (smem > 200 * 1024) { set_error("tc_norm_residual_first: image too wide (%d)", W); return PDS_ERR_UNSUPPORTED; }
   dim3 grid((unsigned)((H + R - 1) / R), (unsigned)(C / 8), (unsigned)B);
   PDS_KERNEL("tc_norm_residual_first", st);
   PDS_KERNEL_WORK(0, (double)B * D * C * HW * (4.0 + 2.0 * S));
-#define PDS_NRF_CASE(FF, SS) \
-  if ((fp16 != 0) == FF && S == SS) {  \
-    PDS_CUDA(allow_dynamic_smem(norm_residual_first_kernel<FF, SS, R>, (int)smem));  \
-    norm_residual_first_kernel<FF, SS, R><<<grid, 256, smem, st>>>(y, stats, gamma, beta, A, Bf, Q, out_ap, C, H, W, D);  \
+#define PDS_NRF_CASE(FF, SS, RR) \
+  if ((fp16 != 0) == FF && S == SS && R == RR) {  \
+    PDS_CUDA(allow_dynamic_smem(norm_residual_first_kernel<FF, SS, RR>, (int)smem));  \
+    norm_residual_first_kernel<FF, SS, RR><<<grid, 256, smem, st>>>(y, stats, gamma, beta, A, Bf, Q, out_ap, C, H, W, D);  \
   }
-  PDS_NRF_CASE(true, 1) PDS_NRF_CASE(true, 2) PDS_NRF_CASE(true, 3)
-  PDS_NRF_CASE(false, 1) PDS_NRF_CASE(false, 2) PDS_NRF_CASE(false, 3)
+#define PDS_NRF_ROWS(FF, SS) PDS_NRF_CASE(FF, SS, 4) PDS_NRF_CASE(FF, SS, 2) PDS_NRF_CASE(FF, SS, 1)
+  PDS_NRF_ROWS(true, 1) PDS_NRF_ROWS(true, 2) PDS_NRF_ROWS(true, 3)
+  PDS_NRF_ROWS(false, 1) PDS_NRF_ROWS(false, 2) PDS_NRF_ROWS(false, 3)
+#undef PDS_NRF_ROWS
 #undef PDS_NRF_CASE
   PDS_LAUNCH_CHECK("norm_residual_first_kernel");
   return PDS_OK;

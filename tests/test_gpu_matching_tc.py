@@ -61,3 +61,17 @@ def test_tc_full_width_slice():
         out = matching.Matching(2, op)(l, r)
         ref = _reference(l, r, params, 2)
     assert max_abs(out, ref) <= 2e-4
+
+
+@pytest.mark.parametrize('W', [600, 1100])
+def test_tc_wide_images_use_fewer_rows_per_cta(W):
+    """Quarter-resolution widths beyond what four staged rows of the per-sample terms fit in
+    shared memory (csrc/matching_factor.cu picks 2 rows, then 1): few rows, 3 disparities,
+    ragged height (rows per CTA do not divide it)."""
+    params = synth.make_params(synth.matching_operation_specs(), 44)
+    op = load_module(matching.MatchingOperation(precision='fp16x2'), params)
+    l, r = cuda(synth.tensor((1, 64, 7, W), 45)), cuda(synth.tensor((1, 64, 7, W), 46))
+    with torch.no_grad():
+        out = matching.Matching(2, op)(l, r)
+        ref = _reference(l, r, params, 2)
+    assert max_abs(out, ref) <= 2e-4
