@@ -302,7 +302,16 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
             v[0][j] = valid ? t : 0.f;
           }
           if (valid) {
-            if (p.merged) {
+            if (p.merged && p.Cout == 4) {
+              // two x-parity classes = 8 consecutive columns = 32 contiguous bytes of the output row
+#pragma unroll
+              for (int j = 0; j < CH; j += 8) {
+                const int mc = (c * CH + j) >> 2;
+                if (mc < 8)
+                  stg256(p.out + ((((size_t)it.n * p.OZ + 2 * gz + ((mc >> 2) & 1)) * p.OY + 2 * gy + ((mc >> 1) & 1)) * p.OX +
+                                  2 * gx) * 4, &v[0][j]);
+              }
+            } else if (p.merged) {
               // column = class * Cout + channel: scatter the 8 parity classes of this input voxel
 #pragma unroll
               for (int j = 0; j < CH; j += 4) {
@@ -314,6 +323,10 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
                   *reinterpret_cast<float4*>(om) = make_float4(v[0][j], v[0][j + 1], v[0][j + 2], v[0][j + 3]);
                 }
               }
+            } else if ((p.Cout & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 8)
+                if (c * CH + j < p.Cout) stg256(o + c * CH + j, &v[0][j]);
             } else {
 #pragma unroll
               for (int j = 0; j < CH; j += 4)
@@ -459,7 +472,7 @@ tcg_norm_to_ap_kernel(const NormParams p) {
   const size_t plane = (size_t)IZ * IY * IX;
   const int rows = p.Z * p.Y, items = p.X * G;
   const int chunks = (items + 255) >> 8, units = rows * chunks;
-  struct Unit { int row, y, x, g; bool live; size_t off; float4 a0, a1, b0, b1, c0, c1; };
+  struct Unit { int row, y, x, g; bool live; size_t off; float a[8], b[8]; float4 c0, c1; };
   auto load = [&](int u, Unit& w) {
     w.live = u < units;
     if (!w.live) return;
@@ -470,12 +483,8 @@ tcg_norm_to_ap_kernel(const NormParams p) {
     w.g = i & (G - 1); w.x = i >> gshift;
     w.y = w.row % p.Y;
     w.off = ((size_t)n * V + (size_t)w.row * p.X + w.x) * p.C + 8 * w.g;
-    const float4* pa = reinterpret_cast<const float4*>(p.ya + w.off);
-    w.a0 = ldg_stream(pa); w.a1 = ldg_stream(pa + 1);
-    if (p.yb) {
-      const float4* pb = reinterpret_cast<const float4*>(p.yb + w.off);
-      w.b0 = ldg_stream(pb); w.b1 = ldg_stream(pb + 1);
-    }
+    ldg256_stream(p.ya + w.off, w.a);              // 8 channels = one 32-byte sector per lane
+    if (p.yb) ldg256_stream(p.yb + w.off, w.b);
     if (p.bcast) {
       const float4* pc = reinterpret_cast<const float4*>(p.bcast + (((size_t)n * p.Y + w.y) * p.X + w.x) * p.C + 8 * w.g);
       w.c0 = __ldg(pc); w.c1 = __ldg(pc + 1);
@@ -484,24 +493,19 @@ tcg_norm_to_ap_kernel(const NormParams p) {
   auto finish = [&](const Unit& w) {
     if (!w.live) return;
     const int z = w.row / p.Y, y = w.y, x = w.x, g = w.g;
-    float v[8] = {w.a0.x, w.a0.y, w.a0.z, w.a0.w, w.a1.x, w.a1.y, w.a1.z, w.a1.w};
+    float v[8];
     const float* sa = sm + 8 * g;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sa[e], sa[p.C + e]);
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(w.a[e], sa[e], sa[p.C + e]);
     if (p.yb) {
-      const float q[8] = {w.b0.x, w.b0.y, w.b0.z, w.b0.w, w.b1.x, w.b1.y, w.b1.z, w.b1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] += fmaf(q[e], sa[2 * p.C + e], sa[3 * p.C + e]);
+      for (int e = 0; e < 8; ++e) v[e] += fmaf(w.b[e], sa[2 * p.C + e], sa[3 * p.C + e]);
     }
     if (p.bcast) {
       v[0] += w.c0.x; v[1] += w.c0.y; v[2] += w.c0.z; v[3] += w.c0.w;
       v[4] += w.c1.x; v[5] += w.c1.y; v[6] += w.c1.z; v[7] += w.c1.w;
     }
-    if (p.out_f32) {
-      float4* po = reinterpret_cast<float4*>(p.out_f32 + w.off);
-      po[0] = make_float4(v[0], v[1], v[2], v[3]);
-      po[1] = make_float4(v[4], v[5], v[6], v[7]);
-    }
+    if (p.out_f32) stg256(p.out_f32 + w.off, v);
     uint16_t t[8][3];
 #pragma unroll
     for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);

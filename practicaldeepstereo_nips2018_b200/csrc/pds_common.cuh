@@ -107,6 +107,18 @@ __device__ __forceinline__ uint2 ldg_stream(const uint2* p) {
                : "l"(p));
   return r;
 }
+// 256-bit accesses (sm_100: LDG/STG.256): one full 32-byte sector per lane, for 8-float records
+// (32-byte aligned)
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ldg256_stream(const float* p, float* v) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
                "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
