@@ -10,10 +10,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
     python bench.py --precision $P --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launches_bench.log 2>&1
 python tools/launch_summary.py gpurun_out/${TAG}_launches_${P}.csv 3 > gpurun_out/${TAG}_launches_${P}.txt 2>&1
 rm -f gpurun_out/${TAG}_launches_${P}.csv
-# one network forward = 72 launches of this library; skip the first forwards (weight preparation)
-ncu --set full --clock-control none --import-source on \
-    -k regex:'conv3x3_tc|tc_norm_split|tc_compose|conv_tcg|tcg_norm|hourglass_tail|subpixel_map|image_' \
-    -s 110 -c 72 -o /tmp/ncu/${TAG}_network_${P} -f \
-    python tools/profile_stages.py --precision $P --reps 1 --stages network > gpurun_out/${TAG}_ncu_network.log 2>&1
+# one network forward, marked by an NVTX range (the earlier forwards prepare weights and warm up)
+ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "capture/" \
+    -o /tmp/ncu/${TAG}_network_${P} -f \
+    python tools/profile_stages.py --precision $P --reps 1 --stages network --nvtx > gpurun_out/${TAG}_ncu_network.log 2>&1
 python tools/ncu_summary.py /tmp/ncu/${TAG}_network_${P}.ncu-rep > gpurun_out/${TAG}_ncu_network_${P}.txt 2>&1
 ls -la gpurun_out | tail -8

@@ -20,6 +20,9 @@ ap.add_argument('--precision', default='fp32')
 ap.add_argument('--reps', type=int, default=3)
 ap.add_argument('--batch', type=int, default=1)
 ap.add_argument('--stages', default='estimator,concat,matching,regularization,network')
+ap.add_argument('--nvtx', action='store_true',
+                help='wrap ONE extra call of the last stage in the NVTX range "capture" '
+                     '(ncu --nvtx --nvtx-include "capture/")')
 args = ap.parse_args()
 H, W, md = {'C1': (64, 128, 63), 'C2': (540, 960, 191), 'C3': (540, 960, 255),
             'C4': (375, 1242, 191)}[args.workload]
@@ -64,3 +67,9 @@ with torch.no_grad():
         left, right = torch.rand(B, 3, H, W, device=dev) * 255, torch.rand(B, 3, H, W, device=dev) * 255
         timed('embedding', lambda: net._embed(net._size_adapter.pad(left), net._size_adapter.pad(right)))
         timed('network', lambda: net(left, right))
+        if args.nvtx:
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_push('capture')
+            net(left, right)
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_pop()
