@@ -819,7 +819,13 @@ int tc_norm_split(const float* y, const double* stats, const float* gamma, const
                   int fp16, cudaStream_t st) {
   const size_t HW = (size_t)H * W;
   if (n_slices == 0 || HW == 0) return PDS_OK;
-  unsigned gx = (unsigned)((HW + 511) / 512);      // two pixels per thread per iteration
+  // two pixels per thread per iteration; several iterations per CTA amortise its prologue (the
+  // double-precision statistics and a barrier) once there are enough CTAs to fill the GPU
+  static const int iters_env = getenv("PDS_B200_NORM_ITERS") ? atoi(getenv("PDS_B200_NORM_ITERS")) : 4;
+  unsigned gx = (unsigned)((HW + 511) / 512);
+  const size_t ctas = (size_t)gx * (C / 8) * n_slices;
+  const unsigned iters = ctas >= (size_t)16 * num_sms() * iters_env ? (unsigned)iters_env : 1u;
+  gx = (gx + iters - 1) / iters;
   if (gx > 128) gx = 128;
   dim3 grid(gx, (unsigned)(C / 8), (unsigned)n_slices);
   PDS_KERNEL(res_ap ? "tc_norm_residual_split" : "tc_norm_split", st);
