@@ -428,8 +428,8 @@ struct NormParams {
   int C, Z, Y, X, S, phases;
 };
 
-template <bool FP16, int S>
-__global__ void __launch_bounds__(256, 2)
+template <bool FP16, int S, bool TWO>     // TWO: a second normalised source is added
+__global__ void __launch_bounds__(256, TWO ? 2 : 3)
 tcg_norm_to_ap_kernel(const NormParams p) {
   extern __shared__ float sm[];          // scale_a[C], shift_a[C], scale_b[C], shift_b[C]
   const int n = blockIdx.y;
@@ -449,7 +449,7 @@ tcg_norm_to_ap_kernel(const NormParams p) {
     }
     sm[c] = sc; sm[p.C + c] = sh;
     sc = 1.f; sh = 0.f;
-    if (p.yb && p.sb) {
+    if (TWO && p.sb) {
       const double s = p.sb[((size_t)n * p.C + c) * 2], q = p.sb[((size_t)n * p.C + c) * 2 + 1];
       const double mean = s / (double)V;
       double var = q / (double)V - mean * mean;
@@ -484,7 +484,7 @@ tcg_norm_to_ap_kernel(const NormParams p) {
     w.y = w.row % p.Y;
     w.off = ((size_t)n * V + (size_t)w.row * p.X + w.x) * p.C + 8 * w.g;
     ldg256_stream(p.ya + w.off, w.a);              // 8 channels = one 32-byte sector per lane
-    if (p.yb) ldg256_stream(p.yb + w.off, w.b);
+    if (TWO) ldg256_stream(p.yb + w.off, w.b);
     if (p.bcast) {
       const float4* pc = reinterpret_cast<const float4*>(p.bcast + (((size_t)n * p.Y + w.y) * p.X + w.x) * p.C + 8 * w.g);
       w.c0 = __ldg(pc); w.c1 = __ldg(pc + 1);
@@ -497,7 +497,7 @@ tcg_norm_to_ap_kernel(const NormParams p) {
     const float* sa = sm + 8 * g;
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = fmaf(w.a[e], sa[e], sa[p.C + e]);
-    if (p.yb) {
+    if (TWO) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += fmaf(w.b[e], sa[2 * p.C + e], sa[3 * p.C + e]);
     }
@@ -737,7 +737,7 @@ int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast,
   // units of 256 items, two per CTA iteration; at most two waves of the resident CTAs
   const unsigned units = (unsigned)(Z * Y) * (unsigned)((X * (C / 8) + 255) / 256);
   unsigned gx = (units + 1) / 2;
-  const unsigned cap = (unsigned)(num_sms() * 4);
+  const unsigned cap = (unsigned)(num_sms() * (b ? 4 : 6));
   if (gx > cap) gx = cap;
   dim3 grid(gx, (unsigned)n);
   static const bool detail = getenv("PDS_B200_PROFILE_DETAIL") && atoi(getenv("PDS_B200_PROFILE_DETAIL"));
@@ -755,7 +755,10 @@ int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast,
   PDS_KERNEL_WORK(0, (double)n * Z * Y * X * C * (4.0 + 2.0 * S + (b ? 4.0 : 0.0) + (out_f32 ? 4.0 : 0.0)));
   const size_t smem = (size_t)4 * C * sizeof(float);
 #define PDS_TCG_NORM_CASE(FF, SS) \
-  if ((fp16 != 0) == FF && S == SS) PDS_CUDA(launch_pdl(tcg_norm_to_ap_kernel<FF, SS>, grid, dim3(256), smem, st, p));
+  if ((fp16 != 0) == FF && S == SS) {  \
+    if (b) PDS_CUDA(launch_pdl(tcg_norm_to_ap_kernel<FF, SS, true>, grid, dim3(256), smem, st, p));  \
+    else PDS_CUDA(launch_pdl(tcg_norm_to_ap_kernel<FF, SS, false>, grid, dim3(256), smem, st, p));  \
+  }
   PDS_TCG_NORM_CASE(true, 1) PDS_TCG_NORM_CASE(true, 2) PDS_TCG_NORM_CASE(true, 3)
   PDS_TCG_NORM_CASE(false, 1) PDS_TCG_NORM_CASE(false, 2) PDS_TCG_NORM_CASE(false, 3)
 #undef PDS_TCG_NORM_CASE
