@@ -237,7 +237,7 @@ def main():
     ap.add_argument('--images', default='f32', choices=['f32', 'u8'],
                     help="host images: float (B,3,H,W) as the reference's loader yields (default) or "
                          "interleaved uint8 (B,H,W,3)")
-    ap.add_argument('--streams', type=int, default=3,
+    ap.add_argument('--streams', type=int, default=4,
                     help='compute streams of the e2e serving pipeline (pairs dealt round-robin)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
