@@ -77,6 +77,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   const uint32_t wfull_bar = bar_base + 8u * (2 * kMaxStages + 4);
   uint32_t* tmem_slot = (uint32_t*)(tail + 8 * (2 * kMaxStages + 5) + 8);
   float* sbias = (float*)(tail + 8 * (2 * kMaxStages + 5) + 32);
+  double* sred = (double*)(tail + 8 * (2 * kMaxStages + 5) + 32 + 128 * sizeof(float));   // [Cout][2] sums of the CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t buf_cols = (uint32_t)p.nacc * ACC_COLS;
@@ -100,6 +101,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   for (uint32_t i = threadIdx.x; i < p.table_bytes / 4; i += kThreads)
     ((uint32_t*)tab)[i] = ((const uint32_t*)p.tables)[i];
   for (int i = threadIdx.x; i < N; i += kThreads) sbias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < 256; i += kThreads) sred[i] = 0.0;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
@@ -248,17 +250,31 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
 #pragma unroll
     for (int c = 0; c < NCH; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
     int stat_n = -1;
+    // The sums of a sample leave the CTA as ONE double atomic per (channel, moment): the eight
+    // epilogue warps first combine in shared memory.  (Every CTA flushes at the same moment, at
+    // the end of the launch; eight warps x 148 CTAs x 8 parity classes on the same few addresses
+    // serialised in L2 for ~35 us in the merged transposed layer.)
     auto flush_stats = [&]() {
-      if (stat_n >= 0 && p.stats && lane < CH) {
+      if (stat_n >= 0 && p.stats) {
+        if (lane < CH) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col = c * CH + lane;
-          const int ch = p.merged ? col % p.Cout : col;       // merged: 8 columns (classes) per channel
-          if (col < (p.merged ? 8 * p.Cout : p.Cout) && (s1[c] != 0.0 || s2[c] != 0.0)) {
-            double* dst = p.stats + ((size_t)stat_n * p.Cout + ch) * 2;
-            atomicAdd(dst, s1[c]); atomicAdd(dst + 1, s2[c]);
+          for (int c = 0; c < NCH; ++c) {
+            const int col = c * CH + lane;
+            const int ch = p.merged ? col % p.Cout : col;       // merged: 8 columns (classes) per channel
+            if (col < (p.merged ? 8 * p.Cout : p.Cout) && (s1[c] != 0.0 || s2[c] != 0.0)) {
+              atomicAdd(&sred[2 * ch], s1[c]); atomicAdd(&sred[2 * ch + 1], s2[c]);
+            }
           }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
+        if (warp == 2) {
+          for (int i = lane; i < 2 * p.Cout; i += 32) {
+            const double v = sred[i];
+            if (v != 0.0) atomicAdd(p.stats + (size_t)stat_n * p.Cout * 2 + i, v);
+            sred[i] = 0.0;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
       }
 #pragma unroll
       for (int c = 0; c < NCH; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
@@ -549,7 +565,7 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-constexpr size_t kTailBytes = 8 * (2 * kMaxStages + 5) + 32 + 128 * sizeof(float) + 256;
+constexpr size_t kTailBytes = 8 * (2 * kMaxStages + 5) + 32 + 128 * sizeof(float) + 256 * sizeof(double) + 256;
 
 struct TableLayout { uint32_t off_boxes, off_entries, off_tiles, table_bytes, off_wsrc, total; };
 
@@ -831,6 +847,13 @@ extern "C" int pds_tcg_conv_debug(int kind, int nd, int Cin, int Cout, int Z, in
     cudaEventRecord(e0, st);
     for (int i = 0; i < 10; ++i) tcg_conv_forward(l, n, ap, y_cl, nullptr, lrelu, st);
     cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_a, e0, e1);
+    float ms_s = 0.f;
+    if (stats) {
+      cudaEventRecord(e0, st);
+      for (int i = 0; i < 10; ++i) tcg_conv_forward(l, n, ap, y_cl, stats, lrelu, st);
+      cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_s, e0, e1);
+      printf("timing: conv back-to-back WITH InstanceNorm sums %.1f us\n", ms_s * 100);
+    }
     cudaEventRecord(e0, st);
     for (int i = 0; i < 10; ++i) tcg_norm_to_ap(src, nullptr, nullptr, ap, n, Cin, Z, Y, X, S, fp16, pl.nph, st);
     cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_n, e0, e1);
