@@ -233,6 +233,20 @@ int pds_subpixel_map(const void* cost, float* disparity, int64_t* argmax,
                      int disparity_step, int crop_top, int crop_left,
                      int dtype, void* stream);
 
+/* ---- f4 (evaluation half): errors.compute_absolute_error and
+ * errors.compute_n_pixels_error (errors.py:9-74) in one pass --------------------
+ * estimated / ground_truth: `count` float32 disparities (any shape, contiguous);
+ * ground truth +-inf marks "unknown" (dataset.py:74-81).  pixelwise_abs and
+ * pixelwise_n_pixels (each NULL or `count` floats) receive |e - g| resp.
+ * [|e - g| > n] with 0 where the ground truth is unknown.  sums (device, 3
+ * doubles): sum of |e - g| over known locations, number of known locations,
+ * number of known locations with |e - g| > n -- the mean absolute error is
+ * sums[0] / sums[1], the n-pixel error 100 * sums[2] / sums[1] (0 when sums[1]
+ * is 0, as the reference returns).                                             */
+int pds_disparity_errors(const float* estimated, const float* ground_truth,
+                         float* pixelwise_abs, float* pixelwise_n_pixels,
+                         size_t count, float n, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

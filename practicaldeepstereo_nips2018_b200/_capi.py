@@ -56,6 +56,7 @@ SIGNATURES = {
     'pds_embedding_forward_images': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _sz,
                                           _vp]),
     'pds_subpixel_map': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'pds_disparity_errors': (_i, [_vp, _vp, _vp, _vp, _sz, ctypes.c_float, _vp, _vp]),
 }
 
 _lib = None

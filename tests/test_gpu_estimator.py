@@ -103,3 +103,39 @@ def test_full_size_properties():
     d2 = SubpixelMap()(x + 3.0, crop_top=36)
     assert max_abs(d, d2) <= 2e-3
     assert float(d.min()) >= 0.0 and float(d.max()) <= 190.0
+
+
+def test_error_metrics_fused_kernel():
+    """pds_disparity_errors (errors.py:9-74 in one pass) against the reference's known answers
+    (test/test_errors.py) and against the tensor expressions on a full-size map with unknown
+    (inf) ground truth, NaN estimates and ties at the threshold."""
+    import math
+    from practicaldeepstereo_nips2018_b200 import errors
+    est = torch.tensor([[1.0, 2.0], [3.0, 4.0]]).cuda()
+    gt = torch.tensor([[2.0, 2.0], [float('inf'), 1.0]]).cuda()
+    pix, mean = errors.compute_absolute_error(est, gt)
+    assert torch.equal(pix.cpu(), torch.tensor([[1.0, 0.0], [0.0, 3.0]])) and math.isclose(mean, 4.0 / 3.0, rel_tol=1e-6)
+    pix, bad = errors.compute_n_pixels_error(est, gt, n=1.0)
+    assert torch.equal(pix.cpu(), torch.tensor([[0.0, 0.0], [0.0, 1.0]])) and math.isclose(bad, 100.0 / 3.0, rel_tol=1e-6)
+    nothing = torch.full((2, 2), float('inf')).cuda()
+    assert errors.compute_absolute_error(est, nothing)[1] == 0.0
+    assert errors.compute_n_pixels_error(est, nothing)[1] == 0.0
+    assert math.isclose(errors.compute_absolute_error(est, gt, use_mean=False)[1], 1.0, rel_tol=1e-6)   # median: tensor path
+
+    g = torch.Generator().manual_seed(7)
+    est = (torch.rand(2, 540, 960, generator=g) * 190).cuda()
+    gt = (est.cpu() + torch.randn(2, 540, 960, generator=g) * 2).cuda()
+    gt[0, :50] = float('inf')
+    gt[1, 100, 100] = float('-inf')
+    gt[1, 7, 7] = est[1, 7, 7] + 3.0                       # exactly n: not an error (strict >)
+    est[1, 9, 9] = float('nan')                            # NaN estimate: mean becomes NaN, gt() is false
+    pa, ma, pb, bad = errors.compute_errors(est, gt, n=3.0)
+    ra, rma = errors.compute_absolute_error(est.cpu(), gt.cpu())
+    rb, rbad = errors.compute_n_pixels_error(est.cpu(), gt.cpu(), n=3.0)
+    assert torch.equal(torch.nan_to_num(pa.cpu(), nan=-1.0), torch.nan_to_num(ra, nan=-1.0))
+    assert torch.equal(pb.cpu(), rb)
+    assert math.isnan(ma) and math.isnan(rma)
+    assert math.isclose(bad, rbad, rel_tol=1e-5)
+    est[1, 9, 9] = 0.0
+    _, ma, _, _ = errors.compute_errors(est, gt, n=3.0)
+    assert math.isclose(ma, errors.compute_absolute_error(est.cpu(), gt.cpu())[1], rel_tol=1e-5)

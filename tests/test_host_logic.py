@@ -156,3 +156,21 @@ def test_kernel_paths_refuse_cpu_tensors_and_keep_autograd():
 def test_host_pipeline_is_importable_without_a_gpu():
     from practicaldeepstereo_nips2018_b200 import pipeline
     assert callable(pipeline.HostPipeline)
+
+
+def test_error_metrics_known_answers_on_cpu():
+    """errors.py mirror: the reference's own known-answer cases (test/test_errors.py:13-66);
+    CPU tensors take the reference's tensor expressions."""
+    import math
+    from practicaldeepstereo_nips2018_b200 import errors
+    est = torch.tensor([[1.0, 2.0], [3.0, 4.0]])
+    gt = torch.tensor([[2.0, 2.0], [float('inf'), 1.0]])
+    pix, mean = errors.compute_absolute_error(est, gt, use_mean=True)
+    assert torch.equal(pix, torch.tensor([[1.0, 0.0], [0.0, 3.0]])) and math.isclose(mean, 4.0 / 3.0, rel_tol=1e-6)
+    pix, median = errors.compute_absolute_error(est, gt, use_mean=False)
+    assert math.isclose(median, 1.0, rel_tol=1e-6)
+    pix, bad = errors.compute_n_pixels_error(est, gt, n=1.0)
+    assert torch.equal(pix, torch.tensor([[0.0, 0.0], [0.0, 1.0]])) and math.isclose(bad, 100.0 / 3.0, rel_tol=1e-6)
+    nothing = torch.full((2, 2), float('inf'))
+    assert errors.compute_absolute_error(est, nothing)[1] == 0.0
+    assert errors.compute_n_pixels_error(est, nothing)[1] == 0.0
