@@ -101,6 +101,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if ((++spins & 0x3ff) == 0 && global_ns() - t0 > 4000000000ull) __trap();
   }
 }
+__host__ __device__ constexpr bool tc_flat_rows(int PW) { return 8 * PW <= 256; }
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
                                             int c2, int c3, uint32_t bar) {
   asm volatile(
@@ -294,13 +296,14 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
           const bool second = c >= p.nchunks1;
 #pragma unroll
           for (int s = 0; s < S; ++s) {
-            if (!second)
-              tma_load_4d(sa + s * A_TERM_BYTES, &p.map0, 0, x0 - 1, y0 - 1,
-                          (slice1 * S + s) * p.planes1 + 2 * c, full_bar(stage));
-            else  // d >= W: the shifted image is all zeros -> park the box fully out of bounds
-              tma_load_4d(sa + s * A_TERM_BYTES, p.maps_d + d, 0,
-                          d >= p.W ? -(PW + 16) : x0 - 1 - d, y0 - 1,
-                          (b * S + s) * p.planes2 + 2 * (c - p.nchunks1), full_bar(stage));
+            // box origin (pixel xo, row y0 - 1, first plane); d >= W: the shifted image is all
+            // zeros -> park the box fully out of bounds
+            const int xo = !second ? x0 - 1 : (d >= p.W ? -(PW + 16) : x0 - 1 - d);
+            const int pl = !second ? (slice1 * S + s) * p.planes1 + 2 * c
+                                   : (b * S + s) * p.planes2 + 2 * (c - p.nchunks1);
+            const CUtensorMap* mp = !second ? &p.map0 : p.maps_d + d;
+            if (tc_flat_rows(PW)) tma_load_4d(sa + s * A_TERM_BYTES, mp, 8 * xo, y0 - 1, pl, 0, full_bar(stage));
+            else tma_load_4d(sa + s * A_TERM_BYTES, mp, 0, xo, y0 - 1, pl, full_bar(stage));
           }
           if (!WRES)
             bulk_load(sa + S * A_TERM_BYTES, p.w + (size_t)c * (W_CHUNK_BYTES / 2), W_CHUNK_BYTES,
@@ -695,9 +698,19 @@ EncodeTiledFn encode_fn() {
 // type only sets the element size: fp16 and bf16 planes use the same map.)
 int encode_ap_map(CUtensorMap* map, const void* base, int W_eff, int W, int H, size_t planes,
                   int PW) {
-  const cuuint64_t dims[4] = {8, (cuuint64_t)W_eff, (cuuint64_t)H, (cuuint64_t)planes};
-  const cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-  const cuuint32_t box[4] = {8, (cuuint32_t)PW, (cuuint32_t)kPH, 2};
+  // The pixel and its 8 channels form ONE tensor-map dimension when the box row fits (8 * PW <=
+  // 256 elements): a box row is then a single 16 * PW byte request instead of PW requests of 16
+  // bytes (same bytes in shared memory; out-of-bounds pixels are still zero-filled, element-wise).
+  const bool flat = tc_flat_rows(PW);
+  const cuuint64_t dims4[4] = {8, (cuuint64_t)W_eff, (cuuint64_t)H, (cuuint64_t)planes};
+  const cuuint64_t strides4[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  const cuuint32_t box4[4] = {8, (cuuint32_t)PW, (cuuint32_t)kPH, 2};
+  const cuuint64_t dimsf[4] = {(cuuint64_t)W_eff * 8, (cuuint64_t)H, (cuuint64_t)planes, 1};
+  const cuuint64_t stridesf[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)planes * H * W * 16};
+  const cuuint32_t boxf[4] = {(cuuint32_t)PW * 8, (cuuint32_t)kPH, 2, 1};
+  const cuuint64_t* dims = flat ? dimsf : dims4;
+  const cuuint64_t* strides = flat ? stridesf : strides4;
+  const cuuint32_t* box = flat ? boxf : box4;
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
