@@ -42,7 +42,7 @@ struct alignas(64) TcgParams {
   int GZ, GY, GX, OZ, OY, OX, Cout, mul, nd3;
   int tiles_x, tiles_y, tiles_z;
   int BX, planes_per_term, ntx_log2, zstride16;
-  int resident, stages, reuse, merged;
+  int resident, stages, reuse, merged, flat;
   uint32_t box_bytes, box_tx_bytes, term_bytes, a_bytes, stage_bytes, wres_bytes, w_total_bytes;
   uint32_t off_boxes, off_entries, off_tiles, table_bytes;
   float inv_wscale;
@@ -156,8 +156,12 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
             const TcgBox b = boxes[un.box_beg + j];
 #pragma unroll
             for (int s = 0; s < S; ++s)
-              tma_load_5d(sa + s * p.term_bytes + j * p.box_bytes, &p.map, 0, x0 + b.dx, y0 + b.dy,
-                          z0 + b.dz, (it.n * S + s) * p.planes_per_term + b.plane, full_bar(stage));
+              if (p.flat)
+                tma_load_5d(sa + s * p.term_bytes + j * p.box_bytes, &p.map, 8 * (x0 + b.dx), y0 + b.dy, z0 + b.dz,
+                            (it.n * S + s) * p.planes_per_term + b.plane, 0, full_bar(stage));
+              else
+                tma_load_5d(sa + s * p.term_bytes + j * p.box_bytes, &p.map, 0, x0 + b.dx, y0 + b.dy,
+                            z0 + b.dz, (it.n * S + s) * p.planes_per_term + b.plane, full_bar(stage));
           }
           if (!p.resident)
             bulk_load(sa + p.a_bytes, (const unsigned char*)p.w + (size_t)un.w_off16 * 16, un.w_bytes,
@@ -672,18 +676,27 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
   const TableLayout tl = table_layout(pl);
   TcgParams p = {};
   {
-    const cuuint64_t dims[5] = {8, (cuuint64_t)pl.IX, (cuuint64_t)pl.IY, (cuuint64_t)pl.IZ,
-                                (cuuint64_t)pl.in_planes(n_samples)};
-    const cuuint64_t strides[4] = {16, (cuuint64_t)pl.IX * 16, (cuuint64_t)pl.IY * pl.IX * 16,
-                                   (cuuint64_t)pl.IZ * pl.IY * pl.IX * 16};
-    const cuuint32_t box[5] = {8, (cuuint32_t)pl.BX, (cuuint32_t)pl.BY, (cuuint32_t)pl.BZ, (cuuint32_t)pl.PB};
+    // pixel and channel group as ONE dimension when the box row fits 256 elements: a box row is a
+    // single request of 16 * BX bytes instead of BX requests of 16 (same bytes in shared memory)
+    const bool flat = 8 * pl.BX <= 256;
+    const cuuint64_t planes = (cuuint64_t)pl.in_planes(n_samples), vol = (cuuint64_t)pl.IZ * pl.IY * pl.IX * 16;
+    const cuuint64_t dims5[5] = {8, (cuuint64_t)pl.IX, (cuuint64_t)pl.IY, (cuuint64_t)pl.IZ, planes};
+    const cuuint64_t strides5[4] = {16, (cuuint64_t)pl.IX * 16, (cuuint64_t)pl.IY * pl.IX * 16, vol};
+    const cuuint32_t box5[5] = {8, (cuuint32_t)pl.BX, (cuuint32_t)pl.BY, (cuuint32_t)pl.BZ, (cuuint32_t)pl.PB};
+    const cuuint64_t dimsf[5] = {(cuuint64_t)pl.IX * 8, (cuuint64_t)pl.IY, (cuuint64_t)pl.IZ, planes, 1};
+    const cuuint64_t stridesf[4] = {(cuuint64_t)pl.IX * 16, (cuuint64_t)pl.IY * pl.IX * 16, vol, planes * vol};
+    const cuuint32_t boxf[5] = {(cuuint32_t)pl.BX * 8, (cuuint32_t)pl.BY, (cuuint32_t)pl.BZ, (cuuint32_t)pl.PB, 1};
+    const cuuint64_t* dims = flat ? dimsf : dims5;
+    const cuuint64_t* strides = flat ? stridesf : strides5;
+    const cuuint32_t* box = flat ? boxf : box5;
+    p.flat = flat ? 1 : 0;
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode_fn()(&p.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(in_ap), dims,
                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      set_error("conv_tcg: cuTensorMapEncodeTiled failed with CUresult %d (dims %d x %d x %d x %zu, box %d x %d x %d x %d)",
-                (int)r, pl.IX, pl.IY, pl.IZ, pl.in_planes(n_samples), pl.BX, pl.BY, pl.BZ, pl.PB);
+      set_error("conv_tcg: cuTensorMapEncodeTiled failed with CUresult %d (dims %d x %d x %d x %zu, box %d x %d x %d x %d, flat %d)",
+                (int)r, pl.IX, pl.IY, pl.IZ, pl.in_planes(n_samples), pl.BX, pl.BY, pl.BZ, pl.PB, (int)flat);
       return PDS_ERR_CUDA;
     }
   }
