@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--precision fp16x2|fp32|bf16x3|bf16x2|bf16|fp16] [--workload C2|C3|C4|C1]
+                    [--images u8|f32] [--streams 4] [--extra-configs C3,C4,C5]
 
 One process per GPU (torchrun for N > 1: ranks are independent replicas, one
 NCCL broadcast of the weights at start-up, NO collective in the timed region).
@@ -212,9 +213,9 @@ def run_reference(args, H, W, md, desc):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': elapsed / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': desc, 'batch_per_gpu': 1, 'maximum_disparity': md,
-                   'implementation': 'torch port of the reference forward on host cores '
-                                     '(oracle/torch_port.py, ATen CPU kernels)'},
+        'config': {'workload': desc, 'batch_per_gpu': 1, 'maximum_disparity': md},
+        'impl_config': {'implementation': 'torch port of the reference forward on host cores '
+                                          '(oracle/torch_port.py, ATen CPU kernels)'},
         'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0,
@@ -222,6 +223,38 @@ def run_reference(args, H, W, md, desc):
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def time_pipeline(pipe, items, steps, barrier, max_over_ranks, out=None, download=True):
+    """CUDA-event time (ms, max over ranks) of `steps` pairs through HostPipeline.run after a
+    short untimed fill of the pipeline."""
+    fill = [items[i % len(items)] for i in range(2 * max(2, len(pipe._streams) or 1))]
+    pipe.run(fill, out=out, download=download)
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    from practicaldeepstereo_nips2018_b200 import _capi
+    launches0 = _capi.launch_count()
+    outs = pipe.run((items[i % len(items)] for i in range(steps)), out=out, download=download)
+    time_pipeline.launches = _capi.launch_count() - launches0      # kernels of the timed region
+    stop.record()
+    barrier()
+    del outs
+    return max_over_ranks(start.elapsed_time(stop))
+
+
+def sync_latency_ms(net, pairs, reps=12):
+    """The reference's own protocol (trainer.py:141-148): wall time of ONE forward bracketed by
+    torch.cuda.synchronize(); median of `reps` after the warm-up the caller has already done."""
+    times = []
+    for i in range(reps):
+        left, right = pairs[i % len(pairs)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        net(left, right)
+        torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3)
+    return statistics.median(times), min(times)
 
 
 def main():
@@ -234,11 +267,17 @@ def main():
     ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=1, help='stereo pairs per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--images', default='f32', choices=['f32', 'u8'],
-                    help="host images: float (B,3,H,W) as the reference's loader yields (default) or "
-                         "interleaved uint8 (B,H,W,3)")
+    ap.add_argument('--images', default='u8', choices=['f32', 'u8'],
+                    help="host images of the e2e leg: interleaved uint8 (B,H,W,3) as the decoder leaves "
+                         "them (default; dataset.py:67-72 converts on the host, here the kernel does) or "
+                         "float (B,3,H,W) as the reference's loader yields; the other one is reported as "
+                         "e2e_other_images")
     ap.add_argument('--streams', type=int, default=4,
                     help='compute streams of the e2e serving pipeline (pairs dealt round-robin)')
+    ap.add_argument('--extra-configs', default='C3,C4,C5',
+                    help="further BASELINE.json configurations measured after the headline one and "
+                         "reported under 'other_configs' of the same JSON line (C5 = 8 pairs per GPU "
+                         "per step at C2: batch 64 on 8 GPUs); '' disables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     H, W, md, desc = WORKLOADS[args.workload]
@@ -249,6 +288,8 @@ def main():
 
     rank, world, local = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
     assert torch.cuda.is_available(), 'bench.py --impl ours needs a CUDA device'
+    from practicaldeepstereo_nips2018_b200 import parallel
+    numa_cpus = parallel.bind_to_gpu_numa_node(local)   # before any pinned allocation (first touch)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist = None
@@ -257,7 +298,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     from practicaldeepstereo_nips2018_b200 import PdsNetwork, _capi
-    from practicaldeepstereo_nips2018_b200 import parallel
+    from practicaldeepstereo_nips2018_b200.pipeline import HostPipeline
 
     torch.backends.cudnn.allow_tf32 = False        # embedding (cuDNN) stays fp32 like the oracle
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -266,10 +307,6 @@ def main():
     net = PdsNetwork.default(md, precision=args.precision).to(dev).eval()
     if world > 1:
         parallel.broadcast_parameters(net, src=0)   # the only collective: weights, once
-
-    Hp, Wp = H + (-H) % 64, W + (-W) % 64
-    pairs = synthetic_pairs(4, args.batch, H, W, dev, seed=1000 + rank)
-    host_pairs = synthetic_pairs(4, args.batch, H, W, dev, seed=2000 + rank, pinned=True, images=args.images)
 
     def barrier():
         torch.cuda.synchronize()
@@ -283,6 +320,11 @@ def main():
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    other_images = 'f32' if args.images == 'u8' else 'u8'
+    pairs = synthetic_pairs(4, args.batch, H, W, dev, seed=1000 + rank)
+    host_pairs = synthetic_pairs(4, args.batch, H, W, dev, seed=2000 + rank, pinned=True, images=args.images)
+    host_pairs_other = synthetic_pairs(4, args.batch, H, W, dev, seed=2000 + rank, pinned=True, images=other_images)
 
     with torch.no_grad():
         for i in range(args.warmup):
@@ -299,34 +341,25 @@ def main():
         # both numbers go through pipeline.HostPipeline, the package's serving call: pairs are
         # dealt round-robin to `--streams` compute streams (the latency-bound deep hourglass
         # layers of one pair overlap the other pairs' work); --streams 1 = plain back-to-back calls
-        from practicaldeepstereo_nips2018_b200.pipeline import HostPipeline
         pipe = HostPipeline(net, dev, streams=args.streams)
-        pipe.run([pairs[i % len(pairs)] for i in range(2 * max(2, args.streams))], download=False)
-        barrier()
-        launches0 = _capi.launch_count()
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        outs = pipe.run((pairs[i % len(pairs)] for i in range(args.steps)), download=False)
-        stop.record()
-        barrier()
-        ms = max_over_ranks(start.elapsed_time(stop))
-        launches = _capi.launch_count() - launches0
-        del outs
+        ms = time_pipeline(pipe, pairs, args.steps, barrier, max_over_ranks, download=False)
+        launches = time_pipeline.launches
 
         # ---- e2e: public API with HOST buffers, H2D + D2H inside the timed region ------
         # pipeline.HostPipeline is the package's serving call: per pair, upload of both images from
         # pinned memory (copy stream, overlapped with the previous pair's forward), forward,
         # download of the disparity map
         d2h = [torch.empty((args.batch, H, W), dtype=torch.float32).pin_memory() for _ in range(2 * max(1, args.streams))]
-        pipe.run([host_pairs[i % len(host_pairs)] for i in range(2 * max(2, args.streams))], out=d2h)
-        barrier()
-        start.record()
-        pipe.run((host_pairs[i % len(host_pairs)] for i in range(args.steps)), out=d2h)
-        stop.record()
-        barrier()
-        e2e_ms = max_over_ranks(start.elapsed_time(stop))
+        e2e_ms = time_pipeline(pipe, host_pairs, args.steps, barrier, max_over_ranks, out=d2h)
         if sampler:
             sampler.stop()
+        e2e_other_ms = time_pipeline(pipe, host_pairs_other, args.steps, barrier, max_over_ranks, out=d2h)
+
+        # ---- back-to-back forwards on ONE stream, and the reference's sync-per-forward latency ----
+        pipe1 = HostPipeline(net, dev, streams=1)
+        ms_1stream = time_pipeline(pipe1, pairs, args.steps, barrier, max_over_ranks, download=False)
+        lat_median, lat_min = sync_latency_ms(net, pairs)
+        lat_median = max_over_ranks(lat_median)
 
         # ---- per-kernel CUDA-event profile (separate instrumented pass) ----------------
         report = {}
@@ -338,6 +371,42 @@ def main():
             torch.cuda.synchronize()
             _capi.profiler_enable(False)
             report = _capi.profiler_report()
+        barrier()
+
+        # ---- the other BASELINE.json configurations, same protocol, fewer steps -------------
+        others = []
+        del pairs, host_pairs, host_pairs_other, d2h
+        for name in [c for c in args.extra_configs.split(',') if c]:
+            if name == 'C5':
+                oH, oW, omd, odesc, obatch = 540, 960, 191, 'batch 64 of 960x540 D=192 over 8 GPUs = 8 pairs per GPU per step', 8
+            elif name in WORKLOADS and name != args.workload:
+                oH, oW, omd, odesc = WORKLOADS[name]
+                obatch = 1
+            else:
+                continue
+            osteps = max(8, args.steps // (3 * obatch)) if obatch > 1 else max(12, args.steps // 3)
+            net.set_maximum_disparity(omd)
+            opairs = synthetic_pairs(2, obatch, oH, oW, dev, seed=3000 + rank)
+            ohost = synthetic_pairs(2, obatch, oH, oW, dev, seed=4000 + rank, pinned=True, images=args.images)
+            od2h = [torch.empty((obatch, oH, oW), dtype=torch.float32).pin_memory() for _ in range(2 * max(1, args.streams))]
+            for i in range(3):
+                net(*opairs[i % 2])
+            opipe = HostPipeline(net, dev, streams=args.streams)
+            oms = time_pipeline(opipe, opairs, osteps, barrier, max_over_ranks, download=False)
+            oe2e = time_pipeline(opipe, ohost, osteps, barrier, max_over_ranks, out=od2h)
+            olat, _ = sync_latency_ms(net, opairs, reps=10)
+            olat = max_over_ranks(olat)
+            total = osteps * obatch * world
+            others.append({'config': name, 'workload': odesc, 'batch_per_gpu': obatch, 'maximum_disparity': omd,
+                           'steps': osteps, 'value': total / (oms / 1e3), 'unit': 'pairs/s',
+                           'ms_per_step': oms / osteps,
+                           'e2e': {'value': total / (oe2e / 1e3), 'unit': 'pairs/s',
+                                   'h2d_bytes_per_step': 2 * obatch * 3 * oH * oW * (4 if args.images == 'f32' else 1),
+                                   'd2h_bytes_per_step': obatch * oH * oW * 4},
+                           'latency_ms': olat})
+            del opairs, ohost, od2h, opipe
+            torch.cuda.empty_cache()
+        net.set_maximum_disparity(md)
     barrier()
 
     if rank == 0:
@@ -368,6 +437,7 @@ def main():
                         'peak_source': peaks['source'],
                         'timing': 'CUDA events around every launch, separate instrumented pass of '
                                   f'{args.steps} steps'}
+        image_bytes = {'f32': 4, 'u8': 1}
         line = {
             'metric': METRIC, 'value': total_pairs / (ms / 1e3), 'unit': 'pairs/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -375,18 +445,30 @@ def main():
             'vs_baseline': (total_pairs / (ms / 1e3)) / (1.0 / 0.62) if args.workload == 'C2' else None,
             'dtype': {'fp32': 'f32', 'bf16': 'bf16'}.get(args.precision, args.precision),
             'data': 'synthetic',
-            'config': {'workload': desc, 'batch_per_gpu': args.batch, 'maximum_disparity': md,
-                       'precision': args.precision, 'parallelism': f'replicas x{world}',
-                       'streams_per_gpu': args.streams, 'host_images': args.images,
-                       'l2': 'per-step working set > 1 GB (>> 126 MB L2); 4 rotating input pairs',
-                       'embedding': ('own tcgen05 kernels' if args.precision != 'fp32'
-                                     else 'ATen/cuDNN fp32 (TF32 off)')},
+            # `config` names the workload only (identical in the reference arm); how this arm runs it
+            # is under `impl_config`
+            'config': {'workload': desc, 'batch_per_gpu': args.batch, 'maximum_disparity': md},
+            'impl_config': {'precision': args.precision, 'parallelism': f'replicas x{world}',
+                            'streams_per_gpu': args.streams, 'host_images': args.images,
+                            'numa_bound_cpus': len(numa_cpus) if numa_cpus else None,
+                            'l2': 'per-step working set > 1 GB (>> 126 MB L2); 4 rotating input pairs',
+                            'embedding': ('own tcgen05 kernels' if args.precision != 'fp32'
+                                          else 'ATen/cuDNN fp32 (TF32 off)')},
             'e2e': {'value': total_pairs / (e2e_ms / 1e3), 'unit': 'pairs/s',
-                    'h2d_bytes_per_step': 2 * args.batch * 3 * H * W * (4 if args.images == 'f32' else 1),
+                    'h2d_bytes_per_step': 2 * args.batch * 3 * H * W * image_bytes[args.images],
                     'd2h_bytes_per_step': args.batch * H * W * 4},
+            'e2e_other_images': {'host_images': other_images, 'value': total_pairs / (e2e_other_ms / 1e3),
+                                 'unit': 'pairs/s',
+                                 'h2d_bytes_per_step': 2 * args.batch * 3 * H * W * image_bytes[other_images],
+                                 'd2h_bytes_per_step': args.batch * H * W * 4},
+            # back-to-back forwards on one stream (no overlap between pairs), and the reference's own
+            # protocol: one forward bracketed by cuda.synchronize() (trainer.py:141-148), median of 12
+            'value_1stream': total_pairs / (ms_1stream / 1e3),
+            'latency_ms': lat_median, 'latency_ms_min': lat_min,
             'gpu_launches': launches,
             'clocks': sampler.summary() if sampler else None,
             'roofline': roofline,
+            'other_configs': others,
             'kernels': kernels,
         }
         if world == 1 and not args.no_cpu_baseline:

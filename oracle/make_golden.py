@@ -42,7 +42,12 @@ def t(a):
     return torch.from_numpy(a)
 
 
+ONLY = sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else None
+
+
 def save(name, **arrays):
+    if ONLY and name != ONLY:
+        return
     path = os.path.join(OUT, name + '.npz')
     np.savez_compressed(path, **arrays)
     print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB')
@@ -127,6 +132,25 @@ with torch.no_grad():
     save('network_md63', disparity=disp, cost_unpadded=cost, cost_padded=padded.numpy(),
          signatures=sigs.numpy(), left_descriptor=ld.numpy(), shortcut=ls.numpy(),
          right_descriptor=rd.numpy())
+    # --- PdsNetwork.forward at a WELL-CONDITIONED small size (round 2): 250x120, md=127 ->
+    # padded 256x128, hourglass bottleneck 2x2x4 voxels (the md=63 fixture above has a 1x1x2
+    # bottleneck whose InstanceNorm amplifies rounding noise 300x).  Stored: the disparity, the
+    # arg-max, the top-1/top-2 margin of every pixel (all on the un-padded image) and the padded
+    # cost volume sub-sampled 4x in y and x.
+    if not ONLY or ONLY == 'network_md127':
+        net.set_maximum_disparity(127)
+        li = synth.tensor((1, 3, 120, 250), 64, scale=255.0, uniform=True)
+        ri = synth.tensor((1, 3, 120, 250), 65, scale=255.0, uniform=True)
+        ri[..., :-9] = 0.8 * li[..., 9:] + 0.2 * ri[..., :-9]
+        disp = net(t(li), t(ri)).numpy()
+        padded = net.pass_through_network(net._size_adapter.pad(t(li)),
+                                          net._size_adapter.pad(t(ri)))[0]
+        top2 = torch.topk(padded, 2, dim=1)[0]
+        save('network_md127', disparity=disp,
+             argmax=torch.max(padded, dim=1)[1][..., 8:, 6:].numpy().astype(np.int16),
+             margin=(top2[:, 0] - top2[:, 1])[..., 8:, 6:].numpy(),
+             cost_padded_sub4=padded[..., ::4, ::4].numpy())
+        net.set_maximum_disparity(63)
     try:
         net.set_maximum_disparity(100)
         raised = False

@@ -18,6 +18,10 @@ if os.environ.get('PDS_B200_LIB'):          # experiments: an alternative build 
 PDS_OK, PDS_ERR_INVALID_ARGUMENT, PDS_ERR_CUDA, PDS_ERR_WORKSPACE, PDS_ERR_UNSUPPORTED = range(5)
 PDS_F32, PDS_BF16 = 0, 1
 PRECISIONS = {'fp32': 0, 'bf16x3': 1, 'bf16x2': 2, 'bf16': 3, 'fp16x2': 4, 'fp16': 5}
+# Arithmetic of the convolution stacks when a module is built without an explicit `precision`:
+# the fp32-grade split-operand tensor-core mode.  'fp32' selects the CUDA-core
+# FFMA kernels (10x slower); PDS_B200_PRECISION overrides the default for a whole process.
+DEFAULT_PRECISION = os.environ.get('PDS_B200_PRECISION', 'fp16x2')
 IMAGE_LAYOUTS = {'f32_nchw': 0, 'u8_nchw': 1, 'u8_nhwc': 2}   # enum pds_image_layout
 
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t

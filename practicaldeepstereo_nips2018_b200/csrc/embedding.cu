@@ -209,6 +209,9 @@ int prepare(pds_embedding* e, int H, int W, cudaStream_t st) {
     layers[i].gamma = pp[2]; layers[i].beta = pp[3];
     cur += used;
   }
+  // the packing kernels ran on `st`; other streams that find the shape already prepared must not
+  // race them (one-time cost per shape)
+  PDS_CUDA(cudaStreamSynchronize(st));
   e->layers = layers;
   e->shape[0] = H; e->shape[1] = W;
   return PDS_OK;

@@ -182,6 +182,9 @@ int prepare_tcg(pds_regularization* reg, int D, int H, int W, cudaStream_t st) {
     layers[i].gamma = pp[2]; layers[i].beta = pp[3];
     cur += used;
   }
+  // the packing kernels ran on `st`; other streams that find the shape already prepared must not
+  // race them (one-time cost per shape)
+  PDS_CUDA(cudaStreamSynchronize(st));
   reg->tcg = layers;
   reg->tcg_shape[0] = D; reg->tcg_shape[1] = H; reg->tcg_shape[2] = W;
   return PDS_OK;

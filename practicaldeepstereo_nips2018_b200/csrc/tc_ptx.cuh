@@ -162,13 +162,14 @@ __device__ __forceinline__ void tmem_ld_fence(float (&v)[W]) {
 }
 
 // x = t0 + t1 + t2 with 16-bit terms (round-to-nearest residual splitting).  fp16 terms
-// saturate at the largest finite half instead of overflowing to infinity.
+// saturate: the VALUE is clamped to the largest finite half before it is split, so neither the
+// leading term nor the remainders can overflow to infinity (|x| > 65504 reads as +-65504).
 template <bool FP16>
 __device__ __forceinline__ void split_terms(float x, uint16_t (&t)[3]) {
   if (FP16) {
     const float c = fminf(fmaxf(x, -65504.f), 65504.f);
     const __half h0 = __float2half_rn(c);
-    float r = x - __half2float(h0);
+    float r = c - __half2float(h0);
     const __half h1 = __float2half_rn(r);
     r -= __half2float(h1);
     const __half h2 = __float2half_rn(r);

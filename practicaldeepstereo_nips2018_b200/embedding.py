@@ -5,18 +5,22 @@ Eval / no-grad CUDA calls in a tensor-core precision run the kernels; the fp32
 precision and gradient-enabled calls (training, outside the inference hot path)
 run the plain ATen composition of the same modules."""
 import ctypes
+import warnings
 
 import torch
 from torch import nn
 
 from . import _capi, network_blocks
-from .matching import _KernelHandle, _needs_autograd
+from .matching import _KernelHandle, _needs_autograd, check_fp16_weight_range
 
 
 class Embedding(nn.Module):
+    _warned_aten = False
+
     def __init__(self, number_of_input_features=3, number_of_embedding_features=64,
-                 number_of_shortcut_features=8, number_of_residual_blocks=2, precision='fp32'):
+                 number_of_shortcut_features=8, number_of_residual_blocks=2, precision=None):
         super().__init__()
+        precision = precision or _capi.DEFAULT_PRECISION
         if precision not in _capi.PRECISIONS:
             raise ValueError(f'precision should be one of {sorted(_capi.PRECISIONS)}')
         f = number_of_embedding_features
@@ -34,6 +38,7 @@ class Embedding(nn.Module):
     # -- C-ABI plumbing -------------------------------------------------------
     def _create_handle(self, handle, params, precision, device):
         cin, f, fs, n_res = self._shape
+        check_fp16_weight_range(params, precision)
         _capi.check(_capi.lib().pds_embedding_create(
             ctypes.byref(handle), _capi.pointer_array(params), len(params), cin, f, fs, n_res,
             _capi.PRECISIONS[precision], _capi.stream_ptr(device)))
@@ -128,6 +133,15 @@ class Embedding(nn.Module):
         if self.uses_kernels(image):
             descriptor, shortcut = self.embed(image, image.size(0) if with_shortcut else 0)
             return descriptor, (shortcut if with_shortcut else None)
+        if (self.precision != 'fp32' and image.is_cuda and not _needs_autograd(image, self)
+                and not Embedding._warned_aten):
+            # never reached from PdsNetwork (SizeAdapter pads to multiples of 64); a standalone
+            # call on other extents keeps the reference's semantics on ATen operators -- loudly
+            Embedding._warned_aten = True
+            warnings.warn(
+                f'Embedding: image extent {tuple(image.shape[2:])} is not a multiple of 4 (or the '
+                'module is not the 3->64->8 tower): this call runs the ATen composition, not the '
+                'sm_100a kernels', RuntimeWarning, stacklevel=2)
         descriptor = image
         for module in self._embedding_modules:
             descriptor = module(descriptor)

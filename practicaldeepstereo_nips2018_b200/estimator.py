@@ -21,10 +21,29 @@ class SubpixelMap(object):
         self._disparity_step = disparity_step
         self._half_support_window = half_support_window
 
+    def _differentiable(self, similarities, crop_top, crop_left, return_argmax):
+        """Gradient-enabled calls (the reference's estimator is differentiable through the
+        soft-arg-max, estimator.py:59-91): tensor expressions, any device, outside the inference
+        hot path like every other gradient-enabled call of this package."""
+        sim = similarities[..., crop_top:, crop_left:]
+        depth = sim.size(1)
+        radius = self._half_support_window // self._disparity_step
+        best = torch.max(sim, dim=1, keepdim=True)[1]
+        taps = best + torch.arange(-radius, radius + 1, device=sim.device).view(1, -1, 1, 1)
+        inside = (taps >= 0) & (taps < depth)
+        scores = torch.gather(sim, 1, taps.clamp(0, depth - 1))
+        scores = torch.where(inside, scores, scores.new_full((), -float('inf')))
+        weights = torch.softmax(scores, dim=1)
+        tap_disparity = (taps * inside).to(sim.dtype) * self._disparity_step
+        disparity = (weights * tap_disparity).sum(dim=1)
+        return (disparity, best.squeeze(1)) if return_argmax else disparity
+
     def __call__(self, similarities, crop_top=0, crop_left=0, return_argmax=False):
         """similarities [B, D, H, W] (float32 or bfloat16, CUDA) -> disparity
         [B, H - crop_top, W - crop_left] float32.  The crop is SizeAdapter.unpad
         fused into the kernel's store."""
+        if torch.is_grad_enabled() and similarities.requires_grad:
+            return self._differentiable(similarities, crop_top, crop_left, return_argmax)
         _capi.require_cuda(similarities)
         if similarities.dim() != 4:
             raise ValueError('similarities should have indices [batch, disparity, y, x]')

@@ -13,7 +13,9 @@ Two kernel paths sit behind the reference API:
 Gradient-enabled calls (training) are outside the inference hot path and run
 the plain ATen composition of the same modules.
 """
+import copy
 import ctypes
+import threading
 
 import torch
 from torch import nn
@@ -35,24 +37,37 @@ def _needs_autograd(*tensors_and_modules):
 
 
 class _KernelHandle(object):
-    """Owns a C-ABI handle built from a module's parameters; rebuilt whenever a
-    parameter is replaced or modified in place (optimizer step, load_state_dict)."""
+    """Owns the C-ABI handles built from a module's parameters, one per device (DataParallel
+    replicas share the module's ``__dict__`` and therefore this object).  A handle is rebuilt
+    whenever a parameter is replaced or modified in place through autograd-visible operations
+    (optimizer step, ``load_state_dict``, ``copy_`` under ``no_grad``: they bump ``_version``).
+
+    Writes through ``param.data`` (``p.data.copy_()``, ``p.data.mul_()``) do NOT bump the version
+    counter: call ``invalidate()`` (or ``PdsNetwork.invalidate_kernels()``) after such an update,
+    as ``parallel.broadcast_parameters`` does."""
 
     def __init__(self, create, destroy):
         self._create, self._destroy = create, destroy
-        self._handle, self._key = None, None
+        self._handles = {}       # device string -> (handle, key)
         self._workspace = None
+        self._lock = threading.Lock()
 
     def get(self, params, precision, device):
-        key = (str(device), precision) + tuple((p.data_ptr(), p._version) for p in params)
-        if key != self._key:
-            self.release()
+        dev = str(device)
+        key = (precision,) + tuple((p.data_ptr(), p._version) for p in params)
+        with self._lock:
+            entry = self._handles.get(dev)
+            if entry is not None and entry[1] == key:
+                return entry[0]
+            if entry is not None:
+                self._destroy(entry[0])
+                del self._handles[dev]
             handle = ctypes.c_void_p()
             with torch.cuda.device(device):
                 self._create(handle, [p.detach().contiguous().float() for p in params],
                              precision, device)
-            self._handle, self._key = handle, key
-        return self._handle
+            self._handles[dev] = (handle, key)
+            return handle
 
     def workspace(self, nbytes, device):
         """Scratch buffer for the calling stream (one per CUDA stream, so that pipelines which
@@ -66,10 +81,26 @@ class _KernelHandle(object):
             self._workspace[key] = ws
         return ws
 
+    def invalidate(self):
+        """Forget every packed copy of the parameters: the next forward re-packs them."""
+        self.release()
+
     def release(self):
-        if self._handle is not None:
-            self._destroy(self._handle)
-            self._handle, self._key = None, None
+        with self._lock:
+            for handle, _ in self._handles.values():
+                self._destroy(handle)
+            self._handles = {}
+
+    # copy.deepcopy(module) / torch.save(module): a fresh, empty handle bound to the copy
+    # (ctypes pointers cannot be pickled and must not be shared between modules)
+    def __deepcopy__(self, memo):
+        return _KernelHandle(copy.deepcopy(self._create, memo), self._destroy)
+
+    def __getstate__(self):
+        return {'_create': self._create, '_destroy': self._destroy}
+
+    def __setstate__(self, state):
+        self.__init__(state['_create'], state['_destroy'])
 
     def __del__(self):
         try:
@@ -78,14 +109,27 @@ class _KernelHandle(object):
             pass
 
 
+def check_fp16_weight_range(params, precision):
+    """fp16-term precisions scale convolution weights by 2^8 before splitting them into half
+    terms (include/pds_b200.h): |w| * 256 must stay below the largest finite half."""
+    if precision not in ('fp16x2', 'fp16'):
+        return
+    for p in params:
+        if p.dim() >= 4 and p.numel() and float(p.detach().abs().max()) * 256.0 >= 65504.0:
+            raise ValueError(
+                f'a convolution weight of magnitude {float(p.detach().abs().max()):.3g} does not fit the '
+                f"'{precision}' operand format (|w| < 255); use precision='bf16x3'")
+
+
 class MatchingOperation(nn.Module):
     """Per-disparity 2-D network applied to cat[left, shifted right]:
     conv3x3 2C->F, `number_of_residual_blocks` residual blocks, conv3x3 F->S."""
 
     def __init__(self, number_of_concatenated_descriptor_features=128, number_of_features=64,
                  number_of_compact_matching_signature_features=8,
-                 number_of_residual_blocks=2, precision='fp32'):
+                 number_of_residual_blocks=2, precision=None):
         super().__init__()
+        precision = precision or _capi.DEFAULT_PRECISION
         if precision not in _capi.PRECISIONS:
             raise ValueError(f'precision should be one of {sorted(_capi.PRECISIONS)}')
         self._shape = (number_of_concatenated_descriptor_features, number_of_features,
@@ -103,6 +147,7 @@ class MatchingOperation(nn.Module):
     # -- C-ABI plumbing -------------------------------------------------------
     def _create_handle(self, handle, params, precision, device):
         cin, f, s, n_res = self._shape
+        check_fp16_weight_range(params, precision)
         arr = _capi.pointer_array(params)
         _capi.check(_capi.lib().pds_matching_op_create(
             ctypes.byref(handle), arr, len(params), cin // 2, f, s, n_res,

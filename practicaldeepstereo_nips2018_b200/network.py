@@ -1,11 +1,12 @@
 """PdsNetwork: drop-in for practical_deep_stereo.network.PdsNetwork
 (reference network.py:14-65) wired to the B200 kernel modules."""
 import os
+import warnings
 
 import torch
 from torch import nn
 
-from . import embedding, estimator, matching, regularization, size_adapter
+from . import _capi, embedding, estimator, matching, regularization, size_adapter
 
 
 # Regularization.forward_disparity: hourglass tail + estimator + crop as one pipeline whose cost
@@ -19,6 +20,7 @@ FUSE_TAIL_AND_ESTIMATOR = os.environ.get('PDS_B200_FUSE_TAIL', '0') == '1'
 class PdsNetwork(nn.Module):
     """Practical Deep Stereo network; same constructor (dependency injection of
     the five stages), methods and tensor shapes as the reference."""
+    _warned_eval_grad = False
 
     def __init__(self, size_adapter_module, embedding_module, matching_module,
                  regularization_module, estimator_module):
@@ -38,6 +40,37 @@ class PdsNetwork(nn.Module):
         self._maximum_disparity = maximum_disparity
         # descriptors are 4x down-sampled -> matching range (md + 1) / 4 - 1
         self._matching.set_maximum_disparity((maximum_disparity + 1) // 4 - 1)
+
+    def invalidate_kernels(self):
+        """Drops every packed copy of the parameters held by the kernel handles.  Needed only
+        after writes that bypass autograd's version counters (``param.data.copy_()`` and
+        friends); optimizer steps, ``load_state_dict`` and ``copy_`` under ``no_grad`` are
+        detected automatically."""
+        for module in self.modules():
+            handle = module.__dict__.get('_kernel')
+            if handle is not None:
+                handle.invalidate()
+
+    def _check_inputs(self, left_image, right_image):
+        """One clear error up front instead of a failure deep inside a stage: the inference
+        kernels need CUDA tensors on one device (there is no CPU path); gradient-enabled calls
+        run the ATen composition on any device."""
+        for name, image in (('left_image', left_image), ('right_image', right_image)):
+            if not torch.is_tensor(image) or image.dim() != 4:
+                raise ValueError(f'"{name}" should be a [B, 3, H, W] tensor (or uint8 [B, H, W, 3])')
+        if left_image.device != right_image.device:
+            raise ValueError('"left_image" and "right_image" should be on the same device')
+        needs_grad = matching._needs_autograd(left_image, right_image, self)
+        if not needs_grad and not left_image.is_cuda:
+            raise RuntimeError(
+                'PdsNetwork.forward without gradients runs on the sm_100a kernels and needs CUDA '
+                'tensors; there is no CPU path (enable gradients for the ATen composition)')
+        if needs_grad and not self.training and not PdsNetwork._warned_eval_grad:
+            PdsNetwork._warned_eval_grad = True
+            warnings.warn(
+                'PdsNetwork is in eval mode but gradients are enabled and parameters require grad: '
+                'this forward runs the ATen composition (a Python loop over every disparity), not '
+                'the sm_100a kernels; wrap inference in torch.no_grad()', RuntimeWarning, stacklevel=3)
 
     def _embed(self, left_image, right_image):
         """Embedding of both images.  With the kernel embedding the two images are
@@ -94,6 +127,7 @@ class PdsNetwork(nn.Module):
         [B, (md + 1) / 2, H, W] in training mode.  Besides the reference's float
         (B,3,H,W) images, uint8 images (B,3,H,W) or (B,H,W,3) are accepted."""
         reg, est = self._regularization, self._estimator
+        self._check_inputs(left_image, right_image)
         embedded = self._embed_unpadded(left_image, right_image)
         if embedded is None:
             left_image, right_image = self._as_float_planes(left_image), self._as_float_planes(right_image)
@@ -121,9 +155,14 @@ class PdsNetwork(nn.Module):
         return self._size_adapter.unpad(est(cost))
 
     @staticmethod
-    def default(maximum_disparity=255, precision='fp32'):
+    def default(maximum_disparity=255, precision=None):
         """Network with the default modules; `precision` selects the arithmetic of
-        the convolution stacks (see include/pds_b200.h, enum pds_precision)."""
+        the convolution stacks (see include/pds_b200.h, enum pds_precision).  The default
+        (``_capi.DEFAULT_PRECISION`` = 'fp16x2') is the fp32-grade split-operand tensor-core
+        mode, so the reference's unchanged ``PdsNetwork.default().cuda()`` call
+        (benchmark_on_flyingthings3d.py:56-59) gets the tcgen05 path; 'fp32' selects the
+        CUDA-core FFMA kernels with the embedding on ATen."""
+        precision = precision or _capi.DEFAULT_PRECISION
         network = PdsNetwork(
             size_adapter_module=size_adapter.SizeAdapter(),
             embedding_module=embedding.Embedding(precision=precision),

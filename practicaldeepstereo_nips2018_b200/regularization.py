@@ -8,11 +8,36 @@ import torch
 from torch import nn
 
 from . import _capi, network_blocks
-from .matching import _KernelHandle, _needs_autograd
+from .matching import _KernelHandle, _needs_autograd, check_fp16_weight_range
 
 
 def _f32(t):
     return t.detach().contiguous().float()
+
+
+class _BlockWorkspace(object):
+    """Scratch memory of a standalone ContractionBlock3d / ExpansionBlock3d call, kept per
+    (device, stream) and grown on demand instead of being allocated on every call."""
+
+    def __init__(self):
+        self._buffers = {}
+
+    def get(self, nbytes, device):
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+        ws = self._buffers.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._buffers[key] = ws
+        return ws
+
+    def __deepcopy__(self, memo):
+        return _BlockWorkspace()
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self._buffers = {}
 
 
 class ContractionBlock3d(nn.Module):
@@ -23,6 +48,7 @@ class ContractionBlock3d(nn.Module):
         n = number_of_features
         self._downsampling_2x = network_blocks.convolutional_block_3x3x3_stride_2(n, 2 * n)
         self._smoothing = network_blocks.convolutional_block_3x3x3(2 * n, 2 * n)
+        self.__dict__['_scratch'] = _BlockWorkspace()
 
     def forward(self, block_input):
         if _needs_autograd(block_input, self):
@@ -37,7 +63,7 @@ class ContractionBlock3d(nn.Module):
         lib = _capi.lib()
         with torch.cuda.device(x.device):
             nbytes = lib.pds_contraction_block_workspace_bytes(B, C, D, H, W)
-            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+            ws = self._scratch.get(nbytes, x.device)
             _capi.check(lib.pds_contraction_block_forward(
                 _capi.pointer_array(params), _capi.ptr(x), _capi.ptr(down), _capi.ptr(smooth),
                 B, C, D, H, W, _capi.ptr(ws), ws.numel(), _capi.stream_ptr(x.device)))
@@ -53,6 +79,7 @@ class ExpansionBlock3d(nn.Module):
         self._upsampling_2x = network_blocks.transposed_convolutional_block_4x4x4_stride_2(
             n, n // 2)
         self._smoothing = network_blocks.convolutional_block_3x3x3(n // 2, n // 2)
+        self.__dict__['_scratch'] = _BlockWorkspace()
 
     def forward(self, block_input, shortcut_from_contraction):
         if _needs_autograd(block_input, shortcut_from_contraction, self):
@@ -67,7 +94,7 @@ class ExpansionBlock3d(nn.Module):
         lib = _capi.lib()
         with torch.cuda.device(x.device):
             nbytes = lib.pds_expansion_block_workspace_bytes(B, C, D, H, W)
-            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+            ws = self._scratch.get(nbytes, x.device)
             _capi.check(lib.pds_expansion_block_forward(
                 _capi.pointer_array(params), _capi.ptr(x), _capi.ptr(skip), _capi.ptr(out),
                 B, C, D, H, W, _capi.ptr(ws), ws.numel(), _capi.stream_ptr(x.device)))
@@ -78,8 +105,9 @@ class Regularization(nn.Module):
     """Hourglass over the (B, 8, D, H, W) signature volume: 16x contraction,
     then expansion to (B, 2D, 4H, 4W) -- matching cost for even disparities."""
 
-    def __init__(self, number_of_features=8, precision='fp32'):
+    def __init__(self, number_of_features=8, precision=None):
         super().__init__()
+        precision = precision or _capi.DEFAULT_PRECISION
         if precision not in _capi.PRECISIONS:
             raise ValueError(f'precision should be one of {sorted(_capi.PRECISIONS)}')
         n = number_of_features
@@ -97,6 +125,7 @@ class Regularization(nn.Module):
         self.__dict__['_kernel'] = _KernelHandle(self._create_handle, self._destroy_handle)
 
     def _create_handle(self, handle, params, precision, device):
+        check_fp16_weight_range(params, precision)
         arr = _capi.pointer_array(params)
         _capi.check(_capi.lib().pds_regularization_create(
             ctypes.byref(handle), arr, len(params), self._number_of_features,

@@ -46,8 +46,12 @@ def test_embedding_vs_torch_port_ragged_batch():
     assert max_abs(s, rs[:2]) <= 2e-4 * float(rs.abs().max())
     assert torch.equal(d_all, d) and torch.equal(d_no, d) and torch.equal(s_all[:2], s)
     assert max_abs(s_all, rs) <= 2e-4 * float(rs.abs().max())
-    with torch.no_grad():                            # extents that are not multiples of 4: ATen path
+    # extents that are not multiples of 4 (never produced by PdsNetwork: SizeAdapter pads to
+    # multiples of 64): the ATen composition, announced with a RuntimeWarning -- not silently
+    embedding.Embedding._warned_aten = False
+    with torch.no_grad(), pytest.warns(RuntimeWarning, match='not a multiple of 4'):
         d5, _ = emb(img[..., :98, :130])
+    with torch.no_grad():
         r5, _ = torch_port.embedding(img[..., :98, :130], tdict(params))
     assert not emb.uses_kernels(img[..., :98, :130]) and max_abs(d5, r5) <= 1e-3
 
@@ -78,7 +82,8 @@ def test_network_fp16x2_vs_torch_port():
     flips, err, safe = margin_aware(disp.cpu().numpy(), idx.cpu().numpy(),
                                     st['disparity'].float().cpu().numpy(),
                                     st['cost'].float().cpu().numpy(), (28, 10), cost_err)
-    assert safe > 0.9 and flips < 1e-2 and err <= 1e-3 + 50 * cost_err
+    print(f'fp16x2 vs fp64 port: cost max-abs {cost_err:.3e} safe {safe:.4f} flips {flips:.3e} disparity {err:.3e}')
+    assert safe >= 0.99 and flips <= 1e-3 and err <= 1e-3, (cost_err, safe, flips, err)
 
 
 def test_input_path_pad_and_uint8_are_bit_identical():

@@ -69,7 +69,7 @@ def test_concat_full_size_checksum():
 
 def test_matching_operation_golden(golden):
     params = synth.make_params(synth.matching_operation_specs(), 31)
-    op = load_module(matching.MatchingOperation(), params)
+    op = load_module(matching.MatchingOperation(precision='fp32'), params)
     x = synth.tensor((2, 128, 12, 14), 32)
     with torch.no_grad():
         out = op(cuda(x))
@@ -81,14 +81,14 @@ def test_matching_operation_golden(golden):
 def test_matching_operation_output_size():
     # reference test/test_matching.py:35-40
     torch.manual_seed(0)
-    op = matching.MatchingOperation().cuda().eval()
+    op = matching.MatchingOperation(precision='fp32').cuda().eval()
     with torch.no_grad():
         assert op(torch.rand(2, 128, 25, 25).cuda()).size() == (2, 8, 25, 25)
 
 
 def test_matching_golden(golden):
     params = synth.make_params(synth.matching_operation_specs(), 31)
-    op = load_module(matching.MatchingOperation(), params)
+    op = load_module(matching.MatchingOperation(precision='fp32'), params)
     l, r = synth.tensor((1, 64, 10, 24), 33), synth.tensor((1, 64, 10, 24), 34)
     with torch.no_grad():
         out = matching.Matching(7, op)(cuda(l), cuda(r))
@@ -104,7 +104,7 @@ def test_matching_vs_torch_port(B, H, W, md):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     params = synth.make_params(synth.matching_operation_specs(), 35)
-    op = load_module(matching.MatchingOperation(), params)
+    op = load_module(matching.MatchingOperation(precision='fp32'), params)
     l, r = cuda(synth.tensor((B, 64, H, W), 36)), cuda(synth.tensor((B, 64, H, W), 37))
     p = tdict(params)
     with torch.no_grad():
@@ -117,7 +117,7 @@ def test_matching_vs_torch_port(B, H, W, md):
 
 def test_parameter_update_rebuilds_kernel_weights():
     params = synth.make_params(synth.matching_operation_specs(), 31)
-    op = load_module(matching.MatchingOperation(), params)
+    op = load_module(matching.MatchingOperation(precision='fp32'), params)
     x = cuda(synth.tensor((1, 128, 8, 8), 5))
     with torch.no_grad():
         a = op(x)

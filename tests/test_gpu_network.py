@@ -33,7 +33,7 @@ def margin_aware(disp, idx, ref_disp, ref_cost, crop, cost_err):
 def test_network_golden(golden):
     torch.backends.cudnn.allow_tf32 = False
     g = golden('network_md63')
-    net = load_module(PdsNetwork.default(63), synth.make_params(synth.network_specs(), 61))
+    net = load_module(PdsNetwork.default(63, precision='fp32'), synth.make_params(synth.network_specs(), 61))
     li, ri = _inputs()
     with torch.no_grad():
         left, right = cuda(li), cuda(ri)
@@ -46,18 +46,38 @@ def test_network_golden(golden):
     cost_err = max_abs(cost, g['cost_padded'])
     # 62x100 / md=63 has a 1x1x2 hourglass bottleneck: InstanceNorm over TWO voxels amplifies
     # input noise by up to 1/sqrt(eps) = 316x, so the reference itself moves by 1.3e-3 between
-    # fp32 and fp64 here (and the GPU embedding runs on cuDNN, the golden one on oneDNN).  The
-    # well-conditioned bound is test_network_vs_torch_port_kitti_like's 1e-3; here the
-    # margin-aware checks below carry the parity claim.
+    # fp32 and fp64 here (and the GPU embedding runs on cuDNN, the golden one on oneDNN).  This
+    # fixture therefore pins the well-conditioned stages (signatures, estimator on an identical
+    # volume, shapes); the END-TO-END bound of north_star (arg-max bit-exact, disparity 1e-3) is
+    # asserted on the well-conditioned fixture in test_network_golden_well_conditioned.
     assert cost_err <= 1e-2
-    flips, err, safe = margin_aware(disp.cpu().numpy(), idx.cpu().numpy(), g['disparity'],
-                                    g['cost_padded'], (2, 28), cost_err)
-    assert safe > 0.95 and flips < 5e-3
-    assert err <= 1e-3 + 50 * cost_err
     # estimator on the identical volume is exact
     rd, ridx = oracle.subpixel_map(cost.cpu().numpy())
     assert np.array_equal(ridx[..., 2:, 28:], idx.cpu().numpy())
     assert max_abs(rd[..., 2:, 28:], disp) <= 1e-4
+
+
+@pytest.mark.parametrize('precision', ['fp16x2', 'bf16x3', 'fp32'])
+def test_network_golden_well_conditioned(golden, precision):
+    """north_star's bound against the UNMODIFIED reference (tests/golden/network_md127.npz, 250x120,
+    md=127, hourglass bottleneck 2x2x4): arg-max bit-exact and disparity <= 1e-3 on every pixel
+    whose reference top-1/top-2 margin exceeds 4x the measured cost error; >= 99 % of the pixels
+    are such pixels."""
+    from test_oracle_golden import margin_checks, md127_inputs
+    torch.backends.cudnn.allow_tf32 = False
+    g = golden('network_md127')
+    net = load_module(PdsNetwork.default(127, precision=precision), synth.make_params(synth.network_specs(), 61))
+    li, ri = md127_inputs()
+    with torch.no_grad():
+        left, right = cuda(li), cuda(ri)
+        disp = net(left, right)
+        cost = net.pass_through_network(net._size_adapter.pad(left), net._size_adapter.pad(right))[0]
+        d2, idx = net._estimator(cost, crop_top=8, crop_left=6, return_argmax=True)
+    assert disp.shape == (1, 120, 250) and torch.equal(disp, d2)
+    cost_err, safe, flips, err = margin_checks(g, cost.cpu().numpy(), disp.cpu().numpy(), idx.cpu().numpy(), 1e-3)
+    print(f'network_md127 {precision}: cost max-abs {cost_err:.3e} safe {safe:.4f} flips {flips:.3e} '
+          f'disparity max-abs on safe pixels {err:.3e}')
+    assert safe >= 0.99 and flips <= 1e-3 and err <= 1e-3, (cost_err, safe, flips, err)
 
 
 def test_network_shapes_and_modes():
@@ -76,11 +96,15 @@ def test_network_shapes_and_modes():
         net.set_maximum_disparity(100)
 
 
-def test_network_vs_torch_port_kitti_like():
-    """C4-like aspect (ragged, needs both pads) at reduced size, batch 2."""
+@pytest.mark.parametrize('precision', [None, 'fp32'])
+def test_network_vs_torch_port_kitti_like(precision):
+    """C4-like aspect (ragged, needs both pads) at reduced size, batch 2; `None` = what the
+    reference's unchanged PdsNetwork.default() call gets (the fp32-grade tensor-core mode)."""
     torch.backends.cudnn.allow_tf32 = False
     params = synth.make_params(synth.network_specs(), 71)
-    net = load_module(PdsNetwork.default(63), params)
+    net = load_module(PdsNetwork.default(63, precision=precision), params)
+    from practicaldeepstereo_nips2018_b200 import _capi
+    assert net._matching._operation.precision == (precision or _capi.DEFAULT_PRECISION)
     left = cuda(synth.tensor((2, 3, 100, 310), 72, scale=255.0, uniform=True))
     right = cuda(synth.tensor((2, 3, 100, 310), 73, scale=255.0, uniform=True))
     right[..., :-9] = 0.7 * left[..., 9:] + 0.3 * right[..., :-9]
@@ -95,7 +119,8 @@ def test_network_vs_torch_port_kitti_like():
     flips, err, safe = margin_aware(disp.cpu().numpy(), idx.cpu().numpy(),
                                     st['disparity'].cpu().numpy(), st['cost'].cpu().numpy(),
                                     (28, 10), cost_err)
-    assert safe > 0.9 and flips < 1e-2 and err <= 1e-3 + 50 * cost_err
+    print(f'kitti-like md63: cost max-abs {cost_err:.3e} safe {safe:.4f} flips {flips:.3e} disparity {err:.3e}')
+    assert safe >= 0.99 and flips <= 1e-3 and err <= 1e-3, (cost_err, safe, flips, err)
 
 
 def test_host_pipeline_matches_direct_calls():
@@ -163,8 +188,14 @@ def test_full_size_configs_vs_torch_port(name, H, W, md, precision):
         assert mae < 6.0 and bad3 < 0.08, (mae, bad3)
         return
     cost_err = max_abs(cost, st['cost'])
-    assert cost_err <= 2e-3, cost_err
+    assert cost_err <= 1e-3, cost_err
     flips, err, safe = margin_aware(disp.cpu().numpy(), idx.cpu().numpy(), ref.cpu().numpy(),
                                     st['cost'].cpu().numpy(), (ph, pw), cost_err)
-    assert safe > 0.9 and flips < 1e-2 and err <= 1e-3 + 50 * cost_err, (safe, flips, err)
-    assert mae < 0.05 and bad3 < 5e-3, (mae, bad3)
+    print(f'{name} {precision}: cost max-abs {cost_err:.3e} safe {safe:.4f} flips {flips:.3e} '
+          f'disparity max-abs on safe pixels {err:.3e} MAE {mae:.3e} 3PE {bad3:.3e}')
+    # north_star: arg-max bit-exact (asserted inside margin_aware on the margin-safe pixels, >= 99 %
+    # of the image) and disparity within 1e-3 there.  Flips elsewhere: at most the reference's OWN
+    # self-flip rate between a batch-1 and a batch-2 run of the same pair, 1.2e-4 (SURVEY.md 0 / 8c;
+    # ATen-fp32 against fp64 flips 1.3e-5, profiles/r02_precision_*.txt)
+    assert safe >= 0.99 and flips <= 1.2e-4 and err <= 1e-3, (safe, flips, err)
+    assert mae < 0.01 and bad3 < 5e-4, (mae, bad3)

@@ -50,7 +50,7 @@ def test_blocks_fast_channel_counts():
 
 def test_hourglass_golden(golden):
     params = synth.make_params(synth.regularization_specs(), 45)
-    reg = load_module(regularization.Regularization(), params)
+    reg = load_module(regularization.Regularization(precision='fp32'), params)
     sig, sc = synth.tensor((1, 8, 16, 16, 32), 46), synth.tensor((1, 8, 16, 32), 47)
     with torch.no_grad():
         out = reg(cuda(sig), cuda(sc))
@@ -65,7 +65,7 @@ def test_hourglass_well_conditioned_vs_torch_port():
     convolution tail) against ATen fp32 on the same device at the fp32 noise floor."""
     torch.backends.cudnn.allow_tf32 = False
     params = synth.make_params(synth.regularization_specs(), 48)
-    reg = load_module(regularization.Regularization(), params)
+    reg = load_module(regularization.Regularization(precision='fp32'), params)
     sig, sc = cuda(synth.tensor((2, 8, 32, 32, 64), 49)), cuda(synth.tensor((2, 8, 32, 64), 50))
     with torch.no_grad():
         out = reg(sig, sc)
@@ -77,7 +77,7 @@ def test_hourglass_well_conditioned_vs_torch_port():
 def test_hourglass_output_size():
     # reference test/test_regularization.py:31-36
     torch.manual_seed(0)
-    reg = regularization.Regularization().cuda().eval()
+    reg = regularization.Regularization(precision='fp32').cuda().eval()
     with torch.no_grad():
         cost = reg(torch.rand(2, 8, 32, 32, 32).cuda(), torch.rand(2, 8, 32, 32).cuda())
     assert cost.size() == (2, 64, 128, 128)
@@ -87,7 +87,7 @@ def test_hourglass_vs_torch_port():
     """Larger volume (bottleneck 2x3x4) with batch 2, against ATen on the same GPU."""
     torch.backends.cudnn.allow_tf32 = False
     params = synth.make_params(synth.regularization_specs(), 48)
-    reg = load_module(regularization.Regularization(), params)
+    reg = load_module(regularization.Regularization(precision='fp32'), params)
     sig, sc = cuda(synth.tensor((2, 8, 32, 48, 64), 49)), cuda(synth.tensor((2, 8, 48, 64), 50))
     with torch.no_grad():
         out = reg(sig, sc)

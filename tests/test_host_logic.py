@@ -174,3 +174,107 @@ def test_error_metrics_known_answers_on_cpu():
     nothing = torch.full((2, 2), float('inf'))
     assert errors.compute_absolute_error(est, nothing)[1] == 0.0
     assert errors.compute_n_pixels_error(est, nothing)[1] == 0.0
+
+
+def test_default_precision_is_the_tensor_core_mode():
+    """The reference's unchanged `PdsNetwork.default().cuda()` (benchmark_on_flyingthings3d.py:
+    56-59) must land on the tcgen05 path: every stage defaults to the fp32-grade split precision."""
+    assert _capi.DEFAULT_PRECISION == os.environ.get('PDS_B200_PRECISION', 'fp16x2')
+    net = PdsNetwork.default(191)
+    assert net._embedding.precision == net._matching._operation.precision == \
+        net._regularization.precision == _capi.DEFAULT_PRECISION
+    assert matching.MatchingOperation().precision == _capi.DEFAULT_PRECISION
+    assert PdsNetwork.default(63, precision='fp32')._regularization.precision == 'fp32'
+
+
+def test_kernel_handles_survive_deepcopy_and_pickle():
+    """the handle holds ctypes pointers -- copies get a fresh empty handle bound to the
+    copied module, and invalidate() drops packed weights after `.data` writes."""
+    import copy
+    import io
+    import ctypes
+    net = PdsNetwork.default(63)
+    op = net._matching._operation
+    op._kernel._handles['cuda:9'] = (ctypes.c_void_p(0), ('fake',))      # as after a kernel forward
+    destroyed = []
+    op._kernel._destroy = destroyed.append
+    clone = copy.deepcopy(net)
+    cop = clone._matching._operation
+    assert cop._kernel is not op._kernel and cop._kernel._handles == {}
+    assert cop._kernel._create.__self__ is cop                          # re-bound to the copy
+    buf = io.BytesIO()
+    torch.save(op, buf)
+    buf.seek(0)
+    loaded = torch.load(buf, weights_only=False)
+    assert loaded._kernel._handles == {} and loaded._kernel._create.__self__ is loaded
+    net.invalidate_kernels()
+    assert op._kernel._handles == {} and len(destroyed) == 1
+    # standalone hourglass blocks keep their scratch buffer between calls (and copies do not share it)
+    blk = regularization.ContractionBlock3d(4)
+    assert copy.deepcopy(blk)._scratch is not blk._scratch
+
+
+def test_handle_key_tracks_in_place_updates():
+    """optimizer steps / load_state_dict / copy_ under no_grad bump `_version` (the handle's key);
+    `.data` writes do not, which is why parallel.broadcast_parameters copies into the parameters."""
+    p = torch.nn.Parameter(torch.zeros(3))
+    v0 = p._version
+    with torch.no_grad():
+        p.copy_(torch.ones(3))
+    assert p._version > v0
+    v1 = p._version
+    p.data.mul_(2.0)
+    assert p._version == v1                # documented restriction -> invalidate_kernels()
+
+
+def test_fp16_operand_range_check():
+    w = [torch.zeros(8, 8, 3, 3), torch.zeros(8)]
+    matching.check_fp16_weight_range(w, 'fp16x2')
+    w[0][0, 0, 0, 0] = 300.0
+    with pytest.raises(ValueError):
+        matching.check_fp16_weight_range(w, 'fp16x2')
+    matching.check_fp16_weight_range(w, 'bf16x3')      # bfloat16 terms have fp32's range
+
+
+def test_forward_validates_inputs_up_front():
+    net = PdsNetwork.default(63).eval()
+    left = torch.rand(1, 3, 64, 128)
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match='no CPU path'):
+            net(left, left)
+        with pytest.raises(ValueError):
+            net(left[0], left[0])
+    with pytest.warns(RuntimeWarning, match='eval mode but gradients are enabled'):
+        network.PdsNetwork._warned_eval_grad = False
+        net(left, left)                    # eval + grad: ATen composition, announced once
+
+
+def test_estimator_gradient_path_known_answers():
+    """reference test/test_estimator.py:14-27 on the gradient-enabled (tensor expression) path."""
+    sim = torch.tensor([0.0, 1.0, 3.0, 2.0, 1.0, 0.5]).view(1, 6, 1, 1).repeat(1, 1, 2, 1)
+    sim[0, :, 1, 0] = torch.tensor([5.0, 1.0, 0.0, 0.0, 0.0, 0.0])
+    sim.requires_grad_(True)
+    est = estimator.SubpixelMap(half_support_window=2, disparity_step=1)
+    out, idx = est(sim, return_argmax=True)
+    w = torch.softmax(torch.tensor([0.0, 1.0, 3.0, 2.0, 1.0]), 0)
+    assert torch.allclose(out[0, 0, 0], (w * torch.arange(5.0)).sum(), atol=1e-6)
+    w = torch.softmax(torch.tensor([5.0, 1.0, 0.0]), 0)        # taps -2, -1 fall outside: weight 0
+    assert torch.allclose(out[0, 1, 0], (w * torch.arange(3.0)).sum(), atol=1e-6)
+    assert idx.tolist() == [[[2], [0]]]
+    out.sum().backward()
+    assert sim.grad is not None
+
+
+def test_numa_binding_helpers(tmp_path):
+    from practicaldeepstereo_nips2018_b200 import parallel
+    assert parallel._parse_cpulist('0-3,8,10-11\n') == [0, 1, 2, 3, 8, 10, 11]
+    dev = tmp_path / 'bus/pci/devices/0000:1b:00.0'
+    dev.mkdir(parents=True)
+    (dev / 'numa_node').write_text('1\n')
+    node = tmp_path / 'devices/system/node/node1'
+    node.mkdir(parents=True)
+    (node / 'cpulist').write_text('16-31\n')
+    assert parallel.gpu_numa_cpus('0000:1B:00.0', sysfs=str(tmp_path)) == list(range(16, 32))
+    (dev / 'numa_node').write_text('-1\n')
+    assert parallel.gpu_numa_cpus('0000:1b:00.0', sysfs=str(tmp_path)) is None
+    assert parallel.gpu_numa_cpus('0000:ff:00.0', sysfs=str(tmp_path)) is None

@@ -186,3 +186,44 @@ def test_network_golden(golden):
     assert np.max(np.abs(disp - g['disparity'])[agree]) < 1e-2 + 100 * err
     with pytest.raises(ValueError):
         oracle.network_forward(li, ri, pe, pm, pr, 100)
+
+
+def md127_inputs():
+    li = synth.tensor((1, 3, 120, 250), 64, scale=255.0, uniform=True)
+    ri = synth.tensor((1, 3, 120, 250), 65, scale=255.0, uniform=True)
+    ri[..., :-9] = 0.8 * li[..., 9:] + 0.2 * ri[..., :-9]
+    return li, ri
+
+
+def margin_checks(g, cost_padded, disparity, argmax, tol_cost, crop=(8, 6)):
+    """Parity against the well-conditioned fixture of the unmodified reference (network_md127):
+    cost volume on the stored 4x sub-sampled grid, arg-max BIT-EXACT and disparity within 1e-3 on
+    every pixel whose reference top-1/top-2 margin exceeds 4x the measured cost error.  Returns
+    (cost error, safe fraction, flip fraction, disparity max-abs on safe pixels)."""
+    cost_err = float(np.max(np.abs(cost_padded[..., ::4, ::4].astype(np.float64) - g['cost_padded_sub4'])))
+    assert cost_err <= tol_cost, cost_err
+    safe = g['margin'] > 4 * cost_err
+    assert np.array_equal(argmax[safe], g['argmax'][safe].astype(argmax.dtype))
+    flips = float((argmax != g['argmax']).mean())
+    err = float(np.abs(disparity - g['disparity'])[safe].max())
+    return cost_err, float(safe.mean()), flips, err
+
+
+def test_network_golden_well_conditioned(golden):
+    """250x120, md=127 (hourglass bottleneck 2x2x4): both oracles against the unmodified reference at
+    north_star's own bound -- arg-max bit-exact and disparity <= 1e-3 on margin-safe pixels."""
+    g = golden('network_md127')
+    params = synth.make_params(synth.network_specs(), 61)
+    li, ri = md127_inputs()
+    with torch.no_grad():
+        st = torch_port.network_stages(torch.from_numpy(li), torch.from_numpy(ri), tdict(params), 127)
+    cost_err, safe, flips, err = margin_checks(
+        g, st['cost'].numpy(), st['disparity'].numpy(), st['argmax'][..., 8:, 6:].numpy(), 1e-5)
+    assert safe > 0.999 and flips == 0.0 and err <= 1e-4, (cost_err, safe, flips, err)
+
+    sub = lambda p: synth.flatten({k: v for k, v in params.items() if k.startswith(p)})
+    disp, cost = oracle.network_forward(li, ri, sub('_embedding.'), sub('_matching.'),
+                                        sub('_regularization.'), 127, return_cost=True)
+    _, idx = oracle.subpixel_map(cost)
+    cost_err, safe, flips, err = margin_checks(g, cost, disp, idx[..., 8:, 6:], 2e-4)
+    assert safe > 0.99 and flips < 1e-3 and err <= 1e-3, (cost_err, safe, flips, err)

@@ -1,11 +1,13 @@
 """Error of every arithmetic option against an fp64 run of the same network.
 
 Runs PdsNetwork.forward stage by stage on the GPU at a BASELINE workload and
-prints, for each precision of the convolution stacks (fp32 CUDA cores, bf16x3,
-bf16x2, bf16) and for plain ATen fp32 (the reference's own arithmetic, TF32
-off), the max-abs / mean-abs error of the matching signatures and of the cost
-volume against the fp64 restatement (oracle/torch_port.py in double), plus the
-arg-max flip fraction.  The ATen-fp32 row is the noise floor any "fp32" claim
+prints, for each precision of the convolution stacks (fp16x2 -- the default --,
+bf16x3, fp32 CUDA cores, bf16x2, bf16, fp16) and for plain ATen fp32 (the
+reference's own arithmetic, TF32 off), the max-abs / mean-abs error of the
+matching signatures and of the cost volume against the fp64 restatement
+(oracle/torch_port.py in double), the arg-max flip fraction, and the max-abs error
+of the final disparity on margin-safe pixels (margin > 4 x the row's cost error) and
+on every pixel whose arg-max agrees.  The ATen-fp32 row is the noise floor any "fp32" claim
 has to be measured against.
 
     python tools/precision_study.py [--workload C2] [--json out.json]
@@ -24,7 +26,7 @@ from practicaldeepstereo_nips2018_b200 import PdsNetwork  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--workload', default='C2')
 ap.add_argument('--json', default=None)
-ap.add_argument('--precisions', default='fp32,fp16x2,bf16x3,bf16x2,bf16,fp16')
+ap.add_argument('--precisions', default='fp16x2,bf16x3,fp32,bf16x2,bf16,fp16')
 args = ap.parse_args()
 H, W, md = {'C1': (64, 128, 63), 'C2': (540, 960, 191), 'C3': (540, 960, 255),
             'C4': (375, 1242, 191), 'S': (256, 512, 127)}[args.workload]
@@ -33,7 +35,7 @@ torch.backends.cuda.matmul.allow_tf32 = False
 dev = 'cuda'
 
 torch.manual_seed(0)
-net = PdsNetwork.default(md).to(dev).eval()
+net = PdsNetwork.default(md, precision='fp32').to(dev).eval()
 g = torch.Generator().manual_seed(7)
 left = torch.rand(1, 3, H, W, generator=g) * 255
 right = torch.rand(1, 3, H, W, generator=g) * 255
@@ -46,23 +48,36 @@ with torch.no_grad():
     ref = torch_port.network_stages(left.double(), right.double(), p64, md)
     rows = {}
 
+    top2 = ref['cost'].topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    ph, pw = -H % 64, -W % 64
+
     def report(name, sig, cost):
         se = (sig.double() - ref['signatures']).abs()
         ce = (cost.double() - ref['cost']).abs()
         idx = cost.argmax(dim=1)
-        flips = (idx != ref['argmax']).double().mean().item()
-        top2 = ref['cost'].topk(2, dim=1).values
-        margin = top2[:, 0] - top2[:, 1]
+        flipped = idx != ref['argmax']
+        flips = flipped.double().mean().item()
         safe = margin > 4 * ce.max()
-        safe_flips = ((idx != ref['argmax']) & safe).double().sum().item()
+        safe_flips = (flipped & safe).double().sum().item()
+        # final disparity (SubpixelMap on this row's own cost volume, torch port) against the fp64
+        # run's, on the un-padded image: max-abs on margin-safe pixels and wherever the arg-max agrees
+        disp = torch_port.subpixel_map(cost.float())[0][..., ph:, pw:].double()
+        de = (disp - ref['disparity']).abs()
+        safe_c, agree_c = safe[..., ph:, pw:], ~flipped[..., ph:, pw:]
+        d_safe = de[safe_c].max().item() if safe_c.any() else 0.0
+        d_agree = de[agree_c].max().item()
         rows[name] = {'sig_max': se.max().item(), 'sig_mean': se.mean().item(),
                       'cost_max': ce.max().item(), 'cost_mean': ce.mean().item(),
                       'argmax_flip_frac': flips, 'safe_frac': safe.double().mean().item(),
-                      'flips_on_safe_pixels': safe_flips}
+                      'flips_on_safe_pixels': safe_flips,
+                      'disparity_max_safe': d_safe, 'disparity_max_agree': d_agree,
+                      'disparity_mean': de.mean().item()}
         print(f'{name:10s} signatures max {se.max().item():.3e} mean {se.mean().item():.3e} | '
               f'cost max {ce.max().item():.3e} mean {ce.mean().item():.3e} | argmax flips '
-              f'{flips:.3e} (safe pixels {safe.double().mean().item():.4f}, flips there {int(safe_flips)})',
-              flush=True)
+              f'{flips:.3e} (safe pixels {safe.double().mean().item():.4f}, flips there {int(safe_flips)}) | '
+              f'disparity max-abs: safe pixels {d_safe:.3e}, arg-max-agreeing pixels {d_agree:.3e}, '
+              f'mean over all {de.mean().item():.3e}', flush=True)
 
     print(f'workload {args.workload}: {W}x{H} md={md}; reference = fp64 ATen; signature scale '
           f'{ref["signatures"].abs().max().item():.2f}, cost scale {ref["cost"].abs().max().item():.2f}')
