@@ -52,6 +52,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -93,6 +100,24 @@ __device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes) {
 }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t lo, uint32_t hi) {
   return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+// The same descriptor from byte quantities: core matrix = 8 rows x 16 B contiguous; SBO = byte
+// distance between 8-row groups, LBO = byte distance between the two 16-byte K halves of one MMA.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return umma_desc(((addr >> 4) & 0x3fff) | (((lbo_bytes >> 4) & 0x3fff) << 16), umma_desc_hi(sbo_bytes));
+}
+// Named barrier among `threads` threads of the CTA (id 1..15; id 0 is __syncthreads()).
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+// gpu-scope acquire load / release increment of a progress counter shared between CTAs
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 template <int W>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[W]);
@@ -182,6 +207,11 @@ __device__ __forceinline__ void split_terms(float x, uint16_t (&t)[3]) {
     const __nv_bfloat16 b2 = __float2bfloat16_rn(r);
     t[0] = __bfloat16_as_ushort(b0); t[1] = __bfloat16_as_ushort(b1); t[2] = __bfloat16_as_ushort(b2);
   }
+}
+
+template <bool FP16>
+__device__ __forceinline__ float term_value(uint16_t t) {
+  return FP16 ? __half2float(__ushort_as_half(t)) : __uint_as_float((uint32_t)t << 16);
 }
 
 // Sum over the 32 lanes of each of W per-lane values (W = 16 or 32); every lane ends with the
