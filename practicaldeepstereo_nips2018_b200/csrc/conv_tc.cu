@@ -32,17 +32,33 @@
 //     double-buffered in TMEM; CTAs are persistent (grid = #SMs).  When the whole
 //     weight tensor fits (64 -> 64 at S = 2: 147 KB) it is loaded ONCE per CTA and
 //     stays resident in shared memory.
+//   * FUSE = true (the 64 -> 64 layers over all disparity slices): the InstanceNorm that follows
+//     the convolution (network_blocks.py:47-58) runs INSIDE the same launch.  Tiles are handed out
+//     in slice order by an atomic counter, every finished tile bumps its slice's counter, and
+//     four extra warps per CTA pick up slices whose last tile has retired -- they read the fp32
+//     activation while it is still in L2, apply IN (+ the residual of the block), and write the
+//     next convolution's operand planes.  The separate normalisation passes (HBM-bound, ~0.15 ms
+//     each at 960x540 D=192) disappear behind the tensor-core time.  Nothing waits on a CTA that
+//     is not resident (tiles and work items are claimed, not assigned), so launches on several
+//     streams cannot dead-lock each other.
 #include <stdlib.h>
 
 #include <string>
 
 #include "conv_tc.cuh"
+#include "matching_first.cuh"
+#include "tc_ptx.cuh"
 
 namespace pds {
 namespace {
 
+using namespace ptx;
+
 constexpr int kPH = 18;          // halo rows of a CTA tile (16 + 2)
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;    // TMA producer warp, MMA issuer warp, four epilogue warps
+constexpr int kNormWarps = 4;    // FUSE kernels: warps that normalise finished slices behind the convolution
+constexpr int kFusedThreads = kThreads + 32 * kNormWarps;
+constexpr int kNormPixels = 256; // pixels of one 8-channel group per normalisation work item
 constexpr int kMaxStages = 6;
 
 struct alignas(64) TcKernelParams {
@@ -62,164 +78,130 @@ struct alignas(64) TcKernelParams {
   int stages;
   uint32_t stage_bytes, wres_bytes;
   float inv_wscale;
-  int dbg;                           // PDS_B200_TC_DEBUG bit mask (experiments only; 0 in production)
+  // ---- FUSE kernels: dynamic tile scheduler + trailing InstanceNorm of the launch's own output ----
+  // sched[0]: next tile to claim; sched[1 + s]: tiles of local slice s whose output and sums are
+  // stored; sched[1 + n_slices + s]: next normalisation work item of slice s.  Zeroed before the launch.
+  int* sched;
+  const float* gamma;                // InstanceNorm affine of this block
+  const float* beta;
+  int norm_mode;                     // TC_NORM_*
+  const uint16_t* res_ap;            // TC_NORM_RESIDUAL: residual planes (may alias norm_out)
+  uint16_t* norm_out;                // operand planes [n][S][N/8][H][W][8] written by the norm warps
+  const float* fA;                   // TC_NORM_RESIDUAL_FIRST: per-sample terms the residual x0 is rebuilt from
+  const float* fB;
+  const float* fQ;
 };
 
-// ---- PTX wrappers ------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a protocol bug traps after ~4 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = global_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && global_ns() - t0 > 4000000000ull) __trap();
-  }
-}
+constexpr uint32_t pow2_cols(uint32_t c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 __host__ __device__ constexpr bool tc_flat_rows(int PW) { return 8 * PW <= 256; }
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
-                                            int c2, int c3, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%2, %3, %4, %5}], [%6];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// One lane of a fully converged warp (warp-uniform control flow stays on the uniform datapath).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]; `accumulate` == 0 overwrites D.
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                       uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// K-major, no-swizzle shared-memory matrix descriptor (sm_100 format, version 1):
-// core matrix = 8 rows x 16 B contiguous; SBO = byte distance between 8-row
-// groups, LBO = byte distance between the two 16-byte K halves of one MMA.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
+// shared memory after the weight / stage buffers: barriers, TMEM slot, bias; FUSE adds the tile
+// ids in flight and the 1 KB exchange buffer of the cross-warp InstanceNorm sums
+constexpr int kNumBars = 2 * kMaxStages + 5 + 2;
+constexpr size_t kTailFixed = 8 * kNumBars + 32 + 64 * sizeof(float);      // barriers | tmem slot | bias
+constexpr size_t kTailFused = 32 + 128 * sizeof(double);                   // tile ids | sums
+constexpr size_t tail_bytes(bool fuse) { return kTailFixed + (fuse ? kTailFused : 0) + 128; }
 
-// x = t0 + t1 + t2 with 16-bit terms (round-to-nearest residual splitting).  fp16
-// terms saturate at the largest finite half instead of overflowing to infinity.
-template <bool FP16>
-__device__ __forceinline__ void split_terms(float x, uint16_t (&t)[3]) {
-  if (FP16) {
-    const float c = fminf(fmaxf(x, -65504.f), 65504.f);
-    const __half h0 = __float2half_rn(c);
-    float r = x - __half2float(h0);
-    const __half h1 = __float2half_rn(r);
-    r -= __half2float(h1);
-    const __half h2 = __float2half_rn(r);
-    t[0] = __half_as_ushort(h0); t[1] = __half_as_ushort(h1); t[2] = __half_as_ushort(h2);
-  } else {
-    const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
-    float r = x - __bfloat162float(b0);
-    const __nv_bfloat16 b1 = __float2bfloat16_rn(r);
-    r -= __bfloat162float(b1);
-    const __nv_bfloat16 b2 = __float2bfloat16_rn(r);
-    t[0] = __bfloat16_as_ushort(b0); t[1] = __bfloat16_as_ushort(b1); t[2] = __bfloat16_as_ushort(b2);
+// Bounded spin on a global progress counter (a protocol bug traps after ~4 s instead of hanging).
+__device__ __forceinline__ void wait_counter(const int* ctr, int target) {
+  if (ld_acquire_gpu(ctr) >= target) return;
+  const unsigned long long t0 = global_ns();
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(ctr) < target) {
+    __nanosleep(200);
+    if ((++spins & 0xff) == 0 && global_ns() - t0 > 4000000000ull) __trap();
   }
 }
-template <bool FP16>
-__device__ __forceinline__ float term_value(uint16_t t) {
-  return FP16 ? __half2float(__ushort_as_half(t)) : __uint_as_float((uint32_t)t << 16);
-}
 
-// Sum over the 32 lanes of each of 32 per-lane values; lane l ends with channel l.
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+// One normalisation work item: kNormPixels pixels of one 8-channel group of one slice.
+//   out = IN(t) [+ residual planes | + x0 rebuilt from A / Bf / Q]  ->  split operand planes.
+// Same arithmetic as tc_norm_split_kernel / norm_residual_first_kernel (bit-identical results).
+// fp16 terms only (the default precision); ONE out-of-line instance per S with a run-time mode:
+// inlining the variants into the convolution kernel cost its epilogue registers.
+template <int S>
+__device__ __noinline__ void norm_work_item(const TcKernelParams& p, int nl, int c8, int pb, int lane) {
+  constexpr int C = 64, U = 4;
+  const size_t HW = (size_t)p.H * p.W;
+  const int ng = p.n0 + nl;
+  const int mode = p.norm_mode;
+  float a[8], b[8];
+  {
+    const int c = c8 * 8 + (lane & 7);
+    const double s = __ldcg(p.stats + ((size_t)ng * C + c) * 2), q = __ldcg(p.stats + ((size_t)ng * C + c) * 2 + 1);
+    const double mean = s / (double)HW;
+    double var = q / (double)HW - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float scale = (float)(1.0 / sqrt(var + 1e-5)) * __ldg(p.gamma + c);
+    const float shift = __ldg(p.beta + c) - (float)mean * scale;
 #pragma unroll
-  for (int step = 16; step >= 1; step >>= 1) {
-    const bool upper = (lane & step) != 0;
+    for (int e = 0; e < 8; ++e) { a[e] = __shfl_sync(0xffffffffu, scale, e); b[e] = __shfl_sync(0xffffffffu, shift, e); }
+  }
+  const float4* y4 = reinterpret_cast<const float4*>(p.out_f32) + ((size_t)nl * (C / 4) + 2 * c8) * HW;
+  const uint4* r4 = reinterpret_cast<const uint4*>(p.res_ap) + ((size_t)nl * S * (C / 8) + c8) * HW;
+  uint4* o4 = reinterpret_cast<uint4*>(p.norm_out) + ((size_t)nl * S * (C / 8) + c8) * HW;
+  const size_t term = (size_t)(C / 8) * HW;          // distance between the terms of one slice
+  const int bs = ng / p.n_div, d = ng - bs * p.n_div;
+  const size_t fbase = ((size_t)bs * (C / 4) + 2 * c8) * HW;
+  const size_t p_begin = (size_t)pb * kNormPixels;
+#pragma unroll 1
+  for (int it = 0; it < kNormPixels / (32 * U); ++it) {
+    const size_t pix0 = p_begin + (size_t)it * (32 * U) + lane;
+    float4 lo[U], hi[U];
+    uint4 rr[U][S];
 #pragma unroll
-    for (int i = 0; i < step; ++i) {
-      const float send = upper ? v[i] : v[i + step];
-      const float keep = upper ? v[i + step] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    for (int u = 0; u < U; ++u) {
+      const size_t pix = pix0 + 32 * u;
+      if (pix < HW) {
+        lo[u] = __ldcg(y4 + pix);            // written by other SMs during this launch: L2, never .nc / L1
+        hi[u] = __ldcg(y4 + HW + pix);
+        if (mode == TC_NORM_RESIDUAL) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) rr[u][s] = __ldcg(r4 + s * term + pix);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t pix = pix0 + 32 * u;
+      if (pix >= HW) continue;
+      float v[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], a[e], b[e]);
+      if (mode == TC_NORM_RESIDUAL) {
+        float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = S - 1; s >= 0; --s) {   // smallest term first
+          const uint32_t w[4] = {rr[u][s].x, rr[u][s].y, rr[u][s].z, rr[u][s].w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) res[e] += term_value<true>((uint16_t)(w[e >> 1] >> (16 * (e & 1))));
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += res[e];
+      } else if (mode == TC_NORM_RESIDUAL_FIRST) {
+        float x0v[8];
+        first_x0(reinterpret_cast<const float4*>(p.fA) + fbase, reinterpret_cast<const float4*>(p.fB) + fbase,
+                 reinterpret_cast<const float4*>(p.fQ) + fbase, HW, pix, (int)(pix % (size_t)p.W), p.W, d, x0v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += x0v[e];
+      }
+      uint16_t t[8][3];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_terms<true>(v[e], t[e]);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        uint4 pk;
+        pk.x = t[0][s] | ((uint32_t)t[1][s] << 16); pk.y = t[2][s] | ((uint32_t)t[3][s] << 16);
+        pk.z = t[4][s] | ((uint32_t)t[5][s] << 16); pk.w = t[6][s] | ((uint32_t)t[7][s] << 16);
+        __stcg(o4 + s * term + pix, pk);
+      }
     }
   }
-  return v[0];
 }
 
-constexpr uint32_t pow2_cols(uint32_t c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
-
-// S terms, NT MMA tiles per CTA tile, N rows per weight term, WRES: weights resident.
-template <int S, int NT, int N, bool WRES>
-__global__ void __launch_bounds__(kThreads, 1)
+// S terms, NT MMA tiles per CTA tile, N rows per weight term, WRES: weights resident, FUSE: dynamic
+// tile scheduler + trailing normalisation warps (N = 64, TC_EPI_ACT only).
+template <int S, int NT, int N, bool WRES, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? kFusedThreads : kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
   constexpr int PW = 8 * NT + 2;                          // halo pitch in pixels
   constexpr uint32_t A_TERM_BYTES = 2 * kPH * PW * 16;    // one term of one 16-channel chunk
@@ -229,26 +211,31 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
   constexpr int NBUF = 2 * BUF_COLS <= 512 ? 2 : 1;
   constexpr uint32_t TMEM_COLS = pow2_cols(NBUF * BUF_COLS);
   static_assert(BUF_COLS <= 512, "accumulators do not fit TMEM");
+  static_assert(!FUSE || N == 64, "the fused normalisation handles 64 output channels");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   const uint32_t wres_base = smem_u32(smem);
   const uint32_t stage_base = wres_base + p.wres_bytes;
   const uint32_t bar_base = stage_base + (uint32_t)p.stages * p.stage_bytes;
-  // barriers: full[stages], empty[stages], tfull[2], tempty[2], wfull; then tmem pointer; then bias
+  // barriers: full[stages], empty[stages], tfull[2], tempty[2], wfull, tid[2]; then tmem pointer; then bias
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
   const uint32_t wfull_bar = bar_base + 8u * (2 * kMaxStages + 4);
-  unsigned char* tail = smem + p.wres_bytes + (size_t)p.stages * p.stage_bytes + 8 * (2 * kMaxStages + 5);
+  auto tid_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 5 + a); };
+  unsigned char* tail = smem + p.wres_bytes + (size_t)p.stages * p.stage_bytes + 8 * kNumBars;
   uint32_t* tmem_slot = (uint32_t*)(tail + 8);
   float* sbias = (float*)(tail + 32);
+  volatile int* stage_tile = (volatile int*)(tail + 32 + 64 * sizeof(float));   // [kMaxStages] tile id carried by a stage
+  volatile int* acc_tile = stage_tile + kMaxStages;                            // [2] tile id of an accumulator buffer
+  double* sred = (double*)(tail + 32 + 64 * sizeof(float) + 32);               // [128] sums of the tile in flight
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); mbar_init(tid_bar(a), 1); }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     pdl_trigger();
@@ -258,7 +245,8 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
         bulk_load(wres_base + c * W_CHUNK_BYTES, p.w + (size_t)c * (W_CHUNK_BYTES / 2), W_CHUNK_BYTES, wfull_bar);
     }
   }
-  for (int i = threadIdx.x; i < N; i += kThreads) sbias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sbias[i] = p.bias[i];
+  if (FUSE && threadIdx.x < 128) sred[threadIdx.x] = 0.0;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -270,19 +258,23 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // everything below reads / writes tensors of the stream's earlier kernels
 
-  // every CTA walks ONE contiguous range of tiles: consecutive tiles share halo rows in L2 and
-  // stay within one or two slices, so the InstanceNorm sums are flushed once per slice change
+  // static schedule (FUSE = false): every CTA walks ONE contiguous range of tiles -- consecutive
+  // tiles share halo rows in L2 and stay within one or two slices, so the InstanceNorm sums are
+  // flushed once per slice change.  FUSE: tiles are claimed from sched[0] in slice order.
   const int tiles_per_slice = p.tiles_x * p.tiles_y;
   const int total_tiles = tiles_per_slice * p.n_slices;
   const int tiles_per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int tile_begin = min((int)blockIdx.x * tiles_per_cta, total_tiles);
-  const int tile_end = min(tile_begin + tiles_per_cta, total_tiles);
+  const int tile_begin = FUSE ? 0 : min((int)blockIdx.x * tiles_per_cta, total_tiles);
+  const int tile_end = FUSE ? total_tiles : min(tile_begin + tiles_per_cta, total_tiles);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      int tile = FUSE ? atomicAdd(p.sched, 1) : tile_begin;
+      while (tile < tile_end) {
+        // FUSE: the next tile is claimed one tile ahead, so the atomic's latency hides behind this tile's loads
+        const int next = FUSE ? atomicAdd(p.sched, 1) : tile + 1;
         const int nl = tile / tiles_per_slice, r = tile - nl * tiles_per_slice;
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         const int x0 = tx * 8 * NT, y0 = ty * 16;
@@ -291,6 +283,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
         const int slice1 = p.in_global ? b : nl;
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(empty_bar(stage), phase ^ 1);
+          if (FUSE && c == 0) stage_tile[stage] = tile;      // published by the arrive below
           mbar_expect_tx(full_bar(stage), S * A_TERM_BYTES + (WRES ? 0u : W_CHUNK_BYTES));
           const uint32_t sa = stage_base + stage * p.stage_bytes;
           const bool second = c >= p.nchunks1;
@@ -310,6 +303,12 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
                       full_bar(stage));
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
+        tile = next;
+      }
+      if (FUSE) {   // end marker: a stage that carries tile id -1 and no data
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        stage_tile[stage] = -1;
+        mbar_arrive(full_bar(stage));
       }
     }
   } else if (warp == 1) {
@@ -321,8 +320,17 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
       for (int s = 0; s < S; ++s) idesc[s] = fmt | ((uint32_t)((N * (S - s)) >> 3) << 17);
       if (WRES) { mbar_wait(wfull_bar, 0); tc_fence_after(); }
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      for (int tile = tile_begin; FUSE || tile < tile_end; ++tile) {
+        if (FUSE) {
+          mbar_wait(full_bar(stage), phase);           // first chunk of the next tile, or the end marker
+          const int id = stage_tile[stage];
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);   // the epilogue has read this buffer's previous tile id
+          if (lane == 0) { acc_tile[acc] = id; mbar_arrive(tid_bar(acc)); }
+          __syncwarp();
+          if (id < 0) break;
+        } else {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        }
         tc_fence_after();
         const uint32_t d_base = tmem_base + acc * BUF_COLS;
         for (int c = 0; c < p.nchunks; ++c) {
@@ -331,10 +339,10 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
           const uint32_t sa = stage_base + stage * p.stage_bytes;
           const uint32_t sw = WRES ? wres_base + c * W_CHUNK_BYTES : sa + S * A_TERM_BYTES;
           if (elect_one()) {
-            const uint64_t wdesc = umma_desc(sw, S * N * 16, 128);
+            const uint64_t wdesc = umma_desc_kmajor(sw, S * N * 16, 128);
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-              const uint64_t adesc = umma_desc(sa + s * A_TERM_BYTES, kPH * PW * 16, PW * 16);
+              const uint64_t adesc = umma_desc_kmajor(sa + s * A_TERM_BYTES, kPH * PW * 16, PW * 16);
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
                 const uint64_t bd = wdesc + (uint64_t)(tap * 2 * S * N);          // 16-byte units
@@ -355,7 +363,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
         if (NBUF == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===== epilogue warps (2..5): TMEM lanes 32*(warp%4) .. +31 =====
     const int q = warp & 3;
     const int row = 32 * q + lane;
@@ -366,34 +374,41 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
     double sa0 = 0.0, sa1 = 0.0, sb0 = 0.0, sb1 = 0.0;
     int stat_slice = -1;
     auto flush_stats = [&]() {
-      if (stat_slice >= 0 && !(p.dbg & 1)) {
+      if (stat_slice >= 0) {
         double* dst = p.stats + ((size_t)stat_slice * N + lane) * 2;
         atomicAdd(dst, sa0); atomicAdd(dst + 1, sa1);
         atomicAdd(dst + 64, sb0); atomicAdd(dst + 65, sb1);
       }
       sa0 = sa1 = sb0 = sb1 = 0.0;
     };
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (int tile_seq = tile_begin; FUSE || tile_seq < tile_end; ++tile_seq) {
+      int tile = tile_seq;
+      if (FUSE) {
+        mbar_wait(tid_bar(acc), acc_phase);
+        tile = acc_tile[acc];
+        if (tile < 0) break;
+      }
       const int nl = tile / tiles_per_slice, r = tile - nl * tiles_per_slice;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const int y = ty * 16 + py;
       const int ng = p.n0 + nl;
-      if (p.epilogue == TC_EPI_ACT && ng != stat_slice) { flush_stats(); stat_slice = ng; }
+      if (!FUSE && p.epilogue == TC_EPI_ACT && ng != stat_slice) { flush_stats(); stat_slice = ng; }
+      double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;    // FUSE: this tile's sums (channels lane, 32 + lane)
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BUF_COLS;
 #pragma unroll 1
-      for (int i = 0; i < ((p.dbg & 4) ? 0 : NT); ++i) {
+      for (int i = 0; i < NT; ++i) {
         const int x = tx * 8 * NT + 8 * i + px;
         const bool valid = (x < p.W) && (y < p.H);
         const size_t pix = (size_t)y * p.W + x;
         if constexpr (N == 16) {   // last convolution: bias -> signatures (B, Cout, D, H, W)
           float v[16];
-          tmem_ld16(t_base + i * ACC_COLS + (S - 1) * N, v);
+          tmem_ld<16>(t_base + i * ACC_COLS + (S - 1) * N, v);
 #pragma unroll
           for (int s = S - 2; s >= 0; --s) {
             float u[16];
-            tmem_ld16(t_base + i * ACC_COLS + s * N, u);
+            tmem_ld<16>(t_base + i * ACC_COLS + s * N, u);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += u[j];
           }
@@ -409,11 +424,11 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
 #pragma unroll 1
         for (int col0 = 0; col0 < N; col0 += 32) {
           float v[32];
-          tmem_ld32(t_base + i * ACC_COLS + (S - 1) * N + col0, v);   // smallest terms first
+          tmem_ld<32>(t_base + i * ACC_COLS + (S - 1) * N + col0, v);   // smallest terms first
 #pragma unroll
           for (int s = S - 2; s >= 0; --s) {
             float u[32];
-            tmem_ld32(t_base + i * ACC_COLS + s * N + col0, u);
+            tmem_ld<32>(t_base + i * ACC_COLS + s * N + col0, u);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += u[j];
           }
@@ -442,7 +457,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
               }
             }
           } else {
-            if (valid && !(p.dbg & 2)) {
+            if (valid) {
               float4* o = reinterpret_cast<float4*>(p.out_f32) + ((size_t)nl * (N / 4) + col0 / 4) * HW + pix;
 #pragma unroll
               for (int k = 0; k < 8; ++k)
@@ -458,8 +473,12 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
             }
             const float s1 = warp_transpose_reduce(v, lane);
             const float s2 = warp_transpose_reduce(sq, lane);
-            if (col0 == 0) { sa0 += (double)s1; sa1 += (double)s2; }
-            else { sb0 += (double)s1; sb1 += (double)s2; }
+            if (FUSE) {
+              if (col0 == 0) { m0 += (double)s1; m1 += (double)s2; } else { m2 += (double)s1; m3 += (double)s2; }
+            } else {
+              if (col0 == 0) { sa0 += (double)s1; sa1 += (double)s2; }
+              else { sb0 += (double)s1; sb1 += (double)s2; }
+            }
           }
         }
         }
@@ -467,8 +486,46 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (NBUF == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
+      if (FUSE) {
+        // sums of the four epilogue warps combined in 1 KB of shared memory (double atomics, four
+        // contributions per address), ONE global double atomic per (channel, moment) and tile; then
+        // the slice's progress counter moves.  The barriers order every epilogue thread's stores of
+        // this tile before the releasing increment (the grid-sync idiom: barrier, then one thread
+        // fences at gpu scope and signals).
+        atomicAdd(&sred[2 * lane], m0); atomicAdd(&sred[2 * lane + 1], m1);
+        atomicAdd(&sred[64 + 2 * lane], m2); atomicAdd(&sred[64 + 2 * lane + 1], m3);
+        named_barrier(1, 128);
+        if (q == 0) {
+          m0 = sred[2 * lane]; m1 = sred[2 * lane + 1]; m2 = sred[64 + 2 * lane]; m3 = sred[64 + 2 * lane + 1];
+          sred[2 * lane] = 0.0; sred[2 * lane + 1] = 0.0; sred[64 + 2 * lane] = 0.0; sred[64 + 2 * lane + 1] = 0.0;
+        }
+        named_barrier(1, 128);                     // the buffer is zero again before anyone adds the next tile
+        if (q == 0) {
+          double* dst = p.stats + ((size_t)ng * N + lane) * 2;
+          atomicAdd(dst, m0); atomicAdd(dst + 1, m1);
+          atomicAdd(dst + 64, m2); atomicAdd(dst + 65, m3);
+          __syncwarp();
+          if (lane == 0) { __threadfence(); red_release_gpu_add(p.sched + 1 + nl, 1); }
+        }
+      }
     }
-    if (p.epilogue == TC_EPI_ACT) flush_stats();
+    if (!FUSE && p.epilogue == TC_EPI_ACT) flush_stats();
+  } else if (FUSE) {
+    // ===== normalisation warps (6..9): slices whose last tile has retired, in slice order =====
+    const int groups = N / 8;
+    const int blocks = (int)(((size_t)p.H * p.W + kNormPixels - 1) / kNormPixels);
+    const int items = blocks * groups;
+    for (int nl = 0; nl < p.n_slices; ++nl) {
+      wait_counter(p.sched + 1 + nl, tiles_per_slice);
+      for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(p.sched + 1 + p.n_slices + nl, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= items) break;
+        const int c8 = item % groups, pb = item / groups;
+        norm_work_item<S>(p, nl, c8, pb, lane);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -724,16 +781,14 @@ int encode_ap_map(CUtensorMap* map, const void* base, int W_eff, int W, int H, s
   return PDS_OK;
 }
 
-constexpr size_t kTailBytes = 8 * (2 * kMaxStages + 5) + 32 + 64 * sizeof(float) + 256;
-
-template <int S, int NT, int N, bool WRES>
+template <int S, int NT, int N, bool WRES, bool FUSE>
 int launch_tc(TcKernelParams& p, cudaStream_t st) {
   constexpr int PW = 8 * NT + 2;
   constexpr uint32_t A_TERM_BYTES = 2 * kPH * PW * 16;
   constexpr uint32_t W_CHUNK_BYTES = 9 * 2 * S * N * 16;
   p.wres_bytes = WRES ? (uint32_t)p.nchunks * W_CHUNK_BYTES : 0;
   p.stage_bytes = (uint32_t)align_up((size_t)S * A_TERM_BYTES + (WRES ? 0 : W_CHUNK_BYTES), 128);
-  const size_t budget = 227 * 1024 - kTailBytes - p.wres_bytes;
+  const size_t budget = 227 * 1024 - tail_bytes(FUSE) - p.wres_bytes;
   int stages = (int)(budget / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   static const int stage_cap = getenv("PDS_B200_TC_STAGES") ? atoi(getenv("PDS_B200_TC_STAGES")) : 0;
@@ -744,12 +799,12 @@ int launch_tc(TcKernelParams& p, cudaStream_t st) {
     return PDS_ERR_UNSUPPORTED;
   }
   p.stages = stages;
-  const size_t smem = p.wres_bytes + (size_t)stages * p.stage_bytes + kTailBytes;
-  PDS_CUDA(allow_dynamic_smem(conv3x3_tc_kernel<S, NT, N, WRES>, 227 * 1024));
+  const size_t smem = p.wres_bytes + (size_t)stages * p.stage_bytes + tail_bytes(FUSE);
+  PDS_CUDA(allow_dynamic_smem(conv3x3_tc_kernel<S, NT, N, WRES, FUSE>, 227 * 1024));
   const int total = p.tiles_x * p.tiles_y * p.n_slices;
   const int grid = total < num_sms() ? total : num_sms();
   static const std::string base = "conv3x3_tc<S=" + std::to_string(S) + ",NT=" + std::to_string(NT) +
-                                  ",N=" + std::to_string(N) + (WRES ? ",Wres>" : ",Wstream>");
+                                  ",N=" + std::to_string(N) + (WRES ? ",Wres" : ",Wstream") + (FUSE ? ",+IN>" : ">");
   // PDS_B200_PROFILE_DETAIL=1: one profiler class per epilogue variant and slice count
   static const bool detail = getenv("PDS_B200_PROFILE_DETAIL") && atoi(getenv("PDS_B200_PROFILE_DETAIL"));
   static std::string names[8][2];
@@ -761,11 +816,15 @@ int launch_tc(TcKernelParams& p, cudaStream_t st) {
   PDS_KERNEL(nm.c_str(), st);
   {
     // reference FLOPs of the layer (real Cout, all Cin); bytes: AP terms in (both inputs), output as written
+    // (FUSE: the operand planes the normalisation warps write -- and the residual they read -- instead
+    // of the fp32 activation, which is consumed from L2)
     const double px = (double)p.H * p.W * p.n_slices;
-    const double out_b = p.epilogue == TC_EPI_SIG ? 4.0 * p.Cout : (p.epilogue == TC_EPI_PLAIN ? 2.0 * S * N : 4.0 * N);
+    double out_b = p.epilogue == TC_EPI_SIG ? 4.0 * p.Cout : (p.epilogue == TC_EPI_PLAIN ? 2.0 * S * N : 4.0 * N);
+    if (FUSE) out_b = 2.0 * S * N * (p.norm_mode == TC_NORM_RESIDUAL ? 2.0 : 1.0);
     PDS_KERNEL_WORK(2.0 * 9 * 16 * p.nchunks * p.Cout * px, px * out_b + (p.in_global ? 0.0 : px * 2.0 * S * 16 * p.nchunks));
   }
-  PDS_CUDA(launch_pdl(conv3x3_tc_kernel<S, NT, N, WRES>, dim3(grid), dim3(kThreads), smem, st, p));
+  PDS_CUDA(launch_pdl(conv3x3_tc_kernel<S, NT, N, WRES, FUSE>, dim3(grid), dim3(FUSE ? kFusedThreads : kThreads), smem,
+                      st, p));
   return PDS_OK;
 }
 
@@ -855,6 +914,14 @@ int tc_norm_split(const float* y, const double* stats, const float* gamma, const
   return PDS_OK;
 }
 
+// PDS_B200_FUSE_NORM=0 (read when a handle is created): normalisation as separate passes
+bool tc_fused_norm_enabled() {
+  const char* e = getenv("PDS_B200_FUSE_NORM");
+  return !(e && atoi(e) == 0);
+}
+
+size_t tc_sched_ints(int n_slices) { return 1 + 2 * (size_t)(n_slices > 0 ? n_slices : 0); }
+
 int tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   const TcLayer& l = *a.layer;
   if (!encode_fn()) {
@@ -874,12 +941,16 @@ int tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   p.in_global = a.in2 ? 1 : 0;
   p.Cout = l.Cout; p.epilogue = a.epilogue; p.fp16 = l.fp16;
   p.inv_wscale = 1.0f / l.wscale;
-  static const int dbg = getenv("PDS_B200_TC_DEBUG") ? atoi(getenv("PDS_B200_TC_DEBUG")) : 0;
-  p.dbg = dbg;
   if ((a.in2 ? a.in_C + a.in2_C : a.in_C) != l.Cin || l.Cin % 16 || (l.N != 16 && l.N != 64) ||
       l.S < 1 || l.S > 3 || (a.epilogue == TC_EPI_SIG) != (l.N == 16)) {
     set_error("conv3x3_tc: unsupported configuration (Cin=%d, N=%d, S=%d)", l.Cin, l.N, l.S);
     return PDS_ERR_UNSUPPORTED;
+  }
+  if (a.norm_mode != TC_NORM_NONE && (a.epilogue != TC_EPI_ACT || !a.norm_out || !a.stats || !a.out_f32 ||
+                                      (a.norm_mode == TC_NORM_RESIDUAL && !a.res_ap) ||
+                                      (a.norm_mode == TC_NORM_RESIDUAL_FIRST && !(a.fA && a.fB && a.fQ && a.n0 == 0)))) {
+    set_error("conv3x3_tc: incomplete arguments for the trailing normalisation");
+    return PDS_ERR_INVALID_ARGUMENT;
   }
   const int NT = nt_for(l.S);
   p.tiles_x = (a.W + 8 * NT - 1) / (8 * NT);
@@ -890,16 +961,39 @@ int tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   // weights resident when the whole layer fits beside >= 3 activation stages
   const size_t w_bytes = l.w_elems() * 2;
   const size_t a_stage = (size_t)l.S * 2 * kPH * PW * 16;
-  const bool wres = w_bytes + 3 * a_stage + kTailBytes <= 227 * 1024;
+  const bool wres = w_bytes + 3 * a_stage + tail_bytes(false) <= 227 * 1024;
+  // trailing normalisation inside the launch: 64 output channels, resident weights, one or two fp16 terms,
+  // a scheduler array from the caller, and enough slices for the passes to overlap the convolution
+  const bool fuse = a.norm_mode != TC_NORM_NONE && a.sched && l.N == 64 && l.Cout == 64 &&
+                    l.S <= 2 && l.fp16 && !a.in2 && w_bytes + 3 * a_stage + tail_bytes(true) <= 227 * 1024 && a.n_slices >= 4;
+  if (fuse) {
+    p.sched = a.sched; p.gamma = l.gamma; p.beta = l.beta; p.norm_mode = a.norm_mode;
+    p.res_ap = a.res_ap; p.norm_out = a.norm_out; p.fA = a.fA; p.fB = a.fB; p.fQ = a.fQ;
+    if (l.S == 1) return launch_tc<1, 4, 64, true, true>(p, st);
+    return launch_tc<2, 2, 64, true, true>(p, st);
+  }
+  rc = PDS_ERR_UNSUPPORTED;
 #define PDS_TC_CASE(SS, NN)                                                       \
   if (l.S == SS && l.N == NN)                                                     \
-    return wres ? launch_tc<SS, (SS == 1 ? 4 : (SS == 2 ? 2 : 1)), NN, true>(p, st) \
-                : launch_tc<SS, (SS == 1 ? 4 : (SS == 2 ? 2 : 1)), NN, false>(p, st);
+    rc = wres ? launch_tc<SS, (SS == 1 ? 4 : (SS == 2 ? 2 : 1)), NN, true, false>(p, st) \
+              : launch_tc<SS, (SS == 1 ? 4 : (SS == 2 ? 2 : 1)), NN, false, false>(p, st);
   PDS_TC_CASE(1, 64) PDS_TC_CASE(1, 16) PDS_TC_CASE(2, 64) PDS_TC_CASE(2, 16)
   PDS_TC_CASE(3, 64) PDS_TC_CASE(3, 16)
 #undef PDS_TC_CASE
-  set_error("conv3x3_tc: no kernel for S=%d N=%d", l.S, l.N);
-  return PDS_ERR_UNSUPPORTED;
+  if (rc != PDS_OK) {
+    if (rc == PDS_ERR_UNSUPPORTED) set_error("conv3x3_tc: no kernel for S=%d N=%d", l.S, l.N);
+    return rc;
+  }
+  // the same normalisation as separate passes (three-term precisions, few slices, PDS_B200_FUSE_NORM=0)
+  const double* stats = a.stats + (size_t)a.n0 * l.N * 2;
+  if (a.norm_mode == TC_NORM_PLAIN)
+    return tc_norm_split(a.out_f32, stats, l.gamma, l.beta, nullptr, a.norm_out, a.n_slices, l.N, a.H, a.W, l.S, l.fp16, st);
+  if (a.norm_mode == TC_NORM_RESIDUAL)
+    return tc_norm_split(a.out_f32, stats, l.gamma, l.beta, a.res_ap, a.norm_out, a.n_slices, l.N, a.H, a.W, l.S, l.fp16, st);
+  if (a.norm_mode == TC_NORM_RESIDUAL_FIRST)
+    return tc_norm_residual_first(a.out_f32, a.stats, l.gamma, l.beta, a.fA, a.fB, a.fQ, a.norm_out,
+                                  a.n_slices / p.n_div, l.N, a.H, a.W, p.n_div, l.S, l.fp16, st);
+  return PDS_OK;
 }
 
 // Right-descriptor maps of the first convolution: map d views the planes with width

@@ -39,6 +39,15 @@ enum TcEpilogue {
   TC_EPI_F32 = 3    // bias -> fp32 planes, no activation, no sums (factorised first convolution)
 };
 
+// InstanceNorm (+ residual) that follows a TC_EPI_ACT convolution, run by tc_conv3x3 either inside
+// the convolution's launch (trailing normalisation warps, conv_tc.cu) or as a separate pass.
+enum TcNorm {
+  TC_NORM_NONE = 0,
+  TC_NORM_PLAIN = 1,           // norm_out = IN(t)
+  TC_NORM_RESIDUAL = 2,        // norm_out = IN(t) + res_ap (planes; norm_out may alias res_ap)
+  TC_NORM_RESIDUAL_FIRST = 3   // norm_out = IN(t) + x0 rebuilt from fA / fB / fQ (matching_first.cuh)
+};
+
 struct TcConvArgs {
   const TcLayer* layer;
   int epilogue;
@@ -62,7 +71,19 @@ struct TcConvArgs {
   // scratch: device array of CUtensorMap (>= 1 + n_div entries, 64-byte aligned) + host staging
   CUtensorMap* maps_dev;
   CUtensorMap* maps_host;
+  // normalisation of this convolution's output with the layer's gamma / beta (TC_EPI_ACT only)
+  int norm_mode;           // TcNorm
+  uint16_t* norm_out;      // operand planes [n][S][N/8][H][W][8]
+  const uint16_t* res_ap;  // TC_NORM_RESIDUAL
+  const float* fA;         // TC_NORM_RESIDUAL_FIRST: per-sample fp32 planes [b][N/4][H][W][4]
+  const float* fB;
+  const float* fQ;
+  int* sched;              // tc_sched_ints(n_slices) ints, ZEROED by the caller on the same stream (or null: separate pass)
 };
+
+// scheduler words a fused convolution + normalisation launch needs for n_slices slices
+size_t tc_sched_ints(int n_slices);
+bool tc_fused_norm_enabled();
 
 size_t tc_conv_max_maps(int n_div);
 
@@ -102,6 +123,14 @@ int tc_column_ops(const float* Bf, const float* Q, const float* wt, float* cols,
 // PA = conv1(A), PB = conv1(Bf) WITHOUT bias
 int tc_compose_second(const float* PA, const float* PB, const float* cols, const float* bias, float* t,
                       double* stats, int B, int C, int H, int W, int D, cudaStream_t st);
+// The same in two passes that never write the fp32 activation: sums only, then the values
+// recomputed, normalised (InstanceNorm affine gamma / beta) and written as split operand planes
+// out_ap [b*D + d][S][C/8][H][W][8] (bit-identical to tc_compose_second + tc_norm_split).
+int tc_compose_second_stats(const float* PA, const float* PB, const float* cols, const float* bias, double* stats,
+                            int B, int C, int H, int W, int D, cudaStream_t st);
+int tc_compose_second_norm(const float* PA, const float* PB, const float* cols, const float* bias,
+                           const double* stats, const float* gamma, const float* beta, uint16_t* out_ap, int B,
+                           int C, int H, int W, int D, int S, int fp16, cudaStream_t st);
 // out_ap[b*D + d] = IN(y) + x0_d with x0_d regenerated from A / Bf / Q
 int tc_norm_residual_first(const float* y, const double* stats, const float* gamma, const float* beta,
                            const float* A, const float* Bf, const float* Q, uint16_t* out_ap, int B, int C, int H,

@@ -19,28 +19,13 @@
 // re-generated on the fly where the residual addition needs it.  All tensors here are fp32 planes
 // [b][C/4][H][W][4]; `cols` is [b][J][H][C] with J = 3 + 2 (D - 1).
 #include "conv_tc.cuh"
+#include "matching_first.cuh"
 #include "tc_ptx.cuh"
 
 namespace pds {
 namespace {
 
 using namespace ptx;
-
-// x0 of slice d at (y, x), channels 8*c8 .. +7 (same arithmetic as tc_compose_first)
-__device__ __forceinline__ void first_x0(const float4* a4, const float4* b4, const float4* q4, size_t HW,
-                                         size_t pix, int x, int W, int d, float (&v)[8]) {
-  const size_t row = pix - x;
-  const float4 lo = __ldg(a4 + pix), hi = __ldg(a4 + HW + pix);
-  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-  auto add = [&](const float4* src, size_t at, float sign) {
-    const float4 l = __ldg(src + at), h = __ldg(src + HW + at);
-    v[0] = fmaf(sign, l.x, v[0]); v[1] = fmaf(sign, l.y, v[1]); v[2] = fmaf(sign, l.z, v[2]); v[3] = fmaf(sign, l.w, v[3]);
-    v[4] = fmaf(sign, h.x, v[4]); v[5] = fmaf(sign, h.y, v[5]); v[6] = fmaf(sign, h.z, v[6]); v[7] = fmaf(sign, h.w, v[7]);
-  };
-  if (x >= d) add(b4, pix - d, 1.f);
-  else if (x == d - 1) add(q4, row, 1.f);
-  if (x == W - 1 && d >= 1 && d <= W) add(q4, row + (W - d), -1.f);
-}
 
 // fp32 planes [n][C/4][HW][4] -> split AP planes [n][S][C/8][HW][8]
 template <bool FP16, int S>
@@ -152,15 +137,22 @@ column_ops_kernel(const float* __restrict__ Bf, const float* __restrict__ Q, con
 // first version re-read both terms from L2 for every slice and ran at half the store bandwidth).
 // InstanceNorm sums: per thread over the R rows, butterfly over the warp (16 shuffles for the 16
 // sums), double atomics in shared memory, one global double atomic per (slice, channel) and CTA.
-template <int R>
+//
+// MODE 0: fp32 planes t + sums (one pass; a separate normalisation pass follows).
+// MODE 1: sums only, nothing is stored.   MODE 2: the same values are recomputed, normalised with
+// the sums of MODE 1 and written straight as split operand planes -- the two-pass form never
+// writes or re-reads the fp32 activation (425 MB each way at 960x540, D = 192): the values cost a
+// few shared-memory reads and adds, far less than the DRAM round trip they replace.
+template <int R, int MODE, bool FP16, int S>
 __global__ void __launch_bounds__(256, 2)
 compose_second_kernel(const float* __restrict__ PA, const float* __restrict__ PB, const float* __restrict__ cols,
-                      const float* __restrict__ bias, float* __restrict__ t, double* __restrict__ stats, int C,
-                      int H, int W, int D) {
+                      const float* __restrict__ bias, float* __restrict__ t, double* stats,
+                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                      uint16_t* __restrict__ out_ap, int C, int H, int W, int D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* sA = reinterpret_cast<float4*>(smem_raw);          // [2][R][W]: channels 0-3 | 4-7
   float4* sB = sA + 2 * R * W;                               // [2][R][W]
-  double* sstat = reinterpret_cast<double*>(sB + 2 * R * W); // [D][16]
+  double* sstat = reinterpret_cast<double*>(sB + 2 * R * W); // [D][16] sums (MODE 2: [D][16] floats scale | shift)
   float4* sC = reinterpret_cast<float4*>(sstat + D * 16);    // [J][R][2]: border-correction columns
   const int c8 = blockIdx.y, b = blockIdx.z, y0 = blockIdx.x * R, nr = min(R, H - y0), J = 3 + 2 * (D - 1);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -172,7 +164,21 @@ compose_second_kernel(const float* __restrict__ PA, const float* __restrict__ PB
       sA[i] = __ldg(a4 + i); sA[R * W + i] = __ldg(a4 + HW + i);
       sB[i] = __ldg(b4 + i); sB[R * W + i] = __ldg(b4 + HW + i);
     }
-    for (int i = tid; i < D * 16; i += 256) sstat[i] = 0.0;
+    if (MODE == 2) {
+      float* sn = reinterpret_cast<float*>(sstat);
+      for (int i = tid; i < D * 8; i += 256) {
+        const int d = i >> 3, e = i & 7, c = c8 * 8 + e;
+        const double s = stats[((size_t)(b * D + d) * C + c) * 2], q = stats[((size_t)(b * D + d) * C + c) * 2 + 1];
+        const double mean = s / (double)HW;
+        double var = q / (double)HW - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float scale = (float)(1.0 / sqrt(var + 1e-5)) * gamma[c];
+        sn[d * 16 + e] = scale;
+        sn[d * 16 + 8 + e] = beta[c] - (float)mean * scale;
+      }
+    } else {
+      for (int i = tid; i < D * 16; i += 256) sstat[i] = 0.0;
+    }
     const float* cb = cols + (size_t)b * J * H * C + 8 * c8;
     for (int i = tid; i < J * R * 2; i += 256) {
       const int h = i & 1, r = (i >> 1) % R, j = (i >> 1) / R;
@@ -184,6 +190,8 @@ compose_second_kernel(const float* __restrict__ PA, const float* __restrict__ PB
 #pragma unroll
   for (int e = 0; e < 8; ++e) b1[e] = __ldg(bias + 8 * c8 + e);
   float4* tb = reinterpret_cast<float4*>(t) + ((size_t)b * D * (C / 4) + 2 * c8) * HW + (size_t)y0 * W;
+  float4* o4 = reinterpret_cast<float4*>(out_ap);
+  const float4* snorm = reinterpret_cast<const float4*>(sstat);
   for (int x0 = 0; x0 < W; x0 += 256) {
     const int x = x0 + tid;
     const bool valid = x < W;
@@ -202,7 +210,13 @@ compose_second_kernel(const float* __restrict__ PA, const float* __restrict__ PB
       const bool shifted = d < W, has_b = valid && shifted && xs >= 0;
       const int jp = !(valid && shifted) ? -1 : (xs == 0 && d >= 1) ? 0 : xs == -1 ? 1 : xs == -2 ? 2 : -1;
       const int jm = !(valid && shifted && d >= 1) ? -1 : x == W - 1 ? 3 + 2 * (d - 1) : x == W - 2 ? 4 + 2 * (d - 1) : -1;
-      float4* o4 = tb + (size_t)d * (C / 4) * HW + x;
+      float4* t4 = tb + (size_t)d * (C / 4) * HW + x;
+      float sc[8], sh[8];
+      if (MODE == 2) {
+        const float4 sc0 = snorm[d * 4], sc1 = snorm[d * 4 + 1], sh0 = snorm[d * 4 + 2], sh1 = snorm[d * 4 + 3];
+        sc[0] = sc0.x; sc[1] = sc0.y; sc[2] = sc0.z; sc[3] = sc0.w; sc[4] = sc1.x; sc[5] = sc1.y; sc[6] = sc1.z; sc[7] = sc1.w;
+        sh[0] = sh0.x; sh[1] = sh0.y; sh[2] = sh0.z; sh[3] = sh0.w; sh[4] = sh1.x; sh[5] = sh1.y; sh[6] = sh1.z; sh[7] = sh1.w;
+      }
       float sum[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) sum[e] = 0.f;
@@ -229,15 +243,32 @@ compose_second_kernel(const float* __restrict__ PA, const float* __restrict__ PB
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           v[e] = fmaxf(v[e], 0.1f * v[e]);       // LeakyReLU(0.1)
-          sum[e] += v[e]; sum[8 + e] = fmaf(v[e], v[e], sum[8 + e]);
+          if (MODE != 2) { sum[e] += v[e]; sum[8 + e] = fmaf(v[e], v[e], sum[8 + e]); }
         }
-        stg_stream(o4 + r * W, make_float4(v[0], v[1], v[2], v[3]));
-        stg_stream(o4 + HW + r * W, make_float4(v[4], v[5], v[6], v[7]));
+        if (MODE == 0) {
+          stg_stream(t4 + r * W, make_float4(v[0], v[1], v[2], v[3]));
+          stg_stream(t4 + HW + r * W, make_float4(v[4], v[5], v[6], v[7]));
+        }
+        if (MODE == 2) {
+          uint16_t tt[8][3];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_terms<FP16>(fmaf(v[e], sc[e], sh[e]), tt[e]);
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            float4 pk;
+            pk.x = __uint_as_float(tt[0][s] | ((uint32_t)tt[1][s] << 16)); pk.y = __uint_as_float(tt[2][s] | ((uint32_t)tt[3][s] << 16));
+            pk.z = __uint_as_float(tt[4][s] | ((uint32_t)tt[5][s] << 16)); pk.w = __uint_as_float(tt[6][s] | ((uint32_t)tt[7][s] << 16));
+            stg_stream(o4 + ((size_t)((b * D + d) * S + s) * (C / 8) + c8) * HW + (size_t)(y0 + r) * W + x, pk);
+          }
+        }
       }
-      const float total = ptx::warp_transpose_reduce<16>(sum, lane);     // lane k (and k + 16): sum k
-      if (lane < 16) atomicAdd(&sstat[d * 16 + lane], (double)total);
+      if (MODE != 2) {
+        const float total = ptx::warp_transpose_reduce<16>(sum, lane);     // lane k (and k + 16): sum k
+        if (lane < 16) atomicAdd(&sstat[d * 16 + lane], (double)total);
+      }
     }
   }
+  if (MODE == 2) return;
   __syncthreads();
   for (int i = tid; i < D * 16; i += 256) {
     const int d = i >> 4, k = i & 15, e = k & 7, which = k >> 3;
@@ -382,10 +413,11 @@ int tc_column_ops(const float* Bf, const float* Q, const float* wt, float* cols,
   return PDS_OK;
 }
 
-int tc_compose_second(const float* PA, const float* PB, const float* cols, const float* bias, float* t,
-                      double* stats, int B, int C, int H, int W, int D, cudaStream_t st) {
-  const size_t HW = (size_t)H * W;
-  if (B == 0 || HW == 0) return PDS_OK;
+namespace {
+template <int MODE, bool FP16, int S>
+int launch_compose_second(const float* PA, const float* PB, const float* cols, const float* bias, float* t,
+                          double* stats, const float* gamma, const float* beta, uint16_t* out_ap, int B, int C,
+                          int H, int W, int D, cudaStream_t st) {
   // rows per CTA: as many as leave two CTAs per SM (wide images fall back to fewer rows)
   auto smem_for = [&](int R) {
     return (size_t)4 * R * W * sizeof(float4) + (size_t)D * 16 * sizeof(double) +
@@ -395,17 +427,49 @@ int tc_compose_second(const float* PA, const float* PB, const float* cols, const
   const size_t smem = smem_for(R);
   if (smem > 200 * 1024) { set_error("tc_compose_second: image too wide (%d)", W); return PDS_ERR_UNSUPPORTED; }
   dim3 grid((unsigned)((H + R - 1) / R), (unsigned)(C / 8), (unsigned)B);
-  PDS_KERNEL("tc_compose_second", st);
-  PDS_KERNEL_WORK(0, (double)B * C * HW * (8.0 + 4.0 * D));
 #define PDS_COMPOSE_CASE(RR) \
   if (R == RR) {  \
-    PDS_CUDA(allow_dynamic_smem(compose_second_kernel<RR>, (int)smem));  \
-    compose_second_kernel<RR><<<grid, 256, smem, st>>>(PA, PB, cols, bias, t, stats, C, H, W, D);  \
+    PDS_CUDA(allow_dynamic_smem(compose_second_kernel<RR, MODE, FP16, S>, (int)smem));  \
+    compose_second_kernel<RR, MODE, FP16, S><<<grid, 256, smem, st>>>(PA, PB, cols, bias, t, stats, gamma, beta, out_ap, C, H, W, D);  \
   }
   PDS_COMPOSE_CASE(4) PDS_COMPOSE_CASE(2) PDS_COMPOSE_CASE(1)
 #undef PDS_COMPOSE_CASE
   PDS_LAUNCH_CHECK("compose_second_kernel");
   return PDS_OK;
+}
+}  // namespace
+
+int tc_compose_second(const float* PA, const float* PB, const float* cols, const float* bias, float* t,
+                      double* stats, int B, int C, int H, int W, int D, cudaStream_t st) {
+  if (B == 0 || (size_t)H * W == 0) return PDS_OK;
+  PDS_KERNEL("tc_compose_second", st);
+  PDS_KERNEL_WORK(0, (double)B * C * H * W * (8.0 + 4.0 * D));
+  return launch_compose_second<0, true, 1>(PA, PB, cols, bias, t, stats, nullptr, nullptr, nullptr, B, C, H, W, D, st);
+}
+
+int tc_compose_second_stats(const float* PA, const float* PB, const float* cols, const float* bias, double* stats,
+                            int B, int C, int H, int W, int D, cudaStream_t st) {
+  if (B == 0 || (size_t)H * W == 0) return PDS_OK;
+  PDS_KERNEL("tc_compose_second[sums]", st);
+  PDS_KERNEL_WORK(0, (double)B * C * H * W * 8.0);
+  return launch_compose_second<1, true, 1>(PA, PB, cols, bias, nullptr, stats, nullptr, nullptr, nullptr, B, C, H, W, D, st);
+}
+
+int tc_compose_second_norm(const float* PA, const float* PB, const float* cols, const float* bias,
+                           const double* stats, const float* gamma, const float* beta, uint16_t* out_ap, int B,
+                           int C, int H, int W, int D, int S, int fp16, cudaStream_t st) {
+  if (B == 0 || (size_t)H * W == 0) return PDS_OK;
+  PDS_KERNEL("tc_compose_second[norm -> planes]", st);
+  PDS_KERNEL_WORK(0, (double)B * C * H * W * (8.0 + 2.0 * S * D));
+  double* sp = const_cast<double*>(stats);
+#define PDS_CSN_CASE(FF, SS) \
+  if ((fp16 != 0) == FF && S == SS) \
+    return launch_compose_second<2, FF, SS>(PA, PB, cols, bias, nullptr, sp, gamma, beta, out_ap, B, C, H, W, D, st);
+  PDS_CSN_CASE(true, 1) PDS_CSN_CASE(true, 2) PDS_CSN_CASE(true, 3)
+  PDS_CSN_CASE(false, 1) PDS_CSN_CASE(false, 2) PDS_CSN_CASE(false, 3)
+#undef PDS_CSN_CASE
+  set_error("tc_compose_second_norm: unsupported split %d", S);
+  return PDS_ERR_UNSUPPORTED;
 }
 
 int tc_norm_residual_first(const float* y, const double* stats, const float* gamma, const float* beta,

@@ -36,6 +36,8 @@ struct pds_matching_op {
   pds::TcLayer second;
   float* wt1 = nullptr;
   int factor2 = 0;
+  int two_pass = 1;                    // tc_compose_second as sums + normalised planes (no fp32 round trip)
+  int fuse_norm = 1;                   // InstanceNorm passes inside the convolution launches (conv_tc.cu, FUSE)
   void* tc_blob = nullptr;
   // tensor maps of the shifted right descriptors, cached per (buffer, shape)
   CUtensorMap* maps_dev = nullptr;
@@ -101,6 +103,8 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
     op->factor = !(getenv("PDS_B200_MATCH_FACTOR") && atoi(getenv("PDS_B200_MATCH_FACTOR")) == 0);
     op->factor2 = op->factor && n_res >= 1 && C == F &&
                   !(getenv("PDS_B200_MATCH_FACTOR2") && atoi(getenv("PDS_B200_MATCH_FACTOR2")) == 0);
+    op->two_pass = !(getenv("PDS_B200_COMPOSE_TWO_PASS") && atoi(getenv("PDS_B200_COMPOSE_TWO_PASS")) == 0);
+    op->fuse_norm = tc_fused_norm_enabled() ? 1 : 0;
     {
       TcLayer& l = op->second;
       l.Cin = F; l.Cout = F; l.N = 64; l.S = op->split; l.fp16 = op->fp16; l.wscale = op->fp16 ? 256.f : 1.f;
@@ -195,7 +199,7 @@ namespace {
 // convolution that writes them and the pass that reads them.
 struct TcPlan {
   int G;
-  size_t lap, rap, xa, t, ya, stats, first, ap2, cols, total;
+  size_t lap, rap, xa, t, ya, stats, sched, first, ap2, cols, total;
 };
 
 TcPlan tc_plan(const pds_matching_op* op, int B, int H, int W, int D) {
@@ -215,10 +219,12 @@ TcPlan tc_plan(const pds_matching_op* op, int B, int H, int W, int D) {
   p.ya = p.xa;
   p.t = align_up((size_t)G * op->F * hw * 4, 256);
   p.stats = align_up(n * op->F * 2 * sizeof(double) * 2 * (op->n_res > 0 ? op->n_res : 1), 256);
+  // scheduler words of the fused convolution + normalisation launches (two per residual block)
+  p.sched = align_up(tc_sched_ints((int)n) * sizeof(int) * 2 * (op->n_res > 0 ? op->n_res : 1), 256);
   p.first = align_up((size_t)B * op->F * hw * 4, 256);     // A, Bf, Q of the factorised first convolution
   p.ap2 = align_up((size_t)2 * B * S * op->F * hw * 2, 256);                         // planes of A and Bf
   p.cols = align_up((size_t)B * tc_column_jobs(D) * H * op->F * 4, 256);             // column corrections
-  p.total = p.lap + p.rap + p.xa + p.t + p.ya + p.stats + 5 * p.first + p.ap2 + p.cols + 1024;
+  p.total = p.lap + p.rap + p.xa + p.t + p.ya + p.stats + p.sched + 5 * p.first + p.ap2 + p.cols + 1024;
   return p;
 }
 
@@ -243,6 +249,7 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
   float* t = (float*)ws.take<char>(pl.t);
   uint16_t* ya = (uint16_t*)ws.take<char>(pl.ya);
   double* stats = (double*)ws.take<char>(pl.stats);
+  int* sched = (int*)ws.take<char>(pl.sched);            // directly behind the sums: one memset clears both
   float* fa = (float*)ws.take<char>(2 * pl.first);    // A then Bf, contiguous (one 2B-slice tensor)
   float* fb = fa + (size_t)B * op->F * H * W;
   float* fq = (float*)ws.take<char>(pl.first);
@@ -251,7 +258,7 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
   float* cols = (float*)ws.take<char>(pl.cols);
   if (ws.overflow) { set_error("pds_matching_op_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
   const size_t stat_elems = (size_t)N * op->F * 2;
-  PDS_CUDA(cudaMemsetAsync(stats, 0, pl.stats, st));
+  PDS_CUDA(cudaMemsetAsync(stats, 0, pl.stats + pl.sched, st));
   int rc;
   if ((rc = tc_pack_nchw(left, lap, B, op->C, H, W, S, fp16, st)) != PDS_OK) return rc;
   if ((rc = tc_pack_nchw(right, rap, B, op->C, H, W, S, fp16, st)) != PDS_OK) return rc;
@@ -308,21 +315,33 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
         f.layer = &op->second; f.in = ap2; f.out_f32 = fp;
         if ((rc = tc_conv3x3(f, st)) != PDS_OK) return rc;
         if ((rc = tc_column_ops(fb, fq, op->wt1, cols, B, op->F, H, W, D, st)) != PDS_OK) return rc;
-        if ((rc = tc_compose_second(fp, fp + (size_t)B * op->F * H * W, cols, c1.bias, t, s1, B, op->F, H, W, D,
-                                    st)) != PDS_OK) return rc;
+        const float* pb = fp + (size_t)B * op->F * H * W;
+        if (op->two_pass) {
+          // sums, then the values recomputed + normalised straight into the operand planes: the
+          // fp32 activation (4 B/element out, 4 B/element back in) never touches memory
+          if ((rc = tc_compose_second_stats(fp, pb, cols, c1.bias, s1, B, op->F, H, W, D, st)) != PDS_OK) return rc;
+          if ((rc = tc_compose_second_norm(fp, pb, cols, c1.bias, s1, c1.gamma, c1.beta, ya, B, op->F, H, W, D, S,
+                                           fp16, st)) != PDS_OK) return rc;
+        } else {
+          if ((rc = tc_compose_second(fp, pb, cols, c1.bias, t, s1, B, op->F, H, W, D, st)) != PDS_OK) return rc;
+          if ((rc = tc_norm_split(t, s1 + soff, c1.gamma, c1.beta, nullptr, ya, g, op->F, H, W, S, fp16, st)) != PDS_OK) return rc;
+        }
       } else {
+        // y = IN(lrelu(conv(x))): the normalisation runs behind the convolution inside its launch
         a.layer = &c1; a.epilogue = TC_EPI_ACT; a.in = xa; a.out_f32 = t; a.stats = s1;
+        a.norm_mode = TC_NORM_PLAIN; a.norm_out = ya; a.res_ap = nullptr;
+        a.sched = (op->fuse_norm && pl.G == N) ? sched + tc_sched_ints(N) * (2 * r) : nullptr;
         if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
       }
-      if ((rc = tc_norm_split(t, s1 + soff, c1.gamma, c1.beta, nullptr, ya, g, op->F, H, W, S, fp16, st)) != PDS_OK) return rc;
+      // x = IN(lrelu(conv(y))) + x (ResidualBlock.forward, network_blocks.py:143-144); block 1's x0 is
+      // rebuilt from the per-sample terms where the factorisation never materialised it
       a.layer = &c2; a.epilogue = TC_EPI_ACT; a.in = ya; a.out_f32 = t; a.stats = s2;
+      a.norm_out = xa;
+      a.sched = (op->fuse_norm && pl.G == N) ? sched + tc_sched_ints(N) * (2 * r + 1) : nullptr;
+      if (r == 0 && second) { a.norm_mode = TC_NORM_RESIDUAL_FIRST; a.fA = fa; a.fB = fb; a.fQ = fq; a.res_ap = nullptr; }
+      else { a.norm_mode = TC_NORM_RESIDUAL; a.res_ap = xa; }
       if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
-      // x = IN(t) + x (ResidualBlock.forward, network_blocks.py:143-144)
-      if (r == 0 && second) {
-        if ((rc = tc_norm_residual_first(t, s2, c2.gamma, c2.beta, fa, fb, fq, xa, B, op->F, H, W, D, S, fp16, st)) != PDS_OK) return rc;
-      } else {   // in place on the planes
-        if ((rc = tc_norm_split(t, s2 + soff, c2.gamma, c2.beta, xa, xa, g, op->F, H, W, S, fp16, st)) != PDS_OK) return rc;
-      }
+      a.norm_mode = TC_NORM_NONE; a.norm_out = nullptr; a.res_ap = nullptr; a.sched = nullptr;
     }
     a.layer = &op->tc.back(); a.epilogue = TC_EPI_SIG; a.in = xa;
     a.out_f32 = nullptr; a.out_ap = nullptr; a.stats = nullptr; a.out_sig = signatures;

@@ -75,3 +75,51 @@ def test_tc_wide_images_use_fewer_rows_per_cta(W):
         out = matching.Matching(2, op)(l, r)
         ref = _reference(l, r, params, 2)
     assert max_abs(out, ref) <= 2e-4
+
+
+@pytest.mark.parametrize('B,H,W,md', [(1, 48, 80, 23), (2, 21, 37, 9), (1, 144, 240, 7), (1, 18, 11, 15)])
+def test_fused_normalisation_matches_the_separate_passes(B, H, W, md, monkeypatch):
+    """Round 2: the InstanceNorm (+ residual) passes run INSIDE the 64->64 convolution launches
+    (trailing normalisation warps, dynamic tile scheduler: csrc/conv_tc.cu FUSE) and
+    tc_compose_second runs as sums + normalised planes.  Both must reproduce the separate-pass
+    pipeline of round 1 (same arithmetic; only the order of the double-precision sum atomics
+    differs) and stay within the fp32-grade bound against the ATen restatement."""
+    params = synth.make_params(synth.matching_operation_specs(), 47)
+    l, r = cuda(synth.tensor((B, 64, H, W), 48)), cuda(synth.tensor((B, 64, H, W), 49))
+    fused = load_module(matching.MatchingOperation(precision='fp16x2'), params)
+    with torch.no_grad():
+        out = matching.Matching(md, fused)(l, r)
+        again = matching.Matching(md, fused)(l, r)
+        ref = _reference(l, r, params, md)
+    monkeypatch.setenv('PDS_B200_FUSE_NORM', '0')
+    monkeypatch.setenv('PDS_B200_COMPOSE_TWO_PASS', '0')
+    separate = load_module(matching.MatchingOperation(precision='fp16x2'), params)   # switches are read at handle creation
+    with torch.no_grad():
+        sep = matching.Matching(md, separate)(l, r)
+    scale = float(ref.abs().max())
+    print(f'fused vs separate: max-abs {max_abs(out, sep):.3e} (run-to-run {max_abs(out, again):.3e}), '
+          f'vs ATen {max_abs(out, ref):.3e}, separate vs ATen {max_abs(sep, ref):.3e}, scale {scale:.2f}')
+    assert max_abs(out, ref) <= 2e-4
+    assert max_abs(out, sep) <= 2e-6 * scale and max_abs(out, again) <= 2e-6 * scale
+
+
+def test_fused_normalisation_on_concurrent_streams():
+    """Fused launches on several streams at once (HostPipeline's serving pattern): tiles and
+    normalisation work items are CLAIMED, never assigned to a CTA that may not be resident, so
+    partially resident grids cannot wait on each other.  Eight forwards on four streams of a
+    96-slice problem; every result must equal the single-stream one."""
+    params = synth.make_params(synth.matching_operation_specs(), 50)
+    op = load_module(matching.MatchingOperation(precision='fp16x2'), params)
+    pairs = [(cuda(synth.tensor((2, 64, 64, 96), 51 + i)), cuda(synth.tensor((2, 64, 64, 96), 61 + i))) for i in range(4)]
+    m = matching.Matching(47, op)
+    with torch.no_grad():
+        expected = [m(l, r) for l, r in pairs]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream() for _ in range(4)]
+        results = []
+        for k in range(8):
+            with torch.cuda.stream(streams[k % 4]):
+                results.append(m(*pairs[k % 4]))
+        torch.cuda.synchronize()
+    for k, out in enumerate(results):
+        assert max_abs(out, expected[k % 4]) <= 1e-5
