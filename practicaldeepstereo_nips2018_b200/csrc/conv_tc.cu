@@ -56,9 +56,19 @@ using namespace ptx;
 
 constexpr int kPH = 18;          // halo rows of a CTA tile (16 + 2)
 constexpr int kThreads = 192;    // TMA producer warp, MMA issuer warp, four epilogue warps
-constexpr int kNormWarps = 4;    // FUSE kernels: warps that normalise finished slices behind the convolution
-constexpr int kFusedThreads = kThreads + 32 * kNormWarps;
-constexpr int kNormPixels = 256; // pixels of one 8-channel group per normalisation work item
+// FUSE kernels: 16 warps (512 threads x 128 registers = the SM's register file)
+//   warp 0 TMA producer, warp 1 MMA issuer, warp 2 progress warp (publishes finished slices)
+//   warps 4-11 eight epilogue warps, two per TMEM lane quarter
+//   warps 3, 12-15 normalisation warps: finished slices are normalised behind the convolution
+// (setmaxnreg was tried to move registers from the control warps to the normalisation warps: ptxas
+// honours it, but with the normalisation code inlined -- a prerequisite -- it spills more than it gains)
+constexpr int kFusedEpilogueWarp0 = 4, kFusedEpilogueWarps = 8;
+constexpr int kProgressWarp = 2;
+constexpr int kNormWarp0 = 12, kNormWarps = 5;      // warp 3 is the fifth
+constexpr int kFusedThreads = 32 * 16;
+constexpr int kNormSliceClasses = 2;   // a normalisation warp serves every second slice
+constexpr int kStatReplicas = 8;       // one private copy of a slice's sums per epilogue warp
+constexpr int kNormPixels = 128;       // pixels of one 8-channel group per normalisation unit
 constexpr int kMaxStages = 6;
 
 struct alignas(64) TcKernelParams {
@@ -80,8 +90,9 @@ struct alignas(64) TcKernelParams {
   float inv_wscale;
   // ---- FUSE kernels: dynamic tile scheduler + trailing InstanceNorm of the launch's own output ----
   // sched[0]: next tile to claim; sched[1 + s]: tiles of local slice s whose output and sums are
-  // stored; sched[1 + n_slices + s]: next normalisation work item of slice s.  Zeroed before the launch.
+  // stored.  Zeroed before the launch.
   int* sched;
+  double* stats_rep;                 // [kStatReplicas][n_slices][N][2] private copies of the sums (zeroed)
   const float* gamma;                // InstanceNorm affine of this block
   const float* beta;
   int norm_mode;                     // TC_NORM_*
@@ -97,105 +108,214 @@ __host__ __device__ constexpr bool tc_flat_rows(int PW) { return 8 * PW <= 256; 
 
 // shared memory after the weight / stage buffers: barriers, TMEM slot, bias; FUSE adds the tile
 // ids in flight and the 1 KB exchange buffer of the cross-warp InstanceNorm sums
-constexpr int kNumBars = 2 * kMaxStages + 5 + 2;
+constexpr int kNumBars = 2 * kMaxStages + 5 + 2 + 4;
 constexpr size_t kTailFixed = 8 * kNumBars + 32 + 64 * sizeof(float);      // barriers | tmem slot | bias
-constexpr size_t kTailFused = 32 + 128 * sizeof(double);                   // tile ids | sums
+constexpr size_t kTailFused = 48;                                          // tile ids in flight | slices to publish
 constexpr size_t tail_bytes(bool fuse) { return kTailFixed + (fuse ? kTailFused : 0) + 128; }
 
 // Bounded spin on a global progress counter (a protocol bug traps after ~4 s instead of hanging).
+#ifndef PDS_FUSE_POLL_NS
+#define PDS_FUSE_POLL_NS 200
+#endif
+// The spin uses RELAXED loads (an acquire load invalidates the SM's whole L1 on every poll) and one
+// acquire fence once the counter has arrived.
 __device__ __forceinline__ void wait_counter(const int* ctr, int target) {
-  if (ld_acquire_gpu(ctr) >= target) return;
-  const unsigned long long t0 = global_ns();
-  uint32_t spins = 0;
-  while (ld_acquire_gpu(ctr) < target) {
-    __nanosleep(200);
-    if ((++spins & 0xff) == 0 && global_ns() - t0 > 4000000000ull) __trap();
+  if (ld_relaxed_gpu(ctr) < target) {
+    const unsigned long long t0 = global_ns();
+    uint32_t spins = 0;
+    while (ld_relaxed_gpu(ctr) < target) {
+      __nanosleep(PDS_FUSE_POLL_NS);
+      if ((++spins & 0xff) == 0 && global_ns() - t0 > 4000000000ull) __trap();
+    }
+  }
+  fence_acq_rel_gpu();
+}
+
+// ---- trailing normalisation (FUSE kernels) ---------------------------------------------------
+// A unit = kNormPixels pixels (two per lane) of one 8-channel group of one slice:
+//   out = IN(t) [+ residual planes | + x0 rebuilt from A / Bf / Q]  ->  split operand planes,
+// the arithmetic of tc_norm_split_kernel / norm_residual_first_kernel (bit-identical results up
+// to the order of the double-precision sum atomics).  fp16 terms only (the default precision).
+// A warp walks a contiguous range of units of one slice with the loads of unit u + 1 in flight
+// while unit u is converted (the warps live on memory-level parallelism: ~1 us to L2 and back).
+// The code is kept small and scalar: it shares the 128 registers per thread of a 512-thread CTA.
+
+// InstanceNorm scale / shift of eight channels from the slice's sums (the kStatReplicas private
+// copies the epilogue warps add into are summed here, in a fixed order).
+__device__ __noinline__ void norm_coefficients(const TcKernelParams& p, int nl, int c8, int lane, float (&a)[8],
+                                               float (&b)[8]) {
+  constexpr int C = 64;
+  const size_t HW = (size_t)p.H * p.W;
+  const int c = c8 * 8 + (lane & 7);
+  const double* st = p.stats_rep + ((size_t)nl * C + c) * 2;
+  const size_t rep = (size_t)p.n_slices * C * 2;
+  double s = 0.0, q = 0.0;
+#pragma unroll
+  for (int r = 0; r < kStatReplicas; ++r) { s += __ldcg(st + r * rep); q += __ldcg(st + r * rep + 1); }
+  const double mean = s / (double)HW;
+  double var = q / (double)HW - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float scale = (float)(1.0 / sqrt(var + 1e-5)) * __ldg(p.gamma + c);
+  const float shift = __ldg(p.beta + c) - (float)mean * scale;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = __shfl_sync(0xffffffffu, scale, e); b[e] = __shfl_sync(0xffffffffu, shift, e); }
+}
+
+// v (8 channels of one pixel, normalised [+ residual]) -> S operand planes
+template <int S>
+__device__ __forceinline__ void norm_emit(uint4* o, size_t term, const float (&v)[8]) {
+  uint16_t t[8][3];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) split_terms<true>(v[e], t[e]);
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    uint4 pk;
+    pk.x = t[0][s] | ((uint32_t)t[1][s] << 16); pk.y = t[2][s] | ((uint32_t)t[3][s] << 16);
+    pk.z = t[4][s] | ((uint32_t)t[5][s] << 16); pk.w = t[6][s] | ((uint32_t)t[7][s] << 16);
+    __stcg(o + (size_t)s * term, pk);
   }
 }
 
-// One normalisation work item: kNormPixels pixels of one 8-channel group of one slice.
-//   out = IN(t) [+ residual planes | + x0 rebuilt from A / Bf / Q]  ->  split operand planes.
-// Same arithmetic as tc_norm_split_kernel / norm_residual_first_kernel (bit-identical results).
-// fp16 terms only (the default precision); ONE out-of-line instance per S with a run-time mode:
-// inlining the variants into the convolution kernel cost its epilogue registers.
-template <int S>
-__device__ __noinline__ void norm_work_item(const TcKernelParams& p, int nl, int c8, int pb, int lane) {
-  constexpr int C = 64, U = 4;
-  const size_t HW = (size_t)p.H * p.W;
-  const int ng = p.n0 + nl;
-  const int mode = p.norm_mode;
+template <int S, bool RES>
+struct NormPixel {
+  float4 lo, hi;
+  uint4 rr[RES ? S : 1];
+};
+
+// TC_NORM_PLAIN / TC_NORM_RESIDUAL: units [u0, u1) of slice nl; unit = c8 * blocks + pixel block of
+// kNormPixels pixels; a lane owns SUB x U pixels of it, U at a time, the next U in flight
+template <int S, bool RES, int U>
+__device__ __noinline__ void norm_range_planes(const TcKernelParams& p, int nl, int u0, int u1, int blocks, int lane) {
+  constexpr int C = 64, SUB = kNormPixels / (32 * U);
+  const size_t HW = (size_t)p.H * p.W, term = (size_t)(C / 8) * HW;
+  const float4* ybase = reinterpret_cast<const float4*>(p.out_f32) + (size_t)nl * (C / 4) * HW;
+  const uint4* rbase = reinterpret_cast<const uint4*>(p.res_ap) + (size_t)nl * S * term;
+  uint4* obase = reinterpret_cast<uint4*>(p.norm_out) + (size_t)nl * S * term;
   float a[8], b[8];
-  {
-    const int c = c8 * 8 + (lane & 7);
-    const double s = __ldcg(p.stats + ((size_t)ng * C + c) * 2), q = __ldcg(p.stats + ((size_t)ng * C + c) * 2 + 1);
-    const double mean = s / (double)HW;
-    double var = q / (double)HW - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float scale = (float)(1.0 / sqrt(var + 1e-5)) * __ldg(p.gamma + c);
-    const float shift = __ldg(p.beta + c) - (float)mean * scale;
+  int cur = -1;
+  NormPixel<S, RES> nx[U];      // the sub-unit in flight
+  auto issue = [&](int sub) {   // sub-unit index = unit * SUB + part
+    const int unit = sub / SUB, part = sub - unit * SUB;
+    const int c8 = unit / blocks, pb = unit - c8 * blocks;
+    const size_t pix = (size_t)pb * kNormPixels + part * (32 * U) + lane;
+    const float4* y4 = ybase + (size_t)(2 * c8) * HW;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { a[e] = __shfl_sync(0xffffffffu, scale, e); b[e] = __shfl_sync(0xffffffffu, shift, e); }
-  }
-  const float4* y4 = reinterpret_cast<const float4*>(p.out_f32) + ((size_t)nl * (C / 4) + 2 * c8) * HW;
-  const uint4* r4 = reinterpret_cast<const uint4*>(p.res_ap) + ((size_t)nl * S * (C / 8) + c8) * HW;
-  uint4* o4 = reinterpret_cast<uint4*>(p.norm_out) + ((size_t)nl * S * (C / 8) + c8) * HW;
-  const size_t term = (size_t)(C / 8) * HW;          // distance between the terms of one slice
-  const int bs = ng / p.n_div, d = ng - bs * p.n_div;
-  const size_t fbase = ((size_t)bs * (C / 4) + 2 * c8) * HW;
-  const size_t p_begin = (size_t)pb * kNormPixels;
+    for (int k = 0; k < U; ++k) {
+      if (pix + 32 * k < HW) {   // written by other SMs during this launch: L2 loads, never .nc / L1
+        nx[k].lo = __ldcg(y4 + pix + 32 * k); nx[k].hi = __ldcg(y4 + HW + pix + 32 * k);
+        if (RES) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) nx[k].rr[s] = __ldcg(rbase + (size_t)s * term + (size_t)c8 * HW + pix + 32 * k);
+        }
+      }
+    }
+  };
+  auto convert = [&](const NormPixel<S, RES>& f, uint4* o) {
+    float v[8] = {f.lo.x, f.lo.y, f.lo.z, f.lo.w, f.hi.x, f.hi.y, f.hi.z, f.hi.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], a[e], b[e]);
+    if (RES) {
+      float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int s = S - 1; s >= 0; --s) {   // smallest term first
+        const uint32_t w[4] = {f.rr[s].x, f.rr[s].y, f.rr[s].z, f.rr[s].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) res[e] += term_value<true>((uint16_t)(w[e >> 1] >> (16 * (e & 1))));
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += res[e];
+    }
+    norm_emit<S>(o, term, v);
+  };
+  const int s0 = u0 * SUB, s1 = u1 * SUB;
+  issue(s0);
 #pragma unroll 1
-  for (int it = 0; it < kNormPixels / (32 * U); ++it) {
-    const size_t pix0 = p_begin + (size_t)it * (32 * U) + lane;
-    float4 lo[U], hi[U];
-    uint4 rr[U][S];
+  for (int sub = s0; sub < s1; ++sub) {
+    NormPixel<S, RES> c[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t pix = pix0 + 32 * u;
+    for (int k = 0; k < U; ++k) c[k] = nx[k];
+    if (sub + 1 < s1) issue(sub + 1);
+    const int unit = sub / SUB, part = sub - unit * SUB;
+    const int c8 = unit / blocks, pb = unit - c8 * blocks;
+    if (c8 != cur) { norm_coefficients(p, nl, c8, lane, a, b); cur = c8; }
+    const size_t pix = (size_t)pb * kNormPixels + part * (32 * U) + lane;
+    uint4* o = obase + (size_t)c8 * HW + pix;
+#pragma unroll
+    for (int k = 0; k < U; ++k)
+      if (pix + 32 * k < HW) convert(c[k], o + 32 * k);
+  }
+}
+
+// TC_NORM_RESIDUAL_FIRST: x0_d = A + shift_d(B~) - [x = W-1, d >= 1] Q[W-d] (matching_first.cuh) is rebuilt
+// per pixel; A and B~ are fetched with the activation, the Q column of the last image column on demand
+template <int S>
+__device__ __noinline__ void norm_range_first(const TcKernelParams& p, int nl, int u0, int u1, int blocks, int lane) {
+  constexpr int C = 64;
+  const size_t HW = (size_t)p.H * p.W, term = (size_t)(C / 8) * HW;
+  const int ng = p.n0 + nl, bs = ng / p.n_div, d = ng - bs * p.n_div, W = p.W;
+  const float4* ybase = reinterpret_cast<const float4*>(p.out_f32) + (size_t)nl * (C / 4) * HW;
+  uint4* obase = reinterpret_cast<uint4*>(p.norm_out) + (size_t)nl * S * term;
+  const size_t fb = (size_t)bs * (C / 4) * HW;
+  float a[8], b[8];
+  int cur = -1;
+#pragma unroll 1
+  for (int sub = u0 * (kNormPixels / 64); sub < u1 * (kNormPixels / 64); ++sub) {   // 64 pixels (two per lane) at a time
+    const int u = sub / (kNormPixels / 64), part = sub - u * (kNormPixels / 64);
+    const int c8 = u / blocks, pb = u - c8 * blocks;
+    const size_t plane = (size_t)(2 * c8) * HW;
+    const float4* y4 = ybase + plane;
+    const float4* fa4 = reinterpret_cast<const float4*>(p.fA) + fb + plane;
+    const float4* fb4 = reinterpret_cast<const float4*>(p.fB) + fb + plane;
+    const float4* fq4 = reinterpret_cast<const float4*>(p.fQ) + fb + plane;
+    float4 lo[2], hi[2], xa[2][4];
+    int xc[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const size_t pix = (size_t)pb * kNormPixels + part * 64 + lane + 32 * k;
       if (pix < HW) {
-        lo[u] = __ldcg(y4 + pix);            // written by other SMs during this launch: L2, never .nc / L1
-        hi[u] = __ldcg(y4 + HW + pix);
-        if (mode == TC_NORM_RESIDUAL) {
-#pragma unroll
-          for (int s = 0; s < S; ++s) rr[u][s] = __ldcg(r4 + s * term + pix);
+        lo[k] = __ldcg(y4 + pix); hi[k] = __ldcg(y4 + HW + pix);
+        const int x = (int)(pix % (size_t)W);
+        xc[k] = x;
+        xa[k][0] = __ldg(fa4 + pix); xa[k][1] = __ldg(fa4 + HW + pix);
+        if (x >= d || x == d - 1) {
+          const float4* src = x >= d ? fb4 + (pix - d) : fq4 + (pix - x);
+          xa[k][2] = __ldg(src); xa[k][3] = __ldg(src + HW);
         }
       }
     }
+    if (c8 != cur) { norm_coefficients(p, nl, c8, lane, a, b); cur = c8; }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t pix = pix0 + 32 * u;
+    for (int k = 0; k < 2; ++k) {
+      const size_t pix = (size_t)pb * kNormPixels + part * 64 + lane + 32 * k;
       if (pix >= HW) continue;
-      float v[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
+      const int x = xc[k];
+      // same operation order as first_x0: A, then + B~, then - Q at the last column
+      float x0v[8] = {xa[k][0].x, xa[k][0].y, xa[k][0].z, xa[k][0].w, xa[k][1].x, xa[k][1].y, xa[k][1].z, xa[k][1].w};
+      if (x >= d || x == d - 1) {
+        const float t2[8] = {xa[k][2].x, xa[k][2].y, xa[k][2].z, xa[k][2].w, xa[k][3].x, xa[k][3].y, xa[k][3].z, xa[k][3].w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], a[e], b[e]);
-      if (mode == TC_NORM_RESIDUAL) {
-        float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int s = S - 1; s >= 0; --s) {   // smallest term first
-          const uint32_t w[4] = {rr[u][s].x, rr[u][s].y, rr[u][s].z, rr[u][s].w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) res[e] += term_value<true>((uint16_t)(w[e >> 1] >> (16 * (e & 1))));
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += res[e];
-      } else if (mode == TC_NORM_RESIDUAL_FIRST) {
-        float x0v[8];
-        first_x0(reinterpret_cast<const float4*>(p.fA) + fbase, reinterpret_cast<const float4*>(p.fB) + fbase,
-                 reinterpret_cast<const float4*>(p.fQ) + fbase, HW, pix, (int)(pix % (size_t)p.W), p.W, d, x0v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += x0v[e];
+        for (int e = 0; e < 8; ++e) x0v[e] = fmaf(1.f, t2[e], x0v[e]);
       }
-      uint16_t t[8][3];
+      if (x == W - 1 && d >= 1 && d <= W) {
+        const float4 l = __ldg(fq4 + (pix - x) + (W - d)), h = __ldg(fq4 + HW + (pix - x) + (W - d));
+        const float t3[8] = {l.x, l.y, l.z, l.w, h.x, h.y, h.z, h.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) split_terms<true>(v[e], t[e]);
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        uint4 pk;
-        pk.x = t[0][s] | ((uint32_t)t[1][s] << 16); pk.y = t[2][s] | ((uint32_t)t[3][s] << 16);
-        pk.z = t[4][s] | ((uint32_t)t[5][s] << 16); pk.w = t[6][s] | ((uint32_t)t[7][s] << 16);
-        __stcg(o4 + s * term + pix, pk);
+        for (int e = 0; e < 8; ++e) x0v[e] = fmaf(-1.f, t3[e], x0v[e]);
       }
+      float v[8] = {lo[k].x, lo[k].y, lo[k].z, lo[k].w, hi[k].x, hi[k].y, hi[k].z, hi[k].w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], a[e], b[e]) + x0v[e];
+      norm_emit<S>(obase + (size_t)c8 * HW + pix, term, v);
     }
   }
+}
+
+template <int S>
+__device__ __forceinline__ void norm_range(const TcKernelParams& p, int nl, int u0, int u1, int blocks, int lane) {
+  if (u0 >= u1) return;
+  if (p.norm_mode == TC_NORM_PLAIN) norm_range_planes<S, false, 4>(p, nl, u0, u1, blocks, lane);
+  else if (p.norm_mode == TC_NORM_RESIDUAL) norm_range_planes<S, true, 2>(p, nl, u0, u1, blocks, lane);
+  else norm_range_first<S>(p, nl, u0, u1, blocks, lane);
 }
 
 // S terms, NT MMA tiles per CTA tile, N rows per weight term, WRES: weights resident, FUSE: dynamic
@@ -211,7 +331,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
   constexpr int NBUF = 2 * BUF_COLS <= 512 ? 2 : 1;
   constexpr uint32_t TMEM_COLS = pow2_cols(NBUF * BUF_COLS);
   static_assert(BUF_COLS <= 512, "accumulators do not fit TMEM");
-  static_assert(!FUSE || N == 64, "the fused normalisation handles 64 output channels");
+  static_assert(!FUSE || (N == 64 && NT % 2 == 0), "the fused normalisation handles 64 output channels, two epilogue warps per lane quarter");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -225,17 +345,22 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
   const uint32_t wfull_bar = bar_base + 8u * (2 * kMaxStages + 4);
   auto tid_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 5 + a); };
+  auto sig_full_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 7 + a); };
+  auto sig_empty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 9 + a); };
   unsigned char* tail = smem + p.wres_bytes + (size_t)p.stages * p.stage_bytes + 8 * kNumBars;
   uint32_t* tmem_slot = (uint32_t*)(tail + 8);
   float* sbias = (float*)(tail + 32);
   volatile int* stage_tile = (volatile int*)(tail + 32 + 64 * sizeof(float));   // [kMaxStages] tile id carried by a stage
   volatile int* acc_tile = stage_tile + kMaxStages;                            // [2] tile id of an accumulator buffer
-  double* sred = (double*)(tail + 32 + 64 * sizeof(float) + 32);               // [128] sums of the tile in flight
+  volatile int* sig_slice = acc_tile + 2;                                      // [2] slice whose tile has just been stored
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); mbar_init(tid_bar(a), 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), FUSE ? 32 * kFusedEpilogueWarps : 128); mbar_init(tid_bar(a), 1);
+      mbar_init(sig_full_bar(a), kFusedEpilogueWarps); mbar_init(sig_empty_bar(a), 1);
+    }
     mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     pdl_trigger();
@@ -246,7 +371,6 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
     }
   }
   for (int i = threadIdx.x; i < N; i += blockDim.x) sbias[i] = p.bias[i];
-  if (FUSE && threadIdx.x < 128) sred[threadIdx.x] = 0.0;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -363,8 +487,8 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
         if (NBUF == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
       }
     }
-  } else if (warp < 6) {
-    // ===== epilogue warps (2..5): TMEM lanes 32*(warp%4) .. +31 =====
+  } else if (!FUSE) {
+    // ===== epilogue warps (2..5), static schedule: TMEM lanes 32*(warp%4) .. +31 =====
     const int q = warp & 3;
     const int row = 32 * q + lane;
     const int px = row & 7, py = row >> 3;
@@ -381,19 +505,12 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
       }
       sa0 = sa1 = sb0 = sb1 = 0.0;
     };
-    for (int tile_seq = tile_begin; FUSE || tile_seq < tile_end; ++tile_seq) {
-      int tile = tile_seq;
-      if (FUSE) {
-        mbar_wait(tid_bar(acc), acc_phase);
-        tile = acc_tile[acc];
-        if (tile < 0) break;
-      }
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int nl = tile / tiles_per_slice, r = tile - nl * tiles_per_slice;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       const int y = ty * 16 + py;
       const int ng = p.n0 + nl;
-      if (!FUSE && p.epilogue == TC_EPI_ACT && ng != stat_slice) { flush_stats(); stat_slice = ng; }
-      double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;    // FUSE: this tile's sums (channels lane, 32 + lane)
+      if (p.epilogue == TC_EPI_ACT && ng != stat_slice) { flush_stats(); stat_slice = ng; }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BUF_COLS;
@@ -473,12 +590,8 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
             }
             const float s1 = warp_transpose_reduce(v, lane);
             const float s2 = warp_transpose_reduce(sq, lane);
-            if (FUSE) {
-              if (col0 == 0) { m0 += (double)s1; m1 += (double)s2; } else { m2 += (double)s1; m3 += (double)s2; }
-            } else {
-              if (col0 == 0) { sa0 += (double)s1; sa1 += (double)s2; }
-              else { sb0 += (double)s1; sb1 += (double)s2; }
-            }
+            if (col0 == 0) { sa0 += (double)s1; sa1 += (double)s2; }
+            else { sb0 += (double)s1; sb1 += (double)s2; }
           }
         }
         }
@@ -486,46 +599,141 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (NBUF == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
-      if (FUSE) {
-        // sums of the four epilogue warps combined in 1 KB of shared memory (double atomics, four
-        // contributions per address), ONE global double atomic per (channel, moment) and tile; then
-        // the slice's progress counter moves.  The barriers order every epilogue thread's stores of
-        // this tile before the releasing increment (the grid-sync idiom: barrier, then one thread
-        // fences at gpu scope and signals).
-        atomicAdd(&sred[2 * lane], m0); atomicAdd(&sred[2 * lane + 1], m1);
-        atomicAdd(&sred[64 + 2 * lane], m2); atomicAdd(&sred[64 + 2 * lane + 1], m3);
-        named_barrier(1, 128);
-        if (q == 0) {
-          m0 = sred[2 * lane]; m1 = sred[2 * lane + 1]; m2 = sred[64 + 2 * lane]; m3 = sred[64 + 2 * lane + 1];
-          sred[2 * lane] = 0.0; sred[2 * lane + 1] = 0.0; sred[64 + 2 * lane] = 0.0; sred[64 + 2 * lane + 1] = 0.0;
+    }
+    if (p.epilogue == TC_EPI_ACT) flush_stats();
+  } else if (warp >= kFusedEpilogueWarp0 && warp < kNormWarp0) {
+    // ===== FUSE epilogue warps (4..11): two per TMEM lane quarter (lanes 32*(warp%4) .. +31), each takes
+    // half of the CTA tile's MMA tiles; 16 output channels at a time (the 512-thread CTA leaves 128
+    // registers per thread).  Every tile: bias, LeakyReLU, fp32 store, the tile's InstanceNorm sums as
+    // fire-and-forget double atomics into this warp's PRIVATE copy of the slice's sums (no two warps of
+    // a CTA share an address), then the slice id goes to the progress warp. =====
+    const int q = warp & 3, half = (warp - kFusedEpilogueWarp0) >> 2;
+    const int row = 32 * q + lane;
+    const int px = row & 7, py = row >> 3;
+    const size_t HW = (size_t)p.H * p.W;
+    uint32_t acc = 0, acc_phase = 0, sig = 0, sig_phase = 0;
+    double* my_stats = p.stats_rep + (size_t)(warp - kFusedEpilogueWarp0) * p.n_slices * N * 2;
+    for (;;) {
+      mbar_wait(tid_bar(acc), acc_phase);
+      const int tile = acc_tile[acc];
+      if (tile < 0) break;
+      const int nl = tile / tiles_per_slice, r = tile - nl * tiles_per_slice;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int y = ty * 16 + py;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BUF_COLS;
+      // after the transposed reduction lane l holds sum(x) of channel 16 j + l (l < 16) or sum(x^2) of
+      // channel 16 j + l - 16 (l >= 16)
+      float ssum[N / 16];
+#pragma unroll
+      for (int j = 0; j < N / 16; ++j) ssum[j] = 0.f;
+#pragma unroll 1
+      for (int i = half * (NT / 2); i < (half + 1) * (NT / 2); ++i) {
+        const int x = tx * 8 * NT + 8 * i + px;
+        const bool valid = (x < p.W) && (y < p.H);
+        const size_t pix = (size_t)y * p.W + x;
+#pragma unroll
+        for (int jc = 0; jc < N / 16; ++jc) {
+          const int col0 = 16 * jc;
+          float v[32];                                                   // [0, 16): values, [16, 32): their squares
+          {
+            float lo16[16];
+            tmem_ld<16>(t_base + i * ACC_COLS + (S - 1) * N + col0, lo16);   // smallest terms first
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = lo16[j];
+          }
+#pragma unroll
+          for (int s = S - 2; s >= 0; --s) {
+            float u[16];
+            tmem_ld<16>(t_base + i * ACC_COLS + s * N + col0, u);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += u[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float t = fmaf(v[j], p.inv_wscale, sbias[col0 + j]);
+            v[j] = t > 0.f ? t : 0.1f * t;
+          }
+          if (valid) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32) + ((size_t)nl * (N / 4) + col0 / 4) * HW + pix;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              o[(size_t)k * HW] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (!valid) v[j] = 0.f;
+            v[16 + j] = v[j] * v[j];
+          }
+          const float part = warp_transpose_reduce(v, lane);     // 32 pixels, as the static kernel sums them
+          ssum[jc] = (NT / 2 == 1) ? part : ssum[jc] + part;
         }
-        named_barrier(1, 128);                     // the buffer is zero again before anyone adds the next tile
-        if (q == 0) {
-          double* dst = p.stats + ((size_t)ng * N + lane) * 2;
-          atomicAdd(dst, m0); atomicAdd(dst + 1, m1);
-          atomicAdd(dst + 64, m2); atomicAdd(dst + 65, m3);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (NBUF == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
+#ifndef PDS_FUSE_DEBUG_NO_STATS
+      {
+        double* dst = my_stats + ((size_t)nl * N + (lane & 15)) * 2 + (lane >> 4);
+#pragma unroll
+        for (int j = 0; j < N / 16; ++j) atomicAdd(dst + 32 * j, (double)ssum[j]);
+        // the progress warp fences at gpu scope and bumps the slice's counter: no epilogue warp ever
+        // waits for its own stores to be acknowledged (nothing to publish when the normalisation runs
+        // as separate passes after this launch)
+        if (p.norm_mode != TC_NORM_NONE) {
+          if (lane == 0) mbar_wait(sig_empty_bar(sig), sig_phase ^ 1);
+          if (warp == kFusedEpilogueWarp0 && lane == 0) sig_slice[sig] = nl;
           __syncwarp();
-          if (lane == 0) { __threadfence(); red_release_gpu_add(p.sched + 1 + nl, 1); }
+          if (lane == 0) mbar_arrive(sig_full_bar(sig));     // release: orders this warp's stores and atomics before it
+          sig ^= 1; if (sig == 0) sig_phase ^= 1;
         }
       }
+#endif
     }
-    if (!FUSE && p.epilogue == TC_EPI_ACT) flush_stats();
-  } else if (FUSE) {
-    // ===== normalisation warps (6..9): slices whose last tile has retired, in slice order =====
-    const int groups = N / 8;
-    const int blocks = (int)(((size_t)p.H * p.W + kNormPixels - 1) / kNormPixels);
-    const int items = blocks * groups;
-    for (int nl = 0; nl < p.n_slices; ++nl) {
-      wait_counter(p.sched + 1 + nl, tiles_per_slice);
+#ifndef PDS_FUSE_DEBUG_NO_STATS
+    // end marker for the progress warp
+    if (p.norm_mode != TC_NORM_NONE) {
+      if (lane == 0) mbar_wait(sig_empty_bar(sig), sig_phase ^ 1);
+      if (warp == kFusedEpilogueWarp0 && lane == 0) sig_slice[sig] = -1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sig_full_bar(sig));
+    }
+#endif
+  } else if (warp == kProgressWarp) {
+    // ===== progress warp: publishes finished tiles.  The epilogue warps arrive (release) on sig_full
+    // after a tile's stores and sum atomics; one thread here acquires, fences at gpu scope (cumulative
+    // over what it has observed: the grid-sync idiom) and moves the slice's counter. =====
+#ifndef PDS_FUSE_DEBUG_NO_STATS
+    if (lane == 0 && p.norm_mode != TC_NORM_NONE) {
+      uint32_t sig = 0, sig_phase = 0;
       for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(p.sched + 1 + p.n_slices + nl, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= items) break;
-        const int c8 = item % groups, pb = item / groups;
-        norm_work_item<S>(p, nl, c8, pb, lane);
+        mbar_wait(sig_full_bar(sig), sig_phase);
+        const int nl = sig_slice[sig];
+        mbar_arrive(sig_empty_bar(sig));
+        if (nl < 0) break;
+        __threadfence();
+        red_release_gpu_add(p.sched + 1 + nl, 1);
+        sig ^= 1; if (sig == 0) sig_phase ^= 1;
       }
     }
+#endif
+  } else if (warp >= kNormWarp0 || warp == 3) {
+    // ===== normalisation warps: slice classes in order, a fixed share of every slice's units.  Nothing
+    // here waits on a CTA that may not be resident: a slice's counter depends only on tiles, and tiles
+    // are claimed by whoever runs. =====
+#ifndef PDS_FUSE_DEBUG_NO_NORM_WARPS
+    const int g = (int)blockIdx.x * kNormWarps + (warp == 3 ? 0 : warp - kNormWarp0 + 1), G = (int)gridDim.x * kNormWarps;
+    const int cls = g % kNormSliceClasses, idx = g / kNormSliceClasses;
+    const int cnt = (G - cls + kNormSliceClasses - 1) / kNormSliceClasses;       // warps of this class
+    const int blocks = (int)(((size_t)p.H * p.W + kNormPixels - 1) / kNormPixels);
+    const long long units = (long long)blocks * (N / 8);
+    const int u0 = (int)(units * idx / cnt), u1 = (int)(units * (idx + 1) / cnt);
+    for (int nl = cls; nl < (p.norm_mode != TC_NORM_NONE ? p.n_slices : 0); nl += kNormSliceClasses) {
+      wait_counter(p.sched + 1 + nl, tiles_per_slice);
+      norm_range<S>(p, nl, u0, u1, blocks, lane);
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -657,7 +865,7 @@ __device__ __forceinline__ void stg_stream_u4(uint4* p, const uint4& v) {
 
 template <bool FP16, int S, bool RES>
 __global__ void __launch_bounds__(256, 3)
-tc_norm_split_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+tc_norm_split_kernel(const float* __restrict__ y, const double* __restrict__ stats, int n_rep, size_t rep_stride,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      const uint16_t* res_ap, uint16_t* out_ap, int C, size_t HW) {
   constexpr int U = 2;   // pixels per thread per iteration
@@ -667,7 +875,11 @@ tc_norm_split_kernel(const float* __restrict__ y, const double* __restrict__ sta
   pdl_wait();
   if (threadIdx.x < 8) {
     const int c = c8 * 8 + threadIdx.x;
-    const double s = stats[((size_t)n * C + c) * 2], q = stats[((size_t)n * C + c) * 2 + 1];
+    double s = 0.0, q = 0.0;     // n_rep private copies of the sums (one per epilogue warp of the dynamic kernel)
+    for (int r = 0; r < n_rep; ++r) {
+      s += stats[r * rep_stride + ((size_t)n * C + c) * 2];
+      q += stats[r * rep_stride + ((size_t)n * C + c) * 2 + 1];
+    }
     const double mean = s / (double)HW;
     double var = q / (double)HW - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -804,15 +1016,16 @@ int launch_tc(TcKernelParams& p, cudaStream_t st) {
   const int total = p.tiles_x * p.tiles_y * p.n_slices;
   const int grid = total < num_sms() ? total : num_sms();
   static const std::string base = "conv3x3_tc<S=" + std::to_string(S) + ",NT=" + std::to_string(NT) +
-                                  ",N=" + std::to_string(N) + (WRES ? ",Wres" : ",Wstream") + (FUSE ? ",+IN>" : ">");
+                                  ",N=" + std::to_string(N) + (WRES ? ",Wres" : ",Wstream") + (FUSE ? ",dyn>" : ">");
   // PDS_B200_PROFILE_DETAIL=1: one profiler class per epilogue variant and slice count
   static const bool detail = getenv("PDS_B200_PROFILE_DETAIL") && atoi(getenv("PDS_B200_PROFILE_DETAIL"));
-  static std::string names[8][2];
+  static std::string names[8][2][2];
   const bool per_sample = p.n_div == 1 && !p.in_global;     // descriptor-level launch (not one slice per disparity)
-  std::string& nm = names[p.epilogue & 7][per_sample ? 0 : 1];
+  const bool with_norm = FUSE && p.norm_mode != TC_NORM_NONE;
+  std::string& nm = names[p.epilogue & 7][per_sample ? 0 : 1][with_norm ? 1 : 0];
   if (nm.empty())
     nm = base + (detail ? "[epi " + std::to_string(p.epilogue) + (per_sample ? ", per sample]" : ", all slices]")
-                        : (per_sample ? "[per sample]" : ""));
+                        : (per_sample ? "[per sample]" : "")) + (with_norm ? "[+IN in the launch]" : "");
   PDS_KERNEL(nm.c_str(), st);
   {
     // reference FLOPs of the layer (real Cout, all Cin); bytes: AP terms in (both inputs), output as written
@@ -820,7 +1033,7 @@ int launch_tc(TcKernelParams& p, cudaStream_t st) {
     // of the fp32 activation, which is consumed from L2)
     const double px = (double)p.H * p.W * p.n_slices;
     double out_b = p.epilogue == TC_EPI_SIG ? 4.0 * p.Cout : (p.epilogue == TC_EPI_PLAIN ? 2.0 * S * N : 4.0 * N);
-    if (FUSE) out_b = 2.0 * S * N * (p.norm_mode == TC_NORM_RESIDUAL ? 2.0 : 1.0);
+    if (with_norm) out_b = 2.0 * S * N * (p.norm_mode == TC_NORM_RESIDUAL ? 2.0 : 1.0);
     PDS_KERNEL_WORK(2.0 * 9 * 16 * p.nchunks * p.Cout * px, px * out_b + (p.in_global ? 0.0 : px * 2.0 * S * 16 * p.nchunks));
   }
   PDS_CUDA(launch_pdl(conv3x3_tc_kernel<S, NT, N, WRES, FUSE>, dim3(grid), dim3(FUSE ? kFusedThreads : kThreads), smem,
@@ -888,7 +1101,7 @@ int tc_pack_nchw(const float* in, uint16_t* ap, int B, int C, int H, int W, int 
 
 int tc_norm_split(const float* y, const double* stats, const float* gamma, const float* beta,
                   const uint16_t* res_ap, uint16_t* out_ap, int n_slices, int C, int H, int W, int S,
-                  int fp16, cudaStream_t st) {
+                  int fp16, cudaStream_t st, int n_rep, size_t rep_stride) {
   const size_t HW = (size_t)H * W;
   if (n_slices == 0 || HW == 0) return PDS_OK;
   // two pixels per thread per iteration; several iterations per CTA amortise its prologue (the
@@ -904,8 +1117,8 @@ int tc_norm_split(const float* y, const double* stats, const float* gamma, const
   PDS_KERNEL_WORK(0, (double)n_slices * C * HW * (4 + 2 * S + (res_ap ? 2 * S : 0)));
 #define PDS_NORM_CASE(FF, SS)                                                                              \
   if ((fp16 != 0) == FF && S == SS) {                                                                      \
-    if (res_ap) PDS_CUDA(launch_pdl(tc_norm_split_kernel<FF, SS, true>, grid, dim3(256), 0, st, y, stats, gamma, beta, res_ap, out_ap, C, HW)); \
-    else PDS_CUDA(launch_pdl(tc_norm_split_kernel<FF, SS, false>, grid, dim3(256), 0, st, y, stats, gamma, beta, res_ap, out_ap, C, HW)); \
+    if (res_ap) PDS_CUDA(launch_pdl(tc_norm_split_kernel<FF, SS, true>, grid, dim3(256), 0, st, y, stats, n_rep, rep_stride, gamma, beta, res_ap, out_ap, C, HW)); \
+    else PDS_CUDA(launch_pdl(tc_norm_split_kernel<FF, SS, false>, grid, dim3(256), 0, st, y, stats, n_rep, rep_stride, gamma, beta, res_ap, out_ap, C, HW)); \
   }
   PDS_NORM_CASE(true, 1) PDS_NORM_CASE(true, 2) PDS_NORM_CASE(true, 3)
   PDS_NORM_CASE(false, 1) PDS_NORM_CASE(false, 2) PDS_NORM_CASE(false, 3)
@@ -914,13 +1127,26 @@ int tc_norm_split(const float* y, const double* stats, const float* gamma, const
   return PDS_OK;
 }
 
-// PDS_B200_FUSE_NORM=0 (read when a handle is created): normalisation as separate passes
+// PDS_B200_FUSE_NORM=1 (read when a handle is created): InstanceNorm passes inside the convolution
+// launches (built, bit-identical, slower than the separate passes today: opt-in)
 bool tc_fused_norm_enabled() {
   const char* e = getenv("PDS_B200_FUSE_NORM");
-  return !(e && atoi(e) == 0);
+  return e && atoi(e) == 1;
+}
+// PDS_B200_DYNAMIC_CONV=1: the dynamically scheduled kernel (tiles claimed in slice order, eight epilogue
+// warps) for the 64 -> 64 layers.  Measured at 960x540 D=192: 281 us per launch against 283-287 us for the
+// statically scheduled kernel -- no gain without the fusion it was built for, so the static kernel stays
+// the default; PDS_B200_FUSE_NORM=1 implies the dynamic kernel.
+bool tc_dynamic_conv_enabled() {
+  const char* e = getenv("PDS_B200_DYNAMIC_CONV");
+  return (e && atoi(e) == 1) || tc_fused_norm_enabled();
 }
 
-size_t tc_sched_ints(int n_slices) { return 1 + 2 * (size_t)(n_slices > 0 ? n_slices : 0); }
+// scratch of one fused launch: kStatReplicas private copies of the sums, then the scheduler words
+static size_t sched_stats_bytes(int n_slices) { return (size_t)kStatReplicas * (n_slices > 0 ? n_slices : 0) * 64 * 2 * sizeof(double); }
+size_t tc_sched_bytes(int n_slices) {
+  return align_up(sched_stats_bytes(n_slices) + (1 + (size_t)(n_slices > 0 ? n_slices : 0)) * sizeof(int), 256);
+}
 
 int tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   const TcLayer& l = *a.layer;
@@ -962,15 +1188,32 @@ int tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   const size_t w_bytes = l.w_elems() * 2;
   const size_t a_stage = (size_t)l.S * 2 * kPH * PW * 16;
   const bool wres = w_bytes + 3 * a_stage + tail_bytes(false) <= 227 * 1024;
-  // trailing normalisation inside the launch: 64 output channels, resident weights, one or two fp16 terms,
-  // a scheduler array from the caller, and enough slices for the passes to overlap the convolution
-  const bool fuse = a.norm_mode != TC_NORM_NONE && a.sched && l.N == 64 && l.Cout == 64 &&
-                    l.S <= 2 && l.fp16 && !a.in2 && w_bytes + 3 * a_stage + tail_bytes(true) <= 227 * 1024 && a.n_slices >= 4;
-  if (fuse) {
-    p.sched = a.sched; p.gamma = l.gamma; p.beta = l.beta; p.norm_mode = a.norm_mode;
+  // The dynamic kernel (tiles claimed in slice order, eight epilogue warps): 64 -> 64 layers with two
+  // fp16 terms and resident weights over enough slices.  a.fuse: the InstanceNorm runs INSIDE the launch
+  // (trailing normalisation warps); otherwise the launch only leaves the sums (one private copy per
+  // epilogue warp) and the normalisation follows as a separate pass -- the default: with at most five
+  // warps x 128 registers beside the convolution the in-kernel passes cannot keep enough loads in flight
+  // and the fused launch is slower than the two kernels.
+  const bool dynamic = a.sched && a.epilogue == TC_EPI_ACT && l.N == 64 && l.Cout == 64 && l.S == 2 && l.fp16 &&
+                       !a.in2 && w_bytes + 3 * a_stage + tail_bytes(true) <= 227 * 1024 && a.n_slices >= 4;
+  if (dynamic) {
+    const bool fuse = a.fuse && a.norm_mode != TC_NORM_NONE;
+    p.stats_rep = (double*)a.sched; p.sched = (int*)((char*)a.sched + sched_stats_bytes(a.n_slices));
+    p.gamma = l.gamma; p.beta = l.beta; p.norm_mode = fuse ? a.norm_mode : TC_NORM_NONE;
     p.res_ap = a.res_ap; p.norm_out = a.norm_out; p.fA = a.fA; p.fB = a.fB; p.fQ = a.fQ;
-    if (l.S == 1) return launch_tc<1, 4, 64, true, true>(p, st);
-    return launch_tc<2, 2, 64, true, true>(p, st);
+    rc = launch_tc<2, 2, 64, true, true>(p, st);
+    if (rc != PDS_OK || fuse) return rc;
+    const size_t rep = (size_t)a.n_slices * 64 * 2;
+    if (a.norm_mode == TC_NORM_PLAIN)
+      return tc_norm_split(a.out_f32, p.stats_rep, l.gamma, l.beta, nullptr, a.norm_out, a.n_slices, l.N, a.H, a.W, l.S,
+                           l.fp16, st, kStatReplicas, rep);
+    if (a.norm_mode == TC_NORM_RESIDUAL)
+      return tc_norm_split(a.out_f32, p.stats_rep, l.gamma, l.beta, a.res_ap, a.norm_out, a.n_slices, l.N, a.H, a.W, l.S,
+                           l.fp16, st, kStatReplicas, rep);
+    if (a.norm_mode == TC_NORM_RESIDUAL_FIRST)
+      return tc_norm_residual_first(a.out_f32, p.stats_rep, l.gamma, l.beta, a.fA, a.fB, a.fQ, a.norm_out,
+                                    a.n_slices / p.n_div, l.N, a.H, a.W, p.n_div, l.S, l.fp16, st, kStatReplicas, rep);
+    return PDS_OK;
   }
   rc = PDS_ERR_UNSUPPORTED;
 #define PDS_TC_CASE(SS, NN)                                                       \

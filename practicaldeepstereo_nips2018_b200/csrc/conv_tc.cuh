@@ -78,12 +78,14 @@ struct TcConvArgs {
   const float* fA;         // TC_NORM_RESIDUAL_FIRST: per-sample fp32 planes [b][N/4][H][W][4]
   const float* fB;
   const float* fQ;
-  int* sched;              // tc_sched_ints(n_slices) ints, ZEROED by the caller on the same stream (or null: separate pass)
+  void* sched;             // tc_sched_bytes(n_slices) bytes, ZEROED by the caller on the same stream (null: static kernel)
+  int fuse;                // run the normalisation inside the convolution launch (needs sched)
 };
 
-// scheduler words a fused convolution + normalisation launch needs for n_slices slices
-size_t tc_sched_ints(int n_slices);
+// scratch (sum replicas + scheduler words) a fused convolution + normalisation launch needs
+size_t tc_sched_bytes(int n_slices);
 bool tc_fused_norm_enabled();
+bool tc_dynamic_conv_enabled();
 
 size_t tc_conv_max_maps(int n_div);
 
@@ -134,14 +136,15 @@ int tc_compose_second_norm(const float* PA, const float* PB, const float* cols, 
 // out_ap[b*D + d] = IN(y) + x0_d with x0_d regenerated from A / Bf / Q
 int tc_norm_residual_first(const float* y, const double* stats, const float* gamma, const float* beta,
                            const float* A, const float* Bf, const float* Q, uint16_t* out_ap, int B, int C, int H,
-                           int W, int D, int S, int fp16, cudaStream_t st);
+                           int W, int D, int S, int fp16, cudaStream_t st, int n_rep = 1, size_t rep_stride = 0);
 
 // InstanceNorm apply on fp32 planes y [n][C/4][H][W][4] with the sums of
 // stats[n][C][2]; the optional residual is READ FROM AP planes (sum of its
 // terms) and the result is written as AP planes (out_ap may alias res_ap).
+// `stats` may be n_rep private copies of the sums, rep_stride doubles apart (summed in the prologue).
 int tc_norm_split(const float* y, const double* stats, const float* gamma, const float* beta,
                   const uint16_t* res_ap, uint16_t* out_ap, int n_slices, int C, int H, int W,
-                  int S, int fp16, cudaStream_t st);
+                  int S, int fp16, cudaStream_t st, int n_rep = 1, size_t rep_stride = 0);
 
 bool tc_available();  // driver entry point for cuTensorMapEncodeTiled resolved?
 

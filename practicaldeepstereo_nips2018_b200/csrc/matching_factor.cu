@@ -283,7 +283,7 @@ compose_second_kernel(const float* __restrict__ PA, const float* __restrict__ PB
 // InstanceNorm scale / shift of every slice are computed once per CTA.
 template <bool FP16, int S, int R>
 __global__ void __launch_bounds__(256, 2)
-norm_residual_first_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+norm_residual_first_kernel(const float* __restrict__ y, const double* __restrict__ stats, int n_rep, size_t rep_stride,
                            const float* __restrict__ gamma, const float* __restrict__ beta,
                            const float* __restrict__ A, const float* __restrict__ Bf, const float* __restrict__ Q,
                            uint16_t* __restrict__ out_ap, int C, int H, int W, int D) {
@@ -308,7 +308,11 @@ norm_residual_first_kernel(const float* __restrict__ y, const double* __restrict
     float* sn = reinterpret_cast<float*>(snorm);
     for (int i = tid; i < D * 8; i += 256) {
       const int d = i >> 3, e = i & 7, c = c8 * 8 + e;
-      const double s = stats[((size_t)(b * D + d) * C + c) * 2], q = stats[((size_t)(b * D + d) * C + c) * 2 + 1];
+      double s = 0.0, q = 0.0;     // n_rep private copies of the sums
+      for (int r = 0; r < n_rep; ++r) {
+        s += stats[r * rep_stride + ((size_t)(b * D + d) * C + c) * 2];
+        q += stats[r * rep_stride + ((size_t)(b * D + d) * C + c) * 2 + 1];
+      }
       const double mean = s / (double)HW;
       double var = q / (double)HW - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -474,7 +478,7 @@ int tc_compose_second_norm(const float* PA, const float* PB, const float* cols, 
 
 int tc_norm_residual_first(const float* y, const double* stats, const float* gamma, const float* beta,
                            const float* A, const float* Bf, const float* Q, uint16_t* out_ap, int B, int C, int H,
-                           int W, int D, int S, int fp16, cudaStream_t st) {
+                           int W, int D, int S, int fp16, cudaStream_t st, int n_rep, size_t rep_stride) {
   const size_t HW = (size_t)H * W;
   if (B == 0 || HW == 0) return PDS_OK;
   auto smem_for = [&](int R) { return (size_t)6 * R * W * sizeof(float4) + (size_t)D * 4 * sizeof(float4); };
@@ -487,7 +491,7 @@ int tc_norm_residual_first(const float* y, const double* stats, const float* gam
 #define PDS_NRF_CASE(FF, SS, RR) \
   if ((fp16 != 0) == FF && S == SS && R == RR) {  \
     PDS_CUDA(allow_dynamic_smem(norm_residual_first_kernel<FF, SS, RR>, (int)smem));  \
-    norm_residual_first_kernel<FF, SS, RR><<<grid, 256, smem, st>>>(y, stats, gamma, beta, A, Bf, Q, out_ap, C, H, W, D);  \
+    norm_residual_first_kernel<FF, SS, RR><<<grid, 256, smem, st>>>(y, stats, n_rep, rep_stride, gamma, beta, A, Bf, Q, out_ap, C, H, W, D);  \
   }
 #define PDS_NRF_ROWS(FF, SS) PDS_NRF_CASE(FF, SS, 4) PDS_NRF_CASE(FF, SS, 2) PDS_NRF_CASE(FF, SS, 1)
   PDS_NRF_ROWS(true, 1) PDS_NRF_ROWS(true, 2) PDS_NRF_ROWS(true, 3)

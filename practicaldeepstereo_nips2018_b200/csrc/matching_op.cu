@@ -37,7 +37,8 @@ struct pds_matching_op {
   float* wt1 = nullptr;
   int factor2 = 0;
   int two_pass = 1;                    // tc_compose_second as sums + normalised planes (no fp32 round trip)
-  int fuse_norm = 1;                   // InstanceNorm passes inside the convolution launches (conv_tc.cu, FUSE)
+  int fuse_norm = 0;                   // InstanceNorm passes inside the convolution launches (conv_tc.cu, FUSE): opt-in
+  int dynamic_conv = 0;                // 64 -> 64 layers on the dynamically scheduled kernel (eight epilogue warps): opt-in
   void* tc_blob = nullptr;
   // tensor maps of the shifted right descriptors, cached per (buffer, shape)
   CUtensorMap* maps_dev = nullptr;
@@ -105,6 +106,7 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
                   !(getenv("PDS_B200_MATCH_FACTOR2") && atoi(getenv("PDS_B200_MATCH_FACTOR2")) == 0);
     op->two_pass = !(getenv("PDS_B200_COMPOSE_TWO_PASS") && atoi(getenv("PDS_B200_COMPOSE_TWO_PASS")) == 0);
     op->fuse_norm = tc_fused_norm_enabled() ? 1 : 0;
+    op->dynamic_conv = tc_dynamic_conv_enabled() ? 1 : 0;
     {
       TcLayer& l = op->second;
       l.Cin = F; l.Cout = F; l.N = 64; l.S = op->split; l.fp16 = op->fp16; l.wscale = op->fp16 ? 256.f : 1.f;
@@ -220,7 +222,7 @@ TcPlan tc_plan(const pds_matching_op* op, int B, int H, int W, int D) {
   p.t = align_up((size_t)G * op->F * hw * 4, 256);
   p.stats = align_up(n * op->F * 2 * sizeof(double) * 2 * (op->n_res > 0 ? op->n_res : 1), 256);
   // scheduler words of the fused convolution + normalisation launches (two per residual block)
-  p.sched = align_up(tc_sched_ints((int)n) * sizeof(int) * 2 * (op->n_res > 0 ? op->n_res : 1), 256);
+  p.sched = tc_sched_bytes((int)n) * 2 * (op->n_res > 0 ? op->n_res : 1);
   p.first = align_up((size_t)B * op->F * hw * 4, 256);     // A, Bf, Q of the factorised first convolution
   p.ap2 = align_up((size_t)2 * B * S * op->F * hw * 2, 256);                         // planes of A and Bf
   p.cols = align_up((size_t)B * tc_column_jobs(D) * H * op->F * 4, 256);             // column corrections
@@ -249,7 +251,7 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
   float* t = (float*)ws.take<char>(pl.t);
   uint16_t* ya = (uint16_t*)ws.take<char>(pl.ya);
   double* stats = (double*)ws.take<char>(pl.stats);
-  int* sched = (int*)ws.take<char>(pl.sched);            // directly behind the sums: one memset clears both
+  char* sched = ws.take<char>(pl.sched);                 // directly behind the sums: one memset clears both
   float* fa = (float*)ws.take<char>(2 * pl.first);    // A then Bf, contiguous (one 2B-slice tensor)
   float* fb = fa + (size_t)B * op->F * H * W;
   float* fq = (float*)ws.take<char>(pl.first);
@@ -330,18 +332,18 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
         // y = IN(lrelu(conv(x))): the normalisation runs behind the convolution inside its launch
         a.layer = &c1; a.epilogue = TC_EPI_ACT; a.in = xa; a.out_f32 = t; a.stats = s1;
         a.norm_mode = TC_NORM_PLAIN; a.norm_out = ya; a.res_ap = nullptr;
-        a.sched = (op->fuse_norm && pl.G == N) ? sched + tc_sched_ints(N) * (2 * r) : nullptr;
+        a.sched = (op->dynamic_conv && pl.G == N) ? sched + tc_sched_bytes(N) * (2 * r) : nullptr; a.fuse = op->fuse_norm;
         if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
       }
       // x = IN(lrelu(conv(y))) + x (ResidualBlock.forward, network_blocks.py:143-144); block 1's x0 is
       // rebuilt from the per-sample terms where the factorisation never materialised it
       a.layer = &c2; a.epilogue = TC_EPI_ACT; a.in = ya; a.out_f32 = t; a.stats = s2;
       a.norm_out = xa;
-      a.sched = (op->fuse_norm && pl.G == N) ? sched + tc_sched_ints(N) * (2 * r + 1) : nullptr;
+      a.sched = (op->dynamic_conv && pl.G == N) ? sched + tc_sched_bytes(N) * (2 * r + 1) : nullptr; a.fuse = op->fuse_norm;
       if (r == 0 && second) { a.norm_mode = TC_NORM_RESIDUAL_FIRST; a.fA = fa; a.fB = fb; a.fQ = fq; a.res_ap = nullptr; }
       else { a.norm_mode = TC_NORM_RESIDUAL; a.res_ap = xa; }
       if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
-      a.norm_mode = TC_NORM_NONE; a.norm_out = nullptr; a.res_ap = nullptr; a.sched = nullptr;
+      a.norm_mode = TC_NORM_NONE; a.norm_out = nullptr; a.res_ap = nullptr; a.sched = nullptr; a.fuse = 0;
     }
     a.layer = &op->tc.back(); a.epilogue = TC_EPI_SIG; a.in = xa;
     a.out_f32 = nullptr; a.out_ap = nullptr; a.stats = nullptr; a.out_sig = signatures;
