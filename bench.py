@@ -234,13 +234,13 @@ def time_pipeline(pipe, items, steps, barrier, max_over_ranks, out=None, downloa
     barrier()
     del warm
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    from practicaldeepstereo_nips2018_b200 import _capi
-    launches0 = _capi.launch_count()
+    from practicaldeepstereo_nips2018_b200 import _capi, pipeline as pds_pipeline
+    launches0 = _capi.launch_count() + pds_pipeline.replayed_launches()
     t0 = time.perf_counter()
     start.record()
     outs = pipe.run((items[i % len(items)] for i in range(steps)), out=out, download=download)
     stop.record()
-    time_pipeline.launches = _capi.launch_count() - launches0      # kernels of the timed region
+    time_pipeline.launches = _capi.launch_count() + pds_pipeline.replayed_launches() - launches0   # kernels of the timed region (eager launches + kernels inside replayed graphs)
     time_pipeline.host_ms = (time.perf_counter() - t0) * 1e3       # host time to enqueue them
     barrier()
     del outs
@@ -278,6 +278,9 @@ def main():
                          "e2e_other_images")
     ap.add_argument('--streams', type=int, default=4,
                     help='compute streams of the e2e serving pipeline (pairs dealt round-robin)')
+    ap.add_argument('--graphs', type=int, default=1,
+                    help='1: every compute stream replays a CUDA graph of the forward (pipeline.GraphedNetwork, '
+                         'HostPipeline(graphs=True)); 0: eager kernel launches')
     ap.add_argument('--extra-configs', default='C3,C4,C5',
                     help="further BASELINE.json configurations measured after the headline one and "
                          "reported under 'other_configs' of the same JSON line (C5 = 8 pairs per GPU "
@@ -302,7 +305,8 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     from practicaldeepstereo_nips2018_b200 import PdsNetwork, _capi
-    from practicaldeepstereo_nips2018_b200.pipeline import HostPipeline
+    from practicaldeepstereo_nips2018_b200 import pipeline as pds_pipeline
+    from practicaldeepstereo_nips2018_b200.pipeline import GraphedNetwork, HostPipeline
 
     torch.backends.cudnn.allow_tf32 = False        # embedding (cuDNN) stays fp32 like the oracle
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -345,7 +349,7 @@ def main():
         # both numbers go through pipeline.HostPipeline, the package's serving call: pairs are
         # dealt round-robin to `--streams` compute streams (the latency-bound deep hourglass
         # layers of one pair overlap the other pairs' work); --streams 1 = plain back-to-back calls
-        pipe = HostPipeline(net, dev, streams=args.streams)
+        pipe = HostPipeline(net, dev, streams=args.streams, graphs=bool(args.graphs))
         ms = time_pipeline(pipe, pairs, args.steps, barrier, max_over_ranks, download=False)
         launches = time_pipeline.launches
 
@@ -360,9 +364,12 @@ def main():
         e2e_other_ms = time_pipeline(pipe, host_pairs_other, args.steps, barrier, max_over_ranks, out=d2h)
 
         # ---- back-to-back forwards on ONE stream, and the reference's sync-per-forward latency ----
-        pipe1 = HostPipeline(net, dev, streams=1)
+        pipe1 = HostPipeline(net, dev, streams=1, graphs=bool(args.graphs))
         ms_1stream = time_pipeline(pipe1, pairs, args.steps, barrier, max_over_ranks, download=False)
-        lat_median, lat_min = sync_latency_ms(net, pairs)
+        call = GraphedNetwork(net) if args.graphs else net
+        for i in range(3):
+            call(*pairs[i % len(pairs)])
+        lat_median, lat_min = sync_latency_ms(call, pairs)
         lat_median = max_over_ranks(lat_median)
 
         # ---- per-kernel CUDA-event profile (separate instrumented pass) ----------------
@@ -395,10 +402,13 @@ def main():
             od2h = [torch.empty((obatch, oH, oW), dtype=torch.float32).pin_memory() for _ in range(2 * max(1, args.streams))]
             for i in range(3):
                 net(*opairs[i % 2])
-            opipe = HostPipeline(net, dev, streams=args.streams)
+            opipe = HostPipeline(net, dev, streams=args.streams, graphs=bool(args.graphs))
             oms = time_pipeline(opipe, opairs, osteps, barrier, max_over_ranks, download=False)
             oe2e = time_pipeline(opipe, ohost, osteps, barrier, max_over_ranks, out=od2h)
-            olat, _ = sync_latency_ms(net, opairs, reps=10)
+            ocall = GraphedNetwork(net) if args.graphs else net
+            for i in range(3):
+                ocall(*opairs[i % 2])
+            olat, _ = sync_latency_ms(ocall, opairs, reps=10)
             olat = max_over_ranks(olat)
             total = osteps * obatch * world
             others.append({'config': name, 'workload': odesc, 'batch_per_gpu': obatch, 'maximum_disparity': omd,
@@ -454,6 +464,7 @@ def main():
             'config': {'workload': desc, 'batch_per_gpu': args.batch, 'maximum_disparity': md},
             'impl_config': {'precision': args.precision, 'parallelism': f'replicas x{world}',
                             'streams_per_gpu': args.streams, 'host_images': args.images,
+                            'cuda_graphs': bool(args.graphs),
                             'numa_bound_cpus': len(numa_cpus) if numa_cpus else None,
                             'l2': 'per-step working set > 1 GB (>> 126 MB L2); 4 rotating input pairs',
                             'embedding': ('own tcgen05 kernels' if args.precision != 'fp32'

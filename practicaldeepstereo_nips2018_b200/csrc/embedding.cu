@@ -29,6 +29,9 @@ struct pds_embedding {
   char* res_blob = nullptr;
   char* blob = nullptr;
   int shape[2] = {0, 0};
+  // plans and weight images of other extents seen by this handle (see pds_regularization::Saved)
+  struct Saved { int shape[2]; std::vector<pds::TcgLayer> layers; char* blob; };
+  std::vector<Saved> saved;
 };
 
 namespace pds {
@@ -185,6 +188,27 @@ std::vector<TcgShape> embedding_shapes(const pds_embedding* e, int H, int W) {
 
 int prepare(pds_embedding* e, int H, int W, cudaStream_t st) {
   if (e->shape[0] == H && e->shape[1] == W && !e->layers.empty()) return PDS_OK;
+  if (!e->layers.empty()) {     // park the current extent: a change of extent swaps, it does not free
+    pds_embedding::Saved sv;
+    sv.shape[0] = e->shape[0]; sv.shape[1] = e->shape[1];
+    sv.layers = std::move(e->layers); sv.blob = e->blob;
+    e->saved.push_back(std::move(sv));
+    e->layers.clear(); e->blob = nullptr; e->shape[0] = e->shape[1] = 0;
+  }
+  for (size_t i = 0; i < e->saved.size(); ++i) {
+    pds_embedding::Saved& sv = e->saved[i];
+    if (sv.shape[0] == H && sv.shape[1] == W) {
+      e->layers = std::move(sv.layers); e->blob = sv.blob;
+      e->shape[0] = H; e->shape[1] = W;
+      e->saved.erase(e->saved.begin() + i);
+      return PDS_OK;
+    }
+  }
+  constexpr size_t kMaxSavedShapes = 8;
+  if (e->saved.size() > kMaxSavedShapes) {
+    cudaFree(e->saved.front().blob);      // implicit device synchronisation
+    e->saved.erase(e->saved.begin());
+  }
   const std::vector<TcgShape> shapes = embedding_shapes(e, H, W);
   std::vector<TcgLayer> layers(shapes.size());
   size_t bytes = 0;
@@ -196,8 +220,6 @@ int prepare(pds_embedding* e, int H, int W, cudaStream_t st) {
     if (i == 0) layers[i].cin_src = e->Cin;
     bytes += tcg_layer_bytes(layers[i]);
   }
-  PDS_CUDA(cudaStreamSynchronize(st));
-  cudaFree(e->blob); e->blob = nullptr; e->layers.clear();
   PDS_CUDA(cudaMalloc(&e->blob, bytes));
   char* cur = e->blob;
   for (size_t i = 0; i < layers.size(); ++i) {
@@ -310,6 +332,7 @@ extern "C" void pds_embedding_destroy(pds_embedding* e) {
   cudaFree(e->raw);
   cudaFree(e->res_blob);
   cudaFree(e->blob);
+  for (auto& sv : e->saved) cudaFree(sv.blob);
   delete e;
 }
 

@@ -40,12 +40,10 @@ struct pds_matching_op {
   int fuse_norm = 0;                   // InstanceNorm passes inside the convolution launches (conv_tc.cu, FUSE): opt-in
   int dynamic_conv = 0;                // 64 -> 64 layers on the dynamically scheduled kernel (eight epilogue warps): opt-in
   void* tc_blob = nullptr;
-  // tensor maps of the shifted right descriptors, cached per (buffer, shape)
-  CUtensorMap* maps_dev = nullptr;
+  // tensor maps of the shifted right descriptors (un-factorised first convolution only): host staging
+  // here, the device copy lives in the CALLER'S workspace (one per stream: no sharing between streams)
   CUtensorMap* maps_host = nullptr;
   int maps_cap = 0;
-  const void* maps_key_ptr = nullptr;
-  int maps_key[4] = {0, 0, 0, 0};
 };
 
 namespace pds {
@@ -186,7 +184,6 @@ extern "C" void pds_matching_op_destroy(pds_matching_op* op) {
   if (!op) return;
   cudaFree(op->blob);
   cudaFree(op->tc_blob);
-  cudaFree(op->maps_dev);
   free(op->maps_host);
   delete op;
 }
@@ -201,7 +198,7 @@ namespace {
 // convolution that writes them and the pass that reads them.
 struct TcPlan {
   int G;
-  size_t lap, rap, xa, t, ya, stats, sched, first, ap2, cols, total;
+  size_t lap, rap, xa, t, ya, stats, sched, first, ap2, cols, maps, total;
 };
 
 TcPlan tc_plan(const pds_matching_op* op, int B, int H, int W, int D) {
@@ -226,7 +223,8 @@ TcPlan tc_plan(const pds_matching_op* op, int B, int H, int W, int D) {
   p.first = align_up((size_t)B * op->F * hw * 4, 256);     // A, Bf, Q of the factorised first convolution
   p.ap2 = align_up((size_t)2 * B * S * op->F * hw * 2, 256);                         // planes of A and Bf
   p.cols = align_up((size_t)B * tc_column_jobs(D) * H * op->F * 4, 256);             // column corrections
-  p.total = p.lap + p.rap + p.xa + p.t + p.ya + p.stats + p.sched + 5 * p.first + p.ap2 + p.cols + 1024;
+  p.maps = align_up((size_t)(D > 64 ? D : 64) * sizeof(CUtensorMap), 256);
+  p.total = p.lap + p.rap + p.xa + p.t + p.ya + p.stats + p.sched + 5 * p.first + p.ap2 + p.cols + p.maps + 1024;
   return p;
 }
 
@@ -234,10 +232,9 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
                int H, int W, int D, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const int N = B * D, S = op->split, fp16 = op->fp16;
   if (op->maps_cap < D) {
-    cudaFree(op->maps_dev); free(op->maps_host);
-    op->maps_dev = nullptr; op->maps_host = nullptr; op->maps_cap = 0; op->maps_key_ptr = nullptr;
+    free(op->maps_host);
+    op->maps_host = nullptr; op->maps_cap = 0;
     const int cap = D > 64 ? D : 64;
-    PDS_CUDA(cudaMalloc(&op->maps_dev, cap * sizeof(CUtensorMap)));
     if (posix_memalign((void**)&op->maps_host, 64, cap * sizeof(CUtensorMap)) != 0) {
       set_error("out of host memory"); return PDS_ERR_CUDA;
     }
@@ -258,26 +255,26 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
   float* fp = (float*)ws.take<char>(2 * pl.first);    // PA then PB
   uint16_t* ap2 = (uint16_t*)ws.take<char>(pl.ap2);
   float* cols = (float*)ws.take<char>(pl.cols);
+  CUtensorMap* maps_dev = (CUtensorMap*)ws.take<char>(pl.maps);
   if (ws.overflow) { set_error("pds_matching_op_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
   const size_t stat_elems = (size_t)N * op->F * 2;
   PDS_CUDA(cudaMemsetAsync(stats, 0, pl.stats + pl.sched, st));
   int rc;
   if ((rc = tc_pack_nchw(left, lap, B, op->C, H, W, S, fp16, st)) != PDS_OK) return rc;
   if ((rc = tc_pack_nchw(right, rap, B, op->C, H, W, S, fp16, st)) != PDS_OK) return rc;
-  // shifted-read tensor maps of the right descriptors: re-encoded only when the buffer or shape changes
-  // (only the un-factorised first convolution reads them)
+  // shifted-read tensor maps of the right descriptors (only the un-factorised first convolution reads
+  // them): encoded per call into this call's workspace -- the copy from pageable host memory is staged
+  // before cudaMemcpyAsync returns, so the host buffer is free again
   const bool need_maps = !(op->factor && pl.G == N);
-  if (need_maps && (op->maps_key_ptr != rap || op->maps_key[0] != B || op->maps_key[1] != H ||
-                    op->maps_key[2] != W || op->maps_key[3] != D)) {
+  if (need_maps) {
     if ((rc = tc_encode_shift_maps(op->maps_host, rap, B, S, op->C, H, W, D)) != PDS_OK) return rc;
-    PDS_CUDA(cudaMemcpyAsync(op->maps_dev, op->maps_host, D * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
-    op->maps_key_ptr = rap; op->maps_key[0] = B; op->maps_key[1] = H; op->maps_key[2] = W; op->maps_key[3] = D;
+    PDS_CUDA(cudaMemcpyAsync(maps_dev, op->maps_host, D * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
   }
 
   for (int n0 = 0; n0 < N; n0 += pl.G) {
     const int g = N - n0 < pl.G ? N - n0 : pl.G;
     TcConvArgs a = {};
-    a.maps_dev = op->maps_dev; a.maps_host = op->maps_host;
+    a.maps_dev = maps_dev; a.maps_host = op->maps_host;
     a.H = H; a.W = W; a.n_slices = g; a.n0 = n0; a.n_div = D;
     if (op->factor && pl.G == N) {
       // conv0 is linear in the concatenation: three convolutions over the B descriptors (instead

@@ -24,9 +24,14 @@ struct pds_regularization {
   int split = 0, fp16 = 0;
   float* raw = nullptr;
   std::vector<const float*> raw_params;
-  std::vector<pds::TcgLayer> tcg;       // all layers but _upsample_to_fullsize
+  std::vector<pds::TcgLayer> tcg;       // all layers but _upsample_to_fullsize (the CURRENT extent)
   char* tcg_blob = nullptr;
   int tcg_shape[3] = {0, 0, 0};
+  // plans and weight images of other extents seen by this handle: a change of extent swaps, it does
+  // not free (CUDA graphs captured for an earlier extent keep pointing at valid memory); at most
+  // kMaxSavedShapes are kept, the oldest is freed beyond that
+  struct Saved { int shape[3]; std::vector<pds::TcgLayer> tcg; char* blob; };
+  std::vector<Saved> saved;
   // host copies for the fused tail kernel (F == 8): last layer's weight (4,1,3,4,4) and bias,
   // InstanceNorm affine of _upsample_to_halfsize
   bool fused_tail = false;
@@ -159,6 +164,27 @@ std::vector<TcgShape> hourglass_shapes(int F, int S, int D, int H, int W) {
 int prepare_tcg(pds_regularization* reg, int D, int H, int W, cudaStream_t st) {
   if (reg->tcg_shape[0] == D && reg->tcg_shape[1] == H && reg->tcg_shape[2] == W && !reg->tcg.empty())
     return PDS_OK;
+  if (!reg->tcg.empty()) {     // park the current extent
+    pds_regularization::Saved sv;
+    for (int i = 0; i < 3; ++i) sv.shape[i] = reg->tcg_shape[i];
+    sv.tcg = std::move(reg->tcg); sv.blob = reg->tcg_blob;
+    reg->saved.push_back(std::move(sv));
+    reg->tcg.clear(); reg->tcg_blob = nullptr; reg->tcg_shape[0] = reg->tcg_shape[1] = reg->tcg_shape[2] = 0;
+  }
+  for (size_t i = 0; i < reg->saved.size(); ++i) {
+    pds_regularization::Saved& sv = reg->saved[i];
+    if (sv.shape[0] == D && sv.shape[1] == H && sv.shape[2] == W) {
+      reg->tcg = std::move(sv.tcg); reg->tcg_blob = sv.blob;
+      reg->tcg_shape[0] = D; reg->tcg_shape[1] = H; reg->tcg_shape[2] = W;
+      reg->saved.erase(reg->saved.begin() + i);
+      return PDS_OK;
+    }
+  }
+  constexpr size_t kMaxSavedShapes = 8;
+  if (reg->saved.size() > kMaxSavedShapes) {
+    cudaFree(reg->saved.front().blob);      // implicit device synchronisation
+    reg->saved.erase(reg->saved.begin());
+  }
   const std::vector<TcgShape> shapes = hourglass_shapes(reg->F, reg->split, D, H, W);
   std::vector<TcgLayer> layers(shapes.size());
   size_t bytes = 0;
@@ -170,8 +196,6 @@ int prepare_tcg(pds_regularization* reg, int D, int H, int W, cudaStream_t st) {
     layers[i].wscale = reg->fp16 ? 256.f : 1.f;
     bytes += tcg_layer_bytes(layers[i]);
   }
-  PDS_CUDA(cudaStreamSynchronize(st));      // the previous shape's buffers may still be in use
-  cudaFree(reg->tcg_blob); reg->tcg_blob = nullptr; reg->tcg.clear();
   PDS_CUDA(cudaMalloc(&reg->tcg_blob, bytes));
   char* cur = reg->tcg_blob;
   for (size_t i = 0; i < layers.size(); ++i) {
@@ -343,6 +367,7 @@ extern "C" void pds_regularization_destroy(pds_regularization* reg) {
   cudaFree(reg->blob);
   cudaFree(reg->raw);
   cudaFree(reg->tcg_blob);
+  for (auto& sv : reg->saved) cudaFree(sv.blob);
   delete reg;
 }
 

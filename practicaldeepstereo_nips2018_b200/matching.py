@@ -36,6 +36,32 @@ def _needs_autograd(*tensors_and_modules):
     return False
 
 
+_WORKSPACE_SCOPE = threading.local()
+
+
+class workspace_scope(object):
+    """``with workspace_scope(tag):`` -- kernel scratch buffers requested inside are keyed by `tag`
+    (not by the current stream); ``release_workspaces(module, tag)`` drops them."""
+
+    def __init__(self, tag):
+        self._tag, self._previous = tag, None
+
+    def __enter__(self):
+        self._previous = getattr(_WORKSPACE_SCOPE, 'tag', None)
+        _WORKSPACE_SCOPE.tag = self._tag
+
+    def __exit__(self, *exc):
+        _WORKSPACE_SCOPE.tag = self._previous
+
+
+def release_workspaces(module, tag):
+    for m in module.modules():
+        handle = m.__dict__.get('_kernel')
+        if handle is not None and handle._workspace:
+            for key in [k for k in handle._workspace if k[1] == ('scope', tag)]:
+                del handle._workspace[key]
+
+
 class _KernelHandle(object):
     """Owns the C-ABI handles built from a module's parameters, one per device (DataParallel
     replicas share the module's ``__dict__`` and therefore this object).  A handle is rebuilt
@@ -71,8 +97,11 @@ class _KernelHandle(object):
 
     def workspace(self, nbytes, device):
         """Scratch buffer for the calling stream (one per CUDA stream, so that pipelines which
-        keep several pairs in flight on different streams do not share scratch memory)."""
-        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+        keep several pairs in flight on different streams do not share scratch memory).  Under
+        ``workspace_scope(tag)`` the buffer is keyed by the tag instead (a CUDA-graph capture owns
+        its scratch memory: it lives in the graph's pool and its address is baked into the graph)."""
+        tag = getattr(_WORKSPACE_SCOPE, 'tag', None)
+        key = (str(device), ('scope', tag) if tag is not None else torch.cuda.current_stream(device).cuda_stream)
         if self._workspace is None:
             self._workspace = {}
         ws = self._workspace.get(key)

@@ -9,14 +9,79 @@ pair i computes; results land in pinned host buffers.
 """
 import torch
 
+from . import _capi, matching
+
+# kernels launched through graph replays (pds_launch_count only sees launches issued by the host)
+_replayed_launches = [0]
+
+
+def replayed_launches():
+    return _replayed_launches[0]
+
+
+class GraphedNetwork(object):
+    """``PdsNetwork.forward`` (eval, no-grad) captured as ONE CUDA graph per input signature and
+    replayed: the ~75 kernel launches of a forward become a single graph launch, so the gaps
+    between the latency-bound kernels (the deep hourglass levels run a few dozen CTAs for ~10 us
+    each) no longer depend on the host.  Inputs are copied into the graph's static buffers; the
+    returned disparity is the graph's static output, VALID UNTIL THE NEXT CALL on this object
+    (``clone()`` it to keep it).  Scratch memory and outputs live in the graph's private pool.
+
+    The reference runs one forward per ``network(left, right)`` call (pds_trainer.py:35-38); this
+    wrapper is called the same way."""
+
+    def __init__(self, network, warmup=2):
+        self._network, self._warmup, self._graphs = network, warmup, {}
+
+    def _signature(self, left, right):
+        return (tuple(left.shape), left.dtype, tuple(right.shape), right.dtype, str(left.device),
+                getattr(self._network, '_maximum_disparity', None))
+
+    def _capture(self, left, right):
+        device = left.device
+        static_left, static_right = torch.empty_like(left), torch.empty_like(right)
+        static_left.copy_(left)
+        static_right.copy_(right)
+        tag = ('graph', id(self), len(self._graphs))
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.no_grad(), torch.cuda.stream(side), matching.workspace_scope(tag):
+            for _ in range(max(1, self._warmup)):      # packs weights, plans layers, sizes the scratch buffers
+                self._network(static_left, static_right)
+        torch.cuda.current_stream(device).wait_stream(side)
+        matching.release_workspaces(self._network, tag)          # re-allocated inside the capture, in the graph's pool
+        graph = torch.cuda.CUDAGraph()
+        launches = _capi.launch_count()
+        with torch.no_grad(), torch.cuda.graph(graph), matching.workspace_scope(tag):
+            static_out = self._network(static_left, static_right)
+        launches = _capi.launch_count() - launches       # kernels recorded into the graph
+        entry = (graph, static_left, static_right, static_out, launches)
+        self._graphs[self._signature(left, right)] = entry
+        return entry
+
+    def __call__(self, left_image, right_image):
+        if not (left_image.is_cuda and right_image.is_cuda):
+            raise RuntimeError('GraphedNetwork needs CUDA tensors')
+        entry = self._graphs.get(self._signature(left_image, right_image))
+        if entry is None:
+            entry = self._capture(left_image.contiguous(), right_image.contiguous())
+        graph, static_left, static_right, static_out, launches = entry
+        static_left.copy_(left_image, non_blocking=True)
+        static_right.copy_(right_image, non_blocking=True)
+        graph.replay()
+        _replayed_launches[0] += launches
+        return static_out
+
 
 class HostPipeline(object):
-    def __init__(self, network, device=None, depth=2, streams=1):
+    def __init__(self, network, device=None, depth=2, streams=1, graphs=False):
         """depth: uploads issued ahead of the forward that consumes them.  streams > 1: pairs are
         dealt round-robin to that many compute streams, so that the latency-bound layers of one
         pair (the deep hourglass levels occupy a few dozen SMs) overlap the other pair's work;
-        every stream has its own scratch memory (matching._KernelHandle.workspace)."""
+        every stream has its own scratch memory (matching._KernelHandle.workspace).  graphs: every
+        compute stream replays its own CUDA graph of the forward (GraphedNetwork)."""
         self._network = network
+        self._graphed = [GraphedNetwork(network) for _ in range(max(1, streams))] if graphs else None
         self._device = device if device is not None else next(network.parameters()).device
         self._copy_stream = torch.cuda.Stream(self._device)
         self._streams = [torch.cuda.Stream(self._device) for _ in range(streams)] if streams > 1 else []
@@ -79,16 +144,22 @@ class HostPipeline(object):
 
     def _dispatch(self, item, caller, out, results, k):
         if not self._streams:
-            return self._step(item, caller, out, results, k)
-        stream = self._streams[k % len(self._streams)]
+            return self._step(item, caller, out, results, k, 0)
+        lane = k % len(self._streams)
+        stream = self._streams[lane]
         with torch.cuda.stream(stream):
-            return self._step(item, stream, out, results, k)
+            return self._step(item, stream, out, results, k, lane)
 
-    def _step(self, item, compute, out, results, k):
+    def _step(self, item, compute, out, results, k, lane=0):
         left, right, ready, slot = item
         if ready is not None:
             compute.wait_event(ready)
-        disparity = self._network(left, right)
+        if self._graphed is not None:
+            disparity = self._graphed[lane](left, right)
+            if not self._download:
+                disparity = disparity.clone()      # the graph's static output is rewritten by the next replay
+        else:
+            disparity = self._network(left, right)
         if slot is not None:
             left.record_stream(compute)            # staging memory is not recycled under the forward
             right.record_stream(compute)

@@ -151,6 +151,40 @@ def test_host_pipeline_matches_direct_calls():
             assert torch.equal(a, b)
 
 
+def test_graphed_network_and_graph_pipeline_match_eager_calls():
+    """pipeline.GraphedNetwork (one CUDA graph per input signature, replayed) and
+    HostPipeline(graphs=True) return exactly what PdsNetwork.forward returns; a change of extent
+    captures a second graph and the first one stays valid (the handles keep the plans and weight
+    images of earlier extents)."""
+    from practicaldeepstereo_nips2018_b200.pipeline import GraphedNetwork, HostPipeline
+    torch.manual_seed(4)
+    net = PdsNetwork.default(63).cuda().eval()
+    small = [(torch.rand(1, 3, 64, 128).mul(255).cuda(), torch.rand(1, 3, 64, 128).mul(255).cuda()) for _ in range(3)]
+    wide = [(torch.rand(2, 3, 100, 310).mul(255).cuda(), torch.rand(2, 3, 100, 310).mul(255).cuda()) for _ in range(2)]
+    with torch.no_grad():
+        eager_small = [net(l, r).clone() for l, r in small]
+        eager_wide = [net(l, r).clone() for l, r in wide]
+    g = GraphedNetwork(net)
+    for (l, r), ref in zip(small, eager_small):
+        assert torch.equal(g(l, r), ref)
+    for (l, r), ref in zip(wide, eager_wide):          # second signature: second graph
+        assert torch.equal(g(l, r), ref)
+    for (l, r), ref in zip(small, eager_small):        # the first graph is still valid
+        assert torch.equal(g(l, r), ref)
+    with torch.no_grad():                              # eager calls still work next to the graphs
+        assert torch.equal(net(*small[0]), eager_small[0])
+    pinned = [(l.cpu().pin_memory(), r.cpu().pin_memory()) for l, r in small]
+    for streams in (1, 2):
+        out = HostPipeline(net, streams=streams, graphs=True).run(pinned + pinned)
+        torch.cuda.synchronize()
+        for a, ref in zip(out, eager_small + eager_small):
+            assert torch.equal(a.cuda(), ref)
+        dev = HostPipeline(net, streams=streams, graphs=True).run(small, download=False)
+        torch.cuda.synchronize()
+        for a, ref in zip(dev, eager_small):
+            assert torch.equal(a, ref)
+
+
 @pytest.mark.parametrize('name,H,W,md,precision', [
     ('C2', 540, 960, 191, 'fp16x2'),
     ('C4', 375, 1242, 191, 'fp16x2'),
