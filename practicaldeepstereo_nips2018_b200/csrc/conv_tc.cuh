@@ -146,6 +146,14 @@ int tc_norm_split(const float* y, const double* stats, const float* gamma, const
                   const uint16_t* res_ap, uint16_t* out_ap, int n_slices, int C, int H, int W,
                   int S, int fp16, cudaStream_t st, int n_rep = 1, size_t rep_stride = 0);
 
+// ---- last convolution (64 -> 8) with the taps on the M axis of the MMA tile (conv_last.cu) ----
+size_t tc_last_weight_bytes();
+bool tc_last_enabled();            // PDS_B200_LAST_TAPS=0: the generic kernel (N = 16 tile)
+int tc_last_prepare(const float* w_oihw, uint16_t* packed, float wscale, cudaStream_t st);
+// in: planes [n_slices][2 terms][8][H][W][8] fp16; out: (B, 8, D, H, W) fp32, slice n = b * n_div + d
+int tc_conv_last(const uint16_t* packed_w, const float* bias, float wscale, const uint16_t* in, float* out,
+                 int n_slices, int n_div, int H, int W, cudaStream_t st);
+
 bool tc_available();  // driver entry point for cuTensorMapEncodeTiled resolved?
 
 }  // namespace pds

@@ -36,6 +36,7 @@ struct pds_matching_op {
   pds::TcLayer second;
   float* wt1 = nullptr;
   int factor2 = 0;
+  uint16_t* last_w = nullptr;          // last convolution with the taps on the M axis (conv_last.cu): packed weights
   int two_pass = 1;                    // tc_compose_second as sums + normalised planes (no fp32 round trip)
   int fuse_norm = 0;                   // InstanceNorm passes inside the convolution launches (conv_tc.cu, FUSE): opt-in
   int dynamic_conv = 0;                // 64 -> 64 layers on the dynamically scheduled kernel (eight epilogue warps): opt-in
@@ -115,6 +116,8 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
       l.Cin = C; l.Cout = F; l.N = 64; l.S = op->split; l.fp16 = op->fp16; l.wscale = op->fp16 ? 256.f : 1.f;
       bytes += align_up(l.w_elems() * 2, 256) + align_up(l.N * 4, 256);
     }
+    const bool last_taps = tc_last_enabled() && op->split == 2 && op->fp16 && S == 8 && F == 64;
+    if (last_taps) bytes += align_up(tc_last_weight_bytes(), 256);
     cudaError_t e = cudaMalloc(&op->tc_blob, bytes);
     if (e != cudaSuccess) { delete op; return cuda_fail(e, "cudaMalloc(matching tensor-core weights)"); }
     char* cur = (char*)op->tc_blob;
@@ -148,6 +151,10 @@ extern "C" int pds_matching_op_create(pds_matching_op** out, const float* const*
       op->wt1 = (float*)cur; cur += align_up((size_t)9 * F * F * 4, 256);
       rc = tc_prepare_weights(l, params[2], nullptr, st);
       if (rc == PDS_OK) rc = tc_transpose_weights(params[2], op->wt1, F, st);
+    }
+    if (rc == PDS_OK && last_taps) {
+      op->last_w = (uint16_t*)cur; cur += align_up(tc_last_weight_bytes(), 256);
+      rc = tc_last_prepare(params[n_params - 2], op->last_w, op->tc.back().wscale, st);
     }
     if (rc != PDS_OK) { cudaFree(op->tc_blob); delete op; return rc; }
     *out = op;
@@ -341,6 +348,11 @@ int tc_forward(pds_matching_op* op, const float* left, const float* right, float
       else { a.norm_mode = TC_NORM_RESIDUAL; a.res_ap = xa; }
       if ((rc = tc_conv3x3(a, st)) != PDS_OK) return rc;
       a.norm_mode = TC_NORM_NONE; a.norm_out = nullptr; a.res_ap = nullptr; a.sched = nullptr; a.fuse = 0;
+    }
+    if (op->last_w && pl.G == N) {     // taps on the M axis: 12 MMAs of 64 cycles per 84 pixels
+      if ((rc = tc_conv_last(op->last_w, op->tc.back().bias, op->tc.back().wscale, xa, signatures, N, D, H, W, st)) != PDS_OK)
+        return rc;
+      continue;
     }
     a.layer = &op->tc.back(); a.epilogue = TC_EPI_SIG; a.in = xa;
     a.out_f32 = nullptr; a.out_ap = nullptr; a.stats = nullptr; a.out_sig = signatures;

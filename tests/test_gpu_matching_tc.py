@@ -81,7 +81,9 @@ def test_tc_wide_images_use_fewer_rows_per_cta(W):
 def test_dynamic_and_fused_kernels_match_the_round1_pipeline(B, H, W, md, monkeypatch):
     """Round 2 kernels of the 64->64 layers against the round-1 pipeline (statically scheduled
     convolution, one-pass tc_compose_second, separate normalisation passes):
-      default  -- tc_compose_second as sums + normalised planes (no fp32 round trip);
+      default  -- tc_compose_second as sums + normalised planes (no fp32 round trip); last convolution
+                  (64 -> 8) with the taps on the M axis of the MMA tile (csrc/conv_last.cu: the nine taps
+                  are summed in fp32 in the epilogue, so this one differs from round 1 by rounding);
       dynamic  -- PDS_B200_DYNAMIC_CONV=1: dynamically scheduled convolution (tiles claimed in slice
                   order, eight epilogue warps, one private copy of the InstanceNorm sums per epilogue
                   warp), separate normalisation passes;
@@ -108,6 +110,7 @@ def test_dynamic_and_fused_kernels_match_the_round1_pipeline(B, H, W, md, monkey
     monkeypatch.setenv('PDS_B200_FUSE_NORM', '0')
     monkeypatch.setenv('PDS_B200_DYNAMIC_CONV', '0')
     monkeypatch.setenv('PDS_B200_COMPOSE_TWO_PASS', '0')
+    monkeypatch.setenv('PDS_B200_LAST_TAPS', '0')
     round1 = load_module(matching.MatchingOperation(precision='fp16x2'), params)
     with torch.no_grad():
         sep = matching.Matching(md, round1)(l, r)
@@ -116,8 +119,8 @@ def test_dynamic_and_fused_kernels_match_the_round1_pipeline(B, H, W, md, monkey
           f'round-1 {max_abs(dyn, sep):.3e}, fused vs round-1 {max_abs(fus, sep):.3e}; vs ATen: default '
           f'{max_abs(out, ref):.3e}, fused {max_abs(fus, ref):.3e}, round-1 {max_abs(sep, ref):.3e}, scale {scale:.2f}')
     assert max_abs(out, ref) <= 2e-4 and max_abs(fus, ref) <= 2e-4 and max_abs(dyn, ref) <= 2e-4
-    assert max_abs(out, sep) <= 2e-6 * scale and max_abs(out, again) <= 2e-6 * scale
-    assert max_abs(fus, sep) <= 2e-6 * scale and max_abs(dyn, sep) <= 2e-6 * scale
+    assert max_abs(out, sep) <= 1e-5 * scale and max_abs(out, again) <= 2e-6 * scale
+    assert max_abs(fus, out) <= 2e-6 * scale and max_abs(dyn, out) <= 2e-6 * scale
 
 
 @pytest.mark.parametrize('fuse', ['0', '1'])
