@@ -54,12 +54,17 @@ class workspace_scope(object):
         _WORKSPACE_SCOPE.tag = self._previous
 
 
-def release_workspaces(module, tag):
+def release_workspaces(module, tag=None):
+    """Detaches the scratch buffers keyed by `tag` (all of them when `tag` is None) from the kernel
+    handles of `module` and returns them: the caller decides how long they live (a captured CUDA
+    graph keeps its own; dropping the list frees the memory)."""
+    detached = []
     for m in module.modules():
         handle = m.__dict__.get('_kernel')
         if handle is not None and handle._workspace:
-            for key in [k for k in handle._workspace if k[1] == ('scope', tag)]:
-                del handle._workspace[key]
+            for key in [k for k in handle._workspace if tag is None or k[1] == ('scope', tag)]:
+                detached.append(handle._workspace.pop(key))
+    return detached
 
 
 class _KernelHandle(object):

@@ -51,6 +51,11 @@ class PdsNetwork(nn.Module):
             if handle is not None:
                 handle.invalidate()
 
+    def release_workspaces(self):
+        """Frees the scratch buffers the kernel handles cache per CUDA stream (they are re-allocated
+        on demand): useful between workloads of very different size."""
+        del matching.release_workspaces(self)[:]
+
     def _check_inputs(self, left_image, right_image):
         """One clear error up front instead of a failure deep inside a stage: the inference
         kernels need CUDA tensors on one device (there is no CPU path); gradient-enabled calls

@@ -55,9 +55,16 @@ class GraphedNetwork(object):
         with torch.no_grad(), torch.cuda.graph(graph), matching.workspace_scope(tag):
             static_out = self._network(static_left, static_right)
         launches = _capi.launch_count() - launches       # kernels recorded into the graph
-        entry = (graph, static_left, static_right, static_out, launches)
+        # the scratch buffers allocated during the capture belong to THIS graph from now on (they would
+        # otherwise stay referenced by the kernel handles for the life of the network)
+        scratch = matching.release_workspaces(self._network, tag)
+        entry = (graph, static_left, static_right, static_out, launches, scratch)
         self._graphs[self._signature(left, right)] = entry
         return entry
+
+    def close(self):
+        """Drops every captured graph with its static buffers and scratch memory."""
+        self._graphs.clear()
 
     def __call__(self, left_image, right_image):
         if not (left_image.is_cuda and right_image.is_cuda):
@@ -65,7 +72,7 @@ class GraphedNetwork(object):
         entry = self._graphs.get(self._signature(left_image, right_image))
         if entry is None:
             entry = self._capture(left_image.contiguous(), right_image.contiguous())
-        graph, static_left, static_right, static_out, launches = entry
+        graph, static_left, static_right, static_out, launches, _ = entry
         static_left.copy_(left_image, non_blocking=True)
         static_right.copy_(right_image, non_blocking=True)
         graph.replay()
@@ -91,6 +98,14 @@ class HostPipeline(object):
         self._slots = [{'left': None, 'right': None, 'consumed': None}
                        for _ in range(self._depth + max(1, streams) + 1)]
         self._next_slot = 0
+
+    def close(self):
+        """Releases the captured graphs (if any) and the staging slots."""
+        if self._graphed is not None:
+            for g in self._graphed:
+                g.close()
+        for slot in self._slots:
+            slot['left'] = slot['right'] = slot['consumed'] = None
 
     def _upload(self, pair):
         """H2D of one (left, right) pair on the copy stream into a preallocated staging slot
