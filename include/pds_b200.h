@@ -247,6 +247,31 @@ int pds_disparity_errors(const float* estimated, const float* ground_truth,
                          float* pixelwise_abs, float* pixelwise_n_pixels,
                          size_t count, float n, double* sums, void* stream);
 
+/* ---- f4 (training half): loss.SubpixelCrossEntropy (loss.py:16-78) -------------
+ * The reference loops over the disparity axis in Python (log_softmax of the whole
+ * volume, then per index an un-normalised Laplace target and two accumulations);
+ * here the forward is ONE pass over similarities (B, D, H, W) float32 contiguous,
+ * the backward another one.  ground_truth (B, H, W): +-inf marks "unknown"
+ * locations (they contribute nothing); weights: NULL or (B, H, W).
+ * Forward outputs per location: entropy (0 where unknown), lse = log-sum-exp of
+ * the similarities, sum_pt = sum_d P_target(d); sums (device, 2 doubles):
+ * sum of w * entropy and sum of w over known locations (w = 1 without weights).
+ * The loss is sums[0] / (sums[1] + 1e-15) with weights, sums[0] / sums[1]
+ * without (loss.py:74-78).
+ * Backward: upstream = d L / d loss (device, one float);
+ * grad_similarities (B, D, H, W) = upstream * c * (softmax(s)_d - P_target(d) /
+ * sum_pt), c = w / (sum w + 1e-15) resp. 1 / N; grad_weights: NULL or (B, H, W) =
+ * upstream * (entropy - loss) / (sum w + 1e-15).                                  */
+int pds_subpixel_cross_entropy_forward(const float* similarities, const float* ground_truth,
+                                       const float* weights, float* entropy, float* lse, float* sum_pt,
+                                       double* sums, int B, int D, int H, int W, float diversity,
+                                       int disparity_step, void* stream);
+int pds_subpixel_cross_entropy_backward(const float* similarities, const float* ground_truth,
+                                        const float* weights, const float* entropy, const float* lse,
+                                        const float* sum_pt, const double* sums, const float* upstream,
+                                        float* grad_similarities, float* grad_weights, int B, int D,
+                                        int H, int W, float diversity, int disparity_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

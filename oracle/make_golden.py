@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, '/root/reference')
 sys.dont_write_bytecode = True
 
-from practical_deep_stereo import (embedding, estimator, matching, network,  # noqa: E402
+from practical_deep_stereo import (embedding, estimator, loss, matching, network,  # noqa: E402
                                    regularization)
 from oracle import synth  # noqa: E402
 
@@ -52,6 +52,26 @@ def save(name, **arrays):
     np.savez_compressed(path, **arrays)
     print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB')
 
+
+# --- SubpixelCrossEntropy (loss.py:16-78): value and gradients on a random volume with unknown
+# locations, with and without weights (round 2; needs autograd, hence outside no_grad) -------------
+if not ONLY or ONLY == 'loss':
+    sim0 = synth.tensor((2, 12, 9, 11), 71)
+    gt0 = np.abs(synth.tensor((2, 9, 11), 72)) * 9.0
+    gt0[0, 2, 3:7] = np.inf
+    gt0[1, 5, :] = np.inf
+    w0 = np.abs(synth.tensor((2, 9, 11), 73)) + 0.1
+    arrays = dict(ground_truth=gt0, weights=w0)
+    for tag, use_w in (('weighted', True), ('mean', False)):
+        sim = t(sim0.copy()).requires_grad_(True)
+        w = t(w0.copy()).requires_grad_(True) if use_w else None
+        value = loss.SubpixelCrossEntropy(diversity=1.5, disparity_step=2)(sim, t(gt0), w)
+        value.backward()
+        arrays[f'{tag}_loss'] = np.array(value.item(), np.float64)
+        arrays[f'{tag}_grad_similarities'] = sim.grad.numpy()
+        if use_w:
+            arrays['weighted_grad_weights'] = w.grad.numpy()
+    save('loss', **arrays)
 
 with torch.no_grad():
     # --- Matching with a mock operation (test/test_matching.py:13-32) ---------

@@ -4,9 +4,9 @@
 Module names mirror the reference package ``practical_deep_stereo``:
 ``network.PdsNetwork``, ``matching.Matching`` / ``MatchingOperation``,
 ``regularization.Regularization``, ``estimator.SubpixelMap``,
-``embedding.Embedding``, ``size_adapter.SizeAdapter``, ``errors``.
+``embedding.Embedding``, ``size_adapter.SizeAdapter``, ``errors``, ``loss.SubpixelCrossEntropy``.
 """
-from . import (embedding, errors, estimator, matching, network, network_blocks,  # noqa: F401
+from . import (embedding, errors, estimator, loss, matching, network, network_blocks,  # noqa: F401
                regularization, size_adapter)
 from .network import PdsNetwork  # noqa: F401
 

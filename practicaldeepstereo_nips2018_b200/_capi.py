@@ -61,6 +61,9 @@ SIGNATURES = {
                                           _vp]),
     'pds_subpixel_map': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'pds_disparity_errors': (_i, [_vp, _vp, _vp, _vp, _sz, ctypes.c_float, _vp, _vp]),
+    'pds_subpixel_cross_entropy_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _i, _vp]),
+    'pds_subpixel_cross_entropy_backward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
+                                                 ctypes.c_float, _i, _vp]),
 }
 
 _lib = None

@@ -227,3 +227,38 @@ def test_network_golden_well_conditioned(golden):
     _, idx = oracle.subpixel_map(cost)
     cost_err, safe, flips, err = margin_checks(g, cost, disp, idx[..., 8:, 6:], 2e-4)
     assert safe > 0.99 and flips < 1e-3 and err <= 1e-3, (cost_err, safe, flips, err)
+
+
+def _loss_case(g, use_weights, module):
+    sim = torch.from_numpy(synth.tensor((2, 12, 9, 11), 71)).requires_grad_(True)
+    gt = torch.from_numpy(g['ground_truth'])
+    w = torch.from_numpy(g['weights'].copy()).requires_grad_(True) if use_weights else None
+    value = module(sim, gt, w)
+    value.backward()
+    return value, sim.grad, (w.grad if use_weights else None)
+
+
+@pytest.mark.parametrize('use_weights', [True, False])
+def test_subpixel_cross_entropy_golden(golden, use_weights):
+    """loss.SubpixelCrossEntropy (loss.py:16-78): the oracle's loop and the package's CPU tensor
+    expression against value and gradients of the unmodified reference; plus the reference's own
+    known-answer test (test/test_loss.py:13-38)."""
+    from practicaldeepstereo_nips2018_b200 import loss as pds_loss
+    g = golden('loss')
+    tag = 'weighted' if use_weights else 'mean'
+    for module in (lambda s, t, w: torch_port.subpixel_cross_entropy(s, t, w, 1.5, 2),
+                   pds_loss.SubpixelCrossEntropy(diversity=1.5, disparity_step=2)):
+        value, grad, grad_w = _loss_case(g, use_weights, module)
+        assert abs(value.item() - float(g[f'{tag}_loss'])) <= 1e-6
+        close(grad.numpy(), g[f'{tag}_grad_similarities'], 1e-7)
+        if use_weights:
+            close(grad_w.numpy(), g['weighted_grad_weights'], 1e-7)
+    sim = torch.tensor([[0.1, 0.3, 0.2, 0.05], [0.2, 0.1, 0.4, 0.0], [0.2, 0.1, 0.4, 0.0]]).t().reshape(1, 4, 3, 1)
+    sim = sim.clone().requires_grad_(True)
+    gt = torch.tensor([1.3, float('inf'), 1.9]).view(1, 3, 1)
+    w = torch.tensor([0.9, 0.0, 0.01]).view(1, 3, 1)
+    value = pds_loss.SubpixelCrossEntropy(diversity=2.0, disparity_step=1)(sim, gt, w)
+    value.backward()
+    expected = torch.tensor([[0.0262, -0.0567, -0.0219, 0.0524], [0.0, 0.0, 0.0, 0.0],
+                             [0.0011, -0.0002, -0.0007, -0.0002]]).t().reshape(1, 4, 3, 1)
+    assert abs(value.item() - 1.3654) <= 1e-3 and torch.allclose(sim.grad, expected, atol=1e-3)
