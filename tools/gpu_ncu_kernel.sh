@@ -2,7 +2,7 @@
 # ncu --set full of one kernel (regex $1, skip $2, count 1) of a network forward; key metrics + top stall sites
 K=${1:-conv_last_kernel}; SKIP=${2:-1}
 mkdir -p /tmp/ncu gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:"$K" -s $SKIP -c 1 -o /tmp/ncu/one -f \
+ncu --set full --clock-control none --import-source on -k regex:"$K" -s $SKIP -c ${3:-1} -o /tmp/ncu/one -f \
     python tools/profile_stages.py --precision fp16x2 --reps 1 --stages network > gpurun_out/ncu_one.log 2>&1
 ncu -i /tmp/ncu/one.ncu-rep --page raw --csv > /tmp/ncu/one_raw.csv 2>/dev/null
 ncu -i /tmp/ncu/one.ncu-rep --page source --csv --print-source sass > /tmp/ncu/one_src.csv 2>/dev/null
