@@ -281,10 +281,10 @@ def main():
     ap.add_argument('--graphs', type=int, default=1,
                     help='1: every compute stream replays a CUDA graph of the forward (pipeline.GraphedNetwork, '
                          'HostPipeline(graphs=True)); 0: eager kernel launches')
-    ap.add_argument('--extra-configs', default='C3,C4,C5',
+    ap.add_argument('--extra-configs', default='C3,C3-bf16,C4,C5',
                     help="further BASELINE.json configurations measured after the headline one and "
-                         "reported under 'other_configs' of the same JSON line (C5 = 8 pairs per GPU "
-                         "per step at C2: batch 64 on 8 GPUs); '' disables")
+                         "reported under 'other_configs' of the same JSON line (C3-bf16 = C3 with plain "
+                         "bf16 operands; C5 = 8 pairs per GPU per step at C2: batch 64 on 8 GPUs); '' disables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     H, W, md, desc = WORKLOADS[args.workload]
@@ -398,7 +398,7 @@ def main():
             gc.collect()
             torch.cuda.empty_cache()
 
-        def run_other_config(name, odesc, oH, oW, omd, obatch, osteps, ostreams):
+        def run_other_config(name, odesc, oH, oW, omd, obatch, osteps, ostreams, net):
             net.set_maximum_disparity(omd)
             opairs = synthetic_pairs(2, obatch, oH, oW, dev, seed=3000 + rank)
             ohost = synthetic_pairs(2, obatch, oH, oW, dev, seed=4000 + rank, pinned=True, images=args.images)
@@ -427,8 +427,17 @@ def main():
 
         free_everything(pipe, pipe1, call)
         for name in [c for c in args.extra_configs.split(',') if c]:
+            onet, oprecision = net, args.precision
             if name == 'C5':
                 oH, oW, omd, odesc, obatch = 540, 960, 191, 'batch 64 of 960x540 D=192 over 8 GPUs = 8 pairs per GPU per step', 8
+            elif name == 'C3-bf16':
+                # BASELINE.json names this configuration with bf16 operands: single-term tensor-core
+                # operands, NOT an fp32-grade mode (tests/test_gpu_network.py judges it on MAE / 3PE)
+                oH, oW, omd, odesc = WORKLOADS['C3']
+                odesc, obatch, oprecision = odesc + ', plain bf16 operands', 1, 'bf16'
+                onet = PdsNetwork.default(omd, precision='bf16')
+                onet.load_state_dict(net.state_dict())
+                onet = onet.to(dev).eval()
             elif name in WORKLOADS and name != args.workload:
                 oH, oW, omd, odesc = WORKLOADS[name]
                 obatch = 1
@@ -437,10 +446,15 @@ def main():
             osteps = max(8, args.steps // (3 * obatch)) if obatch > 1 else max(12, args.steps // 3)
             ostreams = args.streams if obatch == 1 else 1     # eight pairs per step fill the GPU on one stream
             try:
-                others.append(run_other_config(name, odesc, oH, oW, omd, obatch, osteps, ostreams))
+                others.append(run_other_config(name, odesc, oH, oW, omd, obatch, osteps, ostreams, onet))
+                others[-1]['precision'] = oprecision
             except Exception as exc:                           # a failed extra configuration never costs the headline line
                 others.append({'config': name, 'workload': odesc, 'error': f'{type(exc).__name__}: {exc}'[:300]})
                 free_everything()
+            if onet is not net:
+                onet.release_workspaces()
+                del onet
+                torch.cuda.empty_cache()
         net.set_maximum_disparity(md)
     barrier()
 
