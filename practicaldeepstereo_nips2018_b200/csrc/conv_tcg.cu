@@ -43,6 +43,8 @@ struct alignas(64) TcgParams {
   int tiles_x, tiles_y, tiles_z;
   int BX, planes_per_term, ntx_log2, zstride16;
   int resident, stages, reuse, merged, flat;
+  int ksplit;                    // > 1: an item covers 1/ksplit of the units and stores a RAW partial sum
+  size_t ksplit_stride;          //      into out + ks * ksplit_stride (tcg_splitk_finish adds them up)
   uint32_t box_bytes, box_tx_bytes, term_bytes, a_bytes, stage_bytes, wres_bytes, w_total_bytes;
   uint32_t off_boxes, off_entries, off_tiles, table_bytes;
   float inv_wscale;
@@ -100,7 +102,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   }
   for (uint32_t i = threadIdx.x; i < p.table_bytes / 4; i += kThreads)
     ((uint32_t*)tab)[i] = ((const uint32_t*)p.tables)[i];
-  for (int i = threadIdx.x; i < N; i += kThreads) sbias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < N; i += kThreads) sbias[i] = p.ksplit > 1 ? 0.f : p.bias[i];   // split-K: raw partial sums
   for (int i = threadIdx.x; i < 256; i += kThreads) sred[i] = 0.0;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -118,14 +120,17 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   // work item = (CTA tile, output class); every CTA walks one contiguous range of items (whole
   // tiles when a stage is shared by the classes of a tile)
   const int tiles_per_sample = p.tiles_x * p.tiles_y * p.tiles_z;
-  const int total_items = tiles_per_sample * p.n_samples * p.ncls;
+  const int total_items = tiles_per_sample * p.n_samples * p.ncls * p.ksplit;
   int per_cta = (total_items + (int)gridDim.x - 1) / (int)gridDim.x;
   if (p.reuse) per_cta = (per_cta + p.ncls - 1) / p.ncls * p.ncls;
   const int item_begin = min((int)blockIdx.x * per_cta, total_items);
   const int item_end = min(item_begin + per_cta, total_items);
-  struct Item { int n, tx, ty, tz, cls; };
+  struct Item { int n, tx, ty, tz, cls, u0, u1; };
   auto decode = [&](int item) {
     Item it;
+    const int ks = item % p.ksplit;       // split-K: the slices of one tile are neighbouring items (run concurrently)
+    item /= p.ksplit;
+    it.u0 = ks * p.upi / p.ksplit; it.u1 = (ks + 1) * p.upi / p.ksplit;
     it.cls = item % p.ncls;
     const int tile = item / p.ncls;
     it.n = tile / tiles_per_sample;
@@ -146,7 +151,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
         const Item it = decode(item);
         if (p.reuse && it.cls != 0) continue;       // the tile's stage is already resident
         const int x0 = it.tx * 8 * p.ntx, y0 = it.ty * 16, z0 = it.tz * p.ntz;
-        for (int u = 0; u < p.upi; ++u) {
+        for (int u = it.u0; u < it.u1; ++u) {
           const TcgUnit un = units[it.cls * p.upi + u];
           const int nb = un.box_end - un.box_beg;
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -193,12 +198,13 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     bool first_full = true;
     for (int item = item_begin; item < item_end; ++item) {
-      const int cls = item % p.ncls;
+      const int cls = (item / p.ksplit) % p.ncls;
+      const int u0 = (item % p.ksplit) * p.upi / p.ksplit, u1 = (item % p.ksplit + 1) * p.upi / p.ksplit;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + acc * buf_cols;
       const bool hold = p.reuse && cls + 1 < p.ncls;      // the stage serves the next class too
-      for (int u = 0; u < p.upi; ++u) {
+      for (int u = u0; u < u1; ++u) {
         const TcgUnit un = units[cls * p.upi + u];
         if (!(p.reuse && cls > 0)) {
           mbar_wait(full_bar(stage), phase);
@@ -216,7 +222,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
             const uint2 nxt = lds64(ent_base + 8u * min(e + 1, un.ent_end - 1));
             const uint32_t a_lo = en.x + sa16;
             const uint64_t bd = umma_desc((en.y + sw16) | b_lbo, b_hi);
-            const uint32_t accumulate = (u == 0 && e == un.ent_beg) ? 0u : 1u;
+            const uint32_t accumulate = (u == u0 && e == un.ent_beg) ? 0u : 1u;
 #pragma unroll
             for (int i = 0; i < NACC_MAX; ++i) {
               if (i < p.nacc) {
@@ -234,7 +240,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
             en = nxt;
           }
           if (!hold) tc_commit(empty_bar(stage));
-          if (u == p.upi - 1) tc_commit(tfull_bar(acc));
+          if (u == u1 - 1) tc_commit(tfull_bar(acc));
         }
         __syncwarp();
         if (!hold && ++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
@@ -301,7 +307,8 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
         const int gx = it.tx * 8 * p.ntx + 8 * ix + px, gy = it.ty * 16 + py, gz = it.tz * p.ntz + iz;
         const bool valid = gx < p.GX && gy < p.GY && gz < p.GZ;
         const int oz = p.nd3 ? p.mul * gz + cz : 0, oy = p.mul * gy + cy, ox = p.mul * gx + cx;
-        float* o = p.out + ((((size_t)it.n * p.OZ + oz) * p.OY + oy) * p.OX + ox) * p.Cout;
+        float* o = p.out + (size_t)(item % p.ksplit) * p.ksplit_stride +
+                   ((((size_t)it.n * p.OZ + oz) * p.OY + oy) * p.OX + ox) * p.Cout;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           if (!split_tiles && NCH > 1 && (c >= NCH / 2) != (half != 0)) continue;
@@ -665,8 +672,78 @@ int tcg_layer_init(TcgLayer& l, char* blob, const float* w_src, const float* bia
 
 long long* g_tcg_trace = nullptr;   // set by the debug hook (PDS_B200_TCG_TRACE)
 
+namespace {
+
+// Split-K fix-up: out = act(sum over the k slices of the raw partial sums + bias), plus the InstanceNorm
+// sums of the stored values.  The slices are added in a fixed order (deterministic results).  Tensors are
+// channels-last [rows][Cout]; a thread owns four channels and walks rows, the sums of a block leave it
+// as one double atomic per (channel, moment).
+__global__ void __launch_bounds__(256)
+tcg_splitk_finish_kernel(const float* __restrict__ partials, int ksplit, size_t stride, const float* __restrict__ bias,
+                         int lrelu, float* __restrict__ out, double* __restrict__ stats, size_t rows_per_sample,
+                         int Cout) {
+  extern __shared__ float fred[];      // [rows per iteration][2 * Cout]: per-thread sums, combined without atomics
+  const int n = blockIdx.y, groups = Cout / 4;
+  const int cg = threadIdx.x % groups, lane_row = threadIdx.x / groups, rows_per_iter = blockDim.x / groups;
+  const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * cg);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (lane_row < rows_per_iter)
+    for (size_t r = (size_t)blockIdx.x * rows_per_iter + lane_row; r < rows_per_sample; r += (size_t)gridDim.x * rows_per_iter) {
+      const size_t o = ((size_t)n * rows_per_sample + r) * Cout + 4 * cg;
+      float4 a = __ldcg(reinterpret_cast<const float4*>(partials + o));
+      for (int k = 1; k < ksplit; ++k) {
+        const float4 q = __ldcg(reinterpret_cast<const float4*>(partials + (size_t)k * stride + o));
+        a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+      }
+      float v[4] = {a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (lrelu) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
+        s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]);
+      }
+      *reinterpret_cast<float4*>(out + o) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  if (!stats) return;
+  if (lane_row < rows_per_iter) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      fred[lane_row * 2 * Cout + 2 * (4 * cg + j)] = s1[j];
+      fred[lane_row * 2 * Cout + 2 * (4 * cg + j) + 1] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * Cout; i += blockDim.x) {
+    double t = 0.0;
+    for (int r = 0; r < rows_per_iter; ++r) t += (double)fred[r * 2 * Cout + i];
+    if (t != 0.0) atomicAdd(stats + (size_t)n * Cout * 2 + i, t);
+  }
+}
+
+// k slices for a layer: only when its items leave most of the GPU idle (the deep hourglass levels:
+// a handful of tiles, each streaming the whole weight tensor through ONE CTA), never for merged /
+// stage-sharing transposed layers.  PDS_B200_TCG_SPLITK=0 disables.
+int splitk_for(const TcgPlan& pl, int n_samples) {
+  // PDS_B200_TCG_SPLITK: smallest k-slice count worth the fix-up launch (0: never split)
+  static const int least = getenv("PDS_B200_TCG_SPLITK") ? atoi(getenv("PDS_B200_TCG_SPLITK")) : 4;
+  if (least <= 0 || pl.merged || pl.units_per_item < 2 || pl.shape.Cout % 4) return 1;
+  if (pl.ncls > 1 && pl.units_per_item == 1) return 1;
+  const int tiles = ((pl.GX + 8 * pl.ntx - 1) / (8 * pl.ntx)) * ((pl.GY + 15) / 16) * ((pl.GZ + pl.ntz - 1) / pl.ntz);
+  const int items = tiles * n_samples * pl.ncls;
+  int k = num_sms() / (items > 0 ? items : 1);
+  if (k > pl.units_per_item) k = pl.units_per_item;
+  if (k > 8) k = 8;
+  return k >= (least > 2 ? least : 2) ? k : 1;
+}
+
+}  // namespace
+
+size_t tcg_splitk_bytes(const TcgLayer& l, int n_samples) {
+  const int k = splitk_for(l.plan, n_samples);
+  return k > 1 ? align_up((size_t)k * l.plan.out_elems(n_samples) * sizeof(float), 256) : 0;
+}
+
 int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, float* out, double* stats,
-                     int lrelu, cudaStream_t st) {
+                     int lrelu, cudaStream_t st, float* splitk_scratch, size_t splitk_bytes) {
   const TcgPlan& pl = l.plan;
   if (n_samples == 0) return PDS_OK;
   if (!encode_fn()) {
@@ -702,6 +779,13 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
   }
   p.tables = (const unsigned char*)l.prog; p.w = l.w; p.bias = l.bias; p.out = out; p.stats = stats;
   p.n_samples = n_samples; p.lrelu = lrelu; p.fp16 = l.fp16;
+  p.ksplit = 1; p.ksplit_stride = 0;
+  int ksplit = splitk_for(pl, n_samples);
+  if (ksplit > 1 && (!splitk_scratch || splitk_bytes < tcg_splitk_bytes(l, n_samples))) ksplit = 1;
+  if (ksplit > 1) {     // raw partial sums per k slice; tcg_splitk_finish_kernel adds bias, activation, sums
+    p.ksplit = ksplit; p.ksplit_stride = pl.out_elems(n_samples);
+    p.out = splitk_scratch; p.stats = nullptr; p.lrelu = 0;
+  }
   p.nacc = pl.nacc; p.ntx = pl.ntx; p.ntz = pl.ntz; p.ncls = pl.ncls; p.upi = pl.units_per_item;
   p.GZ = pl.GZ; p.GY = pl.GY; p.GX = pl.GX; p.OZ = pl.OZ; p.OY = pl.OY; p.OX = pl.OX;
   p.Cout = pl.shape.Cout; p.mul = (pl.ncls > 1 || pl.merged) ? 2 : 1; p.nd3 = pl.shape.nd == 3;
@@ -731,21 +815,35 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
     set_error("conv_tcg: plan needs %zu bytes of shared memory", smem);
     return PDS_ERR_UNSUPPORTED;
   }
-  const int total = p.tiles_x * p.tiles_y * p.tiles_z * n_samples * (p.reuse ? 1 : pl.ncls);
+  const int total = p.tiles_x * p.tiles_y * p.tiles_z * n_samples * (p.reuse ? 1 : pl.ncls) * p.ksplit;
   const int grid = total < num_sms() ? total : num_sms();
   const int k = (pl.shape.kind == TCG_TCONV4_S2 || pl.merged) ? 2 : (pl.shape.kind == TCG_CONV5_S2 ? 5 : 3);
   const double taps = (double)k * k * (pl.shape.nd == 3 ? k : 1);
   const double rows = (double)n_samples * pl.GZ * pl.GY * pl.GX * (pl.merged ? 8 : pl.ncls);
   const double flops = 2.0 * taps * pl.shape.Cin * pl.shape.Cout * rows;
   const double bytes = (double)pl.in_ap_bytes(n_samples) + 4.0 * pl.out_elems(n_samples);
+  int rc = PDS_ERR_UNSUPPORTED;
 #define PDS_TCG_CASE(SS, NN) \
-  if (pl.shape.S == SS && pl.N == NN) return launch_tcg<SS, NN>(p, pl, smem, grid, st, flops, bytes);
+  if (pl.shape.S == SS && pl.N == NN) rc = launch_tcg<SS, NN>(p, pl, smem, grid, st, flops, bytes);
   PDS_TCG_CASE(2, 16) PDS_TCG_CASE(2, 32) PDS_TCG_CASE(2, 64) PDS_TCG_CASE(2, 128)
   PDS_TCG_CASE(3, 16) PDS_TCG_CASE(3, 32) PDS_TCG_CASE(3, 64) PDS_TCG_CASE(3, 128)
   PDS_TCG_CASE(1, 16) PDS_TCG_CASE(1, 32) PDS_TCG_CASE(1, 64) PDS_TCG_CASE(1, 128)
 #undef PDS_TCG_CASE
-  set_error("conv_tcg: no kernel for S=%d N=%d", pl.shape.S, pl.N);
-  return PDS_ERR_UNSUPPORTED;
+  if (rc == PDS_ERR_UNSUPPORTED) set_error("conv_tcg: no kernel for S=%d N=%d", pl.shape.S, pl.N);
+  if (rc != PDS_OK || ksplit == 1) return rc;
+  {
+    const size_t rows = (size_t)pl.OZ * pl.OY * pl.OX;
+    const int Cout = pl.shape.Cout, rows_per_iter = 256 / (Cout / 4);
+    unsigned gx = (unsigned)((rows + 4 * rows_per_iter - 1) / (4 * rows_per_iter));     // ~4 rows per thread
+    if (gx > 296) gx = 296;
+    if (gx < 1) gx = 1;
+    PDS_KERNEL("tcg_splitk_finish", st);
+    PDS_KERNEL_WORK(0, (double)(ksplit + 1) * pl.out_elems(n_samples) * 4.0);
+    tcg_splitk_finish_kernel<<<dim3(gx, (unsigned)n_samples), 256, (size_t)rows_per_iter * 2 * Cout * sizeof(float), st>>>(
+        splitk_scratch, ksplit, pl.out_elems(n_samples), l.bias, lrelu, out, stats, rows, Cout);
+    PDS_LAUNCH_CHECK("tcg_splitk_finish_kernel");
+  }
+  return PDS_OK;
 }
 
 int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast, uint16_t* out_ap,
@@ -816,12 +914,13 @@ extern "C" int pds_tcg_conv_debug(int kind, int nd, int Cin, int Cout, int Z, in
   const size_t vin = (size_t)Z * Y * X, vout = (size_t)pl.OZ * pl.OY * pl.OX;   // (merged: OZ = 2Z ...)
   char *blob = nullptr, *scratch = nullptr;
   const size_t b_xcl = align_up(n * vin * Cin * 4, 256), b_ap = align_up(pl.in_ap_bytes(n), 256),
-               b_ycl = align_up(n * vout * Cout * 4, 256);
+               b_ycl = align_up(n * vout * Cout * 4, 256), b_sk = tcg_splitk_bytes(l, n);   // 0: layer is not split
   PDS_CUDA(cudaMalloc(&blob, tcg_layer_bytes(l)));
-  if (cudaMalloc(&scratch, b_xcl + b_ap + b_ycl) != cudaSuccess) { cudaFree(blob); set_error("out of memory"); return PDS_ERR_CUDA; }
+  if (cudaMalloc(&scratch, b_xcl + b_ap + b_ycl + b_sk) != cudaSuccess) { cudaFree(blob); set_error("out of memory"); return PDS_ERR_CUDA; }
   float* x_cl = (float*)scratch;
   uint16_t* ap = (uint16_t*)(scratch + b_xcl);
   float* y_cl = (float*)(scratch + b_xcl + b_ap);
+  float* sk = b_sk ? (float*)(scratch + b_xcl + b_ap + b_ycl) : nullptr;
   size_t used = 0;
   rc = tcg_layer_init(l, blob, w, bias, st, &used);
   if (rc == PDS_OK) rc = nchw_to_nhwc(x, x_cl, n, Cin, vin, st);
@@ -835,9 +934,9 @@ extern "C" int pds_tcg_conv_debug(int kind, int nd, int Cin, int Cout, int Z, in
   if (trace) {
     cudaMalloc(&g_tcg_trace, 148 * 8 * sizeof(long long));
     cudaMemset(g_tcg_trace, 0, 148 * 8 * sizeof(long long));
-    if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, nullptr, lrelu, st);   // warm (instruction cache, L2)
+    if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, nullptr, lrelu, st, sk, b_sk);   // warm (instruction cache, L2)
   }
-  if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, stats, lrelu, st);
+  if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, stats, lrelu, st, sk, b_sk);
   if (trace) {
     cudaStreamSynchronize(st);
     long long h[148 * 8];

@@ -126,8 +126,13 @@ int tcg_layer_init(TcgLayer& l, char* blob, const float* w_src, const float* bia
 // in_ap: AP planes [n][S][phase][P][IZ][IY][IX][8]; out: fp32 channels-last
 // [n][OZ][OY][OX][Cout] after bias + LeakyReLU(0.1) (if lrelu); stats[n][Cout][2] (double,
 // pre-zeroed) accumulate sum / sum of squares of the stored values when non-null.
+// splitk_scratch (optional, tcg_splitk_bytes(l, n_samples) bytes): layers whose few tiles would leave
+// most of the GPU idle (the deep hourglass levels) are split along K over several CTAs that store raw
+// partial sums there; a fix-up kernel adds them in a fixed order, then bias, activation and sums.
 int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, float* out,
-                     double* stats, int lrelu, cudaStream_t st);
+                     double* stats, int lrelu, cudaStream_t st, float* splitk_scratch = nullptr,
+                     size_t splitk_bytes = 0);
+size_t tcg_splitk_bytes(const TcgLayer& l, int n_samples);
 
 // One affine source of a normalisation pass: y fp32 channels-last with its
 // InstanceNorm sums (null stats: taken as is).

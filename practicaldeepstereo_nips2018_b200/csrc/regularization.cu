@@ -223,8 +223,28 @@ struct TailFusion {
 };
 
 struct TcgBuffers {
-  size_t sc_cl, ap, y_l0, y_d[4], y_s[4], y_u[4], y_e[4], y_half, stats, tail_state, total;
+  size_t sc_cl, ap, y_l0, y_d[4], y_s[4], y_u[4], y_e[4], y_half, stats, tail_state, splitk, total;
 };
+
+// Scratch of the split-K layers (conv_tcg.cu): the largest need over the layers of this extent.  Uses
+// the plans of the handle when it has seen the extent, otherwise plans it on the spot (host only).
+size_t splitk_scratch_bytes(const pds_regularization* reg, int B, int D, int H, int W) {
+  const std::vector<TcgLayer>* layers = nullptr;
+  if (reg->tcg_shape[0] == D && reg->tcg_shape[1] == H && reg->tcg_shape[2] == W && !reg->tcg.empty()) layers = &reg->tcg;
+  for (const auto& sv : reg->saved)
+    if (!layers && sv.shape[0] == D && sv.shape[1] == H && sv.shape[2] == W) layers = &sv.tcg;
+  std::vector<TcgLayer> planned;
+  if (!layers) {
+    const std::vector<TcgShape> shapes = hourglass_shapes(reg->F, reg->split, D, H, W);
+    planned.resize(shapes.size());
+    for (size_t i = 0; i < shapes.size(); ++i)
+      if (tcg_plan(shapes[i], &planned[i].plan) != PDS_OK) return 0;
+    layers = &planned;
+  }
+  size_t bytes = 0;
+  for (const TcgLayer& l : *layers) bytes = std::max(bytes, tcg_splitk_bytes(l, B));
+  return bytes;
+}
 
 TcgBuffers tcg_buffers(const pds_regularization* reg, int B, int D, int H, int W) {
   TcgBuffers b;
@@ -239,7 +259,8 @@ TcgBuffers tcg_buffers(const pds_regularization* reg, int B, int D, int H, int W
   b.y_half = buf(B * vox * 8 * (F / 2) * 4);
   b.stats = buf((size_t)18 * B * 16 * F * 2 * sizeof(double));
   b.tail_state = hourglass_tail_state_bytes(B, 2 * D, 2 * H, 2 * W);
-  b.total = b.sc_cl + 2 * b.ap + b.y_l0 + b.y_half + b.stats + b.tail_state + 1024;
+  b.splitk = splitk_scratch_bytes(reg, B, D, H, W);
+  b.total = b.sc_cl + 2 * b.ap + b.y_l0 + b.y_half + b.stats + b.tail_state + b.splitk + 1024;
   for (int k = 0; k < 4; ++k) b.total += b.y_d[k] + b.y_s[k] + b.y_u[k] + b.y_e[k];
   return b;
 }
@@ -266,6 +287,7 @@ int tcg_forward(pds_regularization* reg, const float* signatures, const float* s
   float* y_half = (float*)ws.take<char>(bs.y_half);
   double* stats = (double*)ws.take<char>(bs.stats);
   float* tail_state = (float*)ws.take<char>(bs.tail_state);
+  float* splitk = (float*)ws.take<char>(bs.splitk);
   if (ws.overflow) { set_error("pds_regularization_forward: workspace overflow"); return PDS_ERR_WORKSPACE; }
   PDS_CUDA(cudaMemsetAsync(stats, 0, bs.stats, st));
   const size_t stat_stride = (size_t)B * 16 * F * 2;
@@ -279,16 +301,16 @@ int tcg_forward(pds_regularization* reg, const float* signatures, const float* s
   if ((rc = nchw_to_nhwc(shortcut, sc_cl, B, F, (size_t)H * W, st)) != PDS_OK) return rc;
   if ((rc = tc_pack_nchw(signatures, ap[0], B, F, 1, (int)((size_t)D * H * W), S, fp16, st)) != PDS_OK) return rc;
   // layer 0: output = smoothing(signatures); level-0 input = shortcut (broadcast over D) + output
-  if ((rc = tcg_conv_forward(L[0], B, ap[0], y_l0, st_of(0), 1, st)) != PDS_OK) return rc;
+  if ((rc = tcg_conv_forward(L[0], B, ap[0], y_l0, st_of(0), 1, st, splitk, bs.splitk)) != PDS_OK) return rc;
   if ((rc = tcg_norm_to_ap(src(0, y_l0), nullptr, sc_cl, ap[1], B, F, D, H, W, S, fp16, 8, st)) != PDS_OK) return rc;
   int c = F, z = D, y = H, x = W, li = 1;
   for (int k = 0; k < 4; ++k) {
     // ContractionBlock3d (regularization.py:28-31): down = block_s2(in); smooth = block(down)
     const int ld = li++, lsm = li++;
-    if ((rc = tcg_conv_forward(L[ld], B, ap[1], y_d[k], st_of(ld), 1, st)) != PDS_OK) return rc;
+    if ((rc = tcg_conv_forward(L[ld], B, ap[1], y_d[k], st_of(ld), 1, st, splitk, bs.splitk)) != PDS_OK) return rc;
     c *= 2; z /= 2; y /= 2; x /= 2;
     if ((rc = tcg_norm_to_ap(src(ld, y_d[k]), nullptr, nullptr, ap[0], B, c, z, y, x, S, fp16, 1, st)) != PDS_OK) return rc;
-    if ((rc = tcg_conv_forward(L[lsm], B, ap[0], y_s[k], st_of(lsm), 1, st)) != PDS_OK) return rc;
+    if ((rc = tcg_conv_forward(L[lsm], B, ap[0], y_s[k], st_of(lsm), 1, st, splitk, bs.splitk)) != PDS_OK) return rc;
     if (k < 3) {   // next level input = down_k + smooth_k, phase-separated for the stride-2 layer
       const TcgNormSrc d = src(ld, y_d[k]);
       if ((rc = tcg_norm_to_ap(src(lsm, y_s[k]), &d, nullptr, ap[1], B, c, z, y, x, S, fp16, 8, st)) != PDS_OK) return rc;
@@ -300,16 +322,16 @@ int tcg_forward(pds_regularization* reg, const float* signatures, const float* s
     // ExpansionBlock3d (regularization.py:54-57): smoothing(up(out) + skip); skip = the smoothing
     // output pushed before contraction 3 - k (layer 2 * (3 - k) of the contraction part, 0 for k = 3)
     const int lu = li++, lsm = li++;
-    if ((rc = tcg_conv_forward(L[lu], B, ap[1], y_u[k], st_of(lu), 1, st)) != PDS_OK) return rc;
+    if ((rc = tcg_conv_forward(L[lu], B, ap[1], y_u[k], st_of(lu), 1, st, splitk, bs.splitk)) != PDS_OK) return rc;
     c /= 2; z *= 2; y *= 2; x *= 2;
     const int skip_layer = k < 3 ? 2 * (3 - k) : 0;
     const TcgNormSrc skip = src(skip_layer, k < 3 ? y_s[2 - k] : y_l0);
     if ((rc = tcg_norm_to_ap(src(lu, y_u[k]), &skip, nullptr, ap[0], B, c, z, y, x, S, fp16, 1, st)) != PDS_OK) return rc;
-    if ((rc = tcg_conv_forward(L[lsm], B, ap[0], y_e[k], st_of(lsm), 1, st)) != PDS_OK) return rc;
+    if ((rc = tcg_conv_forward(L[lsm], B, ap[0], y_e[k], st_of(lsm), 1, st, splitk, bs.splitk)) != PDS_OK) return rc;
     if ((rc = tcg_norm_to_ap(src(lsm, y_e[k]), nullptr, nullptr, ap[1], B, c, z, y, x, S, fp16, 1, st)) != PDS_OK) return rc;
   }
   // _upsample_to_halfsize (its InstanceNorm is applied by the tail kernel) + _upsample_to_fullsize
-  if ((rc = tcg_conv_forward(L[li], B, ap[1], y_half, st_of(li), 1, st)) != PDS_OK) return rc;
+  if ((rc = tcg_conv_forward(L[li], B, ap[1], y_half, st_of(li), 1, st, splitk, bs.splitk)) != PDS_OK) return rc;
   return hourglass_tail_forward(y_half, cost, st_of(li), reg->tail_gamma, reg->tail_beta, reg->tail_w,
                                 reg->tail_bias, B, 2 * D, 2 * H, 2 * W, st, tf.disparity, tf.argmax, tf.R,
                                 tf.step, tf.crop_top, tf.crop_left, tail_state);

@@ -104,6 +104,42 @@ def test_layer_vs_aten(kind, nd, cin, cout, n, spatial):
     assert max_abs(out2, F.leaky_relu(ref, 0.1)) <= 2e-5 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize('kind,nd,cin,cout,n,spatial', [c for c in CASES if c[2] >= 32 and c[1] == 3])
+def test_split_k_layers_match_unsplit(kind, nd, cin, cout, n, spatial, monkeypatch):
+    """Layers with few tiles are split along K over several CTAs (raw partial sums + a fix-up kernel
+    that adds them in a fixed order).  The deep-level cases above run split by default; here the same
+    inputs with the split disabled and with the smallest factor allowed: same values up to the fp32
+    summation order, and the split result is reproducible bit for bit."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent(f"""
+        import sys, numpy as np, torch
+        sys.path.insert(0, {os.path.dirname(__file__)!r})
+        import test_gpu_tcg as t
+        g = torch.Generator(device='cpu').manual_seed(11)
+        k = 4 if {kind} in (t.TCONV4_S2, t.TCONV4_S2M) else 3
+        x = torch.randn(({n}, {cin}) + {spatial}, generator=g).cuda()
+        wshape = (({cin}, {cout}) if k == 4 else ({cout}, {cin})) + (k,) * 3
+        w = (torch.randn(wshape, generator=g) / np.sqrt({cin} * k ** 3)).cuda()
+        b = torch.randn({cout}, generator=g).cuda()
+        out, stats = t.run_layer({kind}, 3, x, w, b, lrelu=1)
+        out2, stats2 = t.run_layer({kind}, 3, x, w, b, lrelu=1)
+        assert torch.equal(out, out2)
+        np.save(sys.argv[1], out.cpu().numpy()); np.save(sys.argv[2], stats.cpu().numpy())
+    """)
+    import tempfile
+    results = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for least in ('0', '2'):           # the switch is read once per process
+            env = dict(os.environ, PDS_B200_TCG_SPLITK=least,
+                       PYTHONPATH=os.pathsep.join([os.path.dirname(os.path.dirname(__file__)), os.environ.get('PYTHONPATH', '')]))
+            o, s = os.path.join(tmp, f'o{least}.npy'), os.path.join(tmp, f's{least}.npy')
+            subprocess.run([sys.executable, '-c', code, o, s], check=True, env=env, timeout=300)
+            results[least] = (np.load(o), np.load(s))
+    scale = float(np.abs(results['0'][0]).max())
+    assert np.abs(results['0'][0] - results['2'][0]).max() <= 5e-6 * scale        # fp32 order over K = 27 * Cin terms
+    assert np.allclose(results['0'][1], results['2'][1], rtol=1e-5, atol=1e-5 * np.abs(results['0'][1]).max())
+
+
 @pytest.mark.parametrize('S,fp16,tol', [(3, 0, 2e-5), (2, 0, 2e-3), (1, 1, 2e-2), (1, 0, 1e-1)])
 def test_layer_other_precisions(S, fp16, tol):
     g = torch.Generator(device='cpu').manual_seed(5)
