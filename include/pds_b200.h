@@ -98,6 +98,19 @@ int pds_matching_concat(const void* left, const void* right, void* volume,
 int pds_matching_stack(const void* in, void* out, int B, int F, int D, int H,
                        int W, int dtype, void* stream);
 
+/* f4 (training): adjoints of the two kernels above, i.e. what autograd
+ * accumulates through the reference's per-disparity pad / slice / cat nodes
+ * (matching.py:53-60) and through th.stack (matching.py:63):
+ *   grad_left [b,c,y,x] = sum_d grad_volume[b,d,c,y,x]
+ *   grad_right[b,c,y,x] = sum_{d: x+d<W} grad_volume[b,d,C+c,y,x+d]
+ * summed over d in ascending order in fp32 (deterministic).
+ * pds_matching_unstack: in (B, F, D, H, W) -> out (B*D, F, H, W). */
+int pds_matching_concat_backward(const void* grad_volume, void* grad_left,
+                                 void* grad_right, int B, int C, int H, int W,
+                                 int D, int dtype, void* stream);
+int pds_matching_unstack(const void* in, void* out, int B, int F, int D, int H,
+                         int W, int dtype, void* stream);
+
 /* ---- a2: MatchingOperation.forward over all disparities ------------------
  * (matching.py:69-112 applied by the loop of matching.py:53-62.)
  * Weights are given in the reference's own layout, in state_dict() order of

@@ -73,6 +73,21 @@ if not ONLY or ONLY == 'loss':
             arrays['weighted_grad_weights'] = w.grad.numpy()
     save('loss', **arrays)
 
+# --- Matching + MatchingOperation in TRAINING mode (matching.py:34-63 under autograd, f4): the
+# gradients the reference's per-disparity loop accumulates, for a fixed linear functional of the
+# signatures (round 2) ---------------------------------------------------------------------------
+if not ONLY or ONLY == 'matching_grad':
+    opg = load(matching.MatchingOperation(), synth.matching_operation_specs(), 81).train()
+    lg = t(synth.tensor((2, 64, 6, 13), 82)).requires_grad_(True)
+    rg = t(synth.tensor((2, 64, 6, 13), 83)).requires_grad_(True)
+    mg = matching.Matching(maximum_disparity=4, operation=opg)
+    sig = mg(lg, rg)
+    probe = t(synth.tensor(tuple(sig.shape), 84))
+    (sig * probe).sum().backward()
+    named = dict(opg.named_parameters())
+    save('matching_grad', signatures=sig.detach().numpy(), grad_left=lg.grad.numpy(), grad_right=rg.grad.numpy(),
+         **{'grad_param_' + k.replace('.', '__'): v.grad.numpy() for k, v in named.items()})
+
 with torch.no_grad():
     # --- Matching with a mock operation (test/test_matching.py:13-32) ---------
     def mock(x):

@@ -39,6 +39,8 @@ SIGNATURES = {
     'pds_profiler_read_work': (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'pds_matching_concat': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'pds_matching_stack': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'pds_matching_unstack': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'pds_matching_concat_backward': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'pds_matching_op_create': (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp]),
     'pds_matching_op_destroy': (None, [_vp]),
     'pds_matching_op_workspace_bytes': (_sz, [_vp, _i, _i, _i, _i]),

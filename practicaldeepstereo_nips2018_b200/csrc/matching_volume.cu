@@ -53,13 +53,47 @@ matching_concat_kernel(const T* __restrict__ left, const T* __restrict__ right,
   }
 }
 
-// in (B*D, F, H, W) -> out (B, F, D, H, W): plane-granular permutation.
+// Backward of the volume (f4, training): the adjoint of the gather above,
+//   grad_left [b, c, y, x] = sum_d g[b, d, c,     y, x]
+//   grad_right[b, c, y, x] = sum_{d : x + d < W} g[b, d, C + c, y, x + d]
+// (what autograd accumulates through the reference's D cat / pad / slice nodes, matching.py:53-60).
+// Same ownership as the forward: one CTA per (b, channel, y) row, a thread per column walking d in
+// ascending order (fixed summation order: deterministic), four independent partial sums in flight.
+// HBM-bound, read-dominated: the volume gradient is read exactly once.
 template <typename T>
+__global__ void __launch_bounds__(kRowThreads)
+matching_concat_backward_kernel(const T* __restrict__ gvolume, T* __restrict__ gleft, T* __restrict__ gright,
+                                int C, int H, int W, int D) {
+  const int y = blockIdx.x, c2 = blockIdx.y, b = blockIdx.z;
+  const bool is_left = c2 < C;
+  const size_t dstride = (size_t)2 * C * H * W;
+  const T* src = gvolume + (((size_t)b * D) * 2 * C + c2) * H * W + (size_t)y * W;
+  T* dst = is_left ? gleft + ((size_t)(b * C + c2) * H + y) * W : gright + ((size_t)(b * C + (c2 - C)) * H + y) * W;
+  for (int x = threadIdx.x; x < W; x += kRowThreads) {
+    const int nd = is_left ? D : min(D, W - x);        // right: only disparities whose shifted column exists
+    const T* s = src + x;
+    const size_t step = is_left ? dstride : dstride + 1;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int d = 0;
+    for (; d + 4 <= nd; d += 4) {
+      const float v0 = (float)__ldg(s + (size_t)d * step), v1 = (float)__ldg(s + (size_t)(d + 1) * step);
+      const float v2 = (float)__ldg(s + (size_t)(d + 2) * step), v3 = (float)__ldg(s + (size_t)(d + 3) * step);
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    for (; d < nd; ++d) a0 += (float)__ldg(s + (size_t)d * step);
+    dst[x] = T((a0 + a1) + (a2 + a3));
+  }
+}
+
+// in (B*D, F, H, W) -> out (B, F, D, H, W): plane-granular permutation (INVERSE: the other way,
+// which is also its backward).
+template <typename T, bool INVERSE>
 __global__ void matching_stack_kernel(const T* __restrict__ in, T* __restrict__ out, int F,
                                       int D, size_t plane) {
   const int d = blockIdx.y % D, f = blockIdx.y / D, b = blockIdx.z;
-  const T* s = in + (((size_t)b * D + d) * F + f) * plane;
-  T* o = out + (((size_t)b * F + f) * D + d) * plane;
+  const size_t i_bdf = (((size_t)b * D + d) * F + f) * plane, i_bfd = (((size_t)b * F + f) * D + d) * plane;
+  const T* s = in + (INVERSE ? i_bfd : i_bdf);
+  T* o = out + (INVERSE ? i_bdf : i_bfd);
   constexpr int VEC = 16 / sizeof(T);
   const bool vec_ok = (plane % VEC == 0) && (((reinterpret_cast<uintptr_t>(in) |
                                                reinterpret_cast<uintptr_t>(out)) & 15) == 0);
@@ -109,25 +143,65 @@ extern "C" int pds_matching_concat(const void* left, const void* right, void* vo
   return PDS_OK;
 }
 
-extern "C" int pds_matching_stack(const void* in, void* out, int B, int F, int D, int H, int W,
-                                  int dtype, void* stream) {
-  using namespace pds;
-  PDS_CHECK_ARG(in && out, "pds_matching_stack: null pointer");
-  PDS_CHECK_ARG(B >= 0 && F >= 1 && D >= 1 && H >= 0 && W >= 0, "pds_matching_stack: bad shape");
-  PDS_CHECK_ARG(dtype == PDS_F32 || dtype == PDS_BF16, "pds_matching_stack: bad dtype");
-  PDS_CHECK_ARG((size_t)F * D <= 65535 && B <= 65535, "pds_matching_stack: F*D or B too large");
+namespace pds {
+namespace {
+int launch_stack(const char* what, const void* in, void* out, int B, int F, int D, int H, int W, int dtype,
+                 bool inverse, void* stream) {
+  PDS_CHECK_ARG(in && out, "%s: null pointer", what);
+  PDS_CHECK_ARG(B >= 0 && F >= 1 && D >= 1 && H >= 0 && W >= 0, "%s: bad shape", what);
+  PDS_CHECK_ARG(dtype == PDS_F32 || dtype == PDS_BF16, "%s: bad dtype", what);
+  PDS_CHECK_ARG((size_t)F * D <= 65535 && B <= 65535, "%s: F*D or B too large", what);
   const size_t plane = (size_t)H * W;
   if (B == 0 || plane == 0) return PDS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned gx = (unsigned)((plane / 4 + 255) / 256 > 8 ? 8 : (plane / 4 + 255) / 256);
   dim3 grid(gx ? gx : 1, (unsigned)(F * D), (unsigned)B);
-  PDS_KERNEL("matching_stack", st);
+  PDS_KERNEL(inverse ? "matching_unstack" : "matching_stack", st);
   PDS_KERNEL_WORK(0, 2.0 * B * F * D * plane * (dtype == PDS_F32 ? 4 : 2));
-  if (dtype == PDS_F32)
-    matching_stack_kernel<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, F, D, plane);
-  else
-    matching_stack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
-        (const __nv_bfloat16*)in, (__nv_bfloat16*)out, F, D, plane);
+  if (dtype == PDS_F32) {
+    if (inverse) matching_stack_kernel<float, true><<<grid, 256, 0, st>>>((const float*)in, (float*)out, F, D, plane);
+    else matching_stack_kernel<float, false><<<grid, 256, 0, st>>>((const float*)in, (float*)out, F, D, plane);
+  } else {
+    if (inverse)
+      matching_stack_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, F, D, plane);
+    else
+      matching_stack_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, F, D, plane);
+  }
   PDS_LAUNCH_CHECK("matching_stack_kernel");
+  return PDS_OK;
+}
+}  // namespace
+}  // namespace pds
+
+extern "C" int pds_matching_stack(const void* in, void* out, int B, int F, int D, int H, int W,
+                                  int dtype, void* stream) {
+  return pds::launch_stack("pds_matching_stack", in, out, B, F, D, H, W, dtype, false, stream);
+}
+
+extern "C" int pds_matching_unstack(const void* in, void* out, int B, int F, int D, int H, int W,
+                                    int dtype, void* stream) {
+  return pds::launch_stack("pds_matching_unstack", in, out, B, F, D, H, W, dtype, true, stream);
+}
+
+extern "C" int pds_matching_concat_backward(const void* grad_volume, void* grad_left, void* grad_right, int B,
+                                            int C, int H, int W, int D, int dtype, void* stream) {
+  using namespace pds;
+  PDS_CHECK_ARG(grad_volume && grad_left && grad_right, "pds_matching_concat_backward: null pointer");
+  PDS_CHECK_ARG(B >= 0 && C >= 1 && H >= 0 && W >= 0 && D >= 1, "pds_matching_concat_backward: bad shape");
+  PDS_CHECK_ARG(dtype == PDS_F32 || dtype == PDS_BF16, "pds_matching_concat_backward: bad dtype");
+  PDS_CHECK_ARG(2 * C <= 65535 && B <= 65535, "pds_matching_concat_backward: C or B too large");
+  if (B == 0 || H == 0 || W == 0) return PDS_OK;
+  const size_t esz = dtype == PDS_F32 ? 4 : 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)H, (unsigned)(2 * C), (unsigned)B);
+  PDS_KERNEL("matching_concat_backward", st);
+  PDS_KERNEL_WORK(0, (double)B * H * W * esz * (2.0 * C + 2.0 * C * D));
+  if (dtype == PDS_F32)
+    matching_concat_backward_kernel<float><<<grid, kRowThreads, 0, st>>>(
+        (const float*)grad_volume, (float*)grad_left, (float*)grad_right, C, H, W, D);
+  else
+    matching_concat_backward_kernel<__nv_bfloat16><<<grid, kRowThreads, 0, st>>>(
+        (const __nv_bfloat16*)grad_volume, (__nv_bfloat16*)grad_left, (__nv_bfloat16*)grad_right, C, H, W, D);
+  PDS_LAUNCH_CHECK("matching_concat_backward_kernel");
   return PDS_OK;
 }

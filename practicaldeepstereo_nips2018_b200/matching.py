@@ -10,17 +10,24 @@ Two kernel paths sit behind the reference API:
 * ``Matching`` with a ``MatchingOperation``: the fused pipeline of
   csrc/matching_op.cu -- the concatenated volume is never materialised.
 
-Gradient-enabled calls (training) are outside the inference hot path and run
-the plain ATen composition of the same modules.
+Gradient-enabled calls (training) are outside the inference hot path: the
+convolution stacks run the plain ATen composition of the same modules under
+autograd; ``Matching`` itself keeps its volume / stack kernels, with adjoint
+kernels in the backward (``_ConcatVolume``, ``_StackDisparities``).
 """
 import copy
 import ctypes
+import os
 import threading
 
 import torch
 from torch import nn
 
 from . import _capi, network_blocks
+
+# f4: training-mode Matching on the volume / stack kernels and their adjoints (0: the reference's
+# per-disparity composition)
+USE_TRAINING_KERNELS = os.environ.get('PDS_B200_TRAIN_KERNELS', '1') == '1'
 
 
 def _needs_autograd(*tensors_and_modules):
@@ -227,6 +234,66 @@ class MatchingOperation(nn.Module):
         return self.match_all_disparities(left, right, 1)[:, :, 0]
 
 
+class _ConcatVolume(torch.autograd.Function):
+    """f4: the reference's per-disparity pad / slice / cat (matching.py:53-60) as ONE differentiable
+    node.  forward: pds_matching_concat -> [B, D, 2C, H, W]; backward: pds_matching_concat_backward
+    (sum over disparities of the left half, shifted sum of the right half)."""
+
+    @staticmethod
+    def forward(ctx, left, right, number_of_disparities):
+        left, right = left.contiguous(), right.contiguous()
+        B, C, H, W = left.shape
+        D = int(number_of_disparities)
+        ctx.dims = (B, C, H, W, D)
+        volume = torch.empty((B, D, 2 * C, H, W), dtype=left.dtype, device=left.device)
+        with torch.cuda.device(left.device):
+            _capi.check(_capi.lib().pds_matching_concat(
+                _capi.ptr(left), _capi.ptr(right), _capi.ptr(volume), B, C, H, W, D,
+                _capi.dtype_code(left), _capi.stream_ptr(left.device)))
+        return volume
+
+    @staticmethod
+    def backward(ctx, grad_volume):
+        B, C, H, W, D = ctx.dims
+        grad_volume = grad_volume.contiguous()
+        grad_left = torch.empty((B, C, H, W), dtype=grad_volume.dtype, device=grad_volume.device)
+        grad_right = torch.empty_like(grad_left)
+        with torch.cuda.device(grad_volume.device):
+            _capi.check(_capi.lib().pds_matching_concat_backward(
+                _capi.ptr(grad_volume), _capi.ptr(grad_left), _capi.ptr(grad_right), B, C, H, W, D,
+                _capi.dtype_code(grad_volume), _capi.stream_ptr(grad_volume.device)))
+        return grad_left, grad_right, None
+
+
+class _StackDisparities(torch.autograd.Function):
+    """th.stack(signatures, dim=2) (matching.py:63) of a batched operation output:
+    [B * D, F, H, W] -> [B, F, D, H, W]; the backward is the inverse permutation."""
+
+    @staticmethod
+    def forward(ctx, signatures, batch):
+        signatures = signatures.contiguous()
+        N, F, H, W = signatures.shape
+        D = N // batch
+        ctx.dims = (batch, F, D, H, W)
+        out = torch.empty((batch, F, D, H, W), dtype=signatures.dtype, device=signatures.device)
+        with torch.cuda.device(signatures.device):
+            _capi.check(_capi.lib().pds_matching_stack(
+                _capi.ptr(signatures), _capi.ptr(out), batch, F, D, H, W, _capi.dtype_code(signatures),
+                _capi.stream_ptr(signatures.device)))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        B, F, D, H, W = ctx.dims
+        grad_out = grad_out.contiguous()
+        grad_in = torch.empty((B * D, F, H, W), dtype=grad_out.dtype, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            _capi.check(_capi.lib().pds_matching_unstack(
+                _capi.ptr(grad_out), _capi.ptr(grad_in), B, F, D, H, W, _capi.dtype_code(grad_out),
+                _capi.stream_ptr(grad_out.device)))
+        return grad_in, None
+
+
 class Matching(nn.Module):
     def __init__(self, maximum_disparity, operation, batched_operation=True):
         """maximum_disparity: disparity range is [0, maximum_disparity];
@@ -243,7 +310,20 @@ class Matching(nn.Module):
         self._maximum_disparity = maximum_disparity
 
     def _autograd_forward(self, left, right):
+        """Training (gradients required).  CUDA float32 / bfloat16 descriptors with a batched
+        operation: volume kernel (+ its adjoint in the backward) -> ONE call of the operation on the
+        disparity-stacked batch [B * D, 2C, H, W] (InstanceNorm statistics are per sample, so the
+        stacked call equals the reference's D calls, matching.py:53-62) -> stack kernel.  The
+        reference's loop costs D x ~20 operator launches and autograd nodes forward and again
+        backward; this is ~20.  Otherwise (CPU, other dtypes, ``batched_operation=False``) the
+        reference's per-disparity composition."""
         md = self._maximum_disparity
+        if (self._batched_operation and USE_TRAINING_KERNELS and left.is_cuda and right.is_cuda
+                and left.dtype == right.dtype and left.dtype in (torch.float32, torch.bfloat16)
+                and left.shape == right.shape and left.dim() == 4):
+            volume = _ConcatVolume.apply(left, right, md + 1)
+            signatures = self._operation(volume.view(-1, *volume.shape[2:]))
+            return _StackDisparities.apply(signatures, left.size(0))
         padded = nn.functional.pad(right, (md, 0, 0, 0))
         width = right.size(-1)
         out = [self._operation(torch.cat(

@@ -262,3 +262,48 @@ def test_subpixel_cross_entropy_golden(golden, use_weights):
     expected = torch.tensor([[0.0262, -0.0567, -0.0219, 0.0524], [0.0, 0.0, 0.0, 0.0],
                              [0.0011, -0.0002, -0.0007, -0.0002]]).t().reshape(1, 4, 3, 1)
     assert abs(value.item() - 1.3654) <= 1e-3 and torch.allclose(sim.grad, expected, atol=1e-3)
+
+
+# ----------------------------------------------------------------------------
+# f4: gradients of Matching + MatchingOperation in training mode (reference matching.py:34-63 under
+# autograd) -- the torch port and the package's CPU composition against the unmodified reference
+def _matching_grad_case():
+    params = synth.make_params(synth.matching_operation_specs(), 81)
+    left = torch.from_numpy(synth.tensor((2, 64, 6, 13), 82)).requires_grad_(True)
+    right = torch.from_numpy(synth.tensor((2, 64, 6, 13), 83)).requires_grad_(True)
+    probe = torch.from_numpy(synth.tensor((2, 8, 5, 6, 13), 84))
+    return params, left, right, probe
+
+
+def test_torch_port_matching_gradients(golden):
+    g = golden('matching_grad')
+    params, left, right, probe = _matching_grad_case()
+    p = {k: v.clone().requires_grad_(True) for k, v in tdict(params).items()}
+    sig = torch_port.matching(left, right, lambda x: torch_port.matching_operation(x, p, 2), 4)
+    (sig * probe).sum().backward()
+    close(sig.detach().numpy(), g['signatures'], 2e-5)
+    scale = float(np.abs(g['grad_left']).max())
+    close(left.grad.numpy(), g['grad_left'], 2e-5 * scale)
+    close(right.grad.numpy(), g['grad_right'], 2e-5 * scale)
+    for k, v in p.items():
+        ref = g['grad_param_' + k.replace('.', '__')]
+        close(v.grad.numpy(), ref, 1e-4 * max(1.0, float(np.abs(ref).max())))
+
+
+def test_package_matching_gradients_on_cpu(golden):
+    """CPU tensors with gradients: the package runs the reference's per-disparity composition."""
+    from practicaldeepstereo_nips2018_b200 import matching
+    g = golden('matching_grad')
+    params, left, right, probe = _matching_grad_case()
+    op = matching.MatchingOperation(precision='fp32')
+    op.load_state_dict(tdict(params))
+    op.train()
+    sig = matching.Matching(4, op)(left, right)
+    (sig * probe).sum().backward()
+    close(sig.detach().numpy(), g['signatures'], 2e-5)
+    scale = float(np.abs(g['grad_left']).max())
+    close(left.grad.numpy(), g['grad_left'], 2e-5 * scale)
+    close(right.grad.numpy(), g['grad_right'], 2e-5 * scale)
+    for k, v in op.named_parameters():
+        ref = g['grad_param_' + k.replace('.', '__')]
+        close(v.grad.numpy(), ref, 1e-4 * max(1.0, float(np.abs(ref).max())))
