@@ -111,6 +111,25 @@ int pds_matching_concat_backward(const void* grad_volume, void* grad_left,
 int pds_matching_unstack(const void* in, void* out, int B, int F, int D, int H,
                          int W, int dtype, void* stream);
 
+/* f4 (training): InstanceNorm{2,3}d(affine, eps)(LeakyReLU_slope(x)) -- the
+ * tail of every Conv -> LeakyReLU -> InstanceNorm block (network_blocks.py:
+ * 47-58, 88-131) -- forward and backward on fp32 (N, C, L) tensors (L = product
+ * of the spatial extents), slope = 1 for a plain InstanceNorm; gamma / beta may
+ * be null (affine=False).
+ *   forward : y; mean_rstd (N*C, 2) float is kept for the backward; sums is
+ *             (N*C, 2) double scratch.
+ *   backward: dx; on return sums (N*C, 2) double holds, per (sample, channel),
+ *             sum dy and sum dy * zhat: d beta / d gamma are their sums over
+ *             the samples. */
+int pds_instance_norm_forward(const float* x, const float* gamma,
+                              const float* beta, float* y, float* mean_rstd,
+                              double* sums, int N, int C, long long L,
+                              float eps, float slope, void* stream);
+int pds_instance_norm_backward(const float* x, const float* dy,
+                               const float* gamma, const float* mean_rstd,
+                               float* dx, double* sums, int N, int C,
+                               long long L, float slope, void* stream);
+
 /* ---- a2: MatchingOperation.forward over all disparities ------------------
  * (matching.py:69-112 applied by the loop of matching.py:53-62.)
  * Weights are given in the reference's own layout, in state_dict() order of

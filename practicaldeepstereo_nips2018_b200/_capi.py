@@ -41,6 +41,8 @@ SIGNATURES = {
     'pds_matching_stack': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'pds_matching_unstack': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'pds_matching_concat_backward': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'pds_instance_norm_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, _vp]),
+    'pds_instance_norm_backward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, ctypes.c_longlong, ctypes.c_float, _vp]),
     'pds_matching_op_create': (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp]),
     'pds_matching_op_destroy': (None, [_vp]),
     'pds_matching_op_workspace_bytes': (_sz, [_vp, _i, _i, _i, _i]),
@@ -121,7 +123,7 @@ def require_cuda(*tensors):
 
 
 def ptr(t):
-    return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.data_ptr() if t is not None else None)
 
 
 def pointer_array(tensors):

@@ -17,17 +17,12 @@ kernels in the backward (``_ConcatVolume``, ``_StackDisparities``).
 """
 import copy
 import ctypes
-import os
 import threading
 
 import torch
 from torch import nn
 
 from . import _capi, network_blocks
-
-# f4: training-mode Matching on the volume / stack kernels and their adjoints (0: the reference's
-# per-disparity composition)
-USE_TRAINING_KERNELS = os.environ.get('PDS_B200_TRAIN_KERNELS', '1') == '1'
 
 
 def _needs_autograd(*tensors_and_modules):
@@ -318,7 +313,7 @@ class Matching(nn.Module):
         backward; this is ~20.  Otherwise (CPU, other dtypes, ``batched_operation=False``) the
         reference's per-disparity composition."""
         md = self._maximum_disparity
-        if (self._batched_operation and USE_TRAINING_KERNELS and left.is_cuda and right.is_cuda
+        if (self._batched_operation and network_blocks.USE_TRAINING_KERNELS and left.is_cuda and right.is_cuda
                 and left.dtype == right.dtype and left.dtype in (torch.float32, torch.bfloat16)
                 and left.shape == right.shape and left.dim() == 4):
             volume = _ConcatVolume.apply(left, right, md + 1)

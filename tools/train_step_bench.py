@@ -16,11 +16,11 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import torch_port  # noqa: E402
-from practicaldeepstereo_nips2018_b200 import PdsNetwork, loss as pds_loss, matching  # noqa: E402
+from practicaldeepstereo_nips2018_b200 import PdsNetwork, loss as pds_loss, network_blocks  # noqa: E402
 
 
 def step_ms(kernels, H, W, md, steps):
-    matching.USE_TRAINING_KERNELS = kernels
+    network_blocks.USE_TRAINING_KERNELS = kernels
     torch.manual_seed(0)
     net = PdsNetwork.default(md).cuda().train()
     opt = torch.optim.RMSprop(net.parameters(), lr=1e-2)
