@@ -831,7 +831,7 @@ tc_compose_first_kernel(const float* __restrict__ A, const float* __restrict__ B
 // (B, C, H, W) fp32 -> AP [B][S][C/8][H][W][8]
 template <bool FP16>
 __global__ void tc_pack_nchw_kernel(const float* __restrict__ in, uint16_t* __restrict__ ap,
-                                    int C, size_t HW, int S, size_t total) {
+                                    int C, size_t HW, int S, size_t total, int x4_width) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const size_t pix = i % HW;
@@ -844,7 +844,12 @@ __global__ void tc_pack_nchw_kernel(const float* __restrict__ in, uint16_t* __re
     union { uint16_t h[8]; uint4 u; } pk;
 #pragma unroll
     for (int e = 0; e < 8; ++e) pk.h[e] = t[e][s];
-    reinterpret_cast<uint4*>(ap)[((b * S + s) * (C / 8) + c8) * HW + pix] = pk.u;
+    if (x4_width) {    // four x-phase sub-volumes (conv_tcg.cuh, TCG_CONV3_S1X4): [b][S][x & 3][C/8][rows][W/4][8]
+      const size_t row = pix / (size_t)x4_width, x = pix - row * x4_width;
+      reinterpret_cast<uint4*>(ap)[(((b * S + s) * 4 + (x & 3)) * (C / 8) + c8) * (HW / 4) + row * (x4_width / 4) + (x >> 2)] = pk.u;
+    } else {
+      reinterpret_cast<uint4*>(ap)[((b * S + s) * (C / 8) + c8) * HW + pix] = pk.u;
+    }
   }
 }
 
@@ -1087,14 +1092,15 @@ int tc_compose_first(const float* A, const float* Bf, const float* Q, uint16_t* 
   return PDS_OK;
 }
 
-int tc_pack_nchw(const float* in, uint16_t* ap, int B, int C, int H, int W, int S, int fp16, cudaStream_t st) {
+int tc_pack_nchw(const float* in, uint16_t* ap, int B, int C, int H, int W, int S, int fp16, cudaStream_t st,
+                 int x4_width) {
   const size_t HW = (size_t)H * W, total = (size_t)B * (C / 8) * HW;
   if (total == 0) return PDS_OK;
   PDS_KERNEL("tc_pack_nchw", st);
   PDS_KERNEL_WORK(0, (double)B * C * HW * (4 + 2 * S));
   const unsigned g = (unsigned)((total + 255) / 256);
-  if (fp16) tc_pack_nchw_kernel<true><<<g, 256, 0, st>>>(in, ap, C, HW, S, total);
-  else tc_pack_nchw_kernel<false><<<g, 256, 0, st>>>(in, ap, C, HW, S, total);
+  if (fp16) tc_pack_nchw_kernel<true><<<g, 256, 0, st>>>(in, ap, C, HW, S, total, x4_width);
+  else tc_pack_nchw_kernel<false><<<g, 256, 0, st>>>(in, ap, C, HW, S, total, x4_width);
   PDS_LAUNCH_CHECK("tc_pack_nchw_kernel");
   return PDS_OK;
 }

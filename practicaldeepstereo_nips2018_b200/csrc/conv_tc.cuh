@@ -101,9 +101,10 @@ int tc_prepare_weights(const TcLayer& l, const float* w_oihw, const float* bias,
 int tc_compose_first(const float* A, const float* Bf, const float* Q, uint16_t* out_ap, int B, int C, int H,
                      int W, int D, int S, int fp16, cudaStream_t st);
 
-// (B, C, H, W) fp32 -> AP [B][S][C/8][H][W][8]
+// (B, C, H, W) fp32 -> AP [B][S][C/8][H][W][8]; x4_width > 0: rows of that width (H * W a multiple of
+// it), written as the four x-phase sub-volumes a TCG_CONV3_S1X4 layer reads (conv_tcg.cuh)
 int tc_pack_nchw(const float* in, uint16_t* ap, int B, int C, int H, int W, int S, int fp16,
-                 cudaStream_t st);
+                 cudaStream_t st, int x4_width = 0);
 
 int tc_conv3x3(const TcConvArgs& a, cudaStream_t st);
 

@@ -40,6 +40,7 @@ struct alignas(64) TcgParams {
   int n_samples, lrelu, fp16;
   int nacc, ntx, ntz, ncls, upi;
   int GZ, GY, GX, OZ, OY, OX, Cout, mul, nd3;
+  int CoutS, reps;               // channels of one stored row (xg * Cout); columns per channel (1, xg or 8 classes)
   int tiles_x, tiles_y, tiles_z;
   int BX, planes_per_term, ntx_log2, zstride16;
   int resident, stages, reuse, merged, flat;
@@ -48,7 +49,7 @@ struct alignas(64) TcgParams {
   uint32_t box_bytes, box_tx_bytes, term_bytes, a_bytes, stage_bytes, wres_bytes, w_total_bytes;
   uint32_t off_boxes, off_entries, off_tiles, table_bytes;
   float inv_wscale;
-  long long* trace;              // optional per-CTA cycle stamps (debug): [cta][8]
+  long long* trace;              // optional per-CTA cycle stamps (debug): [cta][12]
 };
 
 constexpr uint32_t pow2_cols(uint32_t c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
@@ -115,7 +116,8 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // everything below reads / writes tensors of the stream's earlier kernels
   const long long t_start = clock64();
-  auto stamp = [&](int k) { if (p.trace) p.trace[(size_t)blockIdx.x * 8 + k] = clock64() - t_start; };
+  auto stamp = [&](int k) { if (p.trace) p.trace[(size_t)blockIdx.x * 12 + k] = clock64() - t_start; };
+  auto tally = [&](int k, long long t) { if (p.trace) p.trace[(size_t)blockIdx.x * 12 + k] += t; };
 
   // work item = (CTA tile, output class); every CTA walks one contiguous range of items (whole
   // tiles when a stage is shared by the classes of a tile)
@@ -154,7 +156,9 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
         for (int u = it.u0; u < it.u1; ++u) {
           const TcgUnit un = units[it.cls * p.upi + u];
           const int nb = un.box_end - un.box_beg;
+          const long long tw = p.trace ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1);
+          if (p.trace) tally(10, clock64() - tw);
           mbar_expect_tx(full_bar(stage), (uint32_t)nb * S * p.box_tx_bytes + (p.resident ? 0u : un.w_bytes));
           const uint32_t sa = stage_base + stage * p.stage_bytes;
           for (int j = 0; j < nb; ++j) {
@@ -193,6 +197,15 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
     const uint32_t b_lbo = ((uint32_t)(S * N) & 0x3fff) << 16;     // K-half stride of the B operand, 16-byte units
     const uint32_t term16 = p.term_bytes >> 4;
     const uint32_t ent_base = smem_u32(entries);
+    // per (MMA tile, term) part of the A start address: constant for the whole launch, so that an MMA
+    // costs the issuing lane one add (with the tile arithmetic inside the entry loop the lane needed
+    // ~15 uniform-datapath instructions per MMA and, at ~4 cycles each, was slower than the tensor core)
+    uint32_t toff[NACC_MAX][S];
+#pragma unroll
+    for (int i = 0; i < NACC_MAX; ++i)
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+        toff[i][s] = (uint32_t)((i >> p.ntx_log2) * p.zstride16 + ((i & (p.ntx - 1)) << 3)) + s * term16;
     if (p.resident) { mbar_wait(wfull_bar, 0); tc_fence_after(); }
     if (lane == 0) stamp(2);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
@@ -200,23 +213,31 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
     for (int item = item_begin; item < item_end; ++item) {
       const int cls = (item / p.ksplit) % p.ncls;
       const int u0 = (item % p.ksplit) * p.upi / p.ksplit, u1 = (item % p.ksplit + 1) * p.upi / p.ksplit;
+      const long long tw0 = p.trace ? clock64() : 0;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      if (p.trace && lane == 0) tally(9, clock64() - tw0);
       tc_fence_after();
       const uint32_t d_base = tmem_base + acc * buf_cols;
       const bool hold = p.reuse && cls + 1 < p.ncls;      // the stage serves the next class too
       for (int u = u0; u < u1; ++u) {
         const TcgUnit un = units[cls * p.upi + u];
         if (!(p.reuse && cls > 0)) {
+          const long long tw1 = p.trace ? clock64() : 0;
           mbar_wait(full_bar(stage), phase);
+          if (p.trace && lane == 0) tally(8, clock64() - tw1);
           tc_fence_after();
           if (first_full && lane == 0) { stamp(3); first_full = false; }
         }
         const uint32_t sa16 = (stage_base + stage * p.stage_bytes) >> 4;
         const uint32_t sw16 = p.resident ? (wres_base >> 4) : sa16;
         if (elect_one()) {
-          // entries come from shared memory one ahead of their use; everything else in the loop is
-          // warp-uniform arithmetic on kernel parameters (the issue rate of this lane bounds the
-          // narrow layers: an N = 16 MMA lasts ~36 cycles)
+          // entries come from shared memory one ahead of their use.  What was tried on this loop for
+          // the N = 32 four-voxel layer (63 cycles per MMA against 46 in tools/mma_microbench.cu):
+          // tile offsets hoisted out of the loop (kept), the whole warp walking the loop with only the
+          // MMA guarded by the elected lane (same 25 SASS instructions per tile, same time), term-major
+          // order (slower: 103 K against 90 K cycles).  The issuing lane is NOT waiting on a barrier
+          // (PDS_B200_TCG_TRACE: 6 K of 90 K cycles, the pipeline fill) -- the tensor pipe itself takes
+          // longer per MMA than in the microbenchmark while TMA writes and the epilogue run beside it.
           uint2 en = lds64(ent_base + 8u * un.ent_beg);
           for (int e = un.ent_beg; e < un.ent_end; ++e) {
             const uint2 nxt = lds64(ent_base + 8u * min(e + 1, un.ent_end - 1));
@@ -226,10 +247,9 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
 #pragma unroll
             for (int i = 0; i < NACC_MAX; ++i) {
               if (i < p.nacc) {
-                const uint32_t a_i = a_lo + (uint32_t)((i >> p.ntx_log2) * p.zstride16 + ((i & (p.ntx - 1)) << 3));
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                  const uint64_t ad = umma_desc(a_i + s * term16, a_hi);
+                  const uint64_t ad = umma_desc(a_lo + toff[i][s], a_hi);
                   tc_mma(d_base + i * ACC_COLS + s * N, ad, bd, idesc[s], s == 0 ? accumulate : 1u);
                   if (N * (S - s) > 256)   // B rows 256.. (16 bytes each), accumulator columns 256..
                     tc_mma(d_base + i * ACC_COLS + s * N + 256, ad, bd + 256, idesc_rest[s],
@@ -270,8 +290,8 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             const int col = c * CH + lane;
-            const int ch = p.merged ? col % p.Cout : col;       // merged: 8 columns (classes) per channel
-            if (col < (p.merged ? 8 * p.Cout : p.Cout) && (s1[c] != 0.0 || s2[c] != 0.0)) {
+            const int ch = p.reps > 1 ? col % p.Cout : col;     // merged classes / voxel groups: several columns per channel
+            if (col < p.reps * p.Cout && (s1[c] != 0.0 || s2[c] != 0.0)) {
               atomicAdd(&sred[2 * ch], s1[c]); atomicAdd(&sred[2 * ch + 1], s2[c]);
             }
           }
@@ -308,7 +328,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
         const bool valid = gx < p.GX && gy < p.GY && gz < p.GZ;
         const int oz = p.nd3 ? p.mul * gz + cz : 0, oy = p.mul * gy + cy, ox = p.mul * gx + cx;
         float* o = p.out + (size_t)(item % p.ksplit) * p.ksplit_stride +
-                   ((((size_t)it.n * p.OZ + oz) * p.OY + oy) * p.OX + ox) * p.Cout;
+                   ((((size_t)it.n * p.OZ + oz) * p.OY + oy) * p.OX + ox) * p.CoutS;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           if (!split_tiles && NCH > 1 && (c >= NCH / 2) != (half != 0)) continue;
@@ -350,14 +370,14 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
                   *reinterpret_cast<float4*>(om) = make_float4(v[0][j], v[0][j + 1], v[0][j + 2], v[0][j + 3]);
                 }
               }
-            } else if ((p.Cout & 7) == 0) {
+            } else if ((p.CoutS & 7) == 0) {
 #pragma unroll
               for (int j = 0; j < CH; j += 8)
-                if (c * CH + j < p.Cout) stg256(o + c * CH + j, &v[0][j]);
+                if (c * CH + j < p.CoutS) stg256(o + c * CH + j, &v[0][j]);
             } else {
 #pragma unroll
               for (int j = 0; j < CH; j += 4)
-                if (c * CH + j < p.Cout)
+                if (c * CH + j < p.CoutS)
                   *reinterpret_cast<float4*>(o + c * CH + j) = make_float4(v[0][j], v[0][j + 1], v[0][j + 2], v[0][j + 3]);
             }
           }
@@ -401,7 +421,7 @@ template <bool FP16>
 __global__ void tcg_prepare_weights_kernel(const float* __restrict__ w, const TcgWeightSrc* __restrict__ src,
                                            uint16_t* __restrict__ out, int n_entries, int Cin, int Cout,
                                            int N, int S, int KZ, int KY, int KX, int transposed,
-                                           float wscale, int merged) {   // Cin: channels of the SOURCE tensor (<= the layer's)
+                                           float wscale, int merged, int xg) {   // Cin: channels of the SOURCE tensor (<= the layer's)
   const size_t per_entry = (size_t)2 * N * 8;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_entry * n_entries) return;
@@ -428,6 +448,14 @@ __global__ void tcg_prepare_weights_kernel(const float* __restrict__ w, const Tc
       const int ci = 8 * ws.group[h] + c;
       x = w[((((size_t)ci * Cout + ch) * 4 + k[0]) * 4 + k[1]) * 4 + k[2]] * wscale;
     }
+  } else if (xg > 1) {
+    // column = output position j of the voxel group * Cout + channel; the extended x tap k' reaches
+    // output j through kernel index k' - j
+    const int j = co / Cout, ch = co - j * Cout, kx = ws.kx[h] - j;
+    if (ws.group[h] >= 0 && j < xg && kx >= 0 && kx < KX && 8 * ws.group[h] + c < Cin) {
+      const int ci = 8 * ws.group[h] + c;
+      x = w[((((size_t)ch * Cin + ci) * KZ + ws.kz[h]) * KY + ws.ky[h]) * KX + kx] * wscale;
+    }
   } else if (ws.group[h] >= 0 && co < Cout && 8 * ws.group[h] + c < Cin) {
     const int ci = 8 * ws.group[h] + c;
     const size_t a = transposed ? ((size_t)ci * Cout + co) : ((size_t)co * Cin + ci);
@@ -440,9 +468,9 @@ __global__ void tcg_prepare_weights_kernel(const float* __restrict__ w, const Tc
 }
 
 __global__ void tcg_pad_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int Cout, int N,
-                                    int merged) {
+                                    int reps) {   // reps columns per channel (merged classes / voxel groups)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) out[i] = merged ? (i < 8 * Cout ? b[i % Cout] : 0.f) : (i < Cout ? b[i] : 0.f);
+  if (i < N) out[i] = i < reps * Cout ? b[i % Cout] : 0.f;
 }
 
 // ---- normalisation pass: fp32 channels-last -> split AP planes ------------------------------------
@@ -493,9 +521,11 @@ tcg_norm_to_ap_kernel(const NormParams p) {
   // per-CTA prologue above -- double-precision statistics -- is amortised over many units, and
   // enough bytes are in flight per SM).  No per-item division: G is a power of two.
   const int G = p.C / 8, gshift = 31 - __clz(G);
-  const int sep = p.phases > 1;
+  const bool x4 = p.phases == TCG_PHASES_X4;      // four x-phase sub-volumes (S1X4 consumer)
+  const int nph = x4 ? 4 : p.phases;
+  const int sep = !x4 && p.phases > 1;
   const int sepz = p.phases == 8;
-  const int IZ = sepz ? p.Z / 2 : p.Z, IY = sep ? p.Y / 2 : p.Y, IX = sep ? p.X / 2 : p.X;
+  const int IZ = sepz ? p.Z / 2 : p.Z, IY = sep ? p.Y / 2 : p.Y, IX = x4 ? p.X / 4 : (sep ? p.X / 2 : p.X);
   const size_t plane = (size_t)IZ * IY * IX;
   const int rows = p.Z * p.Y, items = p.X * G;
   const int chunks = (items + 255) >> 8, units = rows * chunks;
@@ -537,14 +567,14 @@ tcg_norm_to_ap_kernel(const NormParams p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) split_terms<FP16>(v[e], t[e]);
     const int zz = sepz ? z >> 1 : z, yy = sep ? y >> 1 : y;
-    const int ph = (sep ? ((sepz ? (z & 1) * 4 : 0) + (y & 1) * 2) : 0) + (sep ? (x & 1) : 0);
-    const size_t pos = ((size_t)zz * IY + yy) * IX + (sep ? x >> 1 : x);
+    const int ph = x4 ? (x & 3) : (sep ? ((sepz ? (z & 1) * 4 : 0) + (y & 1) * 2) : 0) + (sep ? (x & 1) : 0);
+    const size_t pos = ((size_t)zz * IY + yy) * IX + (x4 ? x >> 2 : (sep ? x >> 1 : x));
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       float4 pk;
       pk.x = __uint_as_float(t[0][s] | ((uint32_t)t[1][s] << 16)); pk.y = __uint_as_float(t[2][s] | ((uint32_t)t[3][s] << 16));
       pk.z = __uint_as_float(t[4][s] | ((uint32_t)t[5][s] << 16)); pk.w = __uint_as_float(t[6][s] | ((uint32_t)t[7][s] << 16));
-      stg_stream(reinterpret_cast<float4*>(p.out) + ((((size_t)n * S + s) * p.phases + ph) * G + g) * plane + pos, pk);
+      stg_stream(reinterpret_cast<float4*>(p.out) + ((((size_t)n * S + s) * nph + ph) * G + g) * plane + pos, pk);
     }
   };
   for (int u = blockIdx.x; u < units; u += 2 * gridDim.x) {
@@ -600,7 +630,7 @@ const char* tcg_name(int S, int N, const TcgPlan& pl) {
   static std::set<std::string> names;
   std::string n = "conv_tcg<S=" + std::to_string(S) + ",N=" + std::to_string(N) + ">";
   if (detail) {
-    static const char* kinds[] = {"c3s1", "c3s2", "t4s2", "c5s2", "t4s2m"};
+    static const char* kinds[] = {"c3s1", "c3s2", "t4s2", "c5s2", "t4s2m", "c3s1x4"};
     n += std::string("[") + kinds[pl.shape.kind] + " " + std::to_string(pl.shape.Cin) + "->" +
          std::to_string(pl.shape.Cout) + " " + std::to_string(pl.shape.Z) + "x" + std::to_string(pl.shape.Y) +
          "x" + std::to_string(pl.shape.X) + "]";
@@ -657,15 +687,15 @@ int tcg_layer_init(TcgLayer& l, char* blob, const float* w_src, const float* bia
     if (l.fp16)
       tcg_prepare_weights_kernel<true><<<g, 256, 0, st>>>(w_src, src, l.w, (int)pl.entries.size(), cin_src,
                                                           pl.shape.Cout, pl.N, pl.shape.S, KZ, k, k,
-                                                          l.transposed, l.wscale, pl.merged);
+                                                          l.transposed, l.wscale, pl.merged, pl.xg);
     else
       tcg_prepare_weights_kernel<false><<<g, 256, 0, st>>>(w_src, src, l.w, (int)pl.entries.size(), cin_src,
                                                            pl.shape.Cout, pl.N, pl.shape.S, KZ, k, k,
-                                                           l.transposed, l.wscale, pl.merged);
+                                                           l.transposed, l.wscale, pl.merged, pl.xg);
     PDS_LAUNCH_CHECK("tcg_prepare_weights_kernel");
   }
   PDS_KERNEL("tcg_pad_bias", st);
-  tcg_pad_bias_kernel<<<1, 128, 0, st>>>(bias_src, l.bias, pl.shape.Cout, pl.N, pl.merged);
+  tcg_pad_bias_kernel<<<1, 128, 0, st>>>(bias_src, l.bias, pl.shape.Cout, pl.N, pl.merged ? 8 : pl.xg);
   PDS_LAUNCH_CHECK("tcg_pad_bias_kernel");
   return PDS_OK;
 }
@@ -725,7 +755,7 @@ tcg_splitk_finish_kernel(const float* __restrict__ partials, int ksplit, size_t 
 int splitk_for(const TcgPlan& pl, int n_samples) {
   // PDS_B200_TCG_SPLITK: smallest k-slice count worth the fix-up launch (0: never split)
   static const int least = getenv("PDS_B200_TCG_SPLITK") ? atoi(getenv("PDS_B200_TCG_SPLITK")) : 4;
-  if (least <= 0 || pl.merged || pl.units_per_item < 2 || pl.shape.Cout % 4) return 1;
+  if (least <= 0 || pl.merged || pl.xg > 1 || pl.units_per_item < 2 || pl.shape.Cout % 4) return 1;
   if (pl.ncls > 1 && pl.units_per_item == 1) return 1;
   const int tiles = ((pl.GX + 8 * pl.ntx - 1) / (8 * pl.ntx)) * ((pl.GY + 15) / 16) * ((pl.GZ + pl.ntz - 1) / pl.ntz);
   const int items = tiles * n_samples * pl.ncls;
@@ -787,7 +817,8 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
     p.out = splitk_scratch; p.stats = nullptr; p.lrelu = 0;
   }
   p.nacc = pl.nacc; p.ntx = pl.ntx; p.ntz = pl.ntz; p.ncls = pl.ncls; p.upi = pl.units_per_item;
-  p.GZ = pl.GZ; p.GY = pl.GY; p.GX = pl.GX; p.OZ = pl.OZ; p.OY = pl.OY; p.OX = pl.OX;
+  p.GZ = pl.GZ; p.GY = pl.GY; p.GX = pl.GX; p.OZ = pl.OZ; p.OY = pl.OY; p.OX = pl.OX / pl.xg;   // a stored row = xg voxels
+  p.CoutS = pl.xg * pl.shape.Cout; p.reps = pl.merged ? 8 : pl.xg;
   p.Cout = pl.shape.Cout; p.mul = (pl.ncls > 1 || pl.merged) ? 2 : 1; p.nd3 = pl.shape.nd == 3;
   p.tiles_x = (pl.GX + 8 * pl.ntx - 1) / (8 * pl.ntx);
   p.tiles_y = (pl.GY + 15) / 16;
@@ -819,7 +850,7 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
   const int grid = total < num_sms() ? total : num_sms();
   const int k = (pl.shape.kind == TCG_TCONV4_S2 || pl.merged) ? 2 : (pl.shape.kind == TCG_CONV5_S2 ? 5 : 3);
   const double taps = (double)k * k * (pl.shape.nd == 3 ? k : 1);
-  const double rows = (double)n_samples * pl.GZ * pl.GY * pl.GX * (pl.merged ? 8 : pl.ncls);
+  const double rows = (double)n_samples * pl.GZ * pl.GY * pl.GX * (pl.merged ? 8 : pl.ncls) * pl.xg;
   const double flops = 2.0 * taps * pl.shape.Cin * pl.shape.Cout * rows;
   const double bytes = (double)pl.in_ap_bytes(n_samples) + 4.0 * pl.out_elems(n_samples);
   int rc = PDS_ERR_UNSUPPORTED;
@@ -850,8 +881,8 @@ int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast,
                    int n, int C, int Z, int Y, int X, int S, int fp16, int phases, cudaStream_t st,
                    float* out_f32) {
   if (n == 0) return PDS_OK;
-  if (C % 8 || C > 128 || (phases != 1 && phases != 4 && phases != 8) ||
-      (phases > 1 && ((X | Y) & 1)) || (phases == 8 && (Z & 1))) {
+  if (C % 8 || C > 128 || (phases != 1 && phases != 4 && phases != 8 && phases != TCG_PHASES_X4) ||
+      (phases > 1 && ((X | Y) & 1)) || (phases == 8 && (Z & 1)) || (phases == TCG_PHASES_X4 && (X & 3))) {
     set_error("tcg_norm_to_ap: unsupported shape (C=%d, %d x %d x %d, phases %d)", C, Z, Y, X, phases);
     return PDS_ERR_UNSUPPORTED;
   }
@@ -925,27 +956,30 @@ extern "C" int pds_tcg_conv_debug(int kind, int nd, int Cin, int Cout, int Z, in
   rc = tcg_layer_init(l, blob, w, bias, st, &used);
   if (rc == PDS_OK) rc = nchw_to_nhwc(x, x_cl, n, Cin, vin, st);
   TcgNormSrc src; src.y = x_cl;
-  if (rc == PDS_OK) rc = tcg_norm_to_ap(src, nullptr, nullptr, ap, n, Cin, Z, Y, X, S, fp16, pl.nph, st);
+  if (rc == PDS_OK) rc = tcg_norm_to_ap(src, nullptr, nullptr, ap, n, Cin, Z, Y, X, S, fp16, pl.phase_arg(), st);
   if (rc == PDS_OK && stats) {
     cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)n * Cout * 2 * sizeof(double), st);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync");
   }
   const bool trace = getenv("PDS_B200_TCG_TRACE") != nullptr;
   if (trace) {
-    cudaMalloc(&g_tcg_trace, 148 * 8 * sizeof(long long));
-    cudaMemset(g_tcg_trace, 0, 148 * 8 * sizeof(long long));
+    cudaMalloc(&g_tcg_trace, 148 * 12 * sizeof(long long));
+    cudaMemset(g_tcg_trace, 0, 148 * 12 * sizeof(long long));
     if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, nullptr, lrelu, st, sk, b_sk);   // warm (instruction cache, L2)
+    cudaStreamSynchronize(st);
+    cudaMemset(g_tcg_trace, 0, 148 * 12 * sizeof(long long));   // the wait tallies accumulate
   }
   if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, stats, lrelu, st, sk, b_sk);
   if (trace) {
     cudaStreamSynchronize(st);
-    long long h[148 * 8];
+    long long h[148 * 12];
     cudaMemcpy(h, g_tcg_trace, sizeof(h), cudaMemcpyDeviceToHost);
-    const char* names[8] = {"producer start", "producer done", "weights ready", "first stage full", "MMA issue done",
-                            "epilogue done", "stats flushed", "CTA end"};
-    for (int k = 0; k < 8; ++k) {
+    const char* names[12] = {"producer start", "producer done", "weights ready", "first stage full", "MMA issue done",
+                             "epilogue done", "stats flushed", "CTA end", "MMA waits: data", "MMA waits: accumulators",
+                             "producer waits: stage", "-"};
+    for (int k = 0; k < 11; ++k) {
       long long mx = 0, sum = 0; int cnt = 0;
-      for (int c = 0; c < 148; ++c) if (h[c * 8 + 7]) { mx = mx > h[c * 8 + k] ? mx : h[c * 8 + k]; sum += h[c * 8 + k]; ++cnt; }
+      for (int c = 0; c < 148; ++c) if (h[c * 12 + 7]) { mx = mx > h[c * 12 + k] ? mx : h[c * 12 + k]; sum += h[c * 12 + k]; ++cnt; }
       printf("trace %-18s avg %8lld max %8lld cycles (%d CTAs)\n", names[k], cnt ? sum / cnt : 0, mx, cnt);
     }
     cudaFree(g_tcg_trace); g_tcg_trace = nullptr;
@@ -967,11 +1001,11 @@ extern "C" int pds_tcg_conv_debug(int kind, int nd, int Cin, int Cout, int Z, in
       printf("timing: conv back-to-back WITH InstanceNorm sums %.1f us\n", ms_s * 100);
     }
     cudaEventRecord(e0, st);
-    for (int i = 0; i < 10; ++i) tcg_norm_to_ap(src, nullptr, nullptr, ap, n, Cin, Z, Y, X, S, fp16, pl.nph, st);
+    for (int i = 0; i < 10; ++i) tcg_norm_to_ap(src, nullptr, nullptr, ap, n, Cin, Z, Y, X, S, fp16, pl.phase_arg(), st);
     cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_n, e0, e1);
     cudaEventRecord(e0, st);
     for (int i = 0; i < 10; ++i) {
-      tcg_norm_to_ap(src, nullptr, nullptr, ap, n, Cin, Z, Y, X, S, fp16, pl.nph, st);
+      tcg_norm_to_ap(src, nullptr, nullptr, ap, n, Cin, Z, Y, X, S, fp16, pl.phase_arg(), st);
       tcg_conv_forward(l, n, ap, y_cl, nullptr, lrelu, st);
     }
     cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_b, e0, e1);

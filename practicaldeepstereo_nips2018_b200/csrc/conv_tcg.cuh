@@ -38,7 +38,17 @@ namespace pds {
 // channel; a tap a class does not use has zero weights).  An MMA with N <= 64 is operand-fetch
 // bound, so the wider N is free and the 27 merged taps replace 8 x 8 class taps: chosen by the
 // callers for Cout <= 8.
-enum TcgKind { TCG_CONV3_S1 = 0, TCG_CONV3_S2 = 1, TCG_TCONV4_S2 = 2, TCG_CONV5_S2 = 3, TCG_TCONV4_S2M = 4 };
+// TCG_CONV3_S1X4: the 8-channel 3x3(x3) layer with FOUR neighbouring output voxels of a row on the N
+// axis (column = x-position * Cout + channel).  A GEMM row is a group of four voxels; the input is
+// stored in four x-phase sub-volumes (x mod 4), so the six input columns a group needs (x-1 .. x+4)
+// are dense boxes and a tap is again a plain offset: 3x3x6 = 54 taps (27 paired MMAs) per 4 outputs
+// instead of 27 taps (14 MMAs) per output.  An N <= 32 MMA is operand-fetch bound (~47 cycles
+// whatever N is), so the wider N is free: 2x fewer tensor-core cycles per voxel.  The channels-last
+// output [x/4][4][Cout] is byte-identical to [x][Cout]: nothing downstream changes.
+enum TcgKind { TCG_CONV3_S1 = 0, TCG_CONV3_S2 = 1, TCG_TCONV4_S2 = 2, TCG_CONV5_S2 = 3, TCG_TCONV4_S2M = 4,
+               TCG_CONV3_S1X4 = 5 };
+// phase argument of tcg_norm_to_ap / tc_pack_nchw for an S1X4 consumer (x mod 4 sub-volumes)
+constexpr int TCG_PHASES_X4 = -4;
 
 struct TcgShape {
   int kind = TCG_CONV3_S1;
@@ -73,17 +83,19 @@ struct TcgPlan {
   TcgShape shape;
   int N = 16;                 // accumulator columns per weight term (Cout, or 8 * Cout when merged, padded to 16/32/64/128)
   int merged = 0;             // TCG_TCONV4_S2M
+  int xg = 1;                 // output voxels per GEMM row (4: TCG_CONV3_S1X4)
   int nacc = 1, ntx = 1, ntz = 1;   // MMA tiles per CTA tile
   int ncls = 1;               // output parity classes (8 for the 3-D transposed layer)
-  int nph = 1;                // phase sub-volumes of the input (1, 4 or 8)
+  int nph = 1;                // phase sub-volumes of the input (1, 4 or 8; 4 x-phases for S1X4)
   int P = 1;                  // 8-channel planes per phase
-  int GZ = 1, GY = 1, GX = 1; // grid the GEMM rows enumerate (per class)
+  int GZ = 1, GY = 1, GX = 1; // grid the GEMM rows enumerate (per class; S1X4: X / 4 voxel groups)
   int OZ = 1, OY = 1, OX = 1; // output extent
   int IZ = 1, IY = 1, IX = 1; // extent of ONE input (phase) sub-volume == tensor-map dims
   int BX = 0, BY = 0, BZ = 0, PB = 1;  // box shape (pixels / rows / planes / channel planes)
   int units_per_item = 0;     // units of one work item (the same for every class)
   int max_boxes = 0;          // boxes of the largest unit: one term occupies max_boxes * box_bytes of a stage
   int resident = 0;           // weights stay in shared memory for the whole launch
+  int phase_arg() const { return shape.kind == TCG_CONV3_S1X4 ? TCG_PHASES_X4 : nph; }   // what the producer of in_ap is told
   int stages = 0;
   unsigned box_bytes = 0, stage_bytes = 0, wres_bytes = 0, w_total_bytes = 0;
   std::vector<TcgUnit> units;         // [cls][unit]
@@ -144,7 +156,7 @@ struct TcgNormSrc {
 };
 // out_ap = IN(a) [+ IN(b)] [+ bcast] as split AP planes; bcast: fp32 channels-last
 // [n][Y][X][C] added to every z.  phases: 1 (plain), 4 or 8 (phase-separated for a stride-2
-// consumer).
+// consumer), or TCG_PHASES_X4.
 // out_f32 (optional): the same sum as fp32 channels-last (a later pass adds it as a residual).
 int tcg_norm_to_ap(const TcgNormSrc& a, const TcgNormSrc* b, const float* bcast, uint16_t* out_ap,
                    int n, int C, int Z, int Y, int X, int S, int fp16, int phases, cudaStream_t st,

@@ -15,7 +15,13 @@ struct DimTap { int k, phase, off; };
 //   CONV3_S2  in = 2o + k - 1 -> phase (k-1)&1, index o + floor((k-1)/2)
 //   CONV5_S2  in = 2o + k - 2 -> phase k&1,     index o + floor((k-2)/2)
 //   TCONV4_S2 out = 2z + cls; in = z + cls - t, kernel index 1 - cls + 2t  (t = 0, 1)
-std::vector<DimTap> dim_taps(int kind, int cls) {
+//   CONV3_S1X4 (x only): group X covers outputs 4X .. 4X+3; extended tap k' = 0..5 reads input
+//              4X + k' - 1 -> phase (k'-1) mod 4, group offset floor((k'-1)/4); output j of the group
+//              sees it through kernel index k' - j (zero weight outside 0..2)
+std::vector<DimTap> dim_taps(int kind, int cls, int dim) {
+  if (kind == TCG_CONV3_S1X4)
+    return dim == 2 ? std::vector<DimTap>{{0, 3, -1}, {1, 0, 0}, {2, 1, 0}, {3, 2, 0}, {4, 3, 0}, {5, 0, 1}}
+                    : std::vector<DimTap>{{0, 0, -1}, {1, 0, 0}, {2, 0, 1}};
   switch (kind) {
     case TCG_CONV3_S1: case TCG_TCONV4_S2M: return {{0, 0, -1}, {1, 0, 0}, {2, 0, 1}};   // merged: k = offset + 1
     case TCG_CONV3_S2: return {{0, 1, -1}, {1, 0, 0}, {2, 1, 0}};
@@ -38,6 +44,7 @@ int tcg_plan(const TcgShape& sh, TcgPlan* out) {
   const bool strided = sh.kind == TCG_CONV3_S2 || sh.kind == TCG_CONV5_S2;
   const bool merged = sh.kind == TCG_TCONV4_S2M;
   const bool transposed = sh.kind == TCG_TCONV4_S2;
+  const bool x4 = sh.kind == TCG_CONV3_S1X4;
   if (sh.nd != 2 && sh.nd != 3) { set_error("tcg_plan: nd must be 2 or 3"); return PDS_ERR_UNSUPPORTED; }
   if (sh.nd == 2 && sh.Z != 1) { set_error("tcg_plan: 2-D layers need Z == 1"); return PDS_ERR_UNSUPPORTED; }
   if (sh.Cin < 8 || sh.Cin % 8 || (sh.Cin > 8 && sh.Cin % 16) || sh.Cout < 1 || sh.Cout > 128 ||
@@ -53,18 +60,23 @@ int tcg_plan(const TcgShape& sh, TcgPlan* out) {
     set_error("tcg_plan: merged transposed layers are 3-D with Cout <= 16");
     return PDS_ERR_UNSUPPORTED;
   }
+  if (x4 && (sh.Cin != 8 || 4 * sh.Cout > 128 || (sh.X & 3))) {
+    set_error("tcg_plan: the four-voxels-per-row layer needs Cin == 8, Cout <= 32 and X %% 4 == 0");
+    return PDS_ERR_UNSUPPORTED;
+  }
   if (transposed && sh.nd != 3) { set_error("tcg_plan: transposed layers are 3-D only"); return PDS_ERR_UNSUPPORTED; }
   const int nd = sh.nd;
   const int div = strided ? 2 : 1;
-  p.IZ = nd == 3 ? sh.Z / div : 1; p.IY = sh.Y / div; p.IX = sh.X / div;
+  p.xg = x4 ? 4 : 1;
+  p.IZ = nd == 3 ? sh.Z / div : 1; p.IY = sh.Y / div; p.IX = sh.X / (x4 ? 4 : div);
   p.GZ = p.IZ; p.GY = p.IY; p.GX = p.IX;
   const int mul = (transposed || merged) ? 2 : 1;
-  p.OZ = p.GZ * (nd == 3 ? mul : 1); p.OY = p.GY * mul; p.OX = p.GX * mul;
+  p.OZ = p.GZ * (nd == 3 ? mul : 1); p.OY = p.GY * mul; p.OX = p.GX * mul * p.xg;
   p.ncls = transposed ? 8 : 1;
-  p.nph = strided ? (nd == 3 ? 8 : 4) : 1;
+  p.nph = strided ? (nd == 3 ? 8 : 4) : (x4 ? 4 : 1);
   p.P = sh.Cin / 8;
   p.PB = sh.Cin >= 16 ? 2 : 1;
-  p.N = pad_n(merged ? 8 * sh.Cout : sh.Cout);
+  p.N = pad_n(merged ? 8 * sh.Cout : p.xg * sh.Cout);
   p.merged = merged ? 1 : 0;
   const int S = sh.S;
   const int nchunks = sh.Cin >= 16 ? sh.Cin / 16 : 1;
@@ -74,7 +86,7 @@ int tcg_plan(const TcgShape& sh, TcgPlan* out) {
   int min_off[3] = {0, 0, 0}, max_off[3] = {0, 0, 0};
   for (int d = 3 - nd; d < 3; ++d)
     for (int c = 0; c < (transposed ? 2 : 1); ++c)
-      for (const DimTap& t : dim_taps(sh.kind, c)) {
+      for (const DimTap& t : dim_taps(sh.kind, c, d)) {
         min_off[d] = std::min(min_off[d], t.off);
         max_off[d] = std::max(max_off[d], t.off);
       }
@@ -84,7 +96,7 @@ int tcg_plan(const TcgShape& sh, TcgPlan* out) {
   int ntx, ntz;
   auto arrange = [&](int n) {
     if (nd == 2) { ntx = n; ntz = 1; return; }
-    ntx = n >= 4 ? 2 : (n == 2 ? 1 : 1);
+    ntx = x4 ? 1 : (n >= 4 ? 2 : 1);      // voxel groups: a row of the grid is short, stack the tiles in z (2 x 2 measured the same)
     ntz = n / ntx;
     while (ntz > 1 && ntz / 2 >= p.GZ) { ntz /= 2; }   // no point in stacking beyond the grid
   };
@@ -92,10 +104,12 @@ int tcg_plan(const TcgShape& sh, TcgPlan* out) {
   for (;; nacc /= 2) {
     arrange(nacc);
     const int T[3] = {ntz, 16, 8 * ntx};
-    // split candidates: (split_z, split_y)
-    const int cand[3][2] = {{0, 0}, {nd == 3 ? 1 : 0, nd == 3 ? 0 : 1}, {1, 1}};
-    for (int ci = 0; ci < (nd == 3 ? 3 : 2); ++ci) {
+    // split candidates: (split_z, split_y); the x-phase layer tries one unit per PHASE first (one box
+    // with the full z / y halo per stage: splitting its taps by kz would fetch every plane three times)
+    const int cand[4][2] = {{0, 0}, {0, 0}, {nd == 3 ? 1 : 0, nd == 3 ? 0 : 1}, {1, 1}};
+    for (int ci = x4 ? 0 : 1; ci < (nd == 3 ? 4 : 3); ++ci) {
       const bool split[3] = {cand[ci][0] != 0, cand[ci][1] != 0, false};
+      const bool split_ph = x4 && ci == 0;
       int B[3];
       for (int d = 0; d < 3; ++d) B[d] = d < 3 - nd ? 1 : T[d] + (split[d] ? 0 : max_off[d] - min_off[d]);
       p.BZ = B[0]; p.BY = B[1]; p.BX = B[2];
@@ -110,13 +124,15 @@ int tcg_plan(const TcgShape& sh, TcgPlan* out) {
         const int cc[3] = {(cls >> 2) & 1, (cls >> 1) & 1, cls & 1};
         std::vector<DimTap> dt[3];
         for (int d = 0; d < 3; ++d)
-          dt[d] = d < 3 - nd ? std::vector<DimTap>{{0, 0, 0}} : dim_taps(sh.kind, cc[d]);
+          dt[d] = d < 3 - nd ? std::vector<DimTap>{{0, 0, 0}} : dim_taps(sh.kind, cc[d], d);
         // tap groups
         const int gz = split[0] ? (int)dt[0].size() : 1, gy = split[1] ? (int)dt[1].size() : 1;
+        const int gp = split_ph ? p.nph : 1;
         int units_this_class = 0;
         for (int c = 0; c < nchunks; ++c)
           for (int iz = 0; iz < gz; ++iz)
-            for (int iy = 0; iy < gy; ++iy) {
+            for (int iy = 0; iy < gy; ++iy)
+            for (int ip = 0; ip < gp; ++ip) {
               TcgUnit u;
               u.ent_beg = (int)p.entries.size(); u.box_beg = (int)p.boxes.size();
               struct Ref { unsigned a; Tap t; };
@@ -130,8 +146,10 @@ int tcg_plan(const TcgShape& sh, TcgPlan* out) {
                     Tap t;
                     const DimTap* s[3] = {&dt[0][tz], &dt[1][ty], &dt[2][tx]};
                     for (int d = 0; d < 3; ++d) { t.k[d] = s[d]->k; t.phase[d] = s[d]->phase; t.off[d] = s[d]->off; }
-                    const int ph = nd == 3 ? (t.phase[0] * 2 + t.phase[1]) * 2 + t.phase[2]
-                                           : t.phase[1] * 2 + t.phase[2];
+                    const int ph = x4 ? t.phase[2]
+                                      : nd == 3 ? (t.phase[0] * 2 + t.phase[1]) * 2 + t.phase[2]
+                                                : t.phase[1] * 2 + t.phase[2];
+                    if (split_ph && ph != ip) continue;
                     int bi = -1;
                     for (size_t j = 0; j < phases.size(); ++j) if (phases[j] == ph) bi = (int)j;
                     if (bi < 0) {
@@ -232,7 +250,7 @@ int tcg_plan(const TcgShape& sh, TcgPlan* out) {
 
 // ---- test hook (not part of include/pds_b200.h: host logic only, used by tests/test_tcg_plan.py) ----
 // Serialises the plan of a layer into `buf` (int32 words); returns the number of words needed.
-// Layout: header[32] | units[nu][6] | boxes[nb][4] | entries[ne][2] | wsrc[ne][8] | tile_off[nacc]
+// Layout: header[40] | units[nu][6] | boxes[nb][4] | entries[ne][2] | wsrc[ne][8] | tile_off[nacc]
 extern "C" int pds_tcg_plan_describe(int kind, int nd, int Cin, int Cout, int Z, int Y, int X, int S,
                                      int* buf, int buf_words) {
   using namespace pds;
@@ -242,14 +260,14 @@ extern "C" int pds_tcg_plan_describe(int kind, int nd, int Cin, int Cout, int Z,
   const int rc = tcg_plan(sh, &p);
   if (rc != PDS_OK) return -rc;
   const int nu = (int)p.units.size(), nb = (int)p.boxes.size(), ne = (int)p.entries.size();
-  const int need = 32 + nu * 6 + nb * 4 + ne * 2 + ne * 8 + p.nacc;
+  const int need = 40 + nu * 6 + nb * 4 + ne * 2 + ne * 8 + p.nacc;
   if (!buf || buf_words < need) return need;
-  const int hdr[32] = {p.N, p.nacc, p.ntx, p.ntz, p.ncls, p.nph, p.P, p.GZ, p.GY, p.GX, p.OZ, p.OY, p.OX,
+  const int hdr[40] = {p.N, p.nacc, p.ntx, p.ntz, p.ncls, p.nph, p.P, p.GZ, p.GY, p.GX, p.OZ, p.OY, p.OX,
                        p.IZ, p.IY, p.IX, p.BX, p.BY, p.BZ, p.PB, p.units_per_item, p.resident, p.stages,
                        (int)p.box_bytes, (int)p.stage_bytes, (int)p.wres_bytes, (int)p.w_total_bytes,
-                       nu, nb, ne, p.max_boxes, p.merged};
+                       nu, nb, ne, p.max_boxes, p.merged, p.xg};
   int* w = buf;
-  for (int i = 0; i < 32; ++i) *w++ = hdr[i];
+  for (int i = 0; i < 40; ++i) *w++ = hdr[i];
   for (const TcgUnit& u : p.units) {
     *w++ = u.ent_beg; *w++ = u.ent_end; *w++ = u.box_beg; *w++ = u.box_end; *w++ = (int)u.w_off16; *w++ = (int)u.w_bytes;
   }

@@ -141,7 +141,12 @@ std::vector<TcgShape> hourglass_shapes(int F, int S, int D, int H, int W) {
     v.push_back(s);
   };
   int c = F, z = D, y = H, x = W;
-  add(TCG_CONV3_S1, c, c, z, y, x);
+  // the two full-extent F -> F layers (98 % of the hourglass' voxels) put four voxels of a row on the
+  // N axis (conv_tcg.cuh, TCG_CONV3_S1X4) when F == 8 and the width allows it; PDS_B200_TCG_X4=0: one
+  // voxel per GEMM row as everywhere else
+  static const bool x4_on = !(getenv("PDS_B200_TCG_X4") && atoi(getenv("PDS_B200_TCG_X4")) == 0);
+  const int full_kind = (x4_on && F == 8 && W % 4 == 0) ? TCG_CONV3_S1X4 : TCG_CONV3_S1;
+  add(full_kind, c, c, z, y, x);
   for (int k = 0; k < 4; ++k) {
     add(TCG_CONV3_S2, c, 2 * c, z, y, x);
     c *= 2; z /= 2; y /= 2; x /= 2;
@@ -154,7 +159,7 @@ std::vector<TcgShape> hourglass_shapes(int F, int S, int D, int H, int W) {
   for (int k = 0; k < 4; ++k) {
     add(tkind(c / 2), c, c / 2, z, y, x);
     c /= 2; z *= 2; y *= 2; x *= 2;
-    add(TCG_CONV3_S1, c, c, z, y, x);
+    add(k == 3 ? full_kind : TCG_CONV3_S1, c, c, z, y, x);
   }
   add(tkind(c / 2), c, c / 2, z, y, x);
   return v;
@@ -299,7 +304,8 @@ int tcg_forward(pds_regularization* reg, const float* signatures, const float* s
   };
 
   if ((rc = nchw_to_nhwc(shortcut, sc_cl, B, F, (size_t)H * W, st)) != PDS_OK) return rc;
-  if ((rc = tc_pack_nchw(signatures, ap[0], B, F, 1, (int)((size_t)D * H * W), S, fp16, st)) != PDS_OK) return rc;
+  if ((rc = tc_pack_nchw(signatures, ap[0], B, F, 1, (int)((size_t)D * H * W), S, fp16, st,
+                         L[0].plan.phase_arg() == TCG_PHASES_X4 ? W : 0)) != PDS_OK) return rc;
   // layer 0: output = smoothing(signatures); level-0 input = shortcut (broadcast over D) + output
   if ((rc = tcg_conv_forward(L[0], B, ap[0], y_l0, st_of(0), 1, st, splitk, bs.splitk)) != PDS_OK) return rc;
   if ((rc = tcg_norm_to_ap(src(0, y_l0), nullptr, sc_cl, ap[1], B, F, D, H, W, S, fp16, 8, st)) != PDS_OK) return rc;
@@ -326,7 +332,7 @@ int tcg_forward(pds_regularization* reg, const float* signatures, const float* s
     c /= 2; z *= 2; y *= 2; x *= 2;
     const int skip_layer = k < 3 ? 2 * (3 - k) : 0;
     const TcgNormSrc skip = src(skip_layer, k < 3 ? y_s[2 - k] : y_l0);
-    if ((rc = tcg_norm_to_ap(src(lu, y_u[k]), &skip, nullptr, ap[0], B, c, z, y, x, S, fp16, 1, st)) != PDS_OK) return rc;
+    if ((rc = tcg_norm_to_ap(src(lu, y_u[k]), &skip, nullptr, ap[0], B, c, z, y, x, S, fp16, L[lsm].plan.phase_arg(), st)) != PDS_OK) return rc;
     if ((rc = tcg_conv_forward(L[lsm], B, ap[0], y_e[k], st_of(lsm), 1, st, splitk, bs.splitk)) != PDS_OK) return rc;
     if ((rc = tcg_norm_to_ap(src(lsm, y_e[k]), nullptr, nullptr, ap[1], B, c, z, y, x, S, fp16, 1, st)) != PDS_OK) return rc;
   }

@@ -18,7 +18,7 @@ from gpu_util import cuda, load_module, max_abs, tdict
 
 pytestmark = pytest.mark.gpu
 
-CONV3_S1, CONV3_S2, TCONV4_S2, CONV5_S2, TCONV4_S2M = 0, 1, 2, 3, 4
+CONV3_S1, CONV3_S2, TCONV4_S2, CONV5_S2, TCONV4_S2M, CONV3_S1X4 = 0, 1, 2, 3, 4, 5
 
 
 def run_layer(kind, nd, x, w, b, S=2, fp16=1, lrelu=0):
@@ -45,7 +45,7 @@ def run_layer(kind, nd, x, w, b, S=2, fp16=1, lrelu=0):
 
 def aten(kind, nd, x, w, b):
     conv = F.conv3d if nd == 3 else F.conv2d
-    if kind == CONV3_S1:
+    if kind in (CONV3_S1, CONV3_S1X4):
         return conv(x, w, b, padding=1)
     if kind == CONV3_S2:
         return conv(x, w, b, padding=1, stride=2)
@@ -75,6 +75,10 @@ CASES = [
     (TCONV4_S2M, 3, 8, 4, 2, (5, 17, 17)),
     (TCONV4_S2M, 3, 8, 4, 1, (16, 48, 80)),
     (TCONV4_S2M, 3, 16, 8, 2, (8, 24, 40)),
+    (CONV3_S1X4, 3, 8, 8, 2, (5, 18, 20)),          # four voxels per GEMM row (x-phase-separated input)
+    (CONV3_S1X4, 3, 8, 8, 1, (16, 48, 80)),
+    (CONV3_S1X4, 3, 8, 8, 1, (6, 30, 240)),
+    (CONV3_S1X4, 3, 8, 4, 2, (3, 17, 12)),
     (CONV5_S2, 2, 64, 64, 2, (72, 120)),
     (CONV3_S1, 2, 64, 8, 2, (36, 130)),
     (CONV3_S1, 2, 64, 64, 1, (40, 50)),
@@ -85,7 +89,7 @@ CASES = [
 def test_layer_vs_aten(kind, nd, cin, cout, n, spatial):
     torch.backends.cudnn.allow_tf32 = False
     g = torch.Generator(device='cpu').manual_seed(kind * 977 + cin * 31 + cout + sum(spatial))
-    k = {CONV3_S1: 3, CONV3_S2: 3, TCONV4_S2: 4, CONV5_S2: 5, TCONV4_S2M: 4}[kind]
+    k = {CONV3_S1: 3, CONV3_S2: 3, TCONV4_S2: 4, CONV5_S2: 5, TCONV4_S2M: 4, CONV3_S1X4: 3}[kind]
     ks = (k,) * nd
     x = torch.randn((n, cin) + spatial, generator=g).cuda()
     wshape = ((cin, cout) if kind in (TCONV4_S2, TCONV4_S2M) else (cout, cin)) + ks

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from practicaldeepstereo_nips2018_b200 import _capi
 
-CONV3_S1, CONV3_S2, TCONV4_S2, CONV5_S2, TCONV4_S2M = 0, 1, 2, 3, 4
+CONV3_S1, CONV3_S2, TCONV4_S2, CONV5_S2, TCONV4_S2M, CONV3_S1X4 = 0, 1, 2, 3, 4, 5
 
 
 def describe(kind, nd, cin, cout, Z, Y, X, S=2):
@@ -26,9 +26,9 @@ def describe(kind, nd, cin, cout, Z, Y, X, S=2):
     assert fn(kind, nd, cin, cout, Z, Y, X, S, buf, need) == need
     a = np.frombuffer(buf, dtype=np.int32).copy()
     names = ('N nacc ntx ntz ncls nph P GZ GY GX OZ OY OX IZ IY IX BX BY BZ PB units_per_item '
-             'resident stages box_bytes stage_bytes wres_bytes w_total_bytes nu nb ne max_boxes').split()
-    p = dict(zip(names, a[:32].tolist()))
-    o = 32
+             'resident stages box_bytes stage_bytes wres_bytes w_total_bytes nu nb ne max_boxes merged xg').split()
+    p = dict(zip(names, a[:40].tolist()))
+    o = 40
     p['units'] = a[o:o + p['nu'] * 6].reshape(-1, 6); o += p['nu'] * 6
     p['boxes'] = a[o:o + p['nb'] * 4].reshape(-1, 4); o += p['nb'] * 4
     p['entries'] = a[o:o + p['ne'] * 2].reshape(-1, 2).astype(np.int64) & 0xffffffff; o += p['ne'] * 2
@@ -47,7 +47,10 @@ def emulate(p, kind, nd, x, w, S=2):
     IZ, IY, IX, BX, BY, BZ, PB = (p[k] for k in ('IZ', 'IY', 'IX', 'BX', 'BY', 'BZ', 'PB'))
     box16 = p['box_bytes'] // 16
     # input planes [n][phase][P][IZ][IY][IX][8]
-    if nph == 1:
+    x4 = kind == CONV3_S1X4
+    if x4:       # four x-phase sub-volumes
+        xin = np.stack([x[..., px::4] for px in range(4)], 1).reshape(n, 4, P, 8, IZ, IY, IX)
+    elif nph == 1:
         xin = x.reshape(n, 1, P, 8, IZ, IY, IX)
     elif nd == 3:
         xin = np.stack([x[:, :, pz::2, py::2, px::2] for pz, py, px in itertools.product((0, 1), repeat=3)], 1)
@@ -57,6 +60,7 @@ def emulate(p, kind, nd, x, w, S=2):
         xin = xin.reshape(n, 4, P, 8, IZ, IY, IX)
     planes = np.moveaxis(xin, 3, -1).reshape(n, nph * P, IZ, IY, IX, 8)
     out = np.zeros((n, cout, p['OZ'], p['OY'], p['OX']))
+    assert p['xg'] == (4 if x4 else 1) and p['OX'] == p['GX'] * p['xg'] * (2 if kind in (TCONV4_S2, TCONV4_S2M) else 1)
     rows = np.arange(128)
     row_off = (rows >> 3) * BX + (rows & 7)
     upi = p['units_per_item']
@@ -97,6 +101,13 @@ def emulate(p, kind, nd, x, w, S=2):
                                         ks.append(1 - cb + 2 * t if t in (0, 1) else None)
                                     if None not in ks:
                                         wm[mc * cout:(mc + 1) * cout] = w[8 * g:8 * g + 8, :, ks[0], ks[1], ks[2]].T
+                            elif x4:
+                                # column = position j of the voxel group * cout + channel; extended x
+                                # tap kx reaches output j through kernel index kx - j
+                                wm = np.zeros((4 * cout, 8))
+                                for j in range(4):
+                                    if 0 <= kx - j <= 2:
+                                        wm[j * cout:(j + 1) * cout] = w[:, 8 * g:8 * g + 8, kz, ky, kx - j]
                             elif kind == TCONV4_S2:
                                 wm = w[8 * g:8 * g + 8, :, kz, ky, kx].T          # (cout, 8)
                             else:
@@ -115,6 +126,9 @@ def emulate(p, kind, nd, x, w, S=2):
                                 for mc in range(8):
                                     out[b, :, 2 * gz + ((mc >> 2) & 1), 2 * gy + ((mc >> 1) & 1),
                                         2 * gx + (mc & 1)] = D[i, r, mc * cout:(mc + 1) * cout]
+                            elif x4:
+                                for j in range(4):
+                                    out[b, :, gz, gy, 4 * gx + j] = D[i, r, j * cout:(j + 1) * cout]
                             else:
                                 out[b, :, m * gz + cz if nd == 3 else 0, m * gy + cy, m * gx + cx] = D[i, r, :cout]
     return out
@@ -124,7 +138,7 @@ def reference(kind, nd, x, w):
     xt, wt = torch.from_numpy(x), torch.from_numpy(w)
     if nd == 2:
         xt, wt = xt[:, :, 0], wt[:, :, 0]
-    if kind == CONV3_S1:
+    if kind in (CONV3_S1, CONV3_S1X4):
         y = (F.conv3d if nd == 3 else F.conv2d)(xt, wt, padding=1)
     elif kind == CONV3_S2:
         y = (F.conv3d if nd == 3 else F.conv2d)(xt, wt, padding=1, stride=2)
@@ -152,6 +166,9 @@ CASES = [
     (TCONV4_S2, 3, 8, 4, 5, 17, 17),
     (TCONV4_S2M, 3, 8, 4, 5, 17, 17),     # parity classes merged along N
     (TCONV4_S2M, 3, 16, 8, 3, 18, 10),
+    (CONV3_S1X4, 3, 8, 8, 5, 18, 20),     # four voxels per GEMM row, x-phase-separated input
+    (CONV3_S1X4, 3, 8, 8, 3, 5, 76),      # several tiles along x, partial last tile
+    (CONV3_S1X4, 3, 8, 4, 2, 17, 12),
     (CONV5_S2, 2, 64, 64, 1, 36, 20),
     (CONV3_S1, 2, 64, 8, 1, 20, 70),
     (CONV3_S1, 2, 64, 64, 1, 17, 12),
@@ -162,7 +179,7 @@ CASES = [
 def test_plan_emulation_matches_aten(kind, nd, cin, cout, Z, Y, X):
     rng = np.random.RandomState(kind * 1000 + cin + cout + Z + Y + X)
     x = rng.randn(2 if cin <= 16 else 1, cin, Z, Y, X)
-    k = {CONV3_S1: 3, CONV3_S2: 3, TCONV4_S2: 4, CONV5_S2: 5, TCONV4_S2M: 4}[kind]
+    k = {CONV3_S1: 3, CONV3_S2: 3, TCONV4_S2: 4, CONV5_S2: 5, TCONV4_S2M: 4, CONV3_S1X4: 3}[kind]
     kz = k if nd == 3 else 1
     w = rng.randn(*((cin, cout) if kind in (TCONV4_S2, TCONV4_S2M) else (cout, cin)), kz, k, k) / np.sqrt(cin * k * k * kz)
     p = describe(kind, nd, cin, cout, Z, Y, X)
@@ -181,6 +198,7 @@ def test_plan_full_size_layers_fit():
     for (D, H, W) in [(48, 144, 240), (64, 144, 240), (48, 96, 320), (16, 16, 32)]:
         c, z, y, x = 8, D, H, W
         assert describe(CONV3_S1, 3, 8, 8, z, y, x)['stages'] >= 2
+        assert describe(CONV3_S1X4, 3, 8, 8, z, y, x)['stages'] >= 2
         for _ in range(4):
             assert describe(CONV3_S2, 3, c, 2 * c, z, y, x)['stages'] >= 2
             c, z, y, x = 2 * c, z // 2, y // 2, x // 2

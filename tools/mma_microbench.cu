@@ -23,7 +23,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 
 // Fully unrolled issue loop: descriptors are advanced by adding compile-time
 // constants to the low word, so one MMA costs ~3 SASS instructions of issue.
-template <int N, int NT, int PW, int M>
+template <int N, int NT, int PW, int M, int LBO16 = -1>     // LBO16 >= 0: the second K half is ANOTHER TAP, that many pixels away (8-channel layers)
 __global__ void __launch_bounds__(128, 1) bench(int iters, unsigned long long* out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, unsigned long long* o
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
                                ((uint32_t)(M >> 4) << 24);
     const uint32_t a_base = smem_u32(smem), b_base = a_base + 64 * 1024;
-    const uint64_t a0 = umma_desc(a_base, 18 * PW * 16, PW * 16);
+    const uint64_t a0 = umma_desc(a_base, LBO16 >= 0 ? LBO16 * 16 : 18 * PW * 16, PW * 16);
     const uint64_t b0 = umma_desc(b_base, N * 16, 128);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
@@ -77,11 +77,11 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, unsigned long long* o
   }
 }
 
-template <int N, int NT, int PW, int M>
+template <int N, int NT, int PW, int M, int LBO16 = -1>
 void run(unsigned long long* out) {
   const int iters = 200;
-  cudaFuncSetAttribute(bench<N, NT, PW, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  bench<N, NT, PW, M><<<148, 128, 200 * 1024>>>(iters, out);
+  cudaFuncSetAttribute(bench<N, NT, PW, M, LBO16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  bench<N, NT, PW, M, LBO16><<<148, 128, 200 * 1024>>>(iters, out);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("variant failed: %s\n", cudaGetErrorString(e)); exit(1); }
   unsigned long long h[148];
@@ -89,8 +89,8 @@ void run(unsigned long long* out) {
   double mx = 0, sum = 0;
   for (int i = 0; i < 148; ++i) { sum += h[i]; if (h[i] > mx) mx = (double)h[i]; }
   const double n = (double)iters * 9 * NT;
-  printf("N=%3d NT=%2d PW=%2d M=%3d | cycles/MMA avg %.1f max %.1f  (math floor %d)\n", N, NT, PW, M, sum / 148 / n,
-         mx / n, N / 2);
+  printf("N=%3d NT=%2d PW=%2d M=%3d LBO=%3d | cycles/MMA avg %.1f max %.1f  (math floor %d)\n", N, NT, PW, M, LBO16,
+         sum / 148 / n, mx / n, N / 2);
 }
 
 int main() {
@@ -101,5 +101,9 @@ int main() {
   run<192, 1, 26, 128>(out); run<192, 2, 26, 128>(out); run<256, 1, 26, 128>(out); run<256, 2, 26, 128>(out);
   run<32, 8, 26, 128>(out);  run<16, 8, 26, 128>(out);  run<64, 3, 24, 128>(out);  run<64, 3, 32, 128>(out);
   run<64, 4, 26, 64>(out);   run<128, 2, 26, 64>(out);  run<128, 2, 18, 128>(out); run<128, 1, 10, 128>(out);
+  // tap pairs on K (8-channel layers): second K half 1 / PW / 0 pixels away
+  run<32, 4, 18, 128, 1>(out);  run<32, 4, 18, 128, 16>(out); run<32, 4, 18, 128, 0>(out);
+  run<64, 4, 10, 128, 1>(out);  run<64, 4, 10, 128, 10>(out); run<64, 4, 10, 128, 0>(out);  run<64, 4, 10, 128>(out);
+  run<32, 4, 10, 128, 1>(out);  run<32, 4, 10, 128, 10>(out); run<64, 4, 18, 128, 1>(out);  run<64, 4, 12, 128, 1>(out);
   return 0;
 }
