@@ -77,6 +77,80 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, unsigned long long* o
   }
 }
 
+// The issue pattern of conv_tcg for split operands (S = 2): per entry and tile, a_hi x [w_hi | w_lo]
+// (2N columns) followed by a_lo x w_hi (N columns) into the SECOND half of the same accumulator.
+// OVERLAP = false: the second MMA goes to a separate accumulator instead (same work, no dependency).
+template <int N, int NT, bool OVERLAP>
+__global__ void __launch_bounds__(128, 1) bench_split(int iters, unsigned long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t id0 = base | ((uint32_t)(2 * N >> 3) << 17), id1 = base | ((uint32_t)(N >> 3) << 17);
+    constexpr int PW = 10;
+    const uint32_t a_base = smem_u32(smem), b_base = a_base + 96 * 1024;
+    const uint64_t a0 = umma_desc(a_base, 16, PW * 16);                  // tap pair: second K half one pixel away
+    const uint64_t b0 = umma_desc(b_base, 2 * N * 16, 128);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        const uint64_t bd = b0 + (uint64_t)((e * 2 * 2 * N * 16) >> 4);
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          const uint64_t ad = a0 + (uint64_t)((e / 3) * PW + e % 3 + i * 180);
+          mma(tmem + i * 2 * N, ad, bd, id0, 1);
+          mma(tmem + (OVERLAP ? i * 2 * N + N : NT * 2 * N + i * N), ad + 1080, bd, id1, 1);
+        }
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
+    }
+    out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+template <int N, int NT, bool OVERLAP>
+void run_split(unsigned long long* out) {
+  const int iters = 200;
+  cudaFuncSetAttribute(bench_split<N, NT, OVERLAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  bench_split<N, NT, OVERLAP><<<148, 128, 200 * 1024>>>(iters, out);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("variant failed: %s\n", cudaGetErrorString(e)); exit(1); }
+  unsigned long long h[148];
+  cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+  double sum = 0;
+  for (int i = 0; i < 148; ++i) sum += h[i];
+  printf("split pair N=%3d+%3d NT=%d %s | cycles per PAIR avg %.1f\n", 2 * N, N, NT,
+         OVERLAP ? "second MMA into the first one's upper half" : "second MMA into its own accumulator  ",
+         sum / 148 / ((double)iters * 9 * NT));
+}
+
 template <int N, int NT, int PW, int M, int LBO16 = -1>
 void run(unsigned long long* out) {
   const int iters = 200;
@@ -105,5 +179,7 @@ int main() {
   run<32, 4, 18, 128, 1>(out);  run<32, 4, 18, 128, 16>(out); run<32, 4, 18, 128, 0>(out);
   run<64, 4, 10, 128, 1>(out);  run<64, 4, 10, 128, 10>(out); run<64, 4, 10, 128, 0>(out);  run<64, 4, 10, 128>(out);
   run<32, 4, 10, 128, 1>(out);  run<32, 4, 10, 128, 10>(out); run<64, 4, 18, 128, 1>(out);  run<64, 4, 12, 128, 1>(out);
+  run_split<32, 4, true>(out); run_split<32, 4, false>(out); run_split<16, 8, true>(out); run_split<16, 8, false>(out);
+  run_split<64, 2, true>(out); run_split<64, 2, false>(out);
   return 0;
 }
