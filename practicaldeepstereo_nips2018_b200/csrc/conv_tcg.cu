@@ -41,6 +41,10 @@ struct alignas(64) TcgParams {
   int nacc, ntx, ntz, ncls, upi;
   int GZ, GY, GX, OZ, OY, OX, Cout, mul, nd3;
   int CoutS, reps;               // channels of one stored row (xg * Cout); columns per channel (1, xg or 8 classes)
+  // MMA issue constants, computed on the host so that they reach the issuing lane through the uniform
+  // datapath (kernel parameters) instead of ordinary registers + R2UR
+  uint32_t toff[8][3];           // A start offset of (MMA tile, term), 16-byte units
+  uint32_t idesc[3], idesc_rest[3], a_hi, b_hi, b_lbo;
   int tiles_x, tiles_y, tiles_z;
   int BX, planes_per_term, ntx_log2, zstride16;
   int resident, stages, reuse, merged, flat;
@@ -50,6 +54,7 @@ struct alignas(64) TcgParams {
   uint32_t off_boxes, off_entries, off_tiles, table_bytes;
   float inv_wscale;
   long long* trace;              // optional per-CTA cycle stamps (debug): [cta][12]
+  int dbg;                       // timing experiments (PDS_B200_TCG_DEBUG, only with the trace): 1 no global stores, 2 no TMEM reads, 4 no TMA loads after the first round of stages, 16 no wait tallies
 };
 
 constexpr uint32_t pow2_cols(uint32_t c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
@@ -117,7 +122,7 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
   pdl_wait();      // everything below reads / writes tensors of the stream's earlier kernels
   const long long t_start = clock64();
   auto stamp = [&](int k) { if (p.trace) p.trace[(size_t)blockIdx.x * 12 + k] = clock64() - t_start; };
-  auto tally = [&](int k, long long t) { if (p.trace) p.trace[(size_t)blockIdx.x * 12 + k] += t; };
+  auto tally = [&](int k, long long t) { if (p.trace && !(p.dbg & 16)) p.trace[(size_t)blockIdx.x * 12 + k] += t; };
 
   // work item = (CTA tile, output class); every CTA walks one contiguous range of items (whole
   // tiles when a stage is shared by the classes of a tile)
@@ -159,6 +164,11 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
           const long long tw = p.trace ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (p.trace) tally(10, clock64() - tw);
+          if ((p.dbg & 4) && (phase || item != item_begin)) {      // timing experiment: stages keep their first contents
+            mbar_arrive(full_bar(stage));
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(full_bar(stage), (uint32_t)nb * S * p.box_tx_bytes + (p.resident ? 0u : un.w_bytes));
           const uint32_t sa = stage_base + stage * p.stage_bytes;
           for (int j = 0; j < nb; ++j) {
@@ -182,42 +192,65 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t fmt = (1u << 4) | (p.fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(128 >> 4) << 24);
-    // activation term s multiplies the N * (S - s) concatenated weight rows; an MMA is at most 256
-    // columns wide, so the widest case (S = 3, N = 128) takes a second instruction for the rest
-    uint32_t idesc[S], idesc_rest[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int cols = N * (S - s), first = cols > 256 ? 256 : cols;
-      idesc[s] = fmt | ((uint32_t)(first >> 3) << 17);
-      idesc_rest[s] = fmt | ((uint32_t)((cols - first) >> 3) << 17);
-    }
-    const uint32_t a_hi = umma_desc_hi((uint32_t)p.BX * 16);
-    const uint32_t b_hi = umma_desc_hi(128);
-    const uint32_t b_lbo = ((uint32_t)(S * N) & 0x3fff) << 16;     // K-half stride of the B operand, 16-byte units
-    const uint32_t term16 = p.term_bytes >> 4;
     const uint32_t ent_base = smem_u32(entries);
-    // per (MMA tile, term) part of the A start address: constant for the whole launch, so that an MMA
-    // costs the issuing lane one add (with the tile arithmetic inside the entry loop the lane needed
-    // ~15 uniform-datapath instructions per MMA and, at ~4 cycles each, was slower than the tensor core)
-    uint32_t toff[NACC_MAX][S];
+    // the TMEM base address comes out of shared memory, i.e. in an ordinary register; rebuilt bit by bit
+    // from warp votes it is a value ptxas KNOWS to be warp-uniform (column bits only: the allocation
+    // starts at lane 0), so accumulator addresses stay on the uniform datapath as well
+    uint32_t tmem_u = 0;
 #pragma unroll
-    for (int i = 0; i < NACC_MAX; ++i)
-#pragma unroll
-      for (int s = 0; s < S; ++s)
-        toff[i][s] = (uint32_t)((i >> p.ntx_log2) * p.zstride16 + ((i & (p.ntx - 1)) << 3)) + s * term16;
+    for (int k = 0; k < 10; ++k) tmem_u |= (__ballot_sync(0xffffffffu, (tmem_base >> k) & 1u) != 0u ? 1u : 0u) << k;
     if (p.resident) { mbar_wait(wfull_bar, 0); tc_fence_after(); }
     if (lane == 0) stamp(2);
+    // The whole warp walks the (warp-uniform) loops and waits on the barriers; one elected lane issues.
+    // Stamps of PDS_B200_TCG_TRACE show the bursts of a unit running at the tensor pipe's own rate with
+    // the pipe idle in between (~540 cycles per unit, ~1.6 K per item: commit, barrier wait, unit table,
+    // first entry).  Tried against those gaps: awaiting the next unit's operands before
+    // the last entry of the current one (gaps 370 / 1.1 K cycles, layer times unchanged within noise) and
+    // ONE elected lane running the whole role (shorter gaps, but ptxas then emits a slower issue
+    // sequence: 84 instead of 76 us for the one-voxel 8 -> 8 layer).  Kept: issue constants from kernel
+    // parameters, a warp-uniform accumulate flag, no integer divisions at an item boundary unless the
+    // layer is split along K (12 instead of 26 SASS instructions per tile of an entry).
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     bool first_full = true;
+    int n_regions = 0;      // debug trace: (start, end) stamps of the first 64 issue regions of CTA 0
+    auto issue_entries = [&](const TcgUnit& un, int k0, int k1, uint32_t sa16, uint32_t sw16, uint32_t d_base, bool first_unit) {
+      // entries come from shared memory one ahead of their use
+      uint2 en = lds64(ent_base + 8u * (un.ent_beg + k0));
+      const int n_ent = un.ent_end - un.ent_beg;
+      for (int k = k0; k < k1; ++k) {     // k and first_unit are warp-uniform: so is the accumulate flag (no R2UR / vote per MMA)
+        const uint2 nxt = lds64(ent_base + 8u * (un.ent_beg + min(k + 1, n_ent - 1)));
+        const uint32_t a_lo = en.x + sa16;
+        const uint64_t bd = umma_desc((en.y + sw16) | p.b_lbo, p.b_hi);
+        const uint32_t accumulate = (first_unit && k == 0) ? 0u : 1u;
+#pragma unroll
+        for (int i = 0; i < NACC_MAX; ++i) {
+          if (i < p.nacc) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const uint64_t ad = umma_desc(a_lo + p.toff[i][s], p.a_hi);
+              tc_mma(d_base + i * ACC_COLS + s * N, ad, bd, p.idesc[s], s == 0 ? accumulate : 1u);
+              if (N * (S - s) > 256)   // B rows 256.. (16 bytes each), accumulator columns 256..
+                tc_mma(d_base + i * ACC_COLS + s * N + 256, ad, bd + 256, p.idesc_rest[s],
+                       s == 0 ? accumulate : 1u);
+            }
+          }
+        }
+        en = nxt;
+      }
+    };
     for (int item = item_begin; item < item_end; ++item) {
-      const int cls = (item / p.ksplit) % p.ncls;
-      const int u0 = (item % p.ksplit) * p.upi / p.ksplit, u1 = (item % p.ksplit + 1) * p.upi / p.ksplit;
+      int cls = 0, u0 = 0, u1 = p.upi;
+      if (p.ksplit > 1) {
+        cls = (item / p.ksplit) % p.ncls;
+        u0 = (item % p.ksplit) * p.upi / p.ksplit; u1 = (item % p.ksplit + 1) * p.upi / p.ksplit;
+      } else if (p.ncls > 1) {
+        cls = item % p.ncls;
+      }
       const long long tw0 = p.trace ? clock64() : 0;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       if (p.trace && lane == 0) tally(9, clock64() - tw0);
       tc_fence_after();
-      const uint32_t d_base = tmem_base + acc * buf_cols;
+      const uint32_t d_base = tmem_u + acc * buf_cols;
       const bool hold = p.reuse && cls + 1 < p.ncls;      // the stage serves the next class too
       for (int u = u0; u < u1; ++u) {
         const TcgUnit un = units[cls * p.upi + u];
@@ -230,39 +263,16 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
         }
         const uint32_t sa16 = (stage_base + stage * p.stage_bytes) >> 4;
         const uint32_t sw16 = p.resident ? (wres_base >> 4) : sa16;
+        const long long ti0 = p.trace ? clock64() : 0;
+        if (p.trace && blockIdx.x == 0 && lane == 0 && n_regions < 64) p.trace[148 * 12 + 2 * n_regions] = ti0 - t_start;
         if (elect_one()) {
-          // entries come from shared memory one ahead of their use.  What was tried on this loop for
-          // the N = 32 four-voxel layer (63 cycles per MMA against 46 in tools/mma_microbench.cu):
-          // tile offsets hoisted out of the loop (kept), the whole warp walking the loop with only the
-          // MMA guarded by the elected lane (same 25 SASS instructions per tile, same time), term-major
-          // order (slower: 103 K against 90 K cycles).  The issuing lane is NOT waiting on a barrier
-          // (PDS_B200_TCG_TRACE: 6 K of 90 K cycles, the pipeline fill) -- the tensor pipe itself takes
-          // longer per MMA than in the microbenchmark while TMA writes and the epilogue run beside it.
-          uint2 en = lds64(ent_base + 8u * un.ent_beg);
-          for (int e = un.ent_beg; e < un.ent_end; ++e) {
-            const uint2 nxt = lds64(ent_base + 8u * min(e + 1, un.ent_end - 1));
-            const uint32_t a_lo = en.x + sa16;
-            const uint64_t bd = umma_desc((en.y + sw16) | b_lbo, b_hi);
-            const uint32_t accumulate = (u == u0 && e == un.ent_beg) ? 0u : 1u;
-#pragma unroll
-            for (int i = 0; i < NACC_MAX; ++i) {
-              if (i < p.nacc) {
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                  const uint64_t ad = umma_desc(a_lo + toff[i][s], a_hi);
-                  tc_mma(d_base + i * ACC_COLS + s * N, ad, bd, idesc[s], s == 0 ? accumulate : 1u);
-                  if (N * (S - s) > 256)   // B rows 256.. (16 bytes each), accumulator columns 256..
-                    tc_mma(d_base + i * ACC_COLS + s * N + 256, ad, bd + 256, idesc_rest[s],
-                           s == 0 ? accumulate : 1u);
-                }
-              }
-            }
-            en = nxt;
-          }
+          issue_entries(un, 0, un.ent_end - un.ent_beg, sa16, sw16, d_base, u == u0);
           if (!hold) tc_commit(empty_bar(stage));
           if (u == u1 - 1) tc_commit(tfull_bar(acc));
         }
         __syncwarp();
+        if (p.trace && lane == 0) tally(11, clock64() - ti0);
+        if (p.trace && blockIdx.x == 0 && lane == 0 && n_regions < 64) { p.trace[148 * 12 + 2 * n_regions + 1] = clock64() - t_start; ++n_regions; }
         if (!hold && ++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
       }
       if (nbuf == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
@@ -322,10 +332,10 @@ conv_tcg_kernel(const __grid_constant__ TcgParams p) {
 #pragma unroll
       for (int j = 0; j < CH; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
 #pragma unroll 1
-      for (int i = split_tiles ? half : 0; i < p.nacc; i += split_tiles ? 2 : 1) {
+      for (int i = split_tiles ? half : 0; i < ((p.dbg & 2) ? 0 : p.nacc); i += split_tiles ? 2 : 1) {
         const int ix = i % p.ntx, iz = i / p.ntx;
         const int gx = it.tx * 8 * p.ntx + 8 * ix + px, gy = it.ty * 16 + py, gz = it.tz * p.ntz + iz;
-        const bool valid = gx < p.GX && gy < p.GY && gz < p.GZ;
+        const bool valid = gx < p.GX && gy < p.GY && gz < p.GZ && !(p.dbg & 1);
         const int oz = p.nd3 ? p.mul * gz + cz : 0, oy = p.mul * gy + cy, ox = p.mul * gx + cx;
         float* o = p.out + (size_t)(item % p.ksplit) * p.ksplit_stride +
                    ((((size_t)it.n * p.OZ + oz) * p.OY + oy) * p.OX + ox) * p.CoutS;
@@ -839,7 +849,25 @@ int tcg_conv_forward(const TcgLayer& l, int n_samples, const uint16_t* in_ap, fl
   p.off_boxes = tl.off_boxes; p.off_entries = tl.off_entries; p.off_tiles = tl.off_tiles;
   p.table_bytes = tl.table_bytes;
   p.inv_wscale = 1.0f / l.wscale;
+  {
+    const uint32_t fmt = (1u << 4) | (l.fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(128 >> 4) << 24);
+    const int S = pl.shape.S;
+    for (int s = 0; s < 3; ++s) {
+      // activation term s multiplies the N * (S - s) concatenated weight rows; an MMA is at most 256
+      // columns wide, so the widest case (S = 3, N = 128) takes a second instruction for the rest
+      const int cols = s < S ? pl.N * (S - s) : 0, first = cols > 256 ? 256 : cols;
+      p.idesc[s] = fmt | ((uint32_t)(first >> 3) << 17);
+      p.idesc_rest[s] = fmt | ((uint32_t)((cols - first) >> 3) << 17);
+    }
+    p.a_hi = (((uint32_t)pl.BX * 16 >> 4) & 0x3fff) | (1u << 14);      // umma_desc_hi(SBO = box row pitch)
+    p.b_hi = ((128u >> 4) & 0x3fff) | (1u << 14);
+    p.b_lbo = ((uint32_t)(S * pl.N) & 0x3fff) << 16;                     // K-half stride of the B operand, 16-byte units
+    for (int i = 0; i < 8; ++i)
+      for (int s = 0; s < 3; ++s)
+        p.toff[i][s] = (uint32_t)((i >> p.ntx_log2) * p.zstride16 + ((i & (pl.ntx - 1)) << 3)) + s * (p.term_bytes >> 4);
+  }
   p.trace = g_tcg_trace;
+  p.dbg = (g_tcg_trace && getenv("PDS_B200_TCG_DEBUG")) ? atoi(getenv("PDS_B200_TCG_DEBUG")) : 0;
   if (pl.shape.Cout % 4) { set_error("conv_tcg: Cout must be a multiple of 4"); return PDS_ERR_UNSUPPORTED; }
   const size_t smem = (size_t)pl.wres_bytes + (size_t)pl.stages * pl.stage_bytes + tl.table_bytes + kTailBytes + 128;
   if (smem > 227 * 1024) {
@@ -963,25 +991,30 @@ extern "C" int pds_tcg_conv_debug(int kind, int nd, int Cin, int Cout, int Z, in
   }
   const bool trace = getenv("PDS_B200_TCG_TRACE") != nullptr;
   if (trace) {
-    cudaMalloc(&g_tcg_trace, 148 * 12 * sizeof(long long));
-    cudaMemset(g_tcg_trace, 0, 148 * 12 * sizeof(long long));
+    cudaMalloc(&g_tcg_trace, (148 * 12 + 128) * sizeof(long long));
+    cudaMemset(g_tcg_trace, 0, (148 * 12 + 128) * sizeof(long long));
     if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, nullptr, lrelu, st, sk, b_sk);   // warm (instruction cache, L2)
     cudaStreamSynchronize(st);
-    cudaMemset(g_tcg_trace, 0, 148 * 12 * sizeof(long long));   // the wait tallies accumulate
+    cudaMemset(g_tcg_trace, 0, (148 * 12 + 128) * sizeof(long long));   // the wait tallies accumulate
   }
   if (rc == PDS_OK) rc = tcg_conv_forward(l, n, ap, y_cl, stats, lrelu, st, sk, b_sk);
   if (trace) {
     cudaStreamSynchronize(st);
-    long long h[148 * 12];
+    long long h[148 * 12 + 128];
     cudaMemcpy(h, g_tcg_trace, sizeof(h), cudaMemcpyDeviceToHost);
     const char* names[12] = {"producer start", "producer done", "weights ready", "first stage full", "MMA issue done",
                              "epilogue done", "stats flushed", "CTA end", "MMA waits: data", "MMA waits: accumulators",
-                             "producer waits: stage", "-"};
-    for (int k = 0; k < 11; ++k) {
+                             "producer waits: stage", "MMA issue regions"};
+    for (int k = 0; k < 12; ++k) {
       long long mx = 0, sum = 0; int cnt = 0;
       for (int c = 0; c < 148; ++c) if (h[c * 12 + 7]) { mx = mx > h[c * 12 + k] ? mx : h[c * 12 + k]; sum += h[c * 12 + k]; ++cnt; }
       printf("trace %-18s avg %8lld max %8lld cycles (%d CTAs)\n", names[k], cnt ? sum / cnt : 0, mx, cnt);
     }
+    printf("issue regions of CTA 0 (start, length, gap to the next):");
+    for (int r = 0; r < 64 && h[148 * 12 + 2 * r + 1]; ++r)
+      printf(" [%lld %lld %lld]", h[148 * 12 + 2 * r], h[148 * 12 + 2 * r + 1] - h[148 * 12 + 2 * r],
+             r + 1 < 64 && h[148 * 12 + 2 * r + 3] ? h[148 * 12 + 2 * r + 2] - h[148 * 12 + 2 * r + 1] : 0ll);
+    printf("\n");
     cudaFree(g_tcg_trace); g_tcg_trace = nullptr;
   }
   if (trace && rc == PDS_OK) {

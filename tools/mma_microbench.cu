@@ -81,11 +81,16 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, unsigned long long* o
 // (2N columns) followed by a_lo x w_hi (N columns) into the SECOND half of the same accumulator.
 // OVERLAP = false: the second MMA goes to a separate accumulator instead (same work, no dependency).
 template <int N, int NT, bool OVERLAP>
-__global__ void __launch_bounds__(128, 1) bench_split(int iters, unsigned long long* out) {
+__global__ void __launch_bounds__(128, 1) bench_split(int iters, unsigned long long* out, int random_data) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
-  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0;
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u; h ^= h >> 13; h *= 0x5bd1e995u;
+    // two fp16 values in [-2, 2): sign | exponent 01100..01111 | random mantissa
+    const uint32_t lo = (h & 0x83ffu) | (((h >> 16) & 3u) + 12u) << 10, hi = ((h >> 3) & 0x83ffu) | (((h >> 20) & 3u) + 12u) << 10;
+    ((uint32_t*)smem)[i] = random_data ? (lo | (hi << 16)) : 0u;
+  }
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,17 +141,17 @@ __global__ void __launch_bounds__(128, 1) bench_split(int iters, unsigned long l
 }
 
 template <int N, int NT, bool OVERLAP>
-void run_split(unsigned long long* out) {
+void run_split(unsigned long long* out, int random_data = 0) {
   const int iters = 200;
   cudaFuncSetAttribute(bench_split<N, NT, OVERLAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  bench_split<N, NT, OVERLAP><<<148, 128, 200 * 1024>>>(iters, out);
+  bench_split<N, NT, OVERLAP><<<148, 128, 200 * 1024>>>(iters, out, random_data);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("variant failed: %s\n", cudaGetErrorString(e)); exit(1); }
   unsigned long long h[148];
   cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
   double sum = 0;
   for (int i = 0; i < 148; ++i) sum += h[i];
-  printf("split pair N=%3d+%3d NT=%d %s | cycles per PAIR avg %.1f\n", 2 * N, N, NT,
+  printf("split pair N=%3d+%3d NT=%d %s %s | cycles per PAIR avg %.1f\n", 2 * N, N, NT, random_data ? "random fp16 data" : "zero data       ",
          OVERLAP ? "second MMA into the first one's upper half" : "second MMA into its own accumulator  ",
          sum / 148 / ((double)iters * 9 * NT));
 }
@@ -181,5 +186,6 @@ int main() {
   run<32, 4, 10, 128, 1>(out);  run<32, 4, 10, 128, 10>(out); run<64, 4, 18, 128, 1>(out);  run<64, 4, 12, 128, 1>(out);
   run_split<32, 4, true>(out); run_split<32, 4, false>(out); run_split<16, 8, true>(out); run_split<16, 8, false>(out);
   run_split<64, 2, true>(out); run_split<64, 2, false>(out);
+  run_split<32, 4, true>(out, 1); run_split<16, 8, true>(out, 1); run_split<64, 2, true>(out, 1);
   return 0;
 }
