@@ -101,6 +101,8 @@ struct alignas(64) TcKernelParams {
   const float* fA;                   // TC_NORM_RESIDUAL_FIRST: per-sample terms the residual x0 is rebuilt from
   const float* fB;
   const float* fQ;
+  long long* trace;                  // debug (build with -DPDS_TC_TRACE, run with PDS_B200_TC_TRACE=1): issue-region stamps of CTA 0, [n][2] after a count
+  int continuous;                    // static schedule: one elected lane issues without leaving the stream (PDS_B200_TC_CONTINUOUS)
 };
 
 constexpr uint32_t pow2_cols(uint32_t c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
@@ -444,6 +446,63 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
       for (int s = 0; s < S; ++s) idesc[s] = fmt | ((uint32_t)((N * (S - s)) >> 3) << 17);
       if (WRES) { mbar_wait(wfull_bar, 0); tc_fence_after(); }
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+#ifdef PDS_TC_TRACE
+      const long long t_start = clock64();
+      int n_regions = 0;
+#endif
+      if (!FUSE && p.continuous) {
+        // Static schedule, continuous issue: ONE elected lane runs the whole role.  Between two
+        // chunks the per-chunk form leaves the tensor pipe idle for ~500 cycles (commit, warp
+        // reconvergence, barrier wait, election, ~50 uniform-datapath instructions of descriptor
+        // set-up: stamps of PDS_B200_TC_TRACE, 1.8 K of the 10.8 K cycles of a tile).  Here the lane
+        // never leaves the issue stream: the next chunk's operands are awaited between the bursts of
+        // the two activation terms -- while the pipe still holds the first burst -- and the
+        // descriptors advance by additions.
+        if (elect_one()) {
+          bool have = false;
+          for (int tile = tile_begin; tile < tile_end; ++tile) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_base = tmem_base + acc * BUF_COLS;
+            for (int c = 0; c < p.nchunks; ++c) {
+              if (!have) mbar_wait(full_bar(stage), phase);      // only the very first chunk of the launch
+              have = false;
+              tc_fence_after();
+              const uint32_t sa = stage_base + stage * p.stage_bytes;
+              const uint32_t sw = WRES ? wres_base + c * W_CHUNK_BYTES : sa + S * A_TERM_BYTES;
+              const uint32_t nstage = stage + 1 == (uint32_t)p.stages ? 0u : stage + 1, nphase = nstage == 0 ? phase ^ 1 : phase;
+              const bool more = !(tile + 1 == tile_end && c + 1 == p.nchunks);
+#ifdef PDS_TC_TRACE
+              if (p.trace && blockIdx.x == 0 && n_regions < 60) p.trace[1 + 2 * n_regions] = clock64() - t_start;
+#endif
+              const uint64_t wdesc = umma_desc_kmajor(sw, S * N * 16, 128);
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                const uint64_t adesc = umma_desc_kmajor(sa + s * A_TERM_BYTES, kPH * PW * 16, PW * 16);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                  const uint64_t bd = wdesc + (uint64_t)(tap * 2 * S * N);          // 16-byte units
+#pragma unroll
+                  for (int i = 0; i < NT; ++i) {
+                    const uint64_t ad = adesc + (uint64_t)((tap / 3) * PW + 8 * i + tap % 3);
+                    tc_mma(d_base + i * ACC_COLS + s * N, ad, bd, idesc[s],
+                           (s == 0 && tap == 0) ? (c != 0 ? 1u : 0u) : 1u);
+                  }
+                }
+                if (s == 0 && more) { mbar_wait(full_bar(nstage), nphase); have = true; }
+              }
+              tc_commit(empty_bar(stage));       // frees the smem stage once these MMAs retire
+              if (c == p.nchunks - 1) tc_commit(tfull_bar(acc));   // accumulators ready for the epilogue
+#ifdef PDS_TC_TRACE
+              if (p.trace && blockIdx.x == 0 && n_regions < 60) { p.trace[2 + 2 * n_regions] = clock64() - t_start; p.trace[0] = ++n_regions; }
+#endif
+              stage = nstage; phase = nphase;
+            }
+            if (NBUF == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
+          }
+        }
+        __syncwarp();
+      } else
       for (int tile = tile_begin; FUSE || tile < tile_end; ++tile) {
         if (FUSE) {
           mbar_wait(full_bar(stage), phase);           // first chunk of the next tile, or the end marker
@@ -462,6 +521,9 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
           tc_fence_after();
           const uint32_t sa = stage_base + stage * p.stage_bytes;
           const uint32_t sw = WRES ? wres_base + c * W_CHUNK_BYTES : sa + S * A_TERM_BYTES;
+#ifdef PDS_TC_TRACE
+          if (p.trace && blockIdx.x == 0 && lane == 0 && n_regions < 60) p.trace[1 + 2 * n_regions] = clock64() - t_start;
+#endif
           if (elect_one()) {
             const uint64_t wdesc = umma_desc_kmajor(sw, S * N * 16, 128);
 #pragma unroll
@@ -482,6 +544,9 @@ conv3x3_tc_kernel(const __grid_constant__ TcKernelParams p) {
             if (c == p.nchunks - 1) tc_commit(tfull_bar(acc));   // accumulators ready for the epilogue
           }
           __syncwarp();
+#ifdef PDS_TC_TRACE
+          if (p.trace && blockIdx.x == 0 && lane == 0 && n_regions < 60) { p.trace[2 + 2 * n_regions] = clock64() - t_start; p.trace[0] = ++n_regions; }
+#endif
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
         if (NBUF == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else { acc_phase ^= 1; }
@@ -1154,6 +1219,8 @@ size_t tc_sched_bytes(int n_slices) {
   return align_up(sched_stats_bytes(n_slices) + (1 + (size_t)(n_slices > 0 ? n_slices : 0)) * sizeof(int), 256);
 }
 
+long long* g_tc_trace = nullptr;    // PDS_B200_TC_TRACE: stamps of the latest all-slices 64 -> 64 launch (pds_tc_trace_dump)
+
 int tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   const TcLayer& l = *a.layer;
   if (!encode_fn()) {
@@ -1162,6 +1229,15 @@ int tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   }
   if (a.n_slices == 0) return PDS_OK;
   TcKernelParams p = {};
+  if (getenv("PDS_B200_TC_TRACE") && a.n_slices > 8) {
+    if (!g_tc_trace) { cudaMalloc(&g_tc_trace, 128 * sizeof(long long)); }
+    cudaMemsetAsync(g_tc_trace, 0, 128 * sizeof(long long), st);
+    p.trace = g_tc_trace;
+  }
+  {
+    static const bool cont = !(getenv("PDS_B200_TC_CONTINUOUS") && atoi(getenv("PDS_B200_TC_CONTINUOUS")) == 0);
+    p.continuous = cont ? 1 : 0;
+  }
   p.maps_d = a.in2 ? a.maps_dev : nullptr;
   p.w = l.w; p.bias = l.bias;
   p.out_f32 = a.out_f32; p.out_ap = a.out_ap; p.out_sig = a.out_sig; p.stats = a.stats;
@@ -1259,3 +1335,15 @@ int tc_encode_shift_maps(CUtensorMap* maps_host, const uint16_t* in2, int in_sli
 }
 
 }  // namespace pds
+
+// debug: prints the issue-region stamps (start, length, gap) of CTA 0 of the latest traced launch
+extern "C" void pds_tc_trace_dump() {
+  if (!pds::g_tc_trace) { printf("no trace (PDS_B200_TC_TRACE unset)\n"); return; }
+  long long h[128];
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, pds::g_tc_trace, sizeof(h), cudaMemcpyDeviceToHost);
+  const int n = (int)h[0];
+  printf("conv3x3_tc issue regions of CTA 0 (start, length, gap):");
+  for (int r = 0; r < n; ++r) printf(" [%lld %lld %lld]", h[1 + 2 * r], h[2 + 2 * r] - h[1 + 2 * r], r + 1 < n ? h[3 + 2 * r] - h[2 + 2 * r] : 0ll);
+  printf("\n");
+}
