@@ -47,7 +47,7 @@ class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-             'clocks_event_reasons.sw_power_cap')
+             'clocks_event_reasons.sw_power_cap,power.limit')
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -72,18 +72,22 @@ class ClockSampler(threading.Thread):
             self.proc.terminate()
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons, power, limit = [], 0, set(), [], None
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for s in self.samples:
             try:
                 sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                power.append(float(s[2]))
+                limit = float(s[7]) if len(s) > 7 else limit
                 for name, flag in zip(names, s[3:7]):
                     if flag.lower().startswith('active'):
                         reasons.add(name)
             except (ValueError, IndexError):
                 continue
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': mx or None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm),
+                # the step is energy-bound under the board's power cap: draw vs limit, watts
+                'power_w': statistics.median(power) if power else None, 'power_limit_w': limit}
 
 
 def synthetic_pairs(n, batch, H, W, device, seed=0, pinned=False, images='f32'):
