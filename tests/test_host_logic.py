@@ -278,3 +278,30 @@ def test_numa_binding_helpers(tmp_path):
     (dev / 'numa_node').write_text('-1\n')
     assert parallel.gpu_numa_cpus('0000:1b:00.0', sysfs=str(tmp_path)) is None
     assert parallel.gpu_numa_cpus('0000:ff:00.0', sysfs=str(tmp_path)) is None
+
+
+def test_conv_block_is_a_plain_sequential_on_cpu():
+    """network_blocks.ConvBlock keeps the reference's module indices and, on CPU tensors (or without
+    gradients), runs the plain nn.Sequential composition: equal to Conv -> LeakyReLU -> InstanceNorm."""
+    from practicaldeepstereo_nips2018_b200 import network_blocks
+    torch.manual_seed(1)
+    block = network_blocks.conv_block(3, 8, 8, 3)
+    assert isinstance(block, torch.nn.Sequential)
+    assert sorted(block.state_dict()) == ['0.bias', '0.weight', '2.bias', '2.weight']
+    x = torch.randn(2, 8, 4, 6, 7, requires_grad=True)
+    y = block(x)
+    ref = torch.nn.functional.instance_norm(
+        torch.nn.functional.leaky_relu(block[0](x), 0.1), weight=block[2].weight, bias=block[2].bias, eps=1e-5)
+    assert torch.allclose(y, ref, atol=1e-6)
+    y.sum().backward()
+    assert x.grad is not None and block[2].weight.grad is not None
+
+
+def test_training_entry_points_validate_arguments_without_a_gpu():
+    """The f4 entry points reject bad arguments before any CUDA call (status 1 = invalid argument)."""
+    lib = _capi.lib()
+    assert lib.pds_matching_concat_backward(None, None, None, 1, 4, 3, 5, 2, 0, None) == 1
+    assert lib.pds_matching_unstack(None, None, 1, 2, 3, 4, 5, 0, None) == 1
+    assert lib.pds_instance_norm_forward(None, None, None, None, None, None, 1, 4, 10, 1e-5, 0.1, None) == 1
+    assert lib.pds_instance_norm_backward(None, None, None, None, None, None, 1, 4, 10, 0.1, None) == 1
+    assert b'null pointer' in lib.pds_last_error()
