@@ -264,8 +264,13 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
 // loads are in flight while the current one is consumed; one __syncthreads per plane.
 constexpr int kTileW = 66, kTileH = 10, kTileN = kTileW * kTileH, kTilePer = (kTileN + 255) / 256;
 
+// ARGMAX (f1, round 2): the cost volume is NOT written.  Every thread keeps the running maximum and its
+// index (th.max semantics) of the eight output pixels it owns -- 16 registers, three instructions per
+// value instead of a store -- and leaves (best, index) per pixel and z segment in `state`
+// ([segment][2][B][2H][2W]); tail_window_kernel recomputes the few values around the maximum.
+template <bool ARGMAX>
 __global__ void __launch_bounds__(256, 2)
-hourglass_tail_tiled_kernel(const __grid_constant__ TailParams p) {
+hourglass_tail_tiled_kernel(const __grid_constant__ TailParams p, float* __restrict__ state) {
   __shared__ float4 tile[2][kTileH][kTileW];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
   const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 8, y = y0 + ty;
@@ -331,6 +336,20 @@ hourglass_tail_tiled_kernel(const __grid_constant__ TailParams p) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[px][k][c] = 0.f;
 
+  // ARGMAX: running maximum / first index of the eight pixels of this thread.  With finite statistics
+  // (i.e. a finite input tensor) no value can be NaN short of an overflow, and th.max reduces to
+  // "strictly greater takes over": one compare, one select, one FMNMX per value.  Non-finite
+  // statistics select the exact form (the first NaN wins and stays).
+  float best[2][4];
+  int bidx[2][4];
+  bool exact = false;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) exact = exact || !(fabsf(sc[c]) <= 3.0e38f) || !(fabsf(sh[c]) <= 3.0e38f);
+#pragma unroll
+  for (int px = 0; px < 2; ++px)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { best[px][c] = __int_as_float(0xff800000); bidx[px][c] = z0; }
+
   float4 r[kTilePer];
   bool rz;
   fetch(z0 - 1, r, rz);
@@ -351,7 +370,30 @@ hourglass_tail_tiled_kernel(const __grid_constant__ TailParams p) {
 #undef PDS_TAIL_ROW
     }
     const int zo = zi - 1;
-    if (zo >= z0 && zo < z1) {
+    if (ARGMAX) {
+      if (zo >= z0 && zo < z1) {
+        if (!exact) {
+#pragma unroll
+          for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float val = acc[px][0][c] + p.bias;
+              bidx[px][c] = val > best[px][c] ? zo : bidx[px][c];
+              best[px][c] = fmaxf(best[px][c], val);
+            }
+        } else {
+#pragma unroll
+          for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float val = acc[px][0][c] + p.bias;
+              const bool t = zo == z0 || takes_over(val, best[px][c]);
+              best[px][c] = t ? val : best[px][c];
+              bidx[px][c] = t ? zo : bidx[px][c];
+            }
+        }
+      }
+    } else if (zo >= z0 && zo < z1) {
       float* o = obase + (size_t)zo * oplane;
       if (in0) {
         *reinterpret_cast<float2*>(o) = make_float2(acc[0][0][0] + p.bias, acc[0][0][1] + p.bias);
@@ -370,34 +412,131 @@ hourglass_tail_tiled_kernel(const __grid_constant__ TailParams p) {
     __syncthreads();
     cur ^= 1;
   }
+  if (ARGMAX) {
+    const int OH = 2 * p.H;
+    const size_t fplane = (size_t)p.B * OH * OW;
+    float* sp = state + (size_t)seg * 2 * fplane + ((size_t)b * OH + 2 * y) * OW + 2 * (x0 + tx);
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      if (!(px == 0 ? in0 : in1)) continue;
+      float* q = sp + 64 * px;
+      *reinterpret_cast<float2*>(q) = make_float2(best[px][0], best[px][1]);
+      *reinterpret_cast<float2*>(q + OW) = make_float2(best[px][2], best[px][3]);
+      *reinterpret_cast<float2*>(q + fplane) = make_float2(__int_as_float(bidx[px][0]), __int_as_float(bidx[px][1]));
+      *reinterpret_cast<float2*>(q + fplane + OW) = make_float2(__int_as_float(bidx[px][2]), __int_as_float(bidx[px][3]));
+    }
+  }
 }
 
-// Merges the per-segment SubpixelMap states (lowest index wins ties, the first NaN wins) and
-// writes the cropped disparity.  One thread per output pixel.
-template <int R>
-__global__ void __launch_bounds__(256)
-subpixel_merge_kernel(const float* __restrict__ state, float* __restrict__ disparity, int64_t* __restrict__ argmax,
-                      int B, int OH, int OW, int D, int nseg, int step, int crop_top, int crop_left) {
-  const int Hc = OH - crop_top, Wc = OW - crop_left;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * Hc * Wc) return;
-  const int ox = (int)(i % Wc), oy = (int)((i / Wc) % Hc), b = (int)(i / ((size_t)Wc * Hc));
-  const size_t fplane = (size_t)B * OH * OW;
-  const size_t at = ((size_t)b * OH + oy + crop_top) * OW + ox + crop_left;
-  int win = 0;
-  float best = state[at];
-  for (int s = 1; s < nseg; ++s) {
-    const float v = state[(size_t)s * (2 + 2 * R) * fplane + at];
-    if (takes_over(v, best)) { best = v; win = s; }
-  }
+// Second half of the fused estimator: one thread per (cropped) output pixel merges the z segments'
+// (best, index) -- segments in ascending order, th.max semantics -- and RECOMPUTES the R cost values on
+// either side of the maximum: the seven input planes around it, four voxels each, in exactly the
+// operation order of tail_accumulate_row (planes ascending, input rows ascending, tx ascending, the
+// four channels), so every value is bit-identical to what the plain kernel stores.  Then the windowed
+// softmax of SubpixelMap (estimator.py:66-90) and the SizeAdapter crop.
+template <int R, int CY, int CX>
+__device__ __forceinline__ void tail_window_pixel(const TailParams& p, const float* __restrict__ state, int b, int oy, int ox,
+                                                  const float (&sc)[4], const float (&sh)[4], float* __restrict__ disparity,
+                                                  int64_t* __restrict__ argmax, size_t out_index, int step) {
+  const int OH = 2 * p.H, OW = 2 * p.W;
+  const size_t fplane = (size_t)p.B * OH * OW, at = ((size_t)b * OH + oy) * OW + ox;
   MapState<R> m;
-  const float* sp = state + (size_t)win * (2 + 2 * R) * fplane + at;
-  m.best = best;
-  m.idx = __float_as_int(sp[fplane]);
+  m.init();
+  m.best = state[at];
+  m.idx = __float_as_int(state[fplane + at]);
+  for (int sg = 1; sg < p.nseg; ++sg) {
+    const float v = state[(size_t)sg * 2 * fplane + at];
+    if (takes_over(v, m.best)) { m.best = v; m.idx = __float_as_int(state[(size_t)sg * 2 * fplane + fplane + at]); }
+  }
+  const int y = oy >> 1, x = ox >> 1;
+  const size_t plane = (size_t)p.H * p.W;
+  const float4* base = p.in + (size_t)b * p.D * plane;
+  float a[2 * R + 1];            // outputs z = idx - R + k
 #pragma unroll
-  for (int r = 0; r < R; ++r) { m.before[r] = sp[(size_t)(2 + r) * fplane]; m.after[r] = sp[(size_t)(2 + R + r) * fplane]; }
-  disparity[i] = m.disparity(D, step);
-  if (argmax) argmax[i] = m.idx;
+  for (int k = 0; k < 2 * R + 1; ++k) a[k] = 0.f;
+  // validity / offsets of the 2 x 2 input voxels this output pixel reads (rows y + CY - 1, y + CY; columns x + CX, x + CX - 1)
+  bool ok[2][2];
+  int off[2][2];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int tx = 0; tx < 2; ++tx) {
+      const int gy = y + CY + dy - 1, gx = x + CX - tx;
+      ok[dy][tx] = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+      off[dy][tx] = gy * p.W + gx;
+    }
+#pragma unroll
+  for (int j = -R - 1; j <= R + 1; ++j) {                 // input plane idx + j; every index below is a compile-time constant
+    const int zi = m.idx + j;
+    if (zi < 0 || zi >= p.D) continue;                    // the plain kernel skips these planes as well
+    float4 q[2][2];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int tx = 0; tx < 2; ++tx) {
+        q[dy][tx] = make_float4(0.f, 0.f, 0.f, 0.f);      // zero padding of the NORMALISED tensor
+        if (ok[dy][tx]) {
+          const float4 t = __ldg(base + (size_t)zi * plane + off[dy][tx]);
+          q[dy][tx] = make_float4(fmaf(t.x, sc[0], sh[0]), fmaf(t.y, sc[1], sh[1]), fmaf(t.z, sc[2], sh[2]), fmaf(t.w, sc[3], sh[3]));
+        }
+      }
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; ++k) {
+      if (k == R) continue;                               // the maximum itself comes from the first kernel
+      const int tz = j - (k - R) + 1;                     // out z = zi - tz + 1 (compile-time after unrolling)
+      if (tz < 0 || tz > 2) continue;
+      float v = a[k];
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)                      // DY = CY + dy: ty = 1 - dy, kernel row 1 - CY + 2 * ty
+#pragma unroll
+        for (int tx = 0; tx < 2; ++tx) {
+          const float* ww = p.w[2 - tz][1 - CY + 2 * (1 - dy)][1 - CX + 2 * tx];
+          v = fmaf(q[dy][tx].x, ww[0], v); v = fmaf(q[dy][tx].y, ww[1], v);
+          v = fmaf(q[dy][tx].z, ww[2], v); v = fmaf(q[dy][tx].w, ww[3], v);
+        }
+      a[k] = v;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) { m.before[r] = a[R - 1 - r] + p.bias; m.after[r] = a[R + 1 + r] + p.bias; }
+  disparity[out_index] = m.disparity(p.D, step);
+  if (argmax) argmax[out_index] = m.idx;
+}
+
+// grid (input-column blocks, output rows, B): a thread owns the two output pixels (oy, 2x) and (oy, 2x + 1); the
+// row parity is uniform per CTA, the column parity a compile-time constant, so every weight is a
+// constant-bank operand (with run-time parities the 192 weights went through local memory: 70 us).
+template <int R>
+__global__ void __launch_bounds__(128)
+tail_window_kernel(const __grid_constant__ TailParams p, const float* __restrict__ state, float* __restrict__ disparity,
+                   int64_t* __restrict__ argmax, int step, int crop_top, int crop_left) {
+  const int OW = 2 * p.W, Hc = 2 * p.H - crop_top, Wc = OW - crop_left;
+  const int b = blockIdx.z, oy = crop_top + blockIdx.y;
+  const int x = (crop_left >> 1) + blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= p.W) return;
+  float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.stats) {
+    const double n = (double)p.D * p.H * p.W;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double s = p.stats[(b * 4 + c) * 2], q = p.stats[(b * 4 + c) * 2 + 1];
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+      sc[c] = rstd * p.gamma[c];
+      sh[c] = p.beta[c] - (float)mean * sc[c];
+    }
+  }
+  const size_t orow = ((size_t)b * Hc + blockIdx.y) * Wc;
+  const int ox0 = 2 * x, ox1 = 2 * x + 1;
+  if (oy & 1) {
+    if (ox0 >= crop_left) tail_window_pixel<R, 1, 0>(p, state, b, oy, ox0, sc, sh, disparity, argmax, orow + (ox0 - crop_left), step);
+    if (ox1 >= crop_left) tail_window_pixel<R, 1, 1>(p, state, b, oy, ox1, sc, sh, disparity, argmax, orow + (ox1 - crop_left), step);
+  } else {
+    if (ox0 >= crop_left) tail_window_pixel<R, 0, 0>(p, state, b, oy, ox0, sc, sh, disparity, argmax, orow + (ox0 - crop_left), step);
+    if (ox1 >= crop_left) tail_window_pixel<R, 0, 1>(p, state, b, oy, ox1, sc, sh, disparity, argmax, orow + (ox1 - crop_left), step);
+  }
 }
 
 }  // namespace
@@ -406,8 +545,8 @@ subpixel_merge_kernel(const float* __restrict__ state, float* __restrict__ dispa
 // disparity != null: fused with SubpixelMap (window radius R = half_support_window / step in
 // 1..4) and the SizeAdapter crop; `out` is not written.
 size_t hourglass_tail_state_bytes(int B, int D, int H, int W) {
-  const int nseg = (D + 11) / 12;      // upper bound over the segment lengths in use
-  return align_up((size_t)nseg * (2 + 2 * 4) * B * (2 * H) * (2 * W) * sizeof(float), 256);
+  const int nseg = (D + 11) / 12;      // upper bound over the segment lengths in use (PDS_B200_TAIL_ZSEG >= 12)
+  return align_up((size_t)nseg * 2 * B * (2 * H) * (2 * W) * sizeof(float), 256);
 }
 
 int hourglass_tail_forward(const float* in, float* out, const double* stats, const float* gamma_host,
@@ -419,12 +558,10 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
   p.in = reinterpret_cast<const float4*>(in); p.out = out; p.stats = stats;
   p.B = B; p.D = D; p.H = H; p.W = W;
   const bool fused = disparity != nullptr;
-  // fused with a state buffer: the disparity axis stays segmented (parallelism), every segment
-  // leaves a partial SubpixelMap state and subpixel_merge_kernel finishes; without one a thread
-  // scans the whole axis
-  const int zseg_env = getenv("PDS_B200_TAIL_ZSEG") ? atoi(getenv("PDS_B200_TAIL_ZSEG")) : 48;
+  int zseg_env = getenv("PDS_B200_TAIL_ZSEG") ? atoi(getenv("PDS_B200_TAIL_ZSEG")) : 48;
+  if (zseg_env < 12) zseg_env = 12;     // hourglass_tail_state_bytes sizes the state for segments of >= 12
   const int by = getenv("PDS_B200_TAIL_BY") ? atoi(getenv("PDS_B200_TAIL_BY")) : 8;
-  p.zseg = (fused && !state) ? D : (D > zseg_env ? zseg_env : D);
+  p.zseg = D > zseg_env ? zseg_env : D;
   p.nseg = (D + p.zseg - 1) / p.zseg;
   for (int c = 0; c < 4; ++c) { p.gamma[c] = gamma_host ? gamma_host[c] : 1.f; p.beta[c] = beta_host ? beta_host[c] : 0.f; }
   for (int ci = 0; ci < 4; ++ci)
@@ -433,44 +570,44 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
         for (int kw = 0; kw < 4; ++kw) p.w[kd][kh][kw][ci] = w_host[((ci * 3 + kd) * 4 + kh) * 4 + kw];
   p.bias = bias;
   FusedParams f;
-  f.disparity = disparity; f.argmax = argmax; f.step = step; f.crop_top = crop_top; f.crop_left = crop_left;
-  f.state = (fused && p.nseg > 1) ? state : nullptr;
+  f.disparity = nullptr; f.argmax = nullptr; f.step = step; f.crop_top = crop_top; f.crop_left = crop_left; f.state = nullptr;
   dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + by - 1) / by), (unsigned)(B * p.nseg));
   if (grid.z > 65535) { set_error("hourglass_tail: batch too large"); return PDS_ERR_UNSUPPORTED; }
-  if (fused && (R < 1 || R > 4 || crop_top < 0 || crop_left < 0 || crop_top > 2 * H || crop_left > 2 * W)) {
-    set_error("hourglass_tail: fused estimator needs a window radius in 1..4 and a crop inside the image");
+  if (fused && (R < 1 || R > 4 || crop_top < 0 || crop_left < 0 || crop_top > 2 * H || crop_left > 2 * W || !state)) {
+    set_error("hourglass_tail: fused estimator needs a window radius in 1..4, a crop inside the image and a state buffer");
     return PDS_ERR_UNSUPPORTED;
   }
-  PDS_KERNEL(fused ? "hourglass_tail+subpixel_map" : "hourglass_tail(tconv 4->1 + IN)", st);
-  PDS_KERNEL_WORK(2.0 * 192 * B * D * H * W,
-                  (double)B * D * H * W * 16 + (fused ? 4.0 * B * (2 * H - crop_top) * (2 * W - crop_left)
-                                                       : (double)B * D * H * W * 16));
-  static const bool tiled = !(getenv("PDS_B200_TAIL_TILED") && atoi(getenv("PDS_B200_TAIL_TILED")) == 0);
-  switch (fused ? R : 0) {
-    case 0:
-      if (tiled) hourglass_tail_tiled_kernel<<<dim3((unsigned)((W + 63) / 64), (unsigned)((H + 7) / 8), grid.z), dim3(32, 8), 0, st>>>(p);
-      else hourglass_tail_kernel<0><<<grid, dim3(32, by), 0, st>>>(p, f);
-      break;
-    case 1: hourglass_tail_kernel<1><<<grid, dim3(32, by), 0, st>>>(p, f); break;
-    case 2: hourglass_tail_kernel<2><<<grid, dim3(32, by), 0, st>>>(p, f); break;
-    case 3: hourglass_tail_kernel<3><<<grid, dim3(32, by), 0, st>>>(p, f); break;
-    default: hourglass_tail_kernel<4><<<grid, dim3(32, by), 0, st>>>(p, f); break;
-  }
-  PDS_LAUNCH_CHECK("hourglass_tail_kernel");
-  if (f.state) {
-    const int OH = 2 * H, OW = 2 * W;
-    const size_t n = (size_t)B * (OH - crop_top) * (OW - crop_left);
-    PDS_KERNEL("subpixel_merge", st);
-    PDS_KERNEL_WORK(0, (double)n * (4.0 * p.nseg + 4.0 * (2 + 2 * R)));
-    const unsigned g = (unsigned)((n + 255) / 256);
-    switch (R) {
-      case 1: subpixel_merge_kernel<1><<<g, 256, 0, st>>>(state, disparity, argmax, B, OH, OW, D, p.nseg, step, crop_top, crop_left); break;
-      case 2: subpixel_merge_kernel<2><<<g, 256, 0, st>>>(state, disparity, argmax, B, OH, OW, D, p.nseg, step, crop_top, crop_left); break;
-      case 3: subpixel_merge_kernel<3><<<g, 256, 0, st>>>(state, disparity, argmax, B, OH, OW, D, p.nseg, step, crop_top, crop_left); break;
-      default: subpixel_merge_kernel<4><<<g, 256, 0, st>>>(state, disparity, argmax, B, OH, OW, D, p.nseg, step, crop_top, crop_left); break;
+  const dim3 tgrid((unsigned)((W + 63) / 64), (unsigned)((H + 7) / 8), grid.z);
+  if (fused) {
+    // f1: arg-max inside the transposed convolution, window recomputed (no cost volume in HBM)
+    {
+      PDS_KERNEL("hourglass_tail[arg-max, no volume]", st);
+      PDS_KERNEL_WORK(2.0 * 192 * B * D * H * W, (double)B * D * H * W * 16 + 8.0 * p.nseg * B * 4 * H * W);
+      hourglass_tail_tiled_kernel<true><<<tgrid, dim3(32, 8), 0, st>>>(p, state);
+      PDS_LAUNCH_CHECK("hourglass_tail_tiled_kernel");
     }
-    PDS_LAUNCH_CHECK("subpixel_merge_kernel");
+    const size_t n = (size_t)B * (2 * H - crop_top) * (2 * W - crop_left);
+    if (n == 0) return PDS_OK;
+    PDS_KERNEL("tail_window(subpixel_map)", st);
+    PDS_KERNEL_WORK(2.0 * 48 * 2 * R * n, (double)n * (8.0 * p.nseg + 4.0 + 16.0 * (2 * R + 3)));
+    const int cols = W - (crop_left >> 1);
+    const dim3 g((unsigned)((cols + 127) / 128), (unsigned)(2 * H - crop_top), (unsigned)B);
+    if (g.y > 65535 || g.z > 65535) { set_error("hourglass_tail: image too tall / batch too large for the window kernel"); return PDS_ERR_UNSUPPORTED; }
+    switch (R) {
+      case 1: tail_window_kernel<1><<<g, 128, 0, st>>>(p, state, disparity, argmax, step, crop_top, crop_left); break;
+      case 2: tail_window_kernel<2><<<g, 128, 0, st>>>(p, state, disparity, argmax, step, crop_top, crop_left); break;
+      case 3: tail_window_kernel<3><<<g, 128, 0, st>>>(p, state, disparity, argmax, step, crop_top, crop_left); break;
+      default: tail_window_kernel<4><<<g, 128, 0, st>>>(p, state, disparity, argmax, step, crop_top, crop_left); break;
+    }
+    PDS_LAUNCH_CHECK("tail_window_kernel");
+    return PDS_OK;
   }
+  PDS_KERNEL("hourglass_tail(tconv 4->1 + IN)", st);
+  PDS_KERNEL_WORK(2.0 * 192 * B * D * H * W, (double)B * D * H * W * 16 + (double)B * D * H * W * 16);
+  static const bool tiled = !(getenv("PDS_B200_TAIL_TILED") && atoi(getenv("PDS_B200_TAIL_TILED")) == 0);
+  if (tiled) hourglass_tail_tiled_kernel<false><<<tgrid, dim3(32, 8), 0, st>>>(p, nullptr);
+  else hourglass_tail_kernel<0><<<grid, dim3(32, by), 0, st>>>(p, f);
+  PDS_LAUNCH_CHECK("hourglass_tail_kernel");
   return PDS_OK;
 }
 

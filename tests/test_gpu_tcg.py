@@ -187,10 +187,15 @@ def test_hourglass_tensor_core_golden(golden):
 
 
 @pytest.mark.parametrize('precision', ['fp16x2', 'fp32'])
+@pytest.mark.parametrize('zseg', [None, '12'])
 @pytest.mark.parametrize('hsw,step,crop', [(4, 2, (36, 0)), (2, 1, (0, 0)), (8, 2, (5, 7)), (3, 3, (64, 129))])
-def test_fused_tail_estimator_is_bit_identical(precision, hsw, step, crop):
+def test_fused_tail_estimator_is_bit_identical(precision, hsw, step, crop, zseg, monkeypatch):
     """pds_regularization_forward_disparity == pds_regularization_forward + pds_subpixel_map
-    (+ SizeAdapter.unpad), bit for bit, indices included."""
+    (+ SizeAdapter.unpad), bit for bit, indices included.  The fused form tracks the arg-max inside
+    the transposed convolution (per z segment: zseg = 12 gives three segments here) and recomputes the
+    window around it; the cost volume is never written."""
+    if zseg:
+        monkeypatch.setenv('PDS_B200_TAIL_ZSEG', zseg)
     from practicaldeepstereo_nips2018_b200 import estimator
     params = synth.make_params(synth.regularization_specs(), 48)
     reg = load_module(regularization.Regularization(precision=precision), params)
