@@ -226,7 +226,9 @@ int launch(const T* cost, float* disparity, int64_t* argmax, int B, int D, int H
   // rows above crop_top are never loaded; every other cost element is read once
   PDS_KERNEL_WORK(0, (double)B * Hc * ((double)D * W * sizeof(T) + (double)(W - crop_left) * 4));
   // 128 threads, chunks of 6 planes: measured best at C2 (50 us = 4.0 TB/s; chunks of 4 / 8 / 12 /
-  // 16: 57 / 71 / 63 / 61 us; the element-by-element scan was instruction-bound at 77-112 us)
+  // 16: 57 / 71 / 63 / 61 us; the element-by-element scan was instruction-bound at 77-112 us; with the
+  // next chunk's loads issued before the current chunk is scanned -- twice the bytes in flight per
+  // thread, 24 more registers -- 81 us for chunks of 6 and 72 us for chunks of 4)
   dim3 grid((unsigned)(((size_t)quads * Hc + 127) / 128), (unsigned)B);
 #define PDS_EST(RR)                                                                  \
   subpixel_map_kernel<T, V, RR, 6, 128><<<grid, 128, 0, st>>>(cost, disparity, argmax, D, H, W, \
