@@ -226,7 +226,7 @@ def run_reference(args, H, W, md, desc):
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def time_pipeline(pipe, items, steps, barrier, max_over_ranks, out=None, download=True):
@@ -265,7 +265,25 @@ def sync_latency_ms(net, pairs, reps=12):
     return statistics.median(times), min(times)
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout."""
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # Libraries talk on stdout (NCCL prints its version there when NCCL_DEBUG=VERSION is set in the
+    # image): everything but the JSON line goes to stderr, so that stdout carries exactly one line.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=60)
@@ -544,7 +562,7 @@ def main():
                                     'cores': cores, 'kind': 'port',
                                     'sample': f'{len(times)} x one full {W}x{H} pair, torch port of '
                                               'the reference forward (after 1 warm-up)'}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
