@@ -298,7 +298,7 @@ def main():
                          "them (default; dataset.py:67-72 converts on the host, here the kernel does) or "
                          "float (B,3,H,W) as the reference's loader yields; the other one is reported as "
                          "e2e_other_images")
-    ap.add_argument('--preheat-s', type=float, default=2.0,
+    ap.add_argument('--preheat-s', type=float, default=4.0,
                     help='seconds of untimed forwards before the timed legs (sustained clocks for every leg)')
     ap.add_argument('--streams', type=int, default=4,
                     help='compute streams of the e2e serving pipeline (pairs dealt round-robin)')
