@@ -69,42 +69,16 @@ __device__ __forceinline__ bool takes_over(float v, float best) {
   return (v > best) || ((v != v) && (best == best));
 }
 
-// Running state of SubpixelMap for one output pixel (estimator.py:59-91, same scheme as
-// subpixel_map_kernel): maximum with its index, the R values before it (from a rolling
-// history) and the R values after it (captured as the scan passes them).
+// SubpixelMap window of one output pixel (estimator.py:59-91): the maximum with its index, the R
+// values before it and the R values after it.
 template <int R>
 struct MapState {
-  float best, before[R], after[R], hist[R];
+  float best, before[R], after[R];
   int idx;
   __device__ __forceinline__ void init() {
     best = 0.f; idx = -1;
 #pragma unroll
-    for (int r = 0; r < R; ++r) { before[r] = 0.f; after[r] = 0.f; hist[r] = 0.f; }
-  }
-  // A scan may cover only a SEGMENT [z0, z1) of the disparity axis (segments are merged by
-  // subpixel_merge_kernel): values just before the segment only warm the history up, values just
-  // after it are only captured into the window of a maximum near the segment's end.
-  __device__ __forceinline__ void warm(float x) {
-#pragma unroll
-    for (int r = R - 1; r > 0; --r) hist[r] = hist[r - 1];
-    hist[0] = x;
-  }
-  __device__ __forceinline__ void push(float x, int d, bool first) {
-    const int off = d - idx;
-    if (first || takes_over(x, best)) {
-      best = x; idx = d;
-#pragma unroll
-      for (int r = 0; r < R; ++r) before[r] = hist[r];
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; ++r) if (off == r + 1) after[r] = x;
-    }
-    warm(x);
-  }
-  __device__ __forceinline__ void tail(float x, int d) {
-    const int off = d - idx;
-#pragma unroll
-    for (int r = 0; r < R; ++r) if (off == r + 1) after[r] = x;
+    for (int r = 0; r < R; ++r) { before[r] = 0.f; after[r] = 0.f; }
   }
   // softmax over the window, max-subtracted, summation in shift order (estimator.py:66-90)
   __device__ __forceinline__ float disparity(int D, int step) const {
@@ -128,24 +102,14 @@ struct MapState {
   }
 };
 
-struct FusedParams {
-  float* disparity;      // (B, 2H - crop_top, 2W - crop_left)
-  int64_t* argmax;       // same shape or null
-  int step, crop_top, crop_left;
-  float* state;          // [segment][2 + 2R fields][B][2H][2W]: partial SubpixelMap states
-};
-
-// R == 0: writes the cost volume (B, D, 2H, 2W).  R >= 1: the volume is never written -- every
-// thread feeds the four output pixels it owns into the SubpixelMap state (window radius R) and
-// stores their disparities, cropped (SizeAdapter.unpad), at the end of its march along z.
-template <int R>
-__global__ void __launch_bounds__(256, R > 0 ? 2 : 0)   // fused: two CTAs per SM despite the estimator state
-hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f) {
+// Per-thread form of the plain (cost-volume writing) kernel (PDS_B200_TAIL_TILED=0; the tiled form
+// below is the default): one thread owns one (y, x) column of the input grid.
+__global__ void __launch_bounds__(256)
+hourglass_tail_kernel(const __grid_constant__ TailParams p) {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   const int b = blockIdx.z / p.nseg, seg = blockIdx.z - b * p.nseg;
   const int z0 = seg * p.zseg, z1 = min(p.D, z0 + p.zseg);
   if (x >= p.W || y >= p.H) return;
-  if (R > 0 && (2 * y + 1 < f.crop_top || 2 * x + 1 < f.crop_left)) return;   // all four pixels cropped
   // InstanceNorm of the input as one multiply-add per channel
   float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
   if (p.stats) {
@@ -165,7 +129,7 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
   const float4* base = p.in + (size_t)b * p.D * plane;
   const int OW = 2 * p.W;
   const size_t oplane = (size_t)4 * plane;
-  float* obase = R == 0 ? p.out + (size_t)b * p.D * oplane + (size_t)(2 * y) * OW + 2 * x : nullptr;
+  float* obase = p.out + (size_t)b * p.D * oplane + (size_t)(2 * y) * OW + 2 * x;
   bool okx[3], oky[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) { okx[d] = x + d - 1 >= 0 && x + d - 1 < p.W; oky[d] = y + d - 1 >= 0 && y + d - 1 < p.H; }
@@ -175,15 +139,7 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
   for (int k = 0; k < 3; ++k)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[0][k][c] = 0.f;
-  MapState<(R > 0 ? R : 1)> state[4];
-  if (R > 0) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) state[c].init();
-  }
-
-  // fused: the scan of a segment extends R outputs to either side (history warm-up / window capture)
-  const int zs = R > 0 ? max(0, z0 - R) : z0, ze = R > 0 ? min(p.D, z1 + R) : z1;
-  for (int zi = zs - 1; zi <= ze; ++zi) {
+  for (int zi = z0 - 1; zi <= z1; ++zi) {
     if (zi >= 0 && zi < p.D) {
       float4 v[3][1][3];
       const float4* pl = base + (size_t)zi * plane + (size_t)y * p.W + x;
@@ -205,52 +161,13 @@ hourglass_tail_kernel(const __grid_constant__ TailParams p, const FusedParams f)
       tail_accumulate_row<2, 1>(acc, v[2], p.w);
     }
     const int zo = zi - 1;
-    if (zo >= zs && zo < ze) {
-      if (R == 0) {
-        float* o = obase + (size_t)zo * oplane;
-        *reinterpret_cast<float2*>(o) = make_float2(acc[0][0][0] + p.bias, acc[0][0][1] + p.bias);
-        *reinterpret_cast<float2*>(o + OW) = make_float2(acc[0][0][2] + p.bias, acc[0][0][3] + p.bias);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float val = acc[0][0][c] + p.bias;
-          if (zo < z0) state[c].warm(val);
-          else if (zo < z1) state[c].push(val, zo, zo == z0);
-          else state[c].tail(val, zo);
-        }
-      }
+    if (zo >= z0 && zo < z1) {
+      float* o = obase + (size_t)zo * oplane;
+      *reinterpret_cast<float2*>(o) = make_float2(acc[0][0][0] + p.bias, acc[0][0][1] + p.bias);
+      *reinterpret_cast<float2*>(o + OW) = make_float2(acc[0][0][2] + p.bias, acc[0][0][3] + p.bias);
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) { acc[0][0][c] = acc[0][1][c]; acc[0][1][c] = acc[0][2][c]; acc[0][2][c] = 0.f; }
-  }
-  if (R > 0) {
-    if (f.state) {
-      // partial state of this segment for the four pixels: fields best, idx, before[R], after[R]
-      const int OH = 2 * p.H;
-      const size_t fplane = (size_t)p.B * OH * OW;
-      float* sp = f.state + (size_t)seg * (2 + 2 * R) * fplane + ((size_t)b * OH + 2 * y) * OW + 2 * x;
-      constexpr int RR = R > 0 ? R : 1;
-#pragma unroll
-      for (int k = 0; k < 2 + 2 * RR; ++k) {
-        float q[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          q[c] = k == 0 ? state[c].best : (k == 1 ? __int_as_float(state[c].idx)
-                        : (k < 2 + RR ? state[c].before[k - 2] : state[c].after[k - 2 - RR]));
-        *reinterpret_cast<float2*>(sp + (size_t)k * fplane) = make_float2(q[0], q[1]);
-        *reinterpret_cast<float2*>(sp + (size_t)k * fplane + OW) = make_float2(q[2], q[3]);
-      }
-      return;
-    }
-    const int Hc = 2 * p.H - f.crop_top, Wc = OW - f.crop_left;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int oy = 2 * y + (c >> 1) - f.crop_top, ox = 2 * x + (c & 1) - f.crop_left;
-      if (oy < 0 || ox < 0) continue;
-      const size_t o = ((size_t)b * Hc + oy) * Wc + ox;
-      f.disparity[o] = state[c].disparity(p.D, f.step);
-      if (f.argmax) f.argmax[o] = state[c].idx;
-    }
   }
 }
 
@@ -569,8 +486,6 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
       for (int kh = 0; kh < 4; ++kh)
         for (int kw = 0; kw < 4; ++kw) p.w[kd][kh][kw][ci] = w_host[((ci * 3 + kd) * 4 + kh) * 4 + kw];
   p.bias = bias;
-  FusedParams f;
-  f.disparity = nullptr; f.argmax = nullptr; f.step = step; f.crop_top = crop_top; f.crop_left = crop_left; f.state = nullptr;
   dim3 grid((unsigned)((W + 31) / 32), (unsigned)((H + by - 1) / by), (unsigned)(B * p.nseg));
   if (grid.z > 65535) { set_error("hourglass_tail: batch too large"); return PDS_ERR_UNSUPPORTED; }
   if (fused && (R < 1 || R > 4 || crop_top < 0 || crop_left < 0 || crop_top > 2 * H || crop_left > 2 * W || !state)) {
@@ -606,7 +521,7 @@ int hourglass_tail_forward(const float* in, float* out, const double* stats, con
   PDS_KERNEL_WORK(2.0 * 192 * B * D * H * W, (double)B * D * H * W * 16 + (double)B * D * H * W * 16);
   static const bool tiled = !(getenv("PDS_B200_TAIL_TILED") && atoi(getenv("PDS_B200_TAIL_TILED")) == 0);
   if (tiled) hourglass_tail_tiled_kernel<false><<<tgrid, dim3(32, 8), 0, st>>>(p, nullptr);
-  else hourglass_tail_kernel<0><<<grid, dim3(32, by), 0, st>>>(p, f);
+  else hourglass_tail_kernel<<<grid, dim3(32, by), 0, st>>>(p);
   PDS_LAUNCH_CHECK("hourglass_tail_kernel");
   return PDS_OK;
 }
