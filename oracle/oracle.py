@@ -213,3 +213,49 @@ def network_forward(left, right, p_embedding, p_matching, p_regularization,
     if rc != 0:
         raise ValueError('"maximum_disparity" + 1 should be multiple of 64')
     return (disp, cost) if return_cost else disp
+
+
+# ---- f4 (training): adjoints, restated in numpy (small cases only; float64 inside) -----------------
+def matching_concat_backward(grad_volume):
+    """Adjoint of matching_concat (what autograd accumulates through the reference's per-disparity
+    pad / slice / cat nodes, matching.py:53-60): grad_volume (B, D, 2C, H, W) ->
+    grad_left[b,c,y,x] = sum_d g[b,d,c,y,x];  grad_right[b,c,y,x] = sum_{d: x+d<W} g[b,d,C+c,y,x+d]."""
+    g = np.asarray(grad_volume, dtype=np.float64)
+    B, D, C2, H, W = g.shape
+    C = C2 // 2
+    grad_left = g[:, :, :C].sum(axis=1)
+    grad_right = np.zeros((B, C, H, W))
+    for d in range(min(D, W)):
+        grad_right[..., :W - d] += g[:, d, C:, :, d:]
+    return grad_left.astype(np.float32), grad_right.astype(np.float32)
+
+
+def leaky_instance_norm(x, gamma, beta, eps=1e-5, slope=0.1):
+    """InstanceNorm(affine)(LeakyReLU(x)) (network_blocks.py:47-58) and what its backward needs."""
+    x = np.asarray(x, dtype=np.float64)
+    z = np.where(x > 0, x, slope * x)
+    axes = tuple(range(2, x.ndim))
+    mean = z.mean(axis=axes, keepdims=True)
+    var = z.var(axis=axes, keepdims=True)               # biased
+    rstd = 1.0 / np.sqrt(var + eps)
+    shape = (1, -1) + (1,) * (x.ndim - 2)
+    zhat = (z - mean) * rstd
+    y = zhat * np.asarray(gamma, np.float64).reshape(shape) + np.asarray(beta, np.float64).reshape(shape)
+    return y, (zhat, rstd)
+
+
+def leaky_instance_norm_backward(x, grad_y, gamma, eps=1e-5, slope=0.1):
+    """-> grad_x, grad_gamma, grad_beta:  dz = gamma * rstd * (dy - mean(dy) - zhat * mean(dy * zhat)),
+    dx = dz * LeakyReLU'(x) (slope at x <= 0), d gamma = sum dy * zhat, d beta = sum dy."""
+    x = np.asarray(x, dtype=np.float64)
+    dy = np.asarray(grad_y, dtype=np.float64)
+    _, (zhat, rstd) = leaky_instance_norm(x, gamma, np.zeros_like(np.asarray(gamma, np.float64)), eps, slope)
+    axes = tuple(range(2, x.ndim))
+    shape = (1, -1) + (1,) * (x.ndim - 2)
+    g = np.asarray(gamma, np.float64).reshape(shape)
+    m1 = dy.mean(axis=axes, keepdims=True)
+    m2 = (dy * zhat).mean(axis=axes, keepdims=True)
+    dz = g * rstd * (dy - m1 - zhat * m2)
+    dx = dz * np.where(x > 0, 1.0, slope)
+    red = (0,) + axes
+    return dx, (dy * zhat).sum(axis=red), dy.sum(axis=red)

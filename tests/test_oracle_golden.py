@@ -307,3 +307,33 @@ def test_package_matching_gradients_on_cpu(golden):
     for k, v in op.named_parameters():
         ref = g['grad_param_' + k.replace('.', '__')]
         close(v.grad.numpy(), ref, 1e-4 * max(1.0, float(np.abs(ref).max())))
+
+
+def test_oracle_adjoints_against_autograd():
+    """numpy restatements of the f4 adjoints (oracle.py) against float64 autograd through the torch
+    port's own forward operators: the volume adjoint for more disparities than columns, and
+    LeakyReLU + InstanceNorm in 2-D and 3-D."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(7)
+    for B, C, H, W, D in ((2, 3, 4, 9, 6), (1, 2, 3, 5, 9)):
+        left = torch.from_numpy(rng.randn(B, C, H, W)).requires_grad_(True)
+        right = torch.from_numpy(rng.randn(B, C, H, W)).requires_grad_(True)
+        probe = rng.randn(B, 2 * C, D, H, W)
+        out = torch_port.matching(left, right, lambda x: x, D - 1)            # (B, 2C, D, H, W)
+        (out * torch.from_numpy(probe)).sum().backward()
+        gl, gr = oracle.matching_concat_backward(probe.transpose(0, 2, 1, 3, 4))
+        close(gl, left.grad.numpy().astype(np.float32), 1e-5)
+        close(gr, right.grad.numpy().astype(np.float32), 1e-5)
+    for shape in ((2, 4, 5, 7), (1, 3, 4, 5, 6)):
+        x = torch.from_numpy(rng.randn(*shape) * 2 + 0.3).requires_grad_(True)
+        gamma = torch.from_numpy(rng.rand(shape[1]) + 0.5).requires_grad_(True)
+        beta = torch.from_numpy(rng.randn(shape[1])).requires_grad_(True)
+        probe = rng.randn(*shape)
+        y = F.instance_norm(F.leaky_relu(x, 0.1), weight=gamma, bias=beta, eps=1e-5)
+        (y * torch.from_numpy(probe)).sum().backward()
+        y_o, _ = oracle.leaky_instance_norm(x.detach().numpy(), gamma.detach().numpy(), beta.detach().numpy())
+        dx, dg, db = oracle.leaky_instance_norm_backward(x.detach().numpy(), probe, gamma.detach().numpy())
+        close(y_o, y.detach().numpy(), 1e-9)
+        close(dx, x.grad.numpy(), 1e-9)
+        close(dg, gamma.grad.numpy(), 1e-9)
+        close(db, beta.grad.numpy(), 1e-9)
